@@ -1,0 +1,107 @@
+// capi.cu -- the C ABI of libb200drr.so (see include/b200drr.h for the contract of every entry point).
+#include <cuda_runtime.h>
+
+#include "../../include/b200drr.h"
+#include "kernels.h"
+
+using namespace b200drr;
+
+namespace {
+
+inline bool bad_dims(int D0, int D1, int D2) { return D0 <= 0 || D1 <= 0 || D2 <= 0; }
+inline bool bad_rays(int B, int64_t N) { return B <= 0 || B > 65535 || N <= 0; }
+inline VolDims mk(int D0, int D1, int D2)
+{
+    VolDims d;
+    d.d[0] = D0;
+    d.d[1] = D1;
+    d.d[2] = D2;
+    return d;
+}
+inline int ret(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
+
+}  // namespace
+
+extern "C" {
+
+int b200drr_version(void) { return B200DRR_VERSION; }
+
+const char* b200drr_error_string(int code)
+{
+    if (code == 0) return "success";
+    if (code == B200DRR_EINVAL) return "b200drr: invalid argument (null pointer, non-positive size, B > 65535 or bad enum)";
+    if (code == B200DRR_EUNSUPPORTED) return "b200drr: unsupported option combination for this entry point";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "b200drr: unknown error code";
+}
+
+int b200drr_device_sm_count(void)
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+int b200drr_device_cc(void)
+{
+    int dev = 0, ma = 0, mi = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return 0;
+    return ma * 10 + mi;
+}
+
+int b200drr_siddon_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                       const float* raylen, float* out, int B, int64_t N, float voxel_shift, float eps, int reduce,
+                       int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, reduce,
+                                 align_corners != 0, (cudaStream_t)stream));
+}
+
+int b200drr_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                       const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                       float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int align_corners,
+                       void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    if (align_corners) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_bwd(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, N,
+                                 voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                          const float* raylen, float* out, int B, int64_t N, float voxel_shift, float eps,
+                          int n_points, const float* alpha_range, int reduce, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) ||
+        n_points < 2 || reduce < 0 || reduce > 1)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, n_points,
+                                    alpha_range, reduce, align_corners != 0, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                          const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                          float* g_vol, float* g_alpha_range, int B, int64_t N, float voxel_shift, float eps,
+                          int n_points, const float* alpha_range, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) ||
+        n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol,
+                                    g_alpha_range, B, N, voxel_shift, eps, n_points, alpha_range, align_corners != 0,
+                                    (cudaStream_t)stream));
+}
+
+int b200drr_siddon_visits(int D0, int D1, int D2, const float* src, const float* tgt, int32_t* visits, int B,
+                          int64_t N, float voxel_shift, float eps, void* stream)
+{
+    if (!src || !tgt || !visits || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    return ret(launch_siddon_visits(mk(D0, D1, D2), src, tgt, visits, B, N, voxel_shift, eps, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// common.cuh -- shared helpers for the sm_100a DRR kernels.
+//
+// The per-ray math (ray_math.cuh) is written as host+device functions so that tests/hostemu can compile the very
+// same source with g++ and check it against the oracle in the CPU-only container.  That emulation is test
+// infrastructure; the product library contains device code only and has no CPU path.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+
+namespace b200drr {
+
+constexpr int kWarp = 32;
+
+struct VolDims {
+    int d[3];
+};
+
+B200_HD float ldg(const float* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// single-rounding multiply / add that the compiler may not contract into an fma
+B200_HD float mul_rn(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+B200_HD float add_rn(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+
+// accumulate into the volume gradient: red.global.add.f32 on the device, plain add in the host emulation
+B200_HD void red_add(float* addr, float v)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+#else
+    *addr += v;
+#endif
+}
+
+// One ray: d = (target - source) + eps (renderers.py:104-106), inv = 1/d.
+struct Ray {
+    float s[3];
+    float d[3];
+    float inv[3];
+};
+
+B200_HD Ray load_ray(const float* src, const float* tgt, int b, int64_t r, float eps)
+{
+    Ray ray;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ray.s[a] = ldg(src + b * 3 + a);
+        ray.d[a] = (ldg(tgt + r * 3 + a) - ray.s[a]) + eps;
+        ray.inv[a] = 1.0f / ray.d[a];
+    }
+    return ray;
+}
+
+// alpha of plane i on axis a with the reference's own rounding sequence ((i - shift) - s) / d
+B200_HD float plane_alpha(const Ray& ray, int a, float i, float shift) { return ((i - shift) - ray.s[a]) / ray.d[a]; }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect smem reuse between consecutive calls
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    const int nwarp = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nwarp) ? smem[threadIdx.x] : 0.0f;
+    if (warp == 0) v = warp_sum(v);
+    return v;
+}
+#endif
+
+}  // namespace b200drr

@@ -1,0 +1,29 @@
+// kernels.h -- internal launcher prototypes shared by the .cu files and the C ABI (capi.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200drr {
+
+cudaError_t launch_siddon_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,
+                              const float* raylen, float* out, int B, int64_t N, float shift, float eps, int reduce,
+                              int align_corners, cudaStream_t stream);
+cudaError_t launch_siddon_visits(VolDims dims, const float* src, const float* tgt, int32_t* visits, int B, int64_t N,
+                                 float shift, float eps, cudaStream_t stream);
+cudaError_t launch_siddon_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,
+                              const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                              float* g_vol, int B, int64_t N, float shift, float eps, int stop_grad,
+                              cudaStream_t stream);
+cudaError_t launch_trilinear_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                 const float* raylen, float* out, int B, int64_t N, float shift, float eps,
+                                 int n_points, const float* alpha_range, int reduce, int align_corners,
+                                 cudaStream_t stream);
+cudaError_t launch_trilinear_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                 const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                 float* g_vol, float* g_alpha_range, int B, int64_t N, float shift, float eps,
+                                 int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
+
+}  // namespace b200drr

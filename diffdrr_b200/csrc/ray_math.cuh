@@ -1,0 +1,456 @@
+// ray_math.cuh -- per-ray Siddon / trilinear math (host+device; the kernels are thin wrappers around these).
+//
+// Replaces, per ray, reference renderers.py:34-76 (Siddon.forward), 205-240 (Trilinear.forward) and their
+// autograd graphs.  The reference materialises all D0+D1+D2+3 plane alphas per ray, sorts them, builds
+// (B,N,M,3) sample grids and calls grid_sample; here one thread walks one ray with a 3-way monotone
+// merge, alphas live in registers and nothing of size (B,N,M) ever exists.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200drr {
+
+// ===================================================================================================
+// Siddon, general walk: visits EVERY plane of the volume like the reference (no clipping), samples the
+// nearest voxel at each segment midpoint through the literal normalise / un-normalise chain of
+// renderers.py:143-153 + ATen grid_sampler.  Handles align_corners and reduce="max".  Slow path.
+// ===================================================================================================
+B200_HD float unnormalize(float g, int size, int align_corners)
+{
+    return align_corners ? ((g + 1.0f) / 2.0f) * (float)(size - 1) : ((g + 1.0f) * (float)size - 1.0f) / 2.0f;
+}
+
+B200_HD float siddon_ray_general(const float* vol, const VolDims& dims, const Ray& ray, float L, float shift,
+                                 int reduce, int align_corners)
+{
+    int pos[3], stp[3], left[3];
+    float head[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = ray.d[a] > 0.0f;
+        pos[a] = fwd ? 0 : dims.d[a];
+        stp[a] = fwd ? 1 : -1;
+        left[a] = dims.d[a] + 1;
+        head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+    }
+    const int M = dims.d[0] + dims.d[1] + dims.d[2] + 3;
+    float acc = 0.0f, aprev = 0.0f;
+    bool first = true;
+    for (int m = 0; m < M; ++m) {
+        // pop the smallest head (ties: lowest axis first, like a stable sort of cat([ax, ay, az]))
+        const float h0 = left[0] > 0 ? head[0] : INFINITY;
+        const float h1 = left[1] > 0 ? head[1] : INFINITY;
+        const float h2 = left[2] > 0 ? head[2] : INFINITY;
+        const float acur = fminf(fminf(h0, h1), h2);
+        const int best = (left[0] > 0 && h0 == acur) ? 0 : ((left[1] > 0 && h1 == acur) ? 1 : 2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == best) {
+                pos[a] += stp[a];
+                left[a] -= 1;
+                if (left[a] > 0) head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+            }
+        if (m > 0) {
+            const float amid = (aprev + acur) / 2.0f;
+            bool inb = true;
+            int64_t off = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = add_rn(ray.s[a], mul_rn(amid, ray.d[a]));
+                const float g = 2.0f * (x + shift) / (float)dims.d[a] - 1.0f;
+                const float rr = rintf(unnormalize(g, dims.d[a], align_corners));
+                inb = inb && (rr >= 0.0f) && (rr < (float)dims.d[a]);
+                off = off * dims.d[a] + (inb ? (int64_t)rr : 0);
+            }
+            const float v = inb ? ldg(vol + off) : 0.0f;
+            const float term = mul_rn(mul_rn(L, v), acur - aprev);
+            if (reduce == 0) acc = add_rn(acc, term);
+            else if (first || term > acc) acc = term;
+            first = false;
+        }
+        aprev = acur;
+    }
+    return acc;
+}
+
+// ===================================================================================================
+// Siddon, fast walk (align_corners = False): clipped to the volume's box, incremental voxel index.
+// In "plane space" q = x + shift, voxel k of axis a spans q in [k, k+1] and the reference's plane i
+// (x = i - shift, renderers.py:97-99) sits at q = i.  Every reference segment outside
+// [alpha_in, alpha_out] samples zero padding, so clipping to the box is exact; alphas are NOT clipped to
+// [0,1] (quirk Q1).  Plane alphas are fma(i, 1/d, c) from the integer plane index (never accumulated),
+// c = -(shift + s)/d.
+// ===================================================================================================
+struct Walk {
+    float an[3];   // alpha of the next plane crossing per axis
+    float pf[3];   // next plane index per axis, as float
+    float inv[3];  // 1/d
+    float c[3];    // -(shift + s)/d
+    float stf[3];  // +1 / -1
+    int idx[3];    // current voxel
+    int sti[3];    // +1 / -1
+    float a_in, a_out;
+    int entry_axis;
+    bool hit;
+};
+
+B200_HD Walk start_walk(const Ray& ray, const VolDims& dims, float shift)
+{
+    Walk w;
+    float lo[3];
+    w.a_in = -INFINITY;
+    w.a_out = INFINITY;
+    w.entry_axis = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        w.inv[a] = ray.inv[a];
+        w.c[a] = -(shift + ray.s[a]) * ray.inv[a];
+        const float a0 = w.c[a];                                    // plane 0
+        const float a1 = fmaf((float)dims.d[a], w.inv[a], w.c[a]);  // plane D_a
+        lo[a] = fminf(a0, a1);
+        const float hi = fmaxf(a0, a1);
+        if (lo[a] > w.a_in) {
+            w.a_in = lo[a];
+            w.entry_axis = a;
+        }
+        w.a_out = fminf(w.a_out, hi);
+    }
+    w.hit = w.a_in < w.a_out;  // false for NaN as well
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = ray.d[a] > 0.0f;
+        w.sti[a] = fwd ? 1 : -1;
+        w.stf[a] = fwd ? 1.0f : -1.0f;
+        int i;
+        if (lo[a] >= w.a_in) {
+            i = fwd ? 0 : dims.d[a] - 1;  // entering through a face of this axis
+        } else {
+            const float q = fmaf(w.a_in, ray.d[a], ray.s[a] + shift);
+            i = (int)floorf(q);
+            i = i < 0 ? 0 : (i > dims.d[a] - 1 ? dims.d[a] - 1 : i);
+        }
+        w.idx[a] = i;
+        w.pf[a] = (float)(fwd ? i + 1 : i);
+        w.an[a] = fmaf(w.pf[a], w.inv[a], w.c[a]);
+    }
+    return w;
+}
+
+// Advance the walk across the plane at alpha `anext` (= min of w.an); returns the axis crossed and sets
+// `inside` to whether the new voxel is still in the volume.
+B200_HD int step_walk(Walk& w, const VolDims& dims, float anext, int64_t& off, const int64_t so[3], bool& inside)
+{
+    int ax;
+    if (w.an[0] == anext) ax = 0;
+    else if (w.an[1] == anext) ax = 1;
+    else ax = 2;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a == ax) {
+            w.idx[a] += w.sti[a];
+            inside = (unsigned)w.idx[a] < (unsigned)dims.d[a];
+            off += so[a];
+            w.pf[a] += w.stf[a];
+            w.an[a] = fmaf(w.pf[a], w.inv[a], w.c[a]);
+        }
+    return ax;
+}
+
+// Sum of v * (alpha_{j+1} - alpha_j) over the voxels the line crosses (multiply by raylen outside).
+// COUNT=true skips the loads and returns the number of voxels visited instead.
+template <bool COUNT>
+B200_HD float siddon_ray_fast(const float* vol, const VolDims& dims, const Ray& ray, float shift, int* visits)
+{
+    Walk w = start_walk(ray, dims, shift);
+    if (!w.hit) {
+        if (COUNT) *visits = 0;
+        return 0.0f;
+    }
+    const int64_t s1 = dims.d[2], s0 = (int64_t)dims.d[1] * dims.d[2];
+    int64_t off = ((int64_t)w.idx[0] * dims.d[1] + w.idx[1]) * dims.d[2] + w.idx[2];
+    const int64_t so[3] = {w.sti[0] * s0, w.sti[1] * s1, (int64_t)w.sti[2]};
+    float acur = w.a_in, acc = 0.0f;
+    int count = 0;
+    bool inside = true;
+    while (inside) {
+        const float v = COUNT ? 0.0f : ldg(vol + off);
+        const float anext = fminf(fminf(w.an[0], w.an[1]), w.an[2]);
+        acc = fmaf(anext - acur, v, acc);
+        acur = anext;
+        ++count;
+        step_walk(w, dims, anext, off, so, inside);
+    }
+    if (COUNT) *visits = count;
+    return acc;
+}
+
+// Closed-form backward of one ray.  With v_j the voxel of segment j and crossing m on
+// axis a:  dI/dalpha_m = L (v_{m-1} - v_m),  dalpha/ds_a = (alpha - 1)/d_a,  dalpha/dt_a = -alpha/d_a.
+// Per axis accumulate A_a = sum coef*alpha, C_a = sum coef with coef = v_before - v_after; then
+//   g_t[a] = -g L A_a / d_a,   g_s[a] = g L (A_a - C_a) / d_a.
+// Returns sum_j v_j len_j (for g_raylen); g_vol[voxel_j] += gL * len_j when g_vol != nullptr.
+B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, float gL, float* g_vol,
+                             float gs[3], float gt[3])
+{
+    Walk w = start_walk(ray, dims, shift);
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    float acc = 0.0f;
+    if (w.hit) {
+        const int64_t s1 = dims.d[2], s0 = (int64_t)dims.d[1] * dims.d[2];
+        int64_t off = ((int64_t)w.idx[0] * dims.d[1] + w.idx[1]) * dims.d[2] + w.idx[2];
+        const int64_t so[3] = {w.sti[0] * s0, w.sti[1] * s1, (int64_t)w.sti[2]};
+        float acur = w.a_in, vprev = 0.0f;
+        int axis_in = w.entry_axis;
+        bool inside = true;
+        while (inside) {
+            const float v = ldg(vol + off);
+            const float coef = vprev - v;  // crossing into this voxel at acur through axis_in
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                if (a == axis_in) {
+                    A[a] = fmaf(coef, acur, A[a]);
+                    C[a] += coef;
+                }
+            const float anext = fminf(fminf(w.an[0], w.an[1]), w.an[2]);
+            const float len = anext - acur;
+            acc = fmaf(len, v, acc);
+            if (g_vol) red_add(g_vol + off, gL * len);
+            acur = anext;
+            vprev = v;
+            axis_in = step_walk(w, dims, anext, off, so, inside);
+        }
+        // exit crossing: v_last -> 0 through axis_in at acur
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == axis_in) {
+                A[a] = fmaf(vprev, acur, A[a]);
+                C[a] += vprev;
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        gt[a] = -gL * A[a] * ray.inv[a];
+        gs[a] = gL * (A[a] - C[a]) * ray.inv[a];
+    }
+    return acc;
+}
+
+// ===================================================================================================
+// Trilinear ray marching.  Continuous voxel coordinate as a linear function of alpha:
+//   pix_a = p0_a + alpha * dp_a,   from x = s + alpha d,  g = 2 (x + shift)/D - 1  (renderers.py:148-152) and
+//   ATen's un-normalisation: align_corners=False -> pix = x + shift - 0.5;  True -> pix = (x + shift)(D-1)/D.
+// Interpolation weights are plain fp32 (no texture-unit fixed-point filtering: it would break 1e-4).
+// ===================================================================================================
+struct PixLine {
+    float p0[3], dp[3], ka[3];
+};
+
+B200_HD PixLine make_pixline(const Ray& ray, const VolDims& dims, float shift, int align_corners)
+{
+    PixLine pl;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ka = align_corners ? (float)(dims.d[a] - 1) / (float)dims.d[a] : 1.0f;
+        const float kb = align_corners ? shift * ka : shift - 0.5f;
+        pl.ka[a] = ka;
+        pl.p0[a] = fmaf(ray.s[a], ka, kb);
+        pl.dp[a] = ray.d[a] * ka;
+    }
+    return pl;
+}
+
+// torch.linspace(0, 1, P)[m] exactly as ATen evaluates it in fp32 (symmetric halves, fused end - step*k).
+B200_HD float linspace01(int m, int P, float step)
+{
+    return (m < P / 2) ? mul_rn(step, (float)m) : fmaf(-step, (float)(P - 1 - m), 1.0f);
+}
+
+// Sample index range [m_lo, m_hi] whose points can touch the volume (pix in (-1, D) on every axis);
+// samples outside it interpolate only zero padding.  One sample of slack on both sides.
+B200_HD void sample_range(const PixLine& pl, const VolDims& dims, float amin, float range, int P, int& m_lo, int& m_hi)
+{
+    float lo = -INFINITY, hi = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float inv = 1.0f / pl.dp[a];
+        const float a0 = (-1.0f - pl.p0[a]) * inv, a1 = ((float)dims.d[a] - pl.p0[a]) * inv;
+        lo = fmaxf(lo, fminf(a0, a1));
+        hi = fminf(hi, fmaxf(a0, a1));
+    }
+    if (!(range > 0.0f)) {  // degenerate range: march everything
+        m_lo = 0;
+        m_hi = P - 1;
+        return;
+    }
+    if (!(lo <= hi)) {  // the line misses the (padded) volume
+        m_lo = 1;
+        m_hi = 0;
+        return;
+    }
+    const float scale = (float)(P - 1) / range;
+    const float f_lo = floorf((lo - amin) * scale) - 1.0f, f_hi = ceilf((hi - amin) * scale) + 1.0f;
+    m_lo = (int)fmaxf(0.0f, fminf(f_lo, (float)P));
+    m_hi = (int)fminf((float)(P - 1), fmaxf(f_hi, -1.0f));
+}
+
+struct Corner8 {
+    float v[8];
+    float f[3];
+    int64_t base;   // offset of corner (0,0,0); only dereferenced where the in-bounds mask is set
+    unsigned mask;  // bit c = corner c in bounds, c = o0 | o1<<1 | o2<<2 (o_a = offset along volume axis a)
+};
+
+B200_HD int64_t corner_off(const VolDims& dims, int c)
+{
+    return (int64_t)(c & 1) * dims.d[1] * dims.d[2] + (int64_t)((c >> 1) & 1) * dims.d[2] + ((c >> 2) & 1);
+}
+
+B200_HD Corner8 gather8(const float* vol, const VolDims& dims, const float pix[3])
+{
+    Corner8 k;
+    int i0[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float fl = floorf(pix[a]);
+        k.f[a] = pix[a] - fl;
+        i0[a] = (int)fl;
+    }
+    k.base = ((int64_t)i0[0] * dims.d[1] + i0[1]) * dims.d[2] + i0[2];
+    const bool interior = (unsigned)i0[0] < (unsigned)(dims.d[0] - 1) && (unsigned)i0[1] < (unsigned)(dims.d[1] - 1) &&
+                          (unsigned)i0[2] < (unsigned)(dims.d[2] - 1);
+    if (interior) {
+        k.mask = 0xffu;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) k.v[c] = ldg(vol + k.base + corner_off(dims, c));
+    } else {
+        k.mask = 0u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int x = i0[0] + (c & 1), y = i0[1] + ((c >> 1) & 1), z = i0[2] + ((c >> 2) & 1);
+            const bool inb = (unsigned)x < (unsigned)dims.d[0] && (unsigned)y < (unsigned)dims.d[1] &&
+                             (unsigned)z < (unsigned)dims.d[2];
+            k.v[c] = inb ? ldg(vol + k.base + corner_off(dims, c)) : 0.0f;
+            k.mask |= inb ? (1u << c) : 0u;
+        }
+    }
+    return k;
+}
+
+B200_HD bool outside_padded(const float pix[3], const VolDims& dims)
+{
+    return pix[0] <= -1.0f || pix[1] <= -1.0f || pix[2] <= -1.0f || pix[0] >= (float)dims.d[0] ||
+           pix[1] >= (float)dims.d[1] || pix[2] >= (float)dims.d[2];
+}
+
+// value of the interpolant; axis 2 is the memory-fastest axis
+B200_HD float lerp8(const Corner8& k)
+{
+    const float f0 = k.f[0], f1 = k.f[1], f2 = k.f[2];
+    const float c00 = fmaf(f2, k.v[4] - k.v[0], k.v[0]);  // o0=0 o1=0
+    const float c10 = fmaf(f2, k.v[5] - k.v[1], k.v[1]);  // o0=1 o1=0
+    const float c01 = fmaf(f2, k.v[6] - k.v[2], k.v[2]);  // o0=0 o1=1
+    const float c11 = fmaf(f2, k.v[7] - k.v[3], k.v[3]);  // o0=1 o1=1
+    const float c0 = fmaf(f1, c01 - c00, c00);
+    const float c1 = fmaf(f1, c11 - c10, c10);
+    return fmaf(f0, c1 - c0, c0);
+}
+
+// sum (or max) over the samples of tri(V, x_m); multiply by raylen * step outside.
+B200_HD float trilinear_ray_fwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, int P, float amin,
+                                float amax, int reduce, int align_corners)
+{
+    const PixLine pl = make_pixline(ray, dims, shift, align_corners);
+    const float range = amax - amin;
+    const float lstep = 1.0f / (float)(P - 1);
+    int m_lo, m_hi;
+    sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    float acc = 0.0f;
+    bool have = false;
+    for (int m = m_lo; m <= m_hi; ++m) {
+        const float alpha = add_rn(mul_rn(linspace01(m, P, lstep), range), amin);
+        float pix[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
+        float val = 0.0f;
+        if (!outside_padded(pix, dims)) val = lerp8(gather8(vol, dims, pix));
+        if (reduce == 0) acc += val;
+        else acc = have ? fmaxf(acc, val) : val;
+        have = true;
+    }
+    // samples skipped by sample_range are exact zeros: they take part in a max
+    if (reduce != 0 && (m_lo > 0 || m_hi < P - 1 || !have)) acc = have ? fmaxf(acc, 0.0f) : 0.0f;
+    return acc;
+}
+
+struct TriGrad {
+    float gs[3], gt[3];  // d/d source, d/d target  (already scaled by g L step)
+    float sumV;          // sum of sampled values
+    float ga0, ga1;      // d/d alphamin, d/d alphamax
+};
+
+// Closed-form backward of one ray.  G = gradient of the interpolant w.r.t. pix (zero-padded):
+//   g_s = g L step sum (1-alpha_m) G_m ka,  g_t = g L step sum alpha_m G_m ka,  g_L = g step sum V_m,
+//   g_amin = g L [-sum V/(P-1) + step sum (1-lin_m) G_m.dp],  g_amax = g L [+sum V/(P-1) + step sum lin_m G_m.dp],
+//   g_V[corner] += g L step w_corner.
+B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, int P, float amin,
+                                  float amax, int align_corners, float g, float L, float* g_vol)
+{
+    const PixLine pl = make_pixline(ray, dims, shift, align_corners);
+    const float range = amax - amin;
+    const float step = range / (float)(P - 1);
+    const float lstep = 1.0f / (float)(P - 1);
+    int m_lo, m_hi;
+    sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    const float gLs = g * L * step;
+    float sumV = 0.0f, S[3] = {0.0f, 0.0f, 0.0f}, T[3] = {0.0f, 0.0f, 0.0f}, E0 = 0.0f, E1 = 0.0f;
+    for (int m = m_lo; m <= m_hi; ++m) {
+        const float lin = linspace01(m, P, lstep);
+        const float alpha = add_rn(mul_rn(lin, range), amin);
+        float pix[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
+        if (outside_padded(pix, dims)) continue;
+        const Corner8 k = gather8(vol, dims, pix);
+        const float f0 = k.f[0], f1 = k.f[1], f2 = k.f[2];
+        const float e0 = 1.0f - f0, e1 = 1.0f - f1, e2 = 1.0f - f2;
+        const float c00 = fmaf(f2, k.v[4] - k.v[0], k.v[0]), c10 = fmaf(f2, k.v[5] - k.v[1], k.v[1]);
+        const float c01 = fmaf(f2, k.v[6] - k.v[2], k.v[2]), c11 = fmaf(f2, k.v[7] - k.v[3], k.v[3]);
+        const float c0 = fmaf(f1, c01 - c00, c00), c1 = fmaf(f1, c11 - c10, c10);
+        sumV += fmaf(f0, c1 - c0, c0);
+        float G[3];
+        G[0] = c1 - c0;
+        G[1] = e0 * (c01 - c00) + f0 * (c11 - c10);
+        G[2] = e0 * (e1 * (k.v[4] - k.v[0]) + f1 * (k.v[6] - k.v[2])) +
+               f0 * (e1 * (k.v[5] - k.v[1]) + f1 * (k.v[7] - k.v[3]));
+        float Gd = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            S[a] = fmaf(1.0f - alpha, G[a], S[a]);
+            T[a] = fmaf(alpha, G[a], T[a]);
+            Gd = fmaf(G[a], pl.dp[a], Gd);
+        }
+        E0 = fmaf(1.0f - lin, Gd, E0);
+        E1 = fmaf(lin, Gd, E1);
+        if (g_vol) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (k.mask & (1u << c)) {
+                    const float w = ((c & 1) ? f0 : e0) * (((c >> 1) & 1) ? f1 : e1) * (((c >> 2) & 1) ? f2 : e2);
+                    red_add(g_vol + k.base + corner_off(dims, c), gLs * w);
+                }
+        }
+    }
+    TriGrad out;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        out.gs[a] = gLs * pl.ka[a] * S[a];
+        out.gt[a] = gLs * pl.ka[a] * T[a];
+    }
+    out.sumV = sumV;
+    const float gLv = g * L * sumV / (float)(P - 1);
+    out.ga0 = -gLv + gLs * E0;
+    out.ga1 = gLv + gLs * E1;
+    return out;
+}
+
+}  // namespace b200drr

@@ -1,0 +1,103 @@
+/*
+ * b200drr.h -- C ABI of the B200-native DRR projector (libb200drr.so).
+ *
+ * This is the drop-in boundary for DiffDRR's renderer slot.  The reference is pure Python/PyTorch, so
+ * the "FFI" a maintainer binds is a ctypes stub; every entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/diffdrr/).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to caller-owned, contiguous, row-major fp32 (unless noted).
+ *   - vol is the CT density [D0][D1][D2], axis 2 fastest (reference drr.py:81-85 `density`).
+ *   - src [B][3], tgt [B][N][3] are ray end points in VOXEL-INDEX coordinates, raylen [B][N] the ray
+ *     lengths in world units: exactly the tensors reference drr.py:201-216 hands to the renderer
+ *     (`source (B,1,3)`, `target (B,N,3)`, `img (B,1,N)`).
+ *   - Launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream).  No entry point allocates, frees or synchronises, except where stated.
+ *   - Return value: 0 on success, a negative B200DRR_E* code for bad arguments, or a positive
+ *     cudaError_t value if a launch failed.  Nothing throws; nothing falls back to the CPU.
+ *   - reduce: 0 = "sum", 1 = "max" (reference renderers.py:175-183).
+ */
+#ifndef B200DRR_H
+#define B200DRR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DRR_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define B200DRR_EINVAL (-1)      /* null pointer / non-positive size / bad enum */
+#define B200DRR_EUNSUPPORTED (-2) /* combination the kernels do not implement (documented per call) */
+
+int b200drr_version(void);
+/* Human-readable text for a return code of any function below (static storage). */
+const char *b200drr_error_string(int code);
+/* Number of SMs / compute capability (major*10+minor) of the current device; 0 if there is no device. */
+int b200drr_device_sm_count(void);
+int b200drr_device_cc(void);
+
+/*
+ * Siddon forward: replaces Siddon.forward with mask=None (renderers.py:34-76) = _get_alphas (94-113)
+ * + _get_xyzs (143-153) + _get_voxel / grid_sample(mode="nearest") (156-169) + diff*mul + reduce (70-76).
+ *   out[b][n] = reduce_j  raylen[b][n] * V[nearest(s + mid_j * (t - s + eps))] * (alpha_{j+1} - alpha_j)
+ * over ALL D0+D1+D2+3 plane intersections of the infinite line (no clipping to [0,1]; quirk Q1).
+ * align_corners as in grid_sample.  Fast path: reduce=0 && align_corners=0; anything else takes the
+ * plane-by-plane general kernel (same results, slower).
+ */
+int b200drr_siddon_fwd(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                       const float *raylen, float *out, int B, int64_t N, float voxel_shift, float eps,
+                       int reduce, int align_corners, void *stream);
+
+/*
+ * Siddon backward: replaces the autograd graph of Siddon.forward (sum-backward, diff-backward,
+ * sort-backward, grid_sampler_3d_backward) with one closed-form pass.
+ *   gout [B][N] = dLoss/dout.
+ *   g_src [B][3]        overwritten (zero-filled inside, then accumulated)      -- may be NULL
+ *   g_tgt [B][N][3]     overwritten                                             -- may be NULL
+ *   g_raylen [B][N]     overwritten (zeros when stop_grad)                      -- may be NULL
+ *   g_vol [D0][D1][D2]  ACCUMULATED into with red.global.add (caller zero-fills); NULL = not wanted;
+ *                       ignored when stop_grad
+ * stop_grad != 0 restates stop_gradients_through_grid_sample=True (renderers.py:63-65).
+ * Only reduce="sum", align_corners=0 (B200DRR_EUNSUPPORTED otherwise).
+ */
+int b200drr_siddon_bwd(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                       const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                       float *g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad,
+                       int align_corners, void *stream);
+
+/*
+ * Trilinear forward: replaces Trilinear.forward with mask=None (renderers.py:205-240) for a given
+ * sampling range.  alpha_range is a DEVICE pointer to {alphamin, alphamax} (so that the range computed
+ * on the device by _get_alpha_minmax, renderers.py:124-140,221-223, needs no host round trip).
+ *   out[b][n] = reduce_m raylen * tri(V, s + alpha_m (t - s + eps)) * step,
+ *   alpha_m = linspace(0,1,n_points)[m] * (amax - amin) + amin,  step = (amax - amin)/(n_points - 1)
+ */
+int b200drr_trilinear_fwd(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                          const float *raylen, float *out, int B, int64_t N, float voxel_shift, float eps,
+                          int n_points, const float *alpha_range, int reduce, int align_corners, void *stream);
+
+/*
+ * Trilinear backward (autograd of Trilinear.forward incl. grid_sampler_3d_backward).
+ * Same output conventions as b200drr_siddon_bwd, plus
+ *   g_alpha_range [2]   ACCUMULATED dLoss/d{alphamin, alphamax} (caller zero-fills)  -- may be NULL
+ * Only reduce="sum".
+ */
+int b200drr_trilinear_bwd(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                          const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                          float *g_vol, float *g_alpha_range, int B, int64_t N, float voxel_shift, float eps,
+                          int n_points, const float *alpha_range, int align_corners, void *stream);
+
+/*
+ * Per-ray voxel-visit count of the Siddon walk (number of voxels the line crosses inside the volume),
+ * the unit of the ALGORITHMIC byte count used for roofline accounting: visits [B][N]
+ * int32.  Measurement helper; not part of the reference surface.
+ */
+int b200drr_siddon_visits(int D0, int D1, int D2, const float *src, const float *tgt, int32_t *visits, int B,
+                          int64_t N, float voxel_shift, float eps, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DRR_H */

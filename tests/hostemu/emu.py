@@ -1,0 +1,92 @@
+"""ctypes front-end of tests/hostemu/libhostemu.so (product per-ray math compiled for the CPU; test infra)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhostemu.so")
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_HERE, "hostemu.cpp")] + [
+            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh")]
+        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
+                                   "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _common(vol, src, tgt, raylen):
+    vol, src, tgt, raylen = _f(vol), _f(src), _f(tgt), _f(raylen)
+    return vol, src, tgt, raylen, tgt.shape[0], tgt.shape[1]
+
+
+def siddon_fwd(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, reduce="sum", align_corners=False, general=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    out = np.empty((B, 1, N), np.float32)
+    fn = lib().emu_siddon_general if general else lib().emu_siddon_fwd
+    fn(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out), ctypes.c_int(B), ctypes.c_long(N),
+       ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int({"sum": 0, "max": 1}[reduce]),
+       ctypes.c_int(bool(align_corners)))
+    return out
+
+
+def siddon_visits(shape, src, tgt, voxel_shift=0.5, eps=1e-8):
+    src, tgt = _f(src), _f(tgt)
+    B, N = tgt.shape[0], tgt.shape[1]
+    out = np.empty((B, N), np.int32)
+    lib().emu_siddon_visits(*map(ctypes.c_int, shape), _p(src), _p(tgt), _p(out), ctypes.c_int(B), ctypes.c_long(N),
+                            ctypes.c_float(voxel_shift), ctypes.c_float(eps))
+    return out
+
+
+def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    gout = _f(gout)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
+    lib().emu_siddon_bwd(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
+                         _p(g_tgt), _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N),
+                         ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(bool(stop_grad)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
+
+
+def trilinear_fwd(vol, src, tgt, raylen, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8, reduce="sum",
+                  align_corners=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    out = np.empty((B, 1, N), np.float32)
+    lib().emu_trilinear_fwd(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                            ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                            ctypes.c_int(n_points), ctypes.c_float(alphamin), ctypes.c_float(alphamax),
+                            ctypes.c_int({"sum": 0, "max": 1}[reduce]), ctypes.c_int(bool(align_corners)))
+    return out
+
+
+def trilinear_bwd(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8,
+                  align_corners=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    gout = _f(gout)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
+    g_ar = np.zeros(2, np.float32)
+    lib().emu_trilinear_bwd(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
+                            _p(g_tgt), _p(g_len), _p(g_vol), _p(g_ar), ctypes.c_int(B), ctypes.c_long(N),
+                            ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(n_points),
+                            ctypes.c_float(alphamin), ctypes.c_float(alphamax), ctypes.c_int(bool(align_corners)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=float(g_ar[0]),
+                g_alphamax=float(g_ar[1]))

@@ -1,0 +1,126 @@
+"""The product's per-ray math (diffdrr_b200/csrc/ray_math.cuh) compiled for the CPU, checked against the goldens
+recorded from the unmodified reference and against the oracle.  Catches kernel-logic bugs without a GPU; the real
+parity tests (tests/test_gpu_*.py) run the CUDA build of the same source through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from hostemu import emu
+from oracle import oracle
+from test_oracle import SIDDON, TRILINEAR
+
+IMG_TOL = 1e-4   # north_star: <= 1e-4 relative error vs the reference
+
+
+@pytest.mark.parametrize("name,kw", SIDDON)
+def test_siddon_forward(name, kw):
+    g = load_golden(name)
+    out = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"], **kw)
+    assert relerr(out, g["img_f32"]) < IMG_TOL
+    assert relerr(out, g["img_f64"]) < IMG_TOL
+
+
+@pytest.mark.parametrize("name,kw", [c for c in SIDDON if not c[1]])
+def test_siddon_general_equals_fast(name, kw):
+    g = load_golden(name)
+    fast = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"])
+    gen = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"], general=True)
+    assert relerr(gen, g["img_f32"]) < 2e-5      # the general walk restates the reference op for op
+    assert relerr(fast, gen) < 2e-5
+
+
+def _amm(g, kw):
+    if "alphamin" in kw:
+        return kw["alphamin"], kw["alphamax"]
+    return oracle.alpha_minmax(g["volume"].shape, g["source"], g["target"], kw.get("voxel_shift", 0.5), 1e-8, np.float32)
+
+
+@pytest.mark.parametrize("name,kw", TRILINEAR)
+def test_trilinear_forward(name, kw):
+    g = load_golden(name)
+    kw = dict(kw)
+    amin, amax = _amm(g, kw)
+    kw.pop("alphamin", None), kw.pop("alphamax", None)
+    out = emu.trilinear_fwd(g["volume"], g["source"], g["target"], g["raylen"], alphamin=amin, alphamax=amax, **kw)
+    assert relerr(out, g["img_f32"]) < IMG_TOL
+    assert relerr(out, g["img_f64"]) < IMG_TOL
+
+
+def _grad_tol(g, key, floor=1e-4):
+    """Gradient tolerance rule of SURVEY.md 8c: compare with the fp64 reference and allow
+    max(floor, 2 x the reference's own fp32-vs-fp64 error).  Trilinear gradients are differences of
+    neighbouring voxels accumulated in fp32 over the samples -- the survey measured 7.7e-4..1.1e-2 for the
+    reference itself -- so they get floor = 5e-4."""
+    return max(floor, 2.0 * relerr(g[key + "_f32"], g[key + "_f64"]))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)), ("siddon_nc_b4_ragged", {}),
+    ("siddon_nc_b4_stopgrad", dict(stop_grad=True)),
+])
+def test_siddon_backward(name, kw):
+    g = load_golden(name)
+    out = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], **kw)
+    assert relerr(out["g_target"], g["g_target_f64"]) < _grad_tol(g, "g_target")
+    assert relerr(out["g_source"], g["g_source_f64"]) < _grad_tol(g, "g_source")
+    if kw.get("stop_grad"):
+        assert not out["g_volume"].any() and not out["g_raylen"].any()
+    else:
+        assert relerr(out["g_raylen"], g["g_raylen_f64"]) < _grad_tol(g, "g_raylen")
+        assert relerr(out["g_volume"], g["g_volume_f64"]) < _grad_tol(g, "g_volume")
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("trilinear_nc_b4_alpha", dict(n_points=100, alphamin=0.62, alphamax=0.97)),
+    ("trilinear_nc_b4", dict(n_points=160)),
+    ("trilinear_nc_b4_ragged", dict(n_points=77)),
+    ("trilinear_nc_b4_shift0", dict(n_points=120, voxel_shift=0.0)),
+])
+def test_trilinear_backward_vs_oracle_and_reference(name, kw):
+    g = load_golden(name)
+    kw = dict(kw)
+    explicit = "alphamin" in kw
+    amin, amax = _amm(g, kw)
+    kw.pop("alphamin", None), kw.pop("alphamax", None)
+    out = emu.trilinear_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], alphamin=amin, alphamax=amax, **kw)
+    ref = oracle.trilinear_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], alphamin=amin, alphamax=amax,
+                               dtype=np.float64, **kw)
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        # fp32 kernel math vs the fp64 oracle: the reference's own fp32 gradients are this noisy
+        assert relerr(out[key], ref[key]) < _grad_tol(g, key, 5e-4), key
+    scale = max(abs(ref["g_alphamin"]), abs(ref["g_alphamax"]))
+    assert abs(out["g_alphamin"] - ref["g_alphamin"]) < 5e-3 * scale
+    assert abs(out["g_alphamax"] - ref["g_alphamax"]) < 5e-3 * scale
+    if explicit:  # fixed range: the oracle's partials ARE the reference's full gradients
+        assert relerr(out["g_target"], g["g_target_f64"]) < _grad_tol(g, "g_target", 5e-4)
+        assert relerr(out["g_source"], g["g_source_f64"]) < _grad_tol(g, "g_source", 5e-4)
+    assert relerr(out["g_raylen"], g["g_raylen_f64"]) < _grad_tol(g, "g_raylen")
+    assert relerr(out["g_volume"], g["g_volume_f64"]) < _grad_tol(g, "g_volume")
+
+
+def _random_case(seed, shape, B, N):
+    rng = np.random.default_rng(seed)
+    vol = rng.random(shape, dtype=np.float32)
+    c = np.array(shape, dtype=np.float64) / 2
+    src = (c + rng.normal(size=(B, 1, 3)) * np.array(shape) * 2.5).astype(np.float32)
+    tgt = (c + (c - src) * 0.7 + rng.normal(size=(B, N, 3)) * np.array(shape) * 0.6).astype(np.float32)
+    raylen = np.linalg.norm(tgt - src, axis=-1)[:, None, :].astype(np.float32)
+    return vol, src, tgt, raylen
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (40, 56, 48)), (1, (7, 5, 9)), (2, (64, 64, 64)), (3, (1, 1, 1)), (4, (2, 33, 3))])
+def test_random_rays_vs_oracle(seed, shape):
+    vol, src, tgt, raylen = _random_case(seed, shape, B=3, N=211)
+    ref = oracle.siddon_fwd(vol, src, tgt, raylen, dtype=np.float64)
+    out = emu.siddon_fwd(vol, src, tgt, raylen)
+    assert relerr(out, ref) < IMG_TOL
+    amin, amax = oracle.alpha_minmax(shape, src, tgt, 0.5, 1e-8, np.float32)
+    ref = oracle.trilinear_fwd(vol, src, tgt, raylen, n_points=130, alphamin=amin, alphamax=amax, dtype=np.float64)
+    out = emu.trilinear_fwd(vol, src, tgt, raylen, 130, amin, amax)
+    assert relerr(out, ref) < IMG_TOL
+    # visit counter = number of voxels with a non-degenerate crossing: check against a brute-force count
+    visits = emu.siddon_visits(shape, src, tgt)
+    ones = np.ones(shape, np.float32)
+    nz = oracle.siddon_fwd(ones, src, tgt, np.ones_like(raylen), dtype=np.float64)[:, 0]
+    assert ((visits > 0) == (nz > 1e-9)).mean() > 0.99
+    assert visits.max() <= sum(shape) and visits.min() >= 0
