@@ -1,0 +1,75 @@
+"""ctypes binding of libb200drr.so -- the C ABI declared in include/b200drr.h.
+
+There is NO fallback: if the CUDA library is missing or an entry point fails, this raises.  Tensors are
+passed as raw device pointers (`tensor.data_ptr()`), the stream as `torch.cuda.current_stream().cuda_stream`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_c_float_p = ctypes.c_void_p
+_SIGNATURES = {
+    "b200drr_version": (ctypes.c_int, []),
+    "b200drr_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "b200drr_device_sm_count": (ctypes.c_int, []),
+    "b200drr_device_cc": (ctypes.c_int, []),
+    "b200drr_siddon_fwd": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_siddon_bwd": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_trilinear_fwd": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_int, _c_float_p, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_trilinear_bwd": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
+        ctypes.c_float, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_siddon_visits": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int,
+        ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class B200DRRError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise B200DRRError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). diffdrr_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI and the header drift apart
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().b200drr_error_string(code)
+        raise B200DRRError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
