@@ -62,6 +62,16 @@ int b200drr_siddon_fwd(const float* vol, int D0, int D1, int D2, const float* sr
                                  align_corners != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                            const float* raylen, float* out, int B, int H, int W, float voxel_shift, float eps,
+                            int variant, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd_grid(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, H, W, voxel_shift, eps, variant,
+                                      (cudaStream_t)stream));
+}
+
 int b200drr_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                        float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int align_corners,

@@ -11,6 +11,9 @@ namespace b200drr {
 cudaError_t launch_siddon_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,
                               const float* raylen, float* out, int B, int64_t N, float shift, float eps, int reduce,
                               int align_corners, cudaStream_t stream);
+cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                   int variant, cudaStream_t stream);
 cudaError_t launch_siddon_visits(VolDims dims, const float* src, const float* tgt, int32_t* visits, int B, int64_t N,
                                  float shift, float eps, cudaStream_t stream);
 cudaError_t launch_siddon_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,

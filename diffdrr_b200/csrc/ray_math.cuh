@@ -184,6 +184,44 @@ B200_HD float siddon_ray_fast(const float* vol, const VolDims& dims, const Ray& 
     return acc;
 }
 
+// Same sum as siddon_ray_fast, software-pipelined: U walk steps are resolved (index + segment length) before their
+// U voxel loads are issued together, so every thread keeps U independent loads in flight (the walk itself never
+// depends on loaded data).
+template <int U>
+B200_HD float siddon_ray_fast_ilp(const float* vol, const VolDims& dims, const Ray& ray, float shift)
+{
+    Walk w = start_walk(ray, dims, shift);
+    if (!w.hit) return 0.0f;
+    const int64_t s1 = dims.d[2], s0 = (int64_t)dims.d[1] * dims.d[2];
+    int64_t off = ((int64_t)w.idx[0] * dims.d[1] + w.idx[1]) * dims.d[2] + w.idx[2];
+    const int64_t so[3] = {w.sti[0] * s0, w.sti[1] * s1, (int64_t)w.sti[2]};
+    float acur = w.a_in, acc = 0.0f;
+    bool inside = true;
+    while (inside) {
+        float len[U];
+        int64_t offs[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            offs[k] = off;
+            len[k] = 0.0f;
+            if (inside) {
+                const float anext = fminf(fminf(w.an[0], w.an[1]), w.an[2]);
+                len[k] = anext - acur;
+                acur = anext;
+                step_walk(w, dims, anext, off, so, inside);
+            } else {
+                offs[k] = -1;
+            }
+        }
+        float v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) v[k] = offs[k] >= 0 ? ldg(vol + offs[k]) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < U; ++k) acc = fmaf(len[k], v[k], acc);
+    }
+    return acc;
+}
+
 // Closed-form backward of one ray.  With v_j the voxel of segment j and crossing m on
 // axis a:  dI/dalpha_m = L (v_{m-1} - v_m),  dalpha/ds_a = (alpha - 1)/d_a,  dalpha/dt_a = -alpha/d_a.
 // Per axis accumulate A_a = sum coef*alpha, C_a = sum coef with coef = v_before - v_after; then

@@ -87,6 +87,65 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_kernel(const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Detector-grid kernel: the rays of a pose are the full H x W detector (n = h*W + w).  A CTA owns a
+// TW x TH pixel tile and every warp an 8 x 4 sub-tile, so the 32 lanes of a warp walk a compact ray
+// bundle (~16 x 8 voxels across) and their gathers share 128-byte lines / 32-byte sectors in L1.
+// U = voxel loads kept in flight per thread.
+// ---------------------------------------------------------------------------------------------------
+template <int TW, int TH, int U>
+__global__ void __launch_bounds__(TW* TH) siddon_fwd_grid_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                 const float* __restrict__ src,
+                                                                 const float* __restrict__ tgt,
+                                                                 const float* __restrict__ raylen,
+                                                                 float* __restrict__ out, int H, int W, float shift,
+                                                                 float eps)
+{
+    constexpr int WX = TW / 8;  // warps per tile row
+    const int tiles_x = (W + TW - 1) / TW;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int b = blockIdx.y;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    out[r] = __ldg(raylen + r) * siddon_ray_fast_ilp<U>(vol, dims, ray, shift);
+}
+
+template <int TW, int TH, int U>
+static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                       const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                       cudaStream_t stream)
+{
+    const dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH)), (unsigned)B, 1);
+    siddon_fwd_grid_kernel<TW, TH, U><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                   int variant, cudaStream_t stream)
+{
+#define V(id, TW, TH, U) \
+    case id: return launch_grid_variant<TW, TH, U>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, stream);
+    switch (variant) {
+        V(0, 16, 8, 4)
+        V(1, 16, 8, 1)
+        V(2, 16, 8, 2)
+        V(3, 16, 8, 8)
+        V(4, 16, 16, 4)
+        V(5, 32, 8, 4)
+        V(6, 8, 8, 4)
+        V(7, 8, 16, 4)
+        V(8, 32, 16, 4)
+        V(9, 8, 4, 4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef V
+}
+
 static inline dim3 ray_grid(int B, int64_t N) { return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1); }
 
 cudaError_t launch_siddon_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,

@@ -51,6 +51,17 @@ int b200drr_siddon_fwd(const float *vol, int D0, int D1, int D2, const float *sr
                        int reduce, int align_corners, void *stream);
 
 /*
+ * Siddon forward for a FULL detector grid: the N = H*W rays of every pose are the row-major detector
+ * pixels (n = h*W + w; reference detector.py:126), which lets the kernel map compact pixel tiles onto
+ * warps/CTAs for cache locality.  Same result as b200drr_siddon_fwd(reduce=0, align_corners=0).
+ * variant: 0 = tuned default; other values select tile-shape / unroll variants for benchmarking
+ * (cudaErrorInvalidValue if unknown).
+ */
+int b200drr_siddon_fwd_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                            const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
+                            int variant, void *stream);
+
+/*
  * Siddon backward: replaces the autograd graph of Siddon.forward (sum-backward, diff-backward,
  * sort-backward, grid_sampler_3d_backward) with one closed-form pass.
  *   gout [B][N] = dLoss/dout.

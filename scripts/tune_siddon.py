@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Times Siddon-forward kernel variants on the bench workload and checks them against the plain kernel."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from diffdrr_b200 import DRR, _lib, synthetic  # noqa: E402
+from diffdrr_b200.pose import convert  # noqa: E402
+from diffdrr_b200.renderers import _ptr, _stream, siddon_visits  # noqa: E402
+
+D, H, B = 512, 256, int(os.environ.get("B", 16))
+dev = torch.device("cuda:0")
+lib = _lib.load()
+vol = torch.rand(D, D, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+subj.volume.affine = synthetic.make_affine(D)
+drr = DRR(subj, **synthetic.detector_kwargs(H)).to(dev)
+rot, xyz = synthetic.make_poses(B, seed=0)
+with torch.no_grad():
+    src, tgt = drr.detector(convert(rot.to(dev), xyz.to(dev), parameterization="euler_angles", convention="ZXY"), None)
+    raylen = (tgt - src).norm(dim=-1).reshape(B, -1).contiguous()
+    src = drr.affine_inverse(src).reshape(B, 3).contiguous()
+    tgt = drr.affine_inverse(tgt).contiguous()
+N = H * H
+visits = int(siddon_visits((D, D, D), src, tgt).sum())
+gbytes = (4 * visits + 20 * B * N) / 1e9
+peak = 6570.9
+
+
+def timeit(fn, iters=5):
+    fn(); fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+ref = torch.empty(B, N, device=dev)
+def base():
+    _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(ref), B, N, 0.5, 1e-8, 0, 0, _stream()), "fwd")
+ms = timeit(base)
+print(f"baseline linear       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
+variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4,5,6,7,8,9").split(",")]
+for v in variants:
+    out = torch.zeros(B, N, device=dev)
+    def run():
+        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, v, _stream()), "grid")
+    try:
+        ms = timeit(run)
+    except Exception as e:  # unknown variant
+        print(f"variant {v}: {e}")
+        continue
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print(f"grid variant {v:2d}       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")

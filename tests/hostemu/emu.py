@@ -46,6 +46,15 @@ def siddon_fwd(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, reduce="sum", a
     return out
 
 
+def siddon_fwd_ilp(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, unroll=4):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    out = np.empty((B, 1, N), np.float32)
+    lib().emu_siddon_fwd_ilp(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                             ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                             ctypes.c_int(unroll))
+    return out
+
+
 def siddon_visits(shape, src, tgt, voxel_shift=0.5, eps=1e-8):
     src, tgt = _f(src), _f(tgt)
     B, N = tgt.shape[0], tgt.shape[1]

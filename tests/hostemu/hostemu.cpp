@@ -32,6 +32,19 @@ void emu_siddon_fwd(const float* vol, int D0, int D1, int D2, const float* src, 
         }
 }
 
+void emu_siddon_fwd_ilp(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                        float* out, int B, long N, float shift, float eps, int unroll)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            out[r] = raylen[r] * (unroll == 4 ? siddon_ray_fast_ilp<4>(vol, dims, ray, shift)
+                                              : siddon_ray_fast_ilp<3>(vol, dims, ray, shift));
+        }
+}
+
 void emu_siddon_general(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                         const float* raylen, float* out, int B, long N, float shift, float eps, int reduce,
                         int align_corners)

@@ -29,6 +29,15 @@ def test_siddon_general_equals_fast(name, kw):
     assert relerr(fast, gen) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["siddon_nc_b4", "siddon_nc_axis", "siddon_nc_inside", "siddon_c1"])
+@pytest.mark.parametrize("unroll", [3, 4])
+def test_siddon_pipelined_walk_is_bitwise_the_plain_walk(name, unroll):
+    g = load_golden(name)
+    a = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"])
+    b = emu.siddon_fwd_ilp(g["volume"], g["source"], g["target"], g["raylen"], unroll=unroll)
+    assert np.array_equal(a, b)
+
+
 def _amm(g, kw):
     if "alphamin" in kw:
         return kw["alphamin"], kw["alphamax"]
