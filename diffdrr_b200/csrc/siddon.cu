@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_kernel(const float* __res
 // bundle (~16 x 8 voxels across) and their gathers share 128-byte lines / 32-byte sectors in L1.
 // U = voxel loads kept in flight per thread.
 // ---------------------------------------------------------------------------------------------------
-template <int TW, int TH, int U>
+template <int TW, int TH, int U, int LEAN>
 __global__ void __launch_bounds__(TW* TH) siddon_fwd_grid_kernel(const float* __restrict__ vol, VolDims dims,
                                                                  const float* __restrict__ src,
                                                                  const float* __restrict__ tgt,
@@ -111,16 +111,74 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_grid_kernel(const float* __
     const int b = blockIdx.y;
     const int64_t r = ((int64_t)b * H + py) * W + px;
     const Ray ray = load_ray(src, tgt, b, r, eps);
-    out[r] = __ldg(raylen + r) * siddon_ray_fast_ilp<U>(vol, dims, ray, shift);
+    out[r] = __ldg(raylen + r) *
+             (LEAN ? siddon_ray_lean<U>(vol, dims, ray, shift) : siddon_ray_fast_ilp<U>(vol, dims, ray, shift));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Slab-major detector-grid kernel.  The volume is cut into slabs of `slab` planes along axis 0 (the
+// slowest axis: a slab is one contiguous chunk of memory sized to stay resident in the 126 MB L2).
+// blockIdx.x enumerates (slab, pose, tile) with the slab SLOWEST, so the CTAs in flight at any time --
+// across all poses of the batch -- gather from the same few slabs and the volume streams from HBM about
+// once per BATCH instead of once per pose.  Each CTA integrates its rays over its slab only (splitting a
+// ray at voxel planes is exact) and adds the partial line integral to out with red.global.add.f32
+// (out is zero-filled by the launcher).
+// ---------------------------------------------------------------------------------------------------
+template <int TW, int TH, int U>
+__global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                 const float* __restrict__ src,
+                                                                 const float* __restrict__ tgt,
+                                                                 const float* __restrict__ raylen,
+                                                                 float* __restrict__ out, int B, int H, int W, int slab,
+                                                                 float shift, float eps)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    const float part = siddon_ray_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
+    if (part != 0.0f) red_add(out + r, __ldg(raylen + r) * part);
 }
 
 template <int TW, int TH, int U>
+static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                       const float* raylen, float* out, int B, int H, int W, int slab, float shift,
+                                       float eps, cudaStream_t stream)
+{
+    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
+    if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
+    if (e != cudaSuccess) return e;
+    siddon_fwd_slab_kernel<TW, TH, U><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, B, H, W,
+                                                                              slab, shift, eps);
+    return cudaGetLastError();
+}
+
+template <int TW, int TH, int U, int LEAN>
 static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                        const float* raylen, float* out, int B, int H, int W, float shift, float eps,
                                        cudaStream_t stream)
 {
     const dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH)), (unsigned)B, 1);
-    siddon_fwd_grid_kernel<TW, TH, U><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift, eps);
+    if (LEAN && (int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX)  // 32-bit offsets would overflow
+        siddon_fwd_grid_kernel<TW, TH, U, 0><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift, eps);
+    else
+        siddon_fwd_grid_kernel<TW, TH, U, LEAN><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift,
+                                                                              eps);
     return cudaGetLastError();
 }
 
@@ -128,19 +186,32 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
                                    const float* raylen, float* out, int B, int H, int W, float shift, float eps,
                                    int variant, cudaStream_t stream)
 {
-#define V(id, TW, TH, U) \
-    case id: return launch_grid_variant<TW, TH, U>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, stream);
+#define V(id, TW, TH, U, LEAN) \
+    case id: return launch_grid_variant<TW, TH, U, LEAN>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, stream);
     switch (variant) {
-        V(0, 16, 8, 4)
-        V(1, 16, 8, 1)
-        V(2, 16, 8, 2)
-        V(3, 16, 8, 8)
-        V(4, 16, 16, 4)
-        V(5, 32, 8, 4)
-        V(6, 8, 8, 4)
-        V(7, 8, 16, 4)
-        V(8, 32, 16, 4)
-        V(9, 8, 4, 4)
+        V(0, 16, 8, 4, 1)
+        V(1, 16, 8, 8, 0)
+        V(2, 16, 8, 2, 1)
+        V(3, 16, 8, 8, 1)
+        V(4, 16, 16, 4, 1)
+        V(5, 32, 8, 4, 1)
+        V(6, 8, 8, 4, 1)
+        V(7, 8, 16, 4, 1)
+        V(8, 16, 8, 6, 1)
+        V(9, 8, 8, 8, 1)
+#define S(id, TW, TH, U, SLAB) \
+    case id: return launch_slab_variant<TW, TH, U>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
+        S(10, 16, 8, 4, 32)
+        S(11, 16, 8, 4, 16)
+        S(12, 16, 8, 4, 64)
+        S(13, 16, 8, 2, 32)
+        S(14, 16, 8, 8, 32)
+        S(15, 16, 16, 4, 32)
+        S(16, 8, 8, 4, 32)
+        S(17, 16, 8, 4, 8)
+        S(18, 16, 8, 4, 128)
+        S(19, 32, 8, 4, 32)
+#undef S
         default: return cudaErrorInvalidValue;
     }
 #undef V

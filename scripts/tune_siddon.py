@@ -46,7 +46,7 @@ def base():
     _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(ref), B, N, 0.5, 1e-8, 0, 0, _stream()), "fwd")
 ms = timeit(base)
 print(f"baseline linear       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4,5,6,7,8,9").split(",")]
+variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,10,11,12,13,14,15,16,17,18,19").split(",")]
 for v in variants:
     out = torch.zeros(B, N, device=dev)
     def run():

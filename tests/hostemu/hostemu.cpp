@@ -40,8 +40,10 @@ void emu_siddon_fwd_ilp(const float* vol, int D0, int D1, int D2, const float* s
         for (long n = 0; n < N; ++n) {
             const long r = (long)b * N + n;
             const Ray ray = load_ray(src, tgt, b, r, eps);
-            out[r] = raylen[r] * (unroll == 4 ? siddon_ray_fast_ilp<4>(vol, dims, ray, shift)
-                                              : siddon_ray_fast_ilp<3>(vol, dims, ray, shift));
+            out[r] = raylen[r] * (unroll == 4    ? siddon_ray_fast_ilp<4>(vol, dims, ray, shift)
+                                  : unroll == 3  ? siddon_ray_fast_ilp<3>(vol, dims, ray, shift)
+                                  : unroll == -4 ? siddon_ray_lean<4>(vol, dims, ray, shift)
+                                                 : siddon_ray_lean<1>(vol, dims, ray, shift));
         }
 }
 

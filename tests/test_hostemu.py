@@ -38,6 +38,17 @@ def test_siddon_pipelined_walk_is_bitwise_the_plain_walk(name, unroll):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name", [c[0] for c in SIDDON if not c[1]])
+@pytest.mark.parametrize("unroll", [-1, -4])
+def test_siddon_lean_walk(name, unroll):
+    """Branch-free alpha-terminated walk (the production forward kernel) vs the reference and the plain walk."""
+    g = load_golden(name)
+    a = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"])
+    b = emu.siddon_fwd_ilp(g["volume"], g["source"], g["target"], g["raylen"], unroll=unroll)
+    assert relerr(b, g["img_f64"]) < IMG_TOL
+    assert relerr(b, a) < 1e-6
+
+
 def _amm(g, kw):
     if "alphamin" in kw:
         return kw["alphamin"], kw["alphamax"]
@@ -123,6 +134,7 @@ def test_random_rays_vs_oracle(seed, shape):
     ref = oracle.siddon_fwd(vol, src, tgt, raylen, dtype=np.float64)
     out = emu.siddon_fwd(vol, src, tgt, raylen)
     assert relerr(out, ref) < IMG_TOL
+    assert relerr(emu.siddon_fwd_ilp(vol, src, tgt, raylen, unroll=-4), ref) < IMG_TOL
     amin, amax = oracle.alpha_minmax(shape, src, tgt, 0.5, 1e-8, np.float32)
     ref = oracle.trilinear_fwd(vol, src, tgt, raylen, n_points=130, alphamin=amin, alphamax=amax, dtype=np.float64)
     out = emu.trilinear_fwd(vol, src, tgt, raylen, 130, amin, amax)
