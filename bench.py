@@ -222,12 +222,13 @@ def run_ours(args, rank, local_rank, world):
     def kernel_step(ev=None):
         if ev:
             ev[0].record(stream)
-        _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N, 0.5, 1e-8,
-                                          0, 0, _stream()), "siddon_fwd")
+        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, args.det,
+                                               args.det, 0.5, 1e-8, 0, _stream()), "siddon_fwd_grid")
         if ev:
             ev[1].record(stream)
-        _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src),
-                                          _ptr(g_tgt), _ptr(g_len), None, B, N, 0.5, 1e-8, 0, 0, _stream()), "siddon_bwd")
+        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src),
+                                               _ptr(g_tgt), _ptr(g_len), None, B, args.det, args.det, 0.5, 1e-8, 0, 0,
+                                               _stream()), "siddon_bwd_grid")
         if ev:
             ev[2].record(stream)
         if world > 1:
@@ -298,7 +299,7 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = total_drr / (e2e_ms_total * 1e-3)
     fwd_gbs = fwd_bytes / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
-    dom = ("siddon_bwd_kernel", bwd_gbs, bwd_bytes, bwd_ms) if bwd_ms >= fwd_ms else ("siddon_fwd_fast_kernel", fwd_gbs, fwd_bytes, fwd_ms)
+    dom = ("siddon_bwd_slab_kernel", bwd_gbs, bwd_bytes, bwd_ms) if bwd_ms >= fwd_ms else ("siddon_fwd_slab_kernel", fwd_gbs, fwd_bytes, fwd_ms)
     line = {
         "metric": METRIC, "value": value, "unit": "DRRs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,9 +315,9 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s", "frac": dom[1] / peak,
                      "traffic": None, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
-        "roofline_fwd": {"kernel": "siddon_fwd_fast_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
+        "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
                          "algorithmic_bytes_per_launch": fwd_bytes, "drr_per_s_fwd_only": B / (fwd_ms * 1e-3)},
-        "roofline_bwd": {"kernel": "siddon_bwd_kernel", "achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms_per_launch": bwd_ms,
+        "roofline_bwd": {"kernel": "siddon_bwd_slab_kernel", "achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms_per_launch": bwd_ms,
                          "algorithmic_bytes_per_launch": bwd_bytes},
         "clocks": clocks.summary(),
     }

@@ -83,6 +83,17 @@ int b200drr_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* sr
                                  voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_bwd_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                            const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                            float* g_vol, int B, int H, int W, float voxel_shift, float eps, int stop_grad, int variant,
+                            void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_grid(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W,
+                                      voxel_shift, eps, stop_grad != 0, variant, (cudaStream_t)stream));
+}
+
 int b200drr_trilinear_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                           const float* raylen, float* out, int B, int64_t N, float voxel_shift, float eps,
                           int n_points, const float* alpha_range, int reduce, int align_corners, void* stream)

@@ -14,6 +14,10 @@ cudaError_t launch_siddon_fwd(const float* vol, VolDims dims, const float* src, 
 cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int H, int W, float shift, float eps,
                                    int variant, cudaStream_t stream);
+cudaError_t launch_siddon_bwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                   float* g_vol, int B, int H, int W, float shift, float eps, int stop_grad, int variant,
+                                   cudaStream_t stream);
 cudaError_t launch_siddon_visits(VolDims dims, const float* src, const float* tgt, int32_t* visits, int B, int64_t N,
                                  float shift, float eps, cudaStream_t stream);
 cudaError_t launch_siddon_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,

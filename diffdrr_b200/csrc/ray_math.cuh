@@ -83,46 +83,54 @@ B200_HD float siddon_ray_general(const float* vol, const VolDims& dims, const Ra
 // ===================================================================================================
 struct Walk {
     float an[3];   // alpha of the next plane crossing per axis
-    float pf[3];   // next plane index per axis, as float
+    float nf[3];   // how many planes of this axis have been crossed so far (float counter)
+    float da[3];   // alpha distance between consecutive planes of this axis, |1/d|
+    float a0[3];   // alpha of the FIRST plane crossing per axis: an = fma(nf, da, a0)
+    float nx[3];   // value of nf at which the ray crosses the boundary plane of the box (leaves it)
+    float p0[3];   // index of the first plane crossed per axis
     float inv[3];  // 1/d
-    float c[3];    // -(shift + s)/d
-    float stf[3];  // +1 / -1
-    int idx[3];    // current voxel
+    int idx[3];    // entry voxel
     int sti[3];    // +1 / -1
     float a_in, a_out;
     int entry_axis;
     bool hit;
 };
 
+// alpha of plane p on axis a in the reference's own difference form ((p - shift) - s) / d: the small
+// difference is formed first, so the result is accurate to ~1 ulp even when d is tiny (the fused form
+// fma(p, 1/d, -(shift+s)/d) cancels two huge terms there and loses ~1e-2 voxel along the ray).
+B200_HD float plane_alpha_acc(const Ray& ray, int a, float p, float shift) { return ((p - shift) - ray.s[a]) * ray.inv[a]; }
+
 // Walk restricted to the sub-box of voxels [lo_a, hi_a) per axis (planes lo_a .. hi_a); the whole volume is
 // lo = 0, hi = dims.  Splitting a ray at voxel planes is exact: every Siddon segment ends on a plane anyway.
+// Crossing alphas are generated as fma(n, |1/d|, alpha_first) from an integer crossing count n (never
+// accumulated), with alpha_first in the accurate difference form.
 B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3], float shift)
 {
     Walk w;
     float lo[3];
     w.a_in = -INFINITY;
-    w.a_out = INFINITY;
+    float a_hi = INFINITY;
     w.entry_axis = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         w.inv[a] = ray.inv[a];
-        w.c[a] = -(shift + ray.s[a]) * ray.inv[a];
-        const float a0 = fmaf((float)lo_v[a], w.inv[a], w.c[a]);  // plane lo
-        const float a1 = fmaf((float)hi_v[a], w.inv[a], w.c[a]);  // plane hi
+        w.da[a] = fabsf(ray.inv[a]);
+        const float a0 = plane_alpha_acc(ray, a, (float)lo_v[a], shift);
+        const float a1 = plane_alpha_acc(ray, a, (float)hi_v[a], shift);
         lo[a] = fminf(a0, a1);
-        const float hi = fmaxf(a0, a1);
+        a_hi = fminf(a_hi, fmaxf(a0, a1));
         if (lo[a] > w.a_in) {
             w.a_in = lo[a];
             w.entry_axis = a;
         }
-        w.a_out = fminf(w.a_out, hi);
     }
-    w.hit = w.a_in < w.a_out;  // false for NaN as well
+    w.hit = w.a_in < a_hi;  // false for NaN as well
+    w.a_out = INFINITY;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const bool fwd = ray.d[a] > 0.0f;
         w.sti[a] = fwd ? 1 : -1;
-        w.stf[a] = fwd ? 1.0f : -1.0f;
         int i;
         if (lo[a] >= w.a_in) {
             i = fwd ? lo_v[a] : hi_v[a] - 1;  // entering through a face of this axis
@@ -132,8 +140,14 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
             i = i < lo_v[a] ? lo_v[a] : (i > hi_v[a] - 1 ? hi_v[a] - 1 : i);
         }
         w.idx[a] = i;
-        w.pf[a] = (float)(fwd ? i + 1 : i);
-        w.an[a] = fmaf(w.pf[a], w.inv[a], w.c[a]);
+        w.p0[a] = (float)(fwd ? i + 1 : i);
+        w.nx[a] = fwd ? (float)hi_v[a] - w.p0[a] : w.p0[a] - (float)lo_v[a];
+        w.a0[a] = plane_alpha_acc(ray, a, w.p0[a], shift);
+        w.nf[a] = 0.0f;
+        w.an[a] = w.a0[a];
+        // the exit alpha is produced by the SAME expression the walk uses for its crossings, so that
+        // "crossing alpha == a_out" identifies the exit plane exactly
+        w.a_out = fminf(w.a_out, fmaf(w.nx[a], w.da[a], w.a0[a]));
     }
     return w;
 }
@@ -158,8 +172,8 @@ B200_HD int step_walk(Walk& w, const VolDims& dims, float anext, int64_t& off, c
             w.idx[a] += w.sti[a];
             inside = (unsigned)w.idx[a] < (unsigned)dims.d[a];
             off += so[a];
-            w.pf[a] += w.stf[a];
-            w.an[a] = fmaf(w.pf[a], w.inv[a], w.c[a]);
+            w.nf[a] += 1.0f;
+            w.an[a] = fmaf(w.nf[a], w.da[a], w.a0[a]);
         }
     return ax;
 }
@@ -233,8 +247,8 @@ B200_HD float siddon_ray_fast_ilp(const float* vol, const VolDims& dims, const R
 // ---------------------------------------------------------------------------------------------------
 // Lean walk: the same sum again with a branch-free step of ~19 instructions.
 //   * termination by alpha: the exit plane's alpha is computed by the very expression that produces the
-//     walk's own crossing alphas (fmaf(plane, 1/d, c)), so `anext < a_out` is exact and no per-axis
-//     index/bounds bookkeeping is needed -- the only per-ray state is (an[3], pf[3], off, acur, acc);
+//     walk's own crossing alphas (fma(n, |1/d|, alpha_first)), so `anext < a_out` is exact and no per-axis
+//     index/bounds bookkeeping is needed -- the only per-ray state is (an[3], nf[3], off, acur, acc);
 //   * all axes whose next plane ties with the minimum step together (the zero-length segments in between
 //     contribute nothing), which removes the else-chain;
 //   * the final crossing (anext == a_out) is not taken, so `off` never leaves the volume and the U loads of
@@ -254,13 +268,13 @@ B200_HD float min3f(float a, float b, float c)
 
 struct LeanState {
     float an0, an1, an2;  // alpha of the next plane per axis
-    float pf0, pf1, pf2;  // index of that plane, as float
+    float nf0, nf1, nf2;  // crossing counters (see Walk)
     float acur;           // alpha reached so far
     int off;              // element offset of the current voxel
 };
 
 struct LeanConst {
-    float inv0, inv1, inv2, c0, c1, c2, stf0, stf1, stf2, a_out;
+    float da0, da1, da2, a00, a01, a02, a_out;
     int so0, so1, so2;
 };
 
@@ -280,31 +294,43 @@ B200_HD float lean_step(LeanState& s, const LeanConst& k)
         "setp.eq.and.f32 p0, %0, nx, q;\n\t"
         "setp.eq.and.f32 p1, %1, nx, q;\n\t"
         "setp.eq.and.f32 p2, %2, nx, q;\n\t"
-        "@p0 add.f32 %3, %3, %10;\n\t"
-        "@p1 add.f32 %4, %4, %11;\n\t"
-        "@p2 add.f32 %5, %5, %12;\n\t"
-        "@p0 fma.rn.f32 %0, %3, %13, %16;\n\t"
-        "@p1 fma.rn.f32 %1, %4, %14, %17;\n\t"
-        "@p2 fma.rn.f32 %2, %5, %15, %18;\n\t"
-        "@p0 add.s32 %7, %7, %19;\n\t"
-        "@p1 add.s32 %7, %7, %20;\n\t"
-        "@p2 add.s32 %7, %7, %21;\n\t"
+        "@p0 add.f32 %3, %3, 0f3F800000;\n\t"
+        "@p1 add.f32 %4, %4, 0f3F800000;\n\t"
+        "@p2 add.f32 %5, %5, 0f3F800000;\n\t"
+        "@p0 fma.rn.f32 %0, %3, %10, %13;\n\t"
+        "@p1 fma.rn.f32 %1, %4, %11, %14;\n\t"
+        "@p2 fma.rn.f32 %2, %5, %12, %15;\n\t"
+        "@p0 add.s32 %7, %7, %16;\n\t"
+        "@p1 add.s32 %7, %7, %17;\n\t"
+        "@p2 add.s32 %7, %7, %18;\n\t"
         "}"
-        : "+f"(s.an0), "+f"(s.an1), "+f"(s.an2), "+f"(s.pf0), "+f"(s.pf1), "+f"(s.pf2), "+f"(s.acur), "+r"(s.off),
+        : "+f"(s.an0), "+f"(s.an1), "+f"(s.an2), "+f"(s.nf0), "+f"(s.nf1), "+f"(s.nf2), "+f"(s.acur), "+r"(s.off),
           "=f"(len)
-        : "f"(k.a_out), "f"(k.stf0), "f"(k.stf1), "f"(k.stf2), "f"(k.inv0), "f"(k.inv1), "f"(k.inv2), "f"(k.c0),
-          "f"(k.c1), "f"(k.c2), "r"(k.so0), "r"(k.so1), "r"(k.so2));
+        : "f"(k.a_out), "f"(k.da0), "f"(k.da1), "f"(k.da2), "f"(k.a00), "f"(k.a01), "f"(k.a02), "r"(k.so0), "r"(k.so1),
+          "r"(k.so2));
 #else
     const float nx = fminf(fminf(s.an0, s.an1), s.an2);
     len = nx - s.acur;
     s.acur = nx;
     const bool q = nx < k.a_out;
     const bool p0 = q && s.an0 == nx, p1 = q && s.an1 == nx, p2 = q && s.an2 == nx;
-    if (p0) { s.pf0 += k.stf0; s.an0 = fmaf(s.pf0, k.inv0, k.c0); s.off += k.so0; }
-    if (p1) { s.pf1 += k.stf1; s.an1 = fmaf(s.pf1, k.inv1, k.c1); s.off += k.so1; }
-    if (p2) { s.pf2 += k.stf2; s.an2 = fmaf(s.pf2, k.inv2, k.c2); s.off += k.so2; }
+    if (p0) { s.nf0 += 1.0f; s.an0 = fmaf(s.nf0, k.da0, k.a00); s.off += k.so0; }
+    if (p1) { s.nf1 += 1.0f; s.an1 = fmaf(s.nf1, k.da1, k.a01); s.off += k.so1; }
+    if (p2) { s.nf2 += 1.0f; s.an2 = fmaf(s.nf2, k.da2, k.a02); s.off += k.so2; }
 #endif
     return len;
+}
+
+B200_HD void lean_init(const Walk& w, int st0, int st1, int st2, LeanState& s, LeanConst& k)
+{
+    k.da0 = w.da[0]; k.da1 = w.da[1]; k.da2 = w.da[2];
+    k.a00 = w.a0[0]; k.a01 = w.a0[1]; k.a02 = w.a0[2];
+    k.a_out = w.a_out;
+    k.so0 = w.sti[0] * st0; k.so1 = w.sti[1] * st1; k.so2 = w.sti[2] * st2;
+    s.an0 = w.an[0]; s.an1 = w.an[1]; s.an2 = w.an[2];
+    s.nf0 = 0.0f; s.nf1 = 0.0f; s.nf2 = 0.0f;
+    s.acur = w.hit ? w.a_in : w.a_out;  // a miss has nothing to walk
+    s.off = w.idx[0] * st0 + w.idx[1] * st1 + w.idx[2] * st2;
 }
 
 // Lean walk over the sub-box [lo, hi) of a volume whose element strides are (st0, st1, st2).
@@ -315,16 +341,8 @@ B200_HD float siddon_ray_lean_box(const float* vol, const int lo_v[3], const int
     const Walk w = start_walk_box(ray, lo_v, hi_v, shift);
     if (!w.hit) return 0.0f;
     LeanConst k;
-    k.inv0 = w.inv[0]; k.inv1 = w.inv[1]; k.inv2 = w.inv[2];
-    k.c0 = w.c[0]; k.c1 = w.c[1]; k.c2 = w.c[2];
-    k.stf0 = w.stf[0]; k.stf1 = w.stf[1]; k.stf2 = w.stf[2];
-    k.a_out = w.a_out;
-    k.so0 = w.sti[0] * st0; k.so1 = w.sti[1] * st1; k.so2 = w.sti[2] * st2;
     LeanState s;
-    s.an0 = w.an[0]; s.an1 = w.an[1]; s.an2 = w.an[2];
-    s.pf0 = w.pf[0]; s.pf1 = w.pf[1]; s.pf2 = w.pf[2];
-    s.acur = w.a_in;
-    s.off = w.idx[0] * st0 + w.idx[1] * st1 + w.idx[2] * st2;
+    lean_init(w, st0, st1, st2, s, k);
     float acc = 0.0f;
     while (s.acur < k.a_out) {
         float len[U], v[U];
@@ -347,6 +365,109 @@ B200_HD float siddon_ray_lean(const float* vol, const VolDims& dims, const Ray& 
 {
     const int lo_v[3] = {0, 0, 0};
     return siddon_ray_lean_box<U>(vol, lo_v, dims.d, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
+}
+
+// Lean step for the backward walk: additionally reports which axis' plane ends the current voxel
+// (0/1/2; 3 when the walk has reached the exit plane and no crossing is taken).
+B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
+{
+    float len;
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred q, p0, p1, p2;\n\t"
+        ".reg .f32 nx;\n\t"
+        "min.f32 nx, %0, %1, %2;\n\t"
+        "sub.f32 %8, nx, %6;\n\t"
+        "mov.f32 %6, nx;\n\t"
+        "setp.lt.f32 q, nx, %10;\n\t"
+        "setp.eq.and.f32 p0, %0, nx, q;\n\t"
+        "setp.eq.and.f32 p1, %1, nx, q;\n\t"
+        "setp.eq.and.f32 p2, %2, nx, q;\n\t"
+        "selp.s32 %9, 2, 3, p2;\n\t"
+        "selp.s32 %9, 1, %9, p1;\n\t"
+        "selp.s32 %9, 0, %9, p0;\n\t"
+        "@p0 add.f32 %3, %3, 0f3F800000;\n\t"
+        "@p1 add.f32 %4, %4, 0f3F800000;\n\t"
+        "@p2 add.f32 %5, %5, 0f3F800000;\n\t"
+        "@p0 fma.rn.f32 %0, %3, %11, %14;\n\t"
+        "@p1 fma.rn.f32 %1, %4, %12, %15;\n\t"
+        "@p2 fma.rn.f32 %2, %5, %13, %16;\n\t"
+        "@p0 add.s32 %7, %7, %17;\n\t"
+        "@p1 add.s32 %7, %7, %18;\n\t"
+        "@p2 add.s32 %7, %7, %19;\n\t"
+        "}"
+        : "+f"(s.an0), "+f"(s.an1), "+f"(s.an2), "+f"(s.nf0), "+f"(s.nf1), "+f"(s.nf2), "+f"(s.acur), "+r"(s.off),
+          "=f"(len), "=r"(ax)
+        : "f"(k.a_out), "f"(k.da0), "f"(k.da1), "f"(k.da2), "f"(k.a00), "f"(k.a01), "f"(k.a02), "r"(k.so0), "r"(k.so1),
+          "r"(k.so2));
+#else
+    const float nx = fminf(fminf(s.an0, s.an1), s.an2);
+    len = nx - s.acur;
+    s.acur = nx;
+    const bool q = nx < k.a_out;
+    const bool p0 = q && s.an0 == nx, p1 = q && s.an1 == nx, p2 = q && s.an2 == nx;
+    ax = p0 ? 0 : (p1 ? 1 : (p2 ? 2 : 3));
+    if (p0) { s.nf0 += 1.0f; s.an0 = fmaf(s.nf0, k.da0, k.a00); s.off += k.so0; }
+    if (p1) { s.nf1 += 1.0f; s.an1 = fmaf(s.nf1, k.da1, k.a01); s.off += k.so1; }
+    if (p2) { s.nf2 += 1.0f; s.an2 = fmaf(s.nf2, k.da2, k.a02); s.off += k.so2; }
+#endif
+    return len;
+}
+
+// Backward of one ray restricted to the sub-box [lo, hi) (closed form, see siddon_ray_bwd below for the algebra).
+// Crossing m between voxel values (before, after) on axis a at alpha contributes coef = before - after to
+//   A_a += coef * alpha,  C_a += coef;  box faces count as crossings against 0, which telescopes correctly when a
+// ray is split into slabs (the two halves of an interior face add up to the true coefficient).
+// Returns sum_j v_j len_j; adds gL*len_j to g_vol[voxel_j] when g_vol != nullptr.  A, C are accumulated INTO.
+template <int U>
+B200_HD float siddon_ray_bwd_lean_box(const float* vol, const int lo_v[3], const int hi_v[3], int st0, int st1, int st2,
+                                      const Ray& ray, float shift, float gL, float* g_vol, float A[3], float C[3])
+{
+    const Walk w = start_walk_box(ray, lo_v, hi_v, shift);
+    if (!w.hit) return 0.0f;
+    LeanConst k;
+    LeanState s;
+    lean_init(w, st0, st1, st2, s, k);
+    float acc = 0.0f, vprev = 0.0f, aprev = w.a_in;
+    int axprev = w.entry_axis;
+    while (s.acur < k.a_out) {
+        float len[U], aend[U], v[U];
+        int offs[U], ax[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            offs[j] = s.off;
+            len[j] = lean_step_ax(s, k, ax[j]);
+            aend[j] = s.acur;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = ldg(vol + offs[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (axprev < 3) {  // a real crossing led into voxel j (false only for the padding steps after the exit)
+                const float coef = vprev - v[j];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (a == axprev) {
+                        A[a] = fmaf(coef, aprev, A[a]);
+                        C[a] += coef;
+                    }
+                acc = fmaf(len[j], v[j], acc);
+                if (g_vol) red_add(g_vol + offs[j], gL * len[j]);
+                vprev = v[j];
+            }
+            axprev = ax[j];
+            aprev = aend[j];
+        }
+    }
+    // exit crossing: v_last -> 0 through the axis whose boundary plane is a_out
+    const int ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a == ax_exit) {
+            A[a] = fmaf(vprev, k.a_out, A[a]);
+            C[a] += vprev;
+        }
+    return acc;
 }
 
 // Closed-form backward of one ray.  With v_j the voxel of segment j and crossing m on

@@ -1,6 +1,7 @@
 // siddon.cu -- Siddon exact-path DRR kernels for sm_100a (forward, backward, visit counter).
 // One thread walks one ray (ray_math.cuh); blockIdx.y is the pose, blockIdx.x tiles the rays of that pose.
 #include "kernels.h"
+#include "psync.cuh"
 #include "ray_math.cuh"
 
 namespace b200drr {
@@ -168,6 +169,171 @@ static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const flo
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Plane-synchronous slab-major kernel (psync.cuh): same decomposition as siddon_fwd_slab_kernel, but every
+// lane advances one MAJOR-axis plane per iteration and the lanes of a warp are aligned onto the same plane
+// (WarpAlign), so the 8x4 ray bundle gathers from one voxel plane at a time and shares sectors.
+// ---------------------------------------------------------------------------------------------------
+struct WarpAlign {
+    __device__ __forceinline__ int operator()(int m, bool pos, int p_start, bool active) const
+    {
+        const unsigned full = 0xffffffffu;
+        const unsigned act = __ballot_sync(full, active);
+        if (act == 0u) return 0;
+        const int key = m * 2 + (pos ? 1 : 0);
+        const int lkey = __shfl_sync(full, key, __ffs(act) - 1);
+        const bool uniform = __all_sync(full, !active || key == lkey);
+        const int t = pos ? p_start : -p_start;  // position along the direction of travel
+        const int tmin = __reduce_min_sync(full, active ? t : 0x7fffffff);
+        return (uniform && active) ? t - tmin : 0;
+    }
+};
+
+template <int TW, int TH, int U, int ALIGN>
+__global__ void __launch_bounds__(TW* TH) siddon_fwd_psync_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                  const float* __restrict__ src,
+                                                                  const float* __restrict__ tgt,
+                                                                  const float* __restrict__ raylen,
+                                                                  float* __restrict__ out, int B, int H, int W, int slab,
+                                                                  float shift, float eps)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    const bool valid = px < W && py < H;  // out-of-image lanes shadow the last pixel: the warp stays convergent
+    const int64_t r = ((int64_t)b * H + min(py, H - 1)) * W + min(px, W - 1);
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    const unsigned nvox = (unsigned)(dims.d[0] * dims.d[1] * dims.d[2]);
+    float part;
+    if (ALIGN)
+        part = siddon_ray_psync<U>(vol, nvox, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, WarpAlign());
+    else
+        part = siddon_ray_psync<U>(vol, nvox, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, NoAlign());
+    if (valid && part != 0.0f) red_add(out + r, __ldg(raylen + r) * part);
+}
+
+template <int TW, int TH, int U, int ALIGN>
+static cudaError_t launch_psync_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                        const float* raylen, float* out, int B, int H, int W, int slab, float shift,
+                                        float eps, cudaStream_t stream)
+{
+    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
+    if (blocks > INT32_MAX || (int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
+    if (e != cudaSuccess) return e;
+    siddon_fwd_psync_kernel<TW, TH, U, ALIGN><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, B,
+                                                                                      H, W, slab, shift, eps);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Slab-major detector-grid BACKWARD kernel: same decomposition as siddon_fwd_slab_kernel.  Every CTA adds its
+// slab's share of g_tgt / g_raylen / g_src (and optionally g_vol) with red.global.add; the launcher zero-fills.
+// ---------------------------------------------------------------------------------------------------
+template <int TW, int TH, int U>
+__global__ void __launch_bounds__(TW* TH) siddon_bwd_slab_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                 const float* __restrict__ src,
+                                                                 const float* __restrict__ tgt,
+                                                                 const float* __restrict__ raylen,
+                                                                 const float* __restrict__ gout, float* __restrict__ g_src,
+                                                                 float* __restrict__ g_tgt, float* __restrict__ g_raylen,
+                                                                 float* __restrict__ g_vol, int B, int H, int W, int slab,
+                                                                 float shift, float eps, int stop_grad)
+{
+    __shared__ float red[32];
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    float gs[3] = {0.0f, 0.0f, 0.0f};
+    if (px < W && py < H) {
+        const int64_t r = ((int64_t)b * H + py) * W + px;
+        const Ray ray = load_ray(src, tgt, b, r, eps);
+        const int lo_v[3] = {sl * slab, 0, 0};
+        const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+        const float L = __ldg(raylen + r), g = __ldg(gout + r);
+        const float gL = g * L;
+        float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+        const float acc = siddon_ray_bwd_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, gL,
+                                                     stop_grad ? nullptr : g_vol, A, C);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float gt = -gL * A[a] * ray.inv[a];
+            gs[a] = gL * (A[a] - C[a]) * ray.inv[a];
+            if (g_tgt && gt != 0.0f) red_add(g_tgt + r * 3 + a, gt);
+        }
+        if (g_raylen && !stop_grad && acc != 0.0f) red_add(g_raylen + r, g * acc);
+    }
+    if (g_src) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tot = block_sum(gs[a], red);
+            if (threadIdx.x == 0 && tot != 0.0f) atomicAdd(g_src + b * 3 + a, tot);
+        }
+    }
+}
+
+template <int TW, int TH, int U>
+static cudaError_t launch_bwd_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                           const float* raylen, const float* gout, float* g_src, float* g_tgt,
+                                           float* g_raylen, float* g_vol, int B, int H, int W, int slab, float shift,
+                                           float eps, int stop_grad, cudaStream_t stream)
+{
+    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
+    if (blocks > INT32_MAX || (int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    const size_t n = (size_t)B * H * W;
+    cudaError_t e = cudaSuccess;
+    if (g_src) e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+    if (e == cudaSuccess && g_tgt) e = cudaMemsetAsync(g_tgt, 0, sizeof(float) * 3 * n, stream);
+    if (e == cudaSuccess && g_raylen) e = cudaMemsetAsync(g_raylen, 0, sizeof(float) * n, stream);
+    if (e != cudaSuccess) return e;
+    siddon_bwd_slab_kernel<TW, TH, U><<<(unsigned)blocks, TW * TH, 0, stream>>>(
+        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, slab, shift, eps, stop_grad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_siddon_bwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                   float* g_vol, int B, int H, int W, float shift, float eps, int stop_grad, int variant,
+                                   cudaStream_t stream)
+{
+#define BV(id, TW, TH, U, SLAB)                                                                                          \
+    case id:                                                                                                             \
+        return launch_bwd_slab_variant<TW, TH, U>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, \
+                                                  SLAB, shift, eps, stop_grad, stream);
+    switch (variant) {
+        BV(0, 16, 16, 4, 32)
+        BV(1, 16, 8, 4, 32)
+        BV(2, 16, 16, 2, 32)
+        BV(3, 16, 16, 4, 64)
+        BV(4, 16, 8, 2, 32)
+        BV(5, 16, 16, 8, 32)
+        default: return cudaErrorInvalidValue;
+    }
+#undef BV
+}
+
 template <int TW, int TH, int U, int LEAN>
 static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                        const float* raylen, float* out, int B, int H, int W, float shift, float eps,
@@ -188,8 +354,11 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
 {
 #define V(id, TW, TH, U, LEAN) \
     case id: return launch_grid_variant<TW, TH, U, LEAN>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, stream);
+#define S0(id, TW, TH, U, SLAB) \
+    case id: return launch_slab_variant<TW, TH, U>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
     switch (variant) {
-        V(0, 16, 8, 4, 1)
+        S0(0, 16, 16, 4, 32)
+        V(30, 16, 8, 4, 1)
         V(1, 16, 8, 8, 0)
         V(2, 16, 8, 2, 1)
         V(3, 16, 8, 8, 1)
@@ -212,6 +381,19 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         S(18, 16, 8, 4, 128)
         S(19, 32, 8, 4, 32)
 #undef S
+#define P(id, TW, TH, U, SLAB, ALIGN) \
+    case id: return launch_psync_variant<TW, TH, U, ALIGN>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
+        P(20, 16, 8, 2, 32, 1)
+        P(21, 16, 8, 2, 32, 0)
+        P(22, 16, 8, 1, 32, 1)
+        P(23, 16, 8, 2, 64, 1)
+        P(24, 16, 16, 2, 32, 1)
+        P(25, 16, 16, 2, 64, 1)
+        P(26, 16, 8, 3, 32, 1)
+        P(27, 16, 8, 2, 512, 1)
+        P(28, 8, 8, 2, 32, 1)
+        P(29, 16, 16, 1, 32, 1)
+#undef P
         default: return cudaErrorInvalidValue;
     }
 #undef V

@@ -124,6 +124,10 @@ class DRR(nn.Module):
         source = self.affine_inverse(source)  # world -> voxel-index coordinates
         target = self.affine_inverse(target)
         kwargs["mask"] = self.mask if mask_to_channels else None
+        det = self.detector
+        full_grid = det.n_subsample is None and self.patch_size is None and target.shape[1] == det.height * det.width
+        if hasattr(self.renderer, "detector_shape"):  # hint for the tiled kernels; never changes results
+            self.renderer.detector_shape = (det.height, det.width) if full_grid else None
         if self.patch_size is None:
             return self.renderer(density, source, target, img, **kwargs)
         # serial patches, as the reference does (drr.py:217-225); note Trilinear is not patch-invariant (quirk Q3)

@@ -49,26 +49,34 @@ class _SiddonFunction(torch.autograd.Function):
     """out (B,1,N) = Siddon line integrals; backward = closed-form kernel (include/b200drr.h)."""
 
     @staticmethod
-    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad):
+    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad, grid):
         B, N = _check_inputs(volume, source, target, img)
         vol = volume.contiguous()
         src = source.reshape(B, 3).contiguous()
         tgt = target.contiguous()
         raylen = img.reshape(B, N).contiguous()
         out = torch.empty(B, N, dtype=torch.float32, device=vol.device)
+        # full detector grid + default options -> tiled, slab-major kernels (include/b200drr.h: *_grid)
+        if grid is not None and (grid[0] * grid[1] != N or reduce != 0 or align_corners or vol.numel() >= 2**31 - 1):
+            grid = None
         lib = _lib.load()
         with torch.cuda.device(vol.device):
-            _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N,
-                                              voxel_shift, eps, reduce, int(align_corners), _stream()),
-                       "b200drr_siddon_fwd")
+            if grid is not None:
+                _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
+                                                       B, grid[0], grid[1], voxel_shift, eps, 0, _stream()),
+                           "b200drr_siddon_fwd_grid")
+            else:
+                _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B,
+                                                  N, voxel_shift, eps, reduce, int(align_corners), _stream()),
+                           "b200drr_siddon_fwd")
         ctx.save_for_backward(vol, src, tgt, raylen)
-        ctx.cfg = (voxel_shift, eps, reduce, align_corners, stop_grad, tuple(source.shape), tuple(img.shape))
+        ctx.cfg = (voxel_shift, eps, reduce, align_corners, stop_grad, tuple(source.shape), tuple(img.shape), grid)
         return out.view(B, 1, N)
 
     @staticmethod
     def backward(ctx, gout):
         vol, src, tgt, raylen = ctx.saved_tensors
-        voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape = ctx.cfg
+        voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape, grid = ctx.cfg
         if reduce != 0:
             raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
         if align_corners:
@@ -82,12 +90,18 @@ class _SiddonFunction(torch.autograd.Function):
         g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
         lib = _lib.load()
         with torch.cuda.device(vol.device):
-            _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
-                                              _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift, eps,
-                                              int(stop_grad), int(align_corners), _stream()),
-                       "b200drr_siddon_bwd")
+            if grid is not None:
+                _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                       _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, grid[0], grid[1],
+                                                       voxel_shift, eps, int(stop_grad), 0, _stream()),
+                           "b200drr_siddon_bwd_grid")
+            else:
+                _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                  _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift, eps,
+                                                  int(stop_grad), int(align_corners), _stream()),
+                           "b200drr_siddon_bwd")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
-                None if g_len is None else g_len.view(img_shape), None, None, None, None, None)
+                None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
 
 
 class _TrilinearFunction(torch.autograd.Function):
@@ -159,6 +173,9 @@ class Siddon(torch.nn.Module):
         self.reducefn = reducefn
         self.voxel_shift = voxel_shift
         self.eps = eps
+        # (H, W) when the rays handed to forward() are the full row-major detector grid (set by DRR.render);
+        # enables the tiled slab-major kernels.  None = arbitrary ray set (sub-sampled / patched / user rays).
+        self.detector_shape = None
 
     def dims(self, volume):
         return torch.tensor(volume.shape).to(volume)
@@ -174,7 +191,7 @@ class Siddon(torch.nn.Module):
             raise NotImplementedError("mask_to_channels rendering is not implemented yet in diffdrr_b200")
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
-                                     bool(self.stop_gradients_through_grid_sample))
+                                     bool(self.stop_gradients_through_grid_sample), self.detector_shape)
 
 
 def _get_alpha_minmax(source, target, dims, voxel_shift, eps):

@@ -79,6 +79,16 @@ int b200drr_siddon_bwd(const float *vol, int D0, int D1, int D2, const float *sr
                        int align_corners, void *stream);
 
 /*
+ * Siddon backward for a FULL detector grid (see b200drr_siddon_fwd_grid): same outputs and conventions as
+ * b200drr_siddon_bwd (g_src / g_tgt / g_raylen overwritten, g_vol accumulated into), computed slab-major with
+ * red.global.add partial sums.  align_corners=0 only.
+ */
+int b200drr_siddon_bwd_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                            const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                            float *g_vol, int B, int H, int W, float voxel_shift, float eps, int stop_grad,
+                            int variant, void *stream);
+
+/*
  * Trilinear forward: replaces Trilinear.forward with mask=None (renderers.py:205-240) for a given
  * sampling range.  alpha_range is a DEVICE pointer to {alphamin, alphamax} (so that the range computed
  * on the device by _get_alpha_minmax, renderers.py:124-140,221-223, needs no host round trip).

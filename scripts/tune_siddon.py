@@ -46,7 +46,7 @@ def base():
     _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(ref), B, N, 0.5, 1e-8, 0, 0, _stream()), "fwd")
 ms = timeit(base)
 print(f"baseline linear       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,10,11,12,13,14,15,16,17,18,19").split(",")]
+variants = [int(v) for v in os.environ.get("VARIANTS", "0,15").split(",")]
 for v in variants:
     out = torch.zeros(B, N, device=dev)
     def run():
@@ -58,3 +58,19 @@ for v in variants:
         continue
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"grid variant {v:2d}       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")
+
+# ---- backward variants ----------------------------------------------------------------------------------------
+gout = torch.rand(B, N, device=dev)
+g_src0, g_tgt0, g_len0 = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
+def bbase():
+    _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src0), _ptr(g_tgt0), _ptr(g_len0), None, B, N, 0.5, 1e-8, 0, 0, _stream()), "bwd")
+bbytes = (4 * visits + 36 * B * N) / 1e9
+ms = timeit(bbase, 3)
+print(f"bwd baseline linear   : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {bbytes / ms * 1e3:8.1f} GB/s  {bbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
+for v in [int(x) for x in os.environ.get("BVARIANTS", "0,1,2,3,4,5").split(",")]:
+    g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
+    def run():
+        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, B, H, H, 0.5, 1e-8, 0, v, _stream()), "bwd_grid")
+    ms = timeit(run)
+    e = [float((a - b).abs().max() / b.abs().max()) for a, b in ((g_src, g_src0), (g_tgt, g_tgt0), (g_len, g_len0))]
+    print(f"bwd grid variant {v:2d}   : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {bbytes / ms * 1e3:8.1f} GB/s  {bbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff src/tgt/len {e[0]:.1e} {e[1]:.1e} {e[2]:.1e}")

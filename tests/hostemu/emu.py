@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         srcs = [os.path.join(_HERE, "hostemu.cpp")] + [
-            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh")]
+            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh", "psync.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
                                    "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
@@ -55,6 +55,15 @@ def siddon_fwd_ilp(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, unroll=4):
     return out
 
 
+def siddon_fwd_psync(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, slab=0, unroll=2):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    out = np.empty((B, 1, N), np.float32)
+    lib().emu_siddon_fwd_psync(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                               ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                               ctypes.c_int(slab), ctypes.c_int(unroll))
+    return out
+
+
 def siddon_visits(shape, src, tgt, voxel_shift=0.5, eps=1e-8):
     src, tgt = _f(src), _f(tgt)
     B, N = tgt.shape[0], tgt.shape[1]
@@ -64,14 +73,18 @@ def siddon_visits(shape, src, tgt, voxel_shift=0.5, eps=1e-8):
     return out
 
 
-def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False):
+def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, lean_slab=None):
     vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
     gout = _f(gout)
     g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
     g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
-    lib().emu_siddon_bwd(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
-                         _p(g_tgt), _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N),
-                         ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(bool(stop_grad)))
+    args = (_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src), _p(g_tgt),
+            _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+            ctypes.c_int(bool(stop_grad)))
+    if lean_slab is None:
+        lib().emu_siddon_bwd(*args)
+    else:
+        lib().emu_siddon_bwd_lean(*args, ctypes.c_int(lean_slab))
     return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
 
 

@@ -2,9 +2,11 @@
 // (diffdrr_b200/csrc/ray_math.cuh) with g++ and loops over rays on the CPU, so that the CPU-only build
 // container can check the kernel logic against the oracle and the goldens before any GPU time is spent.
 // Never linked into libb200drr.so and never imported by the product package.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
-#include "../../diffdrr_b200/csrc/ray_math.cuh"
+#include "../../diffdrr_b200/csrc/psync.cuh"
 
 using namespace b200drr;
 
@@ -44,6 +46,27 @@ void emu_siddon_fwd_ilp(const float* vol, int D0, int D1, int D2, const float* s
                                   : unroll == 3  ? siddon_ray_fast_ilp<3>(vol, dims, ray, shift)
                                   : unroll == -4 ? siddon_ray_lean<4>(vol, dims, ray, shift)
                                                  : siddon_ray_lean<1>(vol, dims, ray, shift));
+        }
+}
+
+void emu_siddon_fwd_psync(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                          const float* raylen, float* out, int B, long N, float shift, float eps, int slab, int unroll)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float acc = 0.0f;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                const unsigned nvox = (unsigned)D0 * D1 * D2;
+                acc += unroll == 2 ? siddon_ray_psync<2>(vol, nvox, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, NoAlign())
+                                   : siddon_ray_psync<1>(vol, nvox, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, NoAlign());
+            }
+            out[r] = raylen[r] * acc;
         }
 }
 
@@ -93,6 +116,33 @@ void emu_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* src, 
         }
 }
 
+void emu_siddon_bwd_lean(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                         const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,
+                         int B, long N, float shift, float eps, int stop_grad, int slab)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            const float gL = gout[r] * raylen[r];
+            float A[3] = {0, 0, 0}, C[3] = {0, 0, 0}, acc = 0;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                acc += siddon_ray_bwd_lean_box<4>(vol, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, gL,
+                                                  stop_grad ? nullptr : g_vol, A, C);
+            }
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = -gL * A[a] * ray.inv[a];
+                g_src[b * 3 + a] += gL * (A[a] - C[a]) * ray.inv[a];
+            }
+            g_raylen[r] = stop_grad ? 0.0f : gout[r] * acc;
+        }
+}
+
 void emu_trilinear_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, float* out, int B, long N, float shift, float eps, int P, float amin,
                        float amax, int reduce, int align_corners)
@@ -135,3 +185,61 @@ void emu_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float* sr
 }
 
 }  // extern "C"
+
+// ---- access-pattern analysis (tuning aid): distinct 32-byte sectors / 128-byte lines per warp-wide gather ----------
+// Emulates the lock-step lean walk of one warp = WX x WY pixel patch and counts, per walk step, how many distinct
+// sectors and lines the 32 lanes touch.  strides (st0,st1,st2) describe the volume layout being evaluated.
+#include <set>
+extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const float* tgt, int B, int H, int W,
+                                 int WX, int WY, int slab, long st0, long st1, long st2, float shift, float eps,
+                                 int sample_every, double* out /* [4]: steps, lane-visits, sectors, lines */)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    double steps = 0, visits = 0, sectors = 0, lines = 0;
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    long warp_id = 0;
+    for (int b = 0; b < B; ++b)
+        for (int ty = 0; ty + WY <= H; ty += WY)
+            for (int tx = 0; tx + WX <= W; tx += WX, ++warp_id) {
+                if (warp_id % sample_every) continue;
+                for (int sl = 0; sl < n_slabs; ++sl) {
+                    const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                    const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                    const int n = WX * WY;
+                    std::vector<Walk> w(n);
+                    std::vector<float> acur(n);
+                    std::vector<bool> live(n);
+                    int alive = 0;
+                    for (int l = 0; l < n; ++l) {
+                        const long r = ((long)b * H + ty + l / WX) * W + tx + l % WX;
+                        const Ray ray = load_ray(src, tgt, b, r, eps);
+                        w[l] = start_walk_box(ray, lo_v, hi_v, shift);
+                        live[l] = w[l].hit;
+                        acur[l] = w[l].a_in;
+                        alive += live[l];
+                    }
+                    while (alive > 0) {
+                        std::set<long> sec, lin;
+                        for (int l = 0; l < n; ++l) {
+                            if (!live[l]) continue;
+                            const long off = w[l].idx[0] * st0 + w[l].idx[1] * st1 + w[l].idx[2] * st2;
+                            sec.insert(off >> 3);
+                            lin.insert(off >> 5);
+                            visits += 1;
+                            const float anext = fminf(fminf(w[l].an[0], w[l].an[1]), w[l].an[2]);
+                            if (!(anext < w[l].a_out)) { live[l] = false; --alive; continue; }
+                            for (int a = 0; a < 3; ++a)
+                                if (w[l].an[a] == anext) {
+                                    w[l].idx[a] += w[l].sti[a];
+                                    w[l].nf[a] += 1.0f;
+                                    w[l].an[a] = fmaf(w[l].nf[a], w[l].da[a], w[l].a0[a]);
+                                }
+                        }
+                        steps += 1;
+                        sectors += sec.size();
+                        lines += lin.size();
+                    }
+                }
+            }
+    out[0] = steps; out[1] = visits; out[2] = sectors; out[3] = lines;
+}

@@ -98,6 +98,32 @@ def test_full_size_properties(big):
     assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 5e-3
 
 
+def test_full_size_grid_kernels_match_plain_kernels(big):
+    """The tiled slab-major kernels (used when the rays are a full detector grid) against the one-thread-per-ray
+    kernels on the metric's configuration; gradients too.  Partial sums are combined with red.global.add, so the
+    comparison is to fp32 round-off, not bitwise."""
+    from diffdrr_b200 import Siddon
+    drr, vol, (src, tgt, raylen) = big
+    plain, tiled = Siddon(), Siddon()
+    tiled.detector_shape = (256, 256)
+    w = torch.rand(4, 1, 256 * 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    outs = []
+    for mod in (plain, tiled):
+        s, t_, l = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True), raylen.clone().requires_grad_(True)
+        out = mod(vol, s, t_, l)
+        (out * w).sum().backward()
+        outs.append((out.detach(), s.grad, t_.grad, l.grad))
+    for a, b, tol in zip(outs[0], outs[1], (2e-5, 1e-3, 1e-3, 2e-5)):
+        assert relerr(b.cpu().numpy(), a.cpu().numpy()) < tol
+    # volume gradient through the tiled kernel: adjoint identity
+    v = vol.clone().requires_grad_(True)
+    (tiled(v, src[:2], tgt[:2], raylen[:2]) * w[:2]).sum().backward()
+    vol2 = torch.rand(vol.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    lhs = (tiled(vol2, src[:2], tgt[:2], raylen[:2]) * w[:2]).sum().double()
+    rhs = (vol2.double() * v.grad.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-4
+
+
 def test_full_size_gradients(big):
     """fwd+bwd at 512^3 -> 256^2: the adjoint identity <J v, w> = <v, J^T w> ties backward to forward."""
     from diffdrr_b200 import Siddon

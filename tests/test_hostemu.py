@@ -49,6 +49,17 @@ def test_siddon_lean_walk(name, unroll):
     assert relerr(b, a) < 1e-6
 
 
+@pytest.mark.parametrize("name", [c[0] for c in SIDDON if not c[1]])
+@pytest.mark.parametrize("slab,unroll", [(0, 1), (0, 2), (5, 2), (1, 1)])
+def test_siddon_plane_synchronous_walk(name, slab, unroll):
+    """Closed-form major-slab walk (production forward kernel), whole volume and cut into axis-0 slabs."""
+    g = load_golden(name)
+    a = emu.siddon_fwd(g["volume"], g["source"], g["target"], g["raylen"])
+    b = emu.siddon_fwd_psync(g["volume"], g["source"], g["target"], g["raylen"], slab=slab, unroll=unroll)
+    assert relerr(b, g["img_f64"]) < IMG_TOL
+    assert relerr(b, a) < 2e-5
+
+
 def _amm(g, kw):
     if "alphamin" in kw:
         return kw["alphamin"], kw["alphamax"]
@@ -78,9 +89,11 @@ def _grad_tol(g, key, floor=1e-4):
     ("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)), ("siddon_nc_b4_ragged", {}),
     ("siddon_nc_b4_stopgrad", dict(stop_grad=True)),
 ])
-def test_siddon_backward(name, kw):
+@pytest.mark.parametrize("lean_slab", [None, 0, 5])
+def test_siddon_backward(name, kw, lean_slab):
+    """lean_slab=None: plain walk; 0 / 5: the branch-free backward walk, whole volume / cut into 5-plane slabs."""
     g = load_golden(name)
-    out = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], **kw)
+    out = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], lean_slab=lean_slab, **kw)
     assert relerr(out["g_target"], g["g_target_f64"]) < _grad_tol(g, "g_target")
     assert relerr(out["g_source"], g["g_source_f64"]) < _grad_tol(g, "g_source")
     if kw.get("stop_grad"):
@@ -135,6 +148,8 @@ def test_random_rays_vs_oracle(seed, shape):
     out = emu.siddon_fwd(vol, src, tgt, raylen)
     assert relerr(out, ref) < IMG_TOL
     assert relerr(emu.siddon_fwd_ilp(vol, src, tgt, raylen, unroll=-4), ref) < IMG_TOL
+    assert relerr(emu.siddon_fwd_psync(vol, src, tgt, raylen, slab=0), ref) < IMG_TOL
+    assert relerr(emu.siddon_fwd_psync(vol, src, tgt, raylen, slab=3), ref) < IMG_TOL
     amin, amax = oracle.alpha_minmax(shape, src, tgt, 0.5, 1e-8, np.float32)
     ref = oracle.trilinear_fwd(vol, src, tgt, raylen, n_points=130, alphamin=amin, alphamax=amax, dtype=np.float64)
     out = emu.trilinear_fwd(vol, src, tgt, raylen, 130, amin, amax)
