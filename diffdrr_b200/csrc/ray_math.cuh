@@ -138,6 +138,16 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
             const float q = fmaf(w.a_in, ray.d[a], ray.s[a] + shift);
             i = (int)floorf(q);
             i = i < lo_v[a] ? lo_v[a] : (i > hi_v[a] - 1 ? hi_v[a] - 1 : i);
+            // Make the start voxel consistent with the ORDER of the crossing alphas (floor() of a position that sits
+            // within round-off of a plane is a coin toss): the plane behind must have alpha < a_in, and a plane that
+            // ties with the entry face counts as not crossed yet (the face has the lower axis index for slab cuts,
+            // which reproduces the crossing order of the unsplit walk and hence its gradient attribution).
+            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
+            if (plane_alpha_acc(ray, a, (float)behind, shift) >= w.a_in) {
+                if (fwd ? i > lo_v[a] : i < hi_v[a] - 1) i -= w.sti[a];
+            } else if (plane_alpha_acc(ray, a, (float)ahead, shift) < w.a_in) {
+                if (fwd ? i < hi_v[a] - 1 : i > lo_v[a]) i += w.sti[a];
+            }
         }
         w.idx[a] = i;
         w.p0[a] = (float)(fwd ? i + 1 : i);
@@ -148,6 +158,93 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
         // the exit alpha is produced by the SAME expression the walk uses for its crossings, so that
         // "crossing alpha == a_out" identifies the exit plane exactly
         w.a_out = fminf(w.a_out, fmaf(w.nx[a], w.da[a], w.a0[a]));
+    }
+    return w;
+}
+
+// Same as start_walk_box, but every alpha (crossings AND box faces) is generated from ONE per-ray frame anchored at
+// the ray's entry into the whole VOLUME:  alpha_a(p) = fma(|p - pref_a|, |1/d_a|, alpha_acc(pref_a)).  All slabs a
+// ray is cut into then see bit-identical alphas for the same plane, so a slab's exit alpha equals the next slab's
+// entry alpha and (near-)ties between a slab face and another axis' plane are ordered the same way on both sides.
+// The backward pass needs this: an inconsistent order drops or doubles one crossing coefficient (the forward sum
+// does not care, the affected segment has ~zero length).
+B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_v[3], const int hi_v[3], float shift)
+{
+    Walk w;
+    // ---- frame: entry into the whole volume ----------------------------------------------------------------
+    float vlo[3];
+    float av_in = -INFINITY, av_out = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        w.inv[a] = ray.inv[a];
+        w.da[a] = fabsf(ray.inv[a]);
+        w.sti[a] = ray.d[a] > 0.0f ? 1 : -1;
+        const float a0 = plane_alpha_acc(ray, a, 0.0f, shift), a1 = plane_alpha_acc(ray, a, (float)dims.d[a], shift);
+        vlo[a] = fminf(a0, a1);
+        av_in = fmaxf(av_in, vlo[a]);
+        av_out = fminf(av_out, fmaxf(a0, a1));
+    }
+    float pref[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = w.sti[a] > 0;
+        int i;
+        if (vlo[a] >= av_in) {
+            i = fwd ? 0 : dims.d[a] - 1;
+        } else {
+            i = (int)floorf(fmaf(av_in, ray.d[a], ray.s[a] + shift));
+            i = i < 0 ? 0 : (i > dims.d[a] - 1 ? dims.d[a] - 1 : i);
+            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
+            if (plane_alpha_acc(ray, a, (float)behind, shift) >= av_in) {
+                if (fwd ? i > 0 : i < dims.d[a] - 1) i -= w.sti[a];
+            } else if (plane_alpha_acc(ray, a, (float)ahead, shift) < av_in) {
+                if (fwd ? i < dims.d[a] - 1 : i > 0) i += w.sti[a];
+            }
+        }
+        pref[a] = (float)(fwd ? i + 1 : i);
+        w.a0[a] = plane_alpha_acc(ray, a, pref[a], shift);
+    }
+    // ---- clip to the box with frame alphas -----------------------------------------------------------------
+    float lo[3];
+    w.a_in = -INFINITY;
+    w.a_out = INFINITY;
+    w.entry_axis = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float sg = (float)w.sti[a];
+        const float a0 = fmaf(((float)lo_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
+        const float a1 = fmaf(((float)hi_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
+        lo[a] = fminf(a0, a1);
+        if (lo[a] > w.a_in) {
+            w.a_in = lo[a];
+            w.entry_axis = a;
+        }
+        w.a_out = fminf(w.a_out, fmaxf(a0, a1));
+    }
+    // a_in == a_out is a (zero-length) hit here: the voxel touched still takes part in the crossing bookkeeping
+    w.hit = (av_in < av_out) && (w.a_in <= w.a_out);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = w.sti[a] > 0;
+        const float sg = (float)w.sti[a];
+        int i;
+        if (lo[a] >= w.a_in) {
+            i = fwd ? lo_v[a] : hi_v[a] - 1;
+        } else {
+            i = (int)floorf(fmaf(w.a_in, ray.d[a], ray.s[a] + shift));
+            i = i < lo_v[a] ? lo_v[a] : (i > hi_v[a] - 1 ? hi_v[a] - 1 : i);
+            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
+            if (fmaf(((float)behind - pref[a]) * sg, w.da[a], w.a0[a]) >= w.a_in) {
+                if (fwd ? i > lo_v[a] : i < hi_v[a] - 1) i -= w.sti[a];
+            } else if (fmaf(((float)ahead - pref[a]) * sg, w.da[a], w.a0[a]) < w.a_in) {
+                if (fwd ? i < hi_v[a] - 1 : i > lo_v[a]) i += w.sti[a];
+            }
+        }
+        w.idx[a] = i;
+        w.p0[a] = (float)(fwd ? i + 1 : i);
+        w.nf[a] = (w.p0[a] - pref[a]) * sg;                                     // crossings already behind us
+        w.nx[a] = ((fwd ? (float)hi_v[a] : (float)lo_v[a]) - pref[a]) * sg;      // count of the box's exit plane
+        w.an[a] = fmaf(w.nf[a], w.da[a], w.a0[a]);
     }
     return w;
 }
@@ -328,7 +425,7 @@ B200_HD void lean_init(const Walk& w, int st0, int st1, int st2, LeanState& s, L
     k.a_out = w.a_out;
     k.so0 = w.sti[0] * st0; k.so1 = w.sti[1] * st1; k.so2 = w.sti[2] * st2;
     s.an0 = w.an[0]; s.an1 = w.an[1]; s.an2 = w.an[2];
-    s.nf0 = 0.0f; s.nf1 = 0.0f; s.nf2 = 0.0f;
+    s.nf0 = w.nf[0]; s.nf1 = w.nf[1]; s.nf2 = w.nf[2];
     s.acur = w.hit ? w.a_in : w.a_out;  // a miss has nothing to walk
     s.off = w.idx[0] * st0 + w.idx[1] * st1 + w.idx[2] * st2;
 }
@@ -368,7 +465,10 @@ B200_HD float siddon_ray_lean(const float* vol, const VolDims& dims, const Ray& 
 }
 
 // Lean step for the backward walk: additionally reports which axis' plane ends the current voxel
-// (0/1/2; 3 when the walk has reached the exit plane and no crossing is taken).
+// (0/1/2; 3 when the walk has reached the exit plane and no crossing is taken).  Unlike lean_step, planes that
+// tie are crossed ONE PER STEP (lowest axis first, like a stable sort of the reference's cat([ax, ay, az])): the
+// zero-length voxel in between carries no mass but it decides how the crossing coefficient v_before - v_after is
+// split between the two axes' gradients.  (Ties are not rare: regular detector grids produce exact edge hits.)
 B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
 {
     float len;
@@ -383,6 +483,9 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
         "setp.eq.and.f32 p0, %0, nx, q;\n\t"
         "setp.eq.and.f32 p1, %1, nx, q;\n\t"
         "setp.eq.and.f32 p2, %2, nx, q;\n\t"
+        "and.pred p1, p1, !p0;\n\t"
+        "or.pred q, p0, p1;\n\t"
+        "and.pred p2, p2, !q;\n\t"
         "selp.s32 %9, 2, 3, p2;\n\t"
         "selp.s32 %9, 1, %9, p1;\n\t"
         "selp.s32 %9, 0, %9, p0;\n\t"
@@ -405,7 +508,7 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
     len = nx - s.acur;
     s.acur = nx;
     const bool q = nx < k.a_out;
-    const bool p0 = q && s.an0 == nx, p1 = q && s.an1 == nx, p2 = q && s.an2 == nx;
+    const bool p0 = q && s.an0 == nx, p1 = q && !p0 && s.an1 == nx, p2 = q && !p0 && !p1 && s.an2 == nx;
     ax = p0 ? 0 : (p1 ? 1 : (p2 ? 2 : 3));
     if (p0) { s.nf0 += 1.0f; s.an0 = fmaf(s.nf0, k.da0, k.a00); s.off += k.so0; }
     if (p1) { s.nf1 += 1.0f; s.an1 = fmaf(s.nf1, k.da1, k.a01); s.off += k.so1; }
@@ -420,16 +523,18 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
 // ray is split into slabs (the two halves of an interior face add up to the true coefficient).
 // Returns sum_j v_j len_j; adds gL*len_j to g_vol[voxel_j] when g_vol != nullptr.  A, C are accumulated INTO.
 template <int U>
-B200_HD float siddon_ray_bwd_lean_box(const float* vol, const int lo_v[3], const int hi_v[3], int st0, int st1, int st2,
-                                      const Ray& ray, float shift, float gL, float* g_vol, float A[3], float C[3])
+B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
+                                      int st1, int st2, const Ray& ray, float shift, float gL, float* g_vol, float A[3],
+                                      float C[3])
 {
-    const Walk w = start_walk_box(ray, lo_v, hi_v, shift);
+    const Walk w = start_walk_frame(ray, dims, lo_v, hi_v, shift);
     if (!w.hit) return 0.0f;
     LeanConst k;
     LeanState s;
     lean_init(w, st0, st1, st2, s, k);
     float acc = 0.0f, vprev = 0.0f, aprev = w.a_in;
     int axprev = w.entry_axis;
+    bool any = false;
     while (s.acur < k.a_out) {
         float len[U], aend[U], v[U];
         int offs[U], ax[U];
@@ -454,13 +559,43 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const int lo_v[3], const
                 acc = fmaf(len[j], v[j], acc);
                 if (g_vol) red_add(g_vol + offs[j], gL * len[j]);
                 vprev = v[j];
+                any = true;
             }
             axprev = ax[j];
             aprev = aend[j];
         }
     }
-    // exit crossing: v_last -> 0 through the axis whose boundary plane is a_out
-    const int ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
+    if (!any) {  // the box is only touched (a_in == a_out, e.g. the ray enters the volume exactly on a slab face)
+        const float v0 = ldg(vol + s.off);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == w.entry_axis) {
+                A[a] = fmaf(-v0, w.a_in, A[a]);
+                C[a] -= v0;
+            }
+        vprev = v0;
+    }
+    // Tail: crossings that TIE with the exit alpha are taken lowest axis first (stable-sort order) until the first
+    // boundary plane is met; interior planes among them lead through zero-length voxels that only matter for how the
+    // exit coefficient is split between the axes.  (Regular detector grids hit voxel edges exactly, so this is common.)
+    const float an[3] = {s.an0, s.an1, s.an2}, nf[3] = {s.nf0, s.nf1, s.nf2};
+    const int so[3] = {k.so0, k.so1, k.so2};
+    int ax_exit = 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (ax_exit == 3 && an[a] <= k.a_out) {
+            if (nf[a] == w.nx[a]) {
+                ax_exit = a;  // this axis' boundary plane: the ray leaves the box through it
+            } else {
+                s.off += so[a];
+                const float vmid = ldg(vol + s.off);
+                const float coef = vprev - vmid;
+                A[a] = fmaf(coef, k.a_out, A[a]);
+                C[a] += coef;
+                vprev = vmid;
+            }
+        }
+    if (ax_exit == 3) ax_exit = (an[0] <= an[1] && an[0] <= an[2]) ? 0 : (an[1] <= an[2] ? 1 : 2);
 #pragma unroll
     for (int a = 0; a < 3; ++a)
         if (a == ax_exit) {

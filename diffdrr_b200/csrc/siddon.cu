@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TW* TH) siddon_bwd_slab_kernel(const float* __
         const float L = __ldg(raylen + r), g = __ldg(gout + r);
         const float gL = g * L;
         float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
-        const float acc = siddon_ray_bwd_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, gL,
+        const float acc = siddon_ray_bwd_lean_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, gL,
                                                      stop_grad ? nullptr : g_vol, A, C);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {

@@ -42,20 +42,22 @@ class Subject:
 
 
 def make_volume(shape, kind: str = "rand", seed: int = 0) -> np.ndarray:
-    """fp32 volume of `shape` (int or 3-tuple); 'rand' = U[0,1) noise, 'phantom' = smooth blobs + 1% noise."""
+    """fp32 volume of `shape` (int or 3-tuple); 'rand' = U[0,1) noise, 'phantom' = blobs + hard sphere + 1% noise,
+    'smooth' = the two Gaussian blobs only (for gradient checks: no edges a grazing ray could flip across)."""
     if isinstance(shape, int):
         shape = (shape, shape, shape)
     rng = np.random.Generator(np.random.PCG64(seed))
     if kind == "rand":
         return rng.random(shape, dtype=np.float32)
-    if kind != "phantom":
+    if kind not in ("phantom", "smooth"):
         raise ValueError(kind)
     ax = [np.linspace(-1.0, 1.0, n, dtype=np.float64) for n in shape]
     x, y, z = np.meshgrid(*ax, indexing="ij")
     vol = np.exp(-((x - 0.2) ** 2 + (y + 0.1) ** 2 + (z - 0.05) ** 2) / 0.18)
     vol += 0.6 * np.exp(-((x + 0.35) ** 2 + (y - 0.3) ** 2 + (z + 0.25) ** 2) / 0.05)
-    vol += 0.5 * ((x + 0.1) ** 2 + (y + 0.2) ** 2 + (z - 0.3) ** 2 < 0.09)
-    vol += 0.01 * rng.random(shape)
+    if kind == "phantom":
+        vol += 0.5 * ((x + 0.1) ** 2 + (y + 0.2) ** 2 + (z - 0.3) ** 2 < 0.09)
+        vol += 0.01 * rng.random(shape)
     return vol.astype(np.float32)
 
 

@@ -35,14 +35,19 @@ def test_mid_size_vs_oracle(D, H, B):
     out = Trilinear()(drr.density, src, tgt, raylen, n_points=300).cpu().numpy()
     amin, amax = oracle.alpha_minmax(vol.shape, args[1], args[2], 0.5, 1e-8, np.float32)
     assert relerr(out, oracle.trilinear_fwd(*args, n_points=300, alphamin=amin, alphamax=amax, dtype=np.float64)) < 1e-4
-    # gradients of a random linear functional vs the fp64 oracle on a subset of rays (keeps the oracle fast)
+    # gradients of a random linear functional vs the fp64 oracle on a subset of rays (keeps the oracle fast), on the
+    # SMOOTH volume: on white noise every crossing contributes (v_before - v_after)*alpha with random sign and the fp32
+    # sums are ill-conditioned (the reference's own fp32 run is 2e-4..1e-2 off there), and a hard edge
+    # makes the gradient of a grazing ray an O(1) coin toss between fp32 and fp64
+    phantom = synthetic.make_volume(D, "smooth", seed=4)
+    pv = t(phantom)
     sub = slice(0, 4096)
     w = torch.rand(B, 1, 4096, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
     s, tg, l = src.clone().requires_grad_(True), tgt[:, sub].clone().requires_grad_(True), raylen[:, :, sub].clone().requires_grad_(True)
-    v = drr.density.clone().requires_grad_(True)
+    v = pv.clone().requires_grad_(True)
     (Siddon()(v, s, tg, l) * w).sum().backward()
-    ref = oracle.siddon_bwd(vol, args[1], args[2][:, sub], args[3][:, :, sub], w.cpu().numpy(), dtype=np.float64)
-    assert relerr(tg.grad.cpu().numpy(), ref["g_target"]) < 2e-3   # fp32 pose gradients on a white-noise volume
+    ref = oracle.siddon_bwd(phantom, args[1], args[2][:, sub], args[3][:, :, sub], w.cpu().numpy(), dtype=np.float64)
+    assert relerr(tg.grad.cpu().numpy(), ref["g_target"]) < 2e-3
     assert relerr(s.grad.cpu().numpy(), ref["g_source"]) < 2e-3
     assert relerr(l.grad.cpu().numpy(), ref["g_raylen"]) < 1e-4
     assert relerr(v.grad.cpu().numpy(), ref["g_volume"]) < 1e-4
@@ -107,14 +112,20 @@ def test_full_size_grid_kernels_match_plain_kernels(big):
     plain, tiled = Siddon(), Siddon()
     tiled.detector_shape = (256, 256)
     w = torch.rand(4, 1, 256 * 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
-    outs = []
-    for mod in (plain, tiled):
-        s, t_, l = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True), raylen.clone().requires_grad_(True)
-        out = mod(vol, s, t_, l)
-        (out * w).sum().backward()
-        outs.append((out.detach(), s.grad, t_.grad, l.grad))
-    for a, b, tol in zip(outs[0], outs[1], (2e-5, 1e-3, 1e-3, 2e-5)):
-        assert relerr(b.cpu().numpy(), a.cpu().numpy()) < tol
+    x = torch.linspace(-1, 1, 512, device=DEV)
+    smooth = torch.exp(-(x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2) / 0.3)
+    # images on the white-noise volume; end-point gradients on a smooth one (on white noise they are fp32-ill-conditioned)
+    for volume, tols in ((vol, (2e-5, None, None, 2e-5)), (smooth, (2e-5, 1e-3, 1e-3, 2e-5))):
+        outs = []
+        for mod in (plain, tiled):
+            s, t_, l = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True), raylen.clone().requires_grad_(True)
+            out = mod(volume, s, t_, l)
+            (out * w).sum().backward()
+            outs.append((out.detach(), s.grad, t_.grad, l.grad))
+        for a, b, tol in zip(outs[0], outs[1], tols):
+            if tol is not None:
+                assert relerr(b.cpu().numpy(), a.cpu().numpy()) < tol
+    del smooth
     # volume gradient through the tiled kernel: adjoint identity
     v = vol.clone().requires_grad_(True)
     (tiled(v, src[:2], tgt[:2], raylen[:2]) * w[:2]).sum().backward()
