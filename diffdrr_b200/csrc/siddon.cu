@@ -242,8 +242,8 @@ static cudaError_t launch_psync_variant(const float* vol, VolDims dims, const fl
 // Slab-major detector-grid BACKWARD kernel: same decomposition as siddon_fwd_slab_kernel.  Every CTA adds its
 // slab's share of g_tgt / g_raylen / g_src (and optionally g_vol) with red.global.add; the launcher zero-fills.
 // ---------------------------------------------------------------------------------------------------
-template <int TW, int TH, int U>
-__global__ void __launch_bounds__(TW* TH) siddon_bwd_slab_kernel(const float* __restrict__ vol, VolDims dims,
+template <int TW, int TH, int U, int MINB>
+__global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const float* __restrict__ vol, VolDims dims,
                                                                  const float* __restrict__ src,
                                                                  const float* __restrict__ tgt,
                                                                  const float* __restrict__ raylen,
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(TW* TH) siddon_bwd_slab_kernel(const float* __
     }
 }
 
-template <int TW, int TH, int U>
+template <int TW, int TH, int U, int MINB>
 static cudaError_t launch_bwd_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                            const float* raylen, const float* gout, float* g_src, float* g_tgt,
                                            float* g_raylen, float* g_vol, int B, int H, int W, int slab, float shift,
@@ -308,7 +308,7 @@ static cudaError_t launch_bwd_slab_variant(const float* vol, VolDims dims, const
     if (e == cudaSuccess && g_tgt) e = cudaMemsetAsync(g_tgt, 0, sizeof(float) * 3 * n, stream);
     if (e == cudaSuccess && g_raylen) e = cudaMemsetAsync(g_raylen, 0, sizeof(float) * n, stream);
     if (e != cudaSuccess) return e;
-    siddon_bwd_slab_kernel<TW, TH, U><<<(unsigned)blocks, TW * TH, 0, stream>>>(
+    siddon_bwd_slab_kernel<TW, TH, U, MINB><<<(unsigned)blocks, TW * TH, 0, stream>>>(
         vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, slab, shift, eps, stop_grad);
     return cudaGetLastError();
 }
@@ -318,17 +318,22 @@ cudaError_t launch_siddon_bwd_grid(const float* vol, VolDims dims, const float* 
                                    float* g_vol, int B, int H, int W, float shift, float eps, int stop_grad, int variant,
                                    cudaStream_t stream)
 {
-#define BV(id, TW, TH, U, SLAB)                                                                                          \
+#define BV(id, TW, TH, U, SLAB, MINB)                                                                                    \
     case id:                                                                                                             \
-        return launch_bwd_slab_variant<TW, TH, U>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, \
-                                                  SLAB, shift, eps, stop_grad, stream);
+        return launch_bwd_slab_variant<TW, TH, U, MINB>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, \
+                                                        H, W, SLAB, shift, eps, stop_grad, stream);
     switch (variant) {
-        BV(0, 16, 16, 4, 32)
-        BV(1, 16, 8, 4, 32)
-        BV(2, 16, 16, 2, 32)
-        BV(3, 16, 16, 4, 64)
-        BV(4, 16, 8, 2, 32)
-        BV(5, 16, 16, 8, 32)
+        BV(0, 16, 8, 4, 64, 8)
+        BV(10, 16, 16, 4, 32, 1)
+        BV(1, 16, 8, 4, 32, 1)
+        BV(2, 16, 16, 2, 32, 1)
+        BV(3, 16, 16, 4, 64, 1)
+        BV(4, 16, 16, 4, 64, 4)
+        BV(5, 16, 16, 2, 64, 4)
+        BV(6, 16, 8, 4, 64, 8)
+        BV(7, 16, 8, 2, 64, 8)
+        BV(8, 16, 16, 4, 128, 4)
+        BV(9, 16, 8, 4, 64, 6)
         default: return cudaErrorInvalidValue;
     }
 #undef BV

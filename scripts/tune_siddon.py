@@ -67,7 +67,7 @@ def bbase():
 bbytes = (4 * visits + 36 * B * N) / 1e9
 ms = timeit(bbase, 3)
 print(f"bwd baseline linear   : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {bbytes / ms * 1e3:8.1f} GB/s  {bbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
-for v in [int(x) for x in os.environ.get("BVARIANTS", "0,1,2,3,4,5").split(",")]:
+for v in [int(x) for x in os.environ.get("BVARIANTS", "0,1,2,3,4,5,6,7,8,9").split(",")]:
     g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
     def run():
         _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, B, H, H, 0.5, 1e-8, 0, v, _stream()), "bwd_grid")
