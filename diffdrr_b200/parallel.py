@@ -1,0 +1,100 @@
+"""Multi-GPU rendering: poses shard across ranks, the volume is replicated, ONE gather of the image stack.
+
+The reference has no distributed code.  Every ray is independent given the volume, so the only
+exchange step of the path is assembling the image stack: `all_gather_into_tensor` over NCCL (NVLink/NVSwitch),
+whose backward is the local slice of the incoming gradient (pose gradients never leave their rank).
+One process per GPU (`torchrun`), `torch.distributed` for the plumbing.
+
+Trilinear caveat (quirk Q3): the sampling range alphamin/alphamax is global over all rays of the call, so sharded
+ranks must agree on it -- `global_alpha_range` all-reduces the two scalars (MIN/MAX) and the result is passed
+explicitly through the reference's own `alphamin=`, `alphamax=` keywords (renderers.py:214-215).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of `n_items` for `rank` (first n_items % world ranks get one more)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class _AllGatherBatch(torch.autograd.Function):
+    """Concatenate equally-sized per-rank batches along dim 0; backward keeps this rank's slice of the gradient."""
+
+    @staticmethod
+    def forward(ctx, local, group):
+        world = dist.get_world_size(group)
+        ctx.rank = dist.get_rank(group)
+        ctx.n = local.shape[0]
+        out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n], None
+
+
+def all_gather_images(local: torch.Tensor, batch: int | None = None, group=None) -> torch.Tensor:
+    """(B_local, C, H, W) on every rank -> (B, C, H, W) on every rank (differentiable).  Ragged shards are padded."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    if batch is None or batch % world == 0:
+        return _AllGatherBatch.apply(local, group)
+    per = -(-batch // world)  # ceil: pad every shard to the same size, gather, drop the padding
+    pad = per - local.shape[0]
+    padded = torch.cat([local, local.new_zeros((pad,) + tuple(local.shape[1:]))]) if pad else local
+    full = _AllGatherBatch.apply(padded, group)
+    keep = []
+    for r in range(world):
+        lo, hi = shard_bounds(batch, r, world)
+        keep.append(full[r * per:r * per + (hi - lo)])
+    return torch.cat(keep)
+
+
+def global_alpha_range(alphamin: torch.Tensor, alphamax: torch.Tensor, group=None):
+    """All-reduce the trilinear sampling range so that every rank marches the same alphas as a single-GPU call."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        alphamin, alphamax = alphamin.detach().clone(), alphamax.detach().clone()
+        dist.all_reduce(alphamin, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(alphamax, op=dist.ReduceOp.MAX, group=group)
+    return alphamin, alphamax
+
+
+def render_sharded(drr, *pose_args, group=None, gather: bool = True, **kwargs):
+    """`drr(*pose_args, **kwargs)` with the pose batch sharded over the ranks of `group`.
+
+    Every rank passes the FULL pose batch (rotation, translation tensors or a RigidTransform); it renders only its
+    contiguous slice and, with gather=True, returns the full (B, C, H, W) stack.  Gradients flow to the local slice.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return drr(*pose_args, **kwargs)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    batch = len(pose_args[0])
+    lo, hi = shard_bounds(batch, rank, world)
+    local_args = tuple(a[lo:hi] for a in pose_args)
+    from .renderers import Trilinear, _get_alpha_minmax
+
+    if isinstance(drr.renderer, Trilinear) and kwargs.get("alphamin") is None:
+        # the range must come from ALL rays of the call, not only this rank's (quirk Q3)
+        from .pose import convert
+
+        with torch.no_grad():
+            pose = local_args[0] if kwargs.get("parameterization") is None else convert(
+                *local_args, parameterization=kwargs["parameterization"], convention=kwargs.get("convention"),
+                degrees=kwargs.get("degrees", False))
+            src, tgt = drr.detector(pose, kwargs.get("calibration"))
+            src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+            dims = torch.tensor(drr.density.shape, device=src.device, dtype=src.dtype)
+            amin, amax = _get_alpha_minmax(src, tgt, dims, drr.renderer.voxel_shift, drr.renderer.eps)
+            amin, amax = global_alpha_range(amin.min(), amax.max(), group)
+        kwargs = dict(kwargs, alphamin=amin, alphamax=amax)
+    img = drr(*local_args, **kwargs)
+    return all_gather_images(img, batch, group) if gather else img

@@ -1,0 +1,50 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes (no GPU, no kernels)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from diffdrr_b200.parallel import all_gather_images, global_alpha_range, shard_bounds
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 16, 255, 256):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _worker(rank, world, port, batch):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_bounds(batch, rank, world)
+        full = torch.arange(batch * 6, dtype=torch.float32).reshape(batch, 1, 2, 3)
+        local = full[lo:hi].clone().requires_grad_(True)
+        out = all_gather_images(local * 2.0, batch)
+        assert torch.equal(out, full * 2.0), "gathered stack differs from the unsharded one"
+        # backward: only this rank's slice of the upstream gradient comes back
+        w = torch.linspace(0, 1, out.numel()).reshape(out.shape)
+        (out * w).sum().backward()
+        assert torch.allclose(local.grad, 2.0 * w[lo:hi])
+        # trilinear sampling range: MIN / MAX over ranks
+        amin, amax = global_alpha_range(torch.tensor(0.3 + 0.1 * rank), torch.tensor(0.8 + 0.05 * rank))
+        assert abs(float(amin) - 0.3) < 1e-7 and abs(float(amax) - (0.8 + 0.05 * (world - 1))) < 1e-7
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [4, 5])
+def test_gather_and_range_world2(batch):
+    port = 29500 + (os.getpid() % 2000) + batch
+    mp.spawn(_worker, args=(2, port, batch), nprocs=2, join=True)
