@@ -59,12 +59,30 @@ def all_gather_images(local: torch.Tensor, batch: int | None = None, group=None)
     return torch.cat(keep)
 
 
+class _GlobalExtremum(torch.autograd.Function):
+    """min (or max) of one scalar per rank.  Backward: the upstream gradients of ALL ranks are summed (every rank's
+    rays march the shared range) and handed to the rank(s) that own the extremum -- the distributed form of the
+    arg-min / arg-max branch of reference renderers.py:221-223."""
+
+    @staticmethod
+    def forward(ctx, local, is_min, group):
+        out = local.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.MIN if is_min else dist.ReduceOp.MAX, group=group)
+        ctx.owner = bool(local.detach() == out)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        total = grad.contiguous().clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.group)
+        return (total if ctx.owner else torch.zeros_like(total)), None, None
+
+
 def global_alpha_range(alphamin: torch.Tensor, alphamax: torch.Tensor, group=None):
-    """All-reduce the trilinear sampling range so that every rank marches the same alphas as a single-GPU call."""
+    """Trilinear sampling range shared by all ranks (MIN / MAX of the per-rank ranges), differentiable."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        alphamin, alphamax = alphamin.detach().clone(), alphamax.detach().clone()
-        dist.all_reduce(alphamin, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(alphamax, op=dist.ReduceOp.MAX, group=group)
+        return _GlobalExtremum.apply(alphamin, True, group), _GlobalExtremum.apply(alphamax, False, group)
     return alphamin, alphamax
 
 
@@ -86,15 +104,14 @@ def render_sharded(drr, *pose_args, group=None, gather: bool = True, **kwargs):
         # the range must come from ALL rays of the call, not only this rank's (quirk Q3)
         from .pose import convert
 
-        with torch.no_grad():
-            pose = local_args[0] if kwargs.get("parameterization") is None else convert(
-                *local_args, parameterization=kwargs["parameterization"], convention=kwargs.get("convention"),
-                degrees=kwargs.get("degrees", False))
-            src, tgt = drr.detector(pose, kwargs.get("calibration"))
-            src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
-            dims = torch.tensor(drr.density.shape, device=src.device, dtype=src.dtype)
-            amin, amax = _get_alpha_minmax(src, tgt, dims, drr.renderer.voxel_shift, drr.renderer.eps)
-            amin, amax = global_alpha_range(amin.min(), amax.max(), group)
+        pose = local_args[0] if kwargs.get("parameterization") is None else convert(
+            *local_args, parameterization=kwargs["parameterization"], convention=kwargs.get("convention"),
+            degrees=kwargs.get("degrees", False))
+        src, tgt = drr.detector(pose, kwargs.get("calibration"))
+        src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+        dims = torch.tensor(drr.density.shape, device=src.device, dtype=src.dtype)
+        amin, amax = _get_alpha_minmax(src, tgt, dims, drr.renderer.voxel_shift, drr.renderer.eps)
+        amin, amax = global_alpha_range(amin.min(), amax.max(), group)  # differentiable: owner rank keeps the branch
         kwargs = dict(kwargs, alphamin=amin, alphamax=amax)
     img = drr(*local_args, **kwargs)
     return all_gather_images(img, batch, group) if gather else img

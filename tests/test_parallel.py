@@ -38,8 +38,15 @@ def _worker(rank, world, port, batch):
         (out * w).sum().backward()
         assert torch.allclose(local.grad, 2.0 * w[lo:hi])
         # trilinear sampling range: MIN / MAX over ranks
-        amin, amax = global_alpha_range(torch.tensor(0.3 + 0.1 * rank), torch.tensor(0.8 + 0.05 * rank))
+        a = torch.tensor(0.3 + 0.1 * rank, requires_grad=True)
+        b = torch.tensor(0.8 + 0.05 * rank, requires_grad=True)
+        amin, amax = global_alpha_range(a, b)
         assert abs(float(amin) - 0.3) < 1e-7 and abs(float(amax) - (0.8 + 0.05 * (world - 1))) < 1e-7
+        # backward: every rank contributes (rank+1)*d/d amin and 10*(rank+1)*d/d amax; the owner gets the SUM
+        ((rank + 1.0) * amin + 10.0 * (rank + 1.0) * amax).backward()
+        tot = sum(r + 1.0 for r in range(world))
+        assert float(a.grad) == (tot if rank == 0 else 0.0)
+        assert float(b.grad) == (10.0 * tot if rank == world - 1 else 0.0)
     finally:
         dist.destroy_process_group()
 
