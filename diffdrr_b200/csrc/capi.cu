@@ -118,6 +118,30 @@ int b200drr_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float*
                                     (cudaStream_t)stream));
 }
 
+int b200drr_trilinear_fwd_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                               const float* raylen, float* out, int B, int H, int W, float voxel_shift, float eps,
+                               int n_points, const float* alpha_range, int variant, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) ||
+        H <= 0 || W <= 0 || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_grid(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, H, W, voxel_shift, eps, n_points,
+                                         alpha_range, variant, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_bwd_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                               const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                               float* g_vol, float* g_alpha_range, int B, int H, int W, float voxel_shift, float eps,
+                               int n_points, const float* alpha_range, int variant, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) ||
+        H <= 0 || W <= 0 || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd_grid(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol,
+                                         g_alpha_range, B, H, W, voxel_shift, eps, n_points, alpha_range, variant,
+                                         (cudaStream_t)stream));
+}
+
 int b200drr_siddon_visits(int D0, int D1, int D2, const float* src, const float* tgt, int32_t* visits, int B,
                           int64_t N, float voxel_shift, float eps, void* stream)
 {

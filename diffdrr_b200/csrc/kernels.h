@@ -33,4 +33,12 @@ cudaError_t launch_trilinear_bwd(const float* vol, VolDims dims, const float* sr
                                  float* g_vol, float* g_alpha_range, int B, int64_t N, float shift, float eps,
                                  int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 
+cudaError_t launch_trilinear_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                      int n_points, const float* alpha_range, int variant, cudaStream_t stream);
+cudaError_t launch_trilinear_bwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, const float* gout, float* g_src, float* g_tgt,
+                                      float* g_raylen, float* g_vol, float* g_alpha_range, int B, int H, int W, float shift,
+                                      float eps, int n_points, const float* alpha_range, int variant, cudaStream_t stream);
+
 }  // namespace b200drr

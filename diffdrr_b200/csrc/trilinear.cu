@@ -71,6 +71,138 @@ __global__ void __launch_bounds__(kThreads) trilinear_bwd_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Detector-grid variants: CTA = TW x TH pixel tile, warp = 8 x 4 sub-tile (see siddon.cu).  Fixed-step marching is
+// plane-synchronous by construction (every lane is at the same alpha in the same iteration), so the ray bundle of a
+// warp shares sectors among its 8 corner gathers.
+// ---------------------------------------------------------------------------------------------------
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) trilinear_fwd_grid_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                    const float* __restrict__ src,
+                                                                    const float* __restrict__ tgt,
+                                                                    const float* __restrict__ raylen,
+                                                                    float* __restrict__ out, int H, int W, float shift,
+                                                                    float eps, int P, const float* __restrict__ alpha_range)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int b = blockIdx.y;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+    const float step = (amax - amin) / (float)(P - 1);
+    out[r] = trilinear_ray_fwd(vol, dims, ray, shift, P, amin, amax, 0, 0) * (__ldg(raylen + r) * step);
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) trilinear_bwd_grid_kernel(
+    const float* __restrict__ vol, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, const float* __restrict__ gout, float* __restrict__ g_src,
+    float* __restrict__ g_tgt, float* __restrict__ g_raylen, float* __restrict__ g_vol,
+    float* __restrict__ g_alpha_range, int H, int W, float shift, float eps, int P,
+    const float* __restrict__ alpha_range)
+{
+    __shared__ float red[32];
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    const int b = blockIdx.y;
+    float gs[3] = {0.0f, 0.0f, 0.0f}, ga0 = 0.0f, ga1 = 0.0f;
+    if (px < W && py < H) {
+        const int64_t r = ((int64_t)b * H + py) * W + px;
+        const Ray ray = load_ray(src, tgt, b, r, eps);
+        const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+        const float step = (amax - amin) / (float)(P - 1);
+        const float L = __ldg(raylen + r), g = __ldg(gout + r);
+        const TriGrad tg = trilinear_ray_bwd(vol, dims, ray, shift, P, amin, amax, 0, g, L, g_vol);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            gs[a] = tg.gs[a];
+            if (g_tgt) g_tgt[r * 3 + a] = tg.gt[a];
+        }
+        if (g_raylen) g_raylen[r] = g * step * tg.sumV;
+        ga0 = tg.ga0;
+        ga1 = tg.ga1;
+    }
+    if (g_src) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tot = block_sum(gs[a], red);
+            if (threadIdx.x == 0) atomicAdd(g_src + b * 3 + a, tot);
+        }
+    }
+    if (g_alpha_range) {
+        const float t0 = block_sum(ga0, red);
+        if (threadIdx.x == 0) atomicAdd(g_alpha_range, t0);
+        const float t1 = block_sum(ga1, red);
+        if (threadIdx.x == 0) atomicAdd(g_alpha_range + 1, t1);
+    }
+}
+
+template <int TW, int TH>
+static cudaError_t tri_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                float* out, int B, int H, int W, float shift, float eps, int P, const float* ar,
+                                cudaStream_t stream)
+{
+    const dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH)), (unsigned)B, 1);
+    trilinear_fwd_grid_kernel<TW, TH><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift, eps, P, ar);
+    return cudaGetLastError();
+}
+
+template <int TW, int TH>
+static cudaError_t tri_bwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, float* g_ar,
+                                int B, int H, int W, float shift, float eps, int P, const float* ar, cudaStream_t stream)
+{
+    if (g_src) {
+        cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const dim3 grid((unsigned)(((W + TW - 1) / TW) * ((H + TH - 1) / TH)), (unsigned)B, 1);
+    trilinear_bwd_grid_kernel<TW, TH><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen,
+                                                                   g_vol, g_ar, H, W, shift, eps, P, ar);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trilinear_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                      int n_points, const float* alpha_range, int variant, cudaStream_t stream)
+{
+    switch (variant) {
+        case 0: return tri_fwd_grid<16, 8>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, n_points, alpha_range, stream);
+        case 1: return tri_fwd_grid<16, 16>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, n_points, alpha_range, stream);
+        case 2: return tri_fwd_grid<8, 8>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, n_points, alpha_range, stream);
+        case 3: return tri_fwd_grid<32, 8>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, n_points, alpha_range, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_trilinear_bwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, const float* gout, float* g_src, float* g_tgt,
+                                      float* g_raylen, float* g_vol, float* g_alpha_range, int B, int H, int W, float shift,
+                                      float eps, int n_points, const float* alpha_range, int variant, cudaStream_t stream)
+{
+#define TB(TW, TH) \
+    tri_bwd_grid<TW, TH>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, g_alpha_range, B, H, W, shift, eps, \
+                         n_points, alpha_range, stream)
+    switch (variant) {
+        case 0: return TB(16, 8);
+        case 1: return TB(16, 16);
+        case 2: return TB(8, 8);
+        case 3: return TB(32, 8);
+        default: return cudaErrorInvalidValue;
+    }
+#undef TB
+}
+
 static inline dim3 ray_grid(int B, int64_t N) { return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1); }
 
 cudaError_t launch_trilinear_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,

@@ -108,8 +108,10 @@ class _TrilinearFunction(torch.autograd.Function):
     """out (B,1,N) = fixed-step trilinear line integrals for the range alpha_range = [alphamin, alphamax]."""
 
     @staticmethod
-    def forward(ctx, volume, source, target, img, alpha_range, voxel_shift, eps, n_points, reduce, align_corners):
+    def forward(ctx, volume, source, target, img, alpha_range, voxel_shift, eps, n_points, reduce, align_corners, grid):
         B, N = _check_inputs(volume, source, target, img)
+        if grid is not None and (grid[0] * grid[1] != N or reduce != 0 or align_corners):
+            grid = None
         vol = volume.contiguous()
         src = source.reshape(B, 3).contiguous()
         tgt = target.contiguous()
@@ -118,18 +120,22 @@ class _TrilinearFunction(torch.autograd.Function):
         out = torch.empty(B, N, dtype=torch.float32, device=vol.device)
         lib = _lib.load()
         with torch.cuda.device(vol.device):
-            _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N,
-                                                 voxel_shift, eps, n_points, _ptr(arange), reduce, int(align_corners),
-                                                 _stream()),
-                       "b200drr_trilinear_fwd")
+            if grid is not None:
+                _lib.check(lib.b200drr_trilinear_fwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
+                                                          B, grid[0], grid[1], voxel_shift, eps, n_points, _ptr(arange), 1,
+                                                          _stream()), "b200drr_trilinear_fwd_grid")
+            else:
+                _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N,
+                                                     voxel_shift, eps, n_points, _ptr(arange), reduce, int(align_corners),
+                                                     _stream()), "b200drr_trilinear_fwd")
         ctx.save_for_backward(vol, src, tgt, raylen, arange)
-        ctx.cfg = (voxel_shift, eps, n_points, reduce, align_corners, tuple(source.shape), tuple(img.shape))
+        ctx.cfg = (voxel_shift, eps, n_points, reduce, align_corners, tuple(source.shape), tuple(img.shape), grid)
         return out.view(B, 1, N)
 
     @staticmethod
     def backward(ctx, gout):
         vol, src, tgt, raylen, arange = ctx.saved_tensors
-        voxel_shift, eps, n_points, reduce, align_corners, src_shape, img_shape = ctx.cfg
+        voxel_shift, eps, n_points, reduce, align_corners, src_shape, img_shape, grid = ctx.cfg
         if reduce != 0:
             raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
         B, N = tgt.shape[0], tgt.shape[1]
@@ -143,12 +149,18 @@ class _TrilinearFunction(torch.autograd.Function):
         g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
         lib = _lib.load()
         with torch.cuda.device(dev):
-            _lib.check(lib.b200drr_trilinear_bwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
-                                                 _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), _ptr(g_ar), B, N,
-                                                 voxel_shift, eps, n_points, _ptr(arange), int(align_corners), _stream()),
-                       "b200drr_trilinear_bwd")
+            if grid is not None:
+                _lib.check(lib.b200drr_trilinear_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                          _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol),
+                                                          _ptr(g_ar), B, grid[0], grid[1], voxel_shift, eps, n_points,
+                                                          _ptr(arange), 1, _stream()), "b200drr_trilinear_bwd_grid")
+            else:
+                _lib.check(lib.b200drr_trilinear_bwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                     _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), _ptr(g_ar), B, N,
+                                                     voxel_shift, eps, n_points, _ptr(arange), int(align_corners), _stream()),
+                           "b200drr_trilinear_bwd")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
-                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None)
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None)
 
 
 def _reduce_code(reducefn):
@@ -215,6 +227,7 @@ class Trilinear(torch.nn.Module):
         self.reducefn = reducefn
         self.voxel_shift = voxel_shift
         self.eps = eps
+        self.detector_shape = None  # (H, W) when the rays are the full row-major detector grid (set by DRR.render)
 
     def dims(self, volume):
         return torch.tensor(volume.shape).to(volume)
@@ -233,7 +246,8 @@ class Trilinear(torch.nn.Module):
         alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=torch.float32, device=volume.device),
                                    torch.as_tensor(alphamax, dtype=torch.float32, device=volume.device)])
         return _TrilinearFunction.apply(volume, source, target, img, alpha_range, float(self.voxel_shift), float(self.eps),
-                                        int(n_points), _reduce_code(self.reducefn), bool(align_corners))
+                                        int(n_points), _reduce_code(self.reducefn), bool(align_corners),
+                                        self.detector_shape)
 
 
 def siddon_visits(volume_shape, source, target, voxel_shift: float = 0.5, eps: float = 1e-8) -> torch.Tensor:

@@ -111,6 +111,18 @@ int b200drr_trilinear_bwd(const float *vol, int D0, int D1, int D2, const float 
                           int n_points, const float *alpha_range, int align_corners, void *stream);
 
 /*
+ * Trilinear forward / backward for a FULL detector grid (n = h*W + w), reduce="sum", align_corners=0: same results
+ * as b200drr_trilinear_fwd / _bwd with pixel tiles mapped onto warps/CTAs for cache locality.
+ */
+int b200drr_trilinear_fwd_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                               const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
+                               int n_points, const float *alpha_range, int variant, void *stream);
+int b200drr_trilinear_bwd_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                               const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                               float *g_vol, float *g_alpha_range, int B, int H, int W, float voxel_shift, float eps,
+                               int n_points, const float *alpha_range, int variant, void *stream);
+
+/*
  * Per-ray voxel-visit count of the Siddon walk (number of voxels the line crosses inside the volume),
  * the unit of the ALGORITHMIC byte count used for roofline accounting: visits [B][N]
  * int32.  Measurement helper; not part of the reference surface.

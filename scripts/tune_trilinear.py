@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Times the trilinear kernels on BASELINE config 3's shape (512^3 -> 512^2, n_points=500) at a reduced batch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from diffdrr_b200 import DRR, _lib, synthetic
+from diffdrr_b200.pose import convert
+from diffdrr_b200.renderers import _ptr, _stream, _get_alpha_minmax
+
+D, H, B, P = 512, int(os.environ.get("H", 512)), int(os.environ.get("B", 4)), 500
+dev = torch.device("cuda:0")
+lib = _lib.load()
+vol = torch.rand(D, D, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1)); subj.volume.affine = synthetic.make_affine(D)
+drr = DRR(subj, **synthetic.detector_kwargs(H)).to(dev)
+rot, xyz = synthetic.make_poses(B, seed=0)
+with torch.no_grad():
+    src, tgt = drr.detector(convert(rot.to(dev), xyz.to(dev), parameterization="euler_angles", convention="ZXY"), None)
+    raylen = (tgt - src).norm(dim=-1).reshape(B, -1).contiguous()
+    src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt).contiguous()
+    amin, amax = _get_alpha_minmax(src, tgt, torch.tensor([D, D, D], device=dev, dtype=torch.float32), 0.5, 1e-8)
+    ar = torch.stack([amin.min(), amax.max()]).contiguous()
+    src = src.reshape(B, 3).contiguous()
+N = H * H
+# in-volume samples (>= 1 corner in bounds) for the algorithmic byte count: 32 B per such sample
+with torch.no_grad():
+    lin = torch.linspace(0, 1, P, device=dev) * (ar[1] - ar[0]) + ar[0]
+    cnt = 0
+    for b in range(B):
+        for c in range(0, N, 65536):
+            pts = src[b][None, None, :] + lin[None, :, None] * (tgt[b, c:c + 65536][:, None, :] - src[b][None, None, :])
+            pix = pts  # shift 0.5 -> pix = x
+            cnt += int(((pix > -1) & (pix < D)).all(-1).sum())
+gb = cnt * 32 / 1e9
+print(f"in-volume samples {cnt / (B * N * P):.3f} of all; algorithmic {gb:.2f} GB fwd")
+def timeit(fn, iters=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+out = torch.empty(B, N, device=dev)
+gout = torch.rand(B, N, device=dev)
+g_src, g_tgt, g_len, g_ar = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev), torch.zeros(2, device=dev)
+for variant in [int(v) for v in os.environ.get("VARIANTS", "-1").split(",")]:
+    def fwd():
+        if variant < 0:
+            _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N, 0.5, 1e-8, P, _ptr(ar), 0, 0, _stream()), "tri fwd")
+        else:
+            _lib.check(lib.b200drr_trilinear_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), variant, _stream()), "tri fwd grid")
+    def bwd():
+        if variant < 0:
+            _lib.check(lib.b200drr_trilinear_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, _ptr(g_ar), B, N, 0.5, 1e-8, P, _ptr(ar), 0, _stream()), "tri bwd")
+        else:
+            _lib.check(lib.b200drr_trilinear_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), variant, _stream()), "tri bwd grid")
+    if variant < 0:
+        ref = None
+    f = timeit(fwd)
+    if variant < 0:
+        ref = out.clone()
+    err = float((out - ref).abs().max() / ref.abs().max())
+    b_ = timeit(bwd)
+    print(f"variant {variant:2d}: fwd {f:8.3f} ms {B / f * 1e3:8.1f} DRR/s {gb / f * 1e3:7.1f} GB/s ({gb / f * 1e3 / 65.709:5.1f}%)   bwd {b_:8.3f} ms   fwd+bwd {B / (f + b_) * 1e3:7.1f} DRR/s  {2 * gb / (f + b_) * 1e3:7.1f} GB/s   maxdiff {err:.1e}")
