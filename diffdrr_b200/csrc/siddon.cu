@@ -399,6 +399,7 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         P(28, 8, 8, 2, 32, 1)
         P(29, 16, 16, 1, 32, 1)
 #undef P
+
         default: return cudaErrorInvalidValue;
     }
 #undef V
