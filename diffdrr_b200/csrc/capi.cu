@@ -142,6 +142,31 @@ int b200drr_trilinear_bwd_grid(const float* vol, int D0, int D1, int D2, const f
                                          (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_pose(const float* vol, int D0, int D1, int D2, const float* src, const float* G, const float* Wd,
+                            const float* rows, const float* cols, float* out, int B, int H, int W, float voxel_shift,
+                            float eps, void* stream)
+{
+    if (!vol || !src || !G || !Wd || !rows || !cols || !out || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) ||
+        H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_pose(vol, mk(D0, D1, D2), src, G, Wd, rows, cols, out, B, H, W, voxel_shift, eps,
+                                      (cudaStream_t)stream));
+}
+
+int b200drr_siddon_bwd_pose(const float* vol, int D0, int D1, int D2, const float* src, const float* G, const float* Wd,
+                            const float* rows, const float* cols, const float* gout, float* g_src, float* g_G, float* g_Wd,
+                            float* g_vol, float* ws_tgt, float* ws_len, int B, int H, int W, float voxel_shift, float eps,
+                            int stop_grad, void* stream)
+{
+    if (!vol || !src || !G || !Wd || !rows || !cols || !gout || !g_src || !g_G || !g_Wd || !ws_tgt || !ws_len ||
+        bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_bwd_pose(vol, mk(D0, D1, D2), src, G, Wd, rows, cols, gout, g_src, g_G, g_Wd, g_vol, ws_tgt,
+                                      ws_len, B, H, W, voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_visits(int D0, int D1, int D2, const float* src, const float* tgt, int32_t* visits, int B,
                           int64_t N, float voxel_shift, float eps, void* stream)
 {

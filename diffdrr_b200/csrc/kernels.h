@@ -41,4 +41,12 @@ cudaError_t launch_trilinear_bwd_grid(const float* vol, VolDims dims, const floa
                                       float* g_raylen, float* g_vol, float* g_alpha_range, int B, int H, int W, float shift,
                                       float eps, int n_points, const float* alpha_range, int variant, cudaStream_t stream);
 
+cudaError_t launch_siddon_fwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                   const float* rows, const float* cols, float* out, int B, int H, int W, float shift,
+                                   float eps, cudaStream_t stream);
+cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                   const float* rows, const float* cols, const float* gout, float* g_src, float* g_G,
+                                   float* g_Wd, float* g_vol, float* ws_tgt, float* ws_len, int B, int H, int W, float shift,
+                                   float eps, int stop_grad, cudaStream_t stream);
+
 }  // namespace b200drr

@@ -8,6 +8,44 @@ namespace b200drr {
 
 constexpr int kThreads = 128;
 
+// Optional in-kernel ray generation ("pose-in" entry points): when G != nullptr the rays of pose b are made from
+//   target_voxel(h, w) = G[b] . (cols[w], rows[h], 1, 1),   raylen(h, w) = | Wd[b] . (cols[w], rows[h], 1, 1) |
+// (G = affine_inverse . extrinsic . reorient . calibration, Wd = the same without affine_inverse and with the source
+// subtracted; reference detector.py:144-154 + drr.py:201-205 collapsed into two 3x4 matrices per pose), so the
+// (B, N, 3) target tensor and the ray-length image never exist in HBM.
+struct PoseRays {
+    const float* G;     // [B][3][4]
+    const float* Wd;    // [B][3][4]
+    const float* rows;  // [H]  canonical detector y of image row h   (detector.py:114-126)
+    const float* cols;  // [W]  canonical detector x of image column w
+};
+
+__device__ __forceinline__ Ray make_ray(const PoseRays& pr, const float* __restrict__ src, const float* __restrict__ tgt,
+                                        const float* __restrict__ raylen, int b, int64_t r, int px, int py, float eps,
+                                        float& L)
+{
+    if (pr.G == nullptr) {
+        L = __ldg(raylen + r);
+        return load_ray(src, tgt, b, r, eps);
+    }
+    const float c = __ldg(pr.cols + px), rr = __ldg(pr.rows + py);
+    const float* g = pr.G + b * 12;
+    const float* wd = pr.Wd + b * 12;
+    Ray ray;
+    float l2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t = fmaf(__ldg(g + a * 4), c, fmaf(__ldg(g + a * 4 + 1), rr, __ldg(g + a * 4 + 2) + __ldg(g + a * 4 + 3)));
+        const float dw = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), rr, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+        l2 = fmaf(dw, dw, l2);
+        ray.s[a] = __ldg(src + b * 3 + a);
+        ray.d[a] = (t - ray.s[a]) + eps;
+        ray.inv[a] = 1.0f / ray.d[a];
+    }
+    L = sqrtf(l2);
+    return ray;
+}
+
 __global__ void __launch_bounds__(kThreads) siddon_fwd_general_kernel(const float* __restrict__ vol, VolDims dims,
                                                                       const float* __restrict__ src,
                                                                       const float* __restrict__ tgt,
@@ -131,7 +169,7 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __
                                                                  const float* __restrict__ tgt,
                                                                  const float* __restrict__ raylen,
                                                                  float* __restrict__ out, int B, int H, int W, int slab,
-                                                                 float shift, float eps)
+                                                                 float shift, float eps, PoseRays pr)
 {
     constexpr int WX = TW / 8;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
@@ -147,17 +185,18 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __
     const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
     if (px >= W || py >= H) return;
     const int64_t r = ((int64_t)b * H + py) * W + px;
-    const Ray ray = load_ray(src, tgt, b, r, eps);
+    float L;
+    const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
     const int lo_v[3] = {sl * slab, 0, 0};
     const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
     const float part = siddon_ray_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
-    if (part != 0.0f) red_add(out + r, __ldg(raylen + r) * part);
+    if (part != 0.0f) red_add(out + r, L * part);
 }
 
 template <int TW, int TH, int U>
 static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                        const float* raylen, float* out, int B, int H, int W, int slab, float shift,
-                                       float eps, cudaStream_t stream)
+                                       float eps, cudaStream_t stream, PoseRays pr = PoseRays{nullptr, nullptr, nullptr, nullptr})
 {
     const int n_slabs = (dims.d[0] + slab - 1) / slab;
     const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
@@ -165,7 +204,7 @@ static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const flo
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
     if (e != cudaSuccess) return e;
     siddon_fwd_slab_kernel<TW, TH, U><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, B, H, W,
-                                                                              slab, shift, eps);
+                                                                              slab, shift, eps, pr);
     return cudaGetLastError();
 }
 
@@ -250,7 +289,7 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const flo
                                                                  const float* __restrict__ gout, float* __restrict__ g_src,
                                                                  float* __restrict__ g_tgt, float* __restrict__ g_raylen,
                                                                  float* __restrict__ g_vol, int B, int H, int W, int slab,
-                                                                 float shift, float eps, int stop_grad)
+                                                                 float shift, float eps, int stop_grad, PoseRays pr)
 {
     __shared__ float red[32];
     constexpr int WX = TW / 8;
@@ -268,10 +307,11 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const flo
     float gs[3] = {0.0f, 0.0f, 0.0f};
     if (px < W && py < H) {
         const int64_t r = ((int64_t)b * H + py) * W + px;
-        const Ray ray = load_ray(src, tgt, b, r, eps);
+        float L;
+        const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
         const int lo_v[3] = {sl * slab, 0, 0};
         const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
-        const float L = __ldg(raylen + r), g = __ldg(gout + r);
+        const float g = __ldg(gout + r);
         const float gL = g * L;
         float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
         const float acc = siddon_ray_bwd_lean_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, gL,
@@ -297,7 +337,8 @@ template <int TW, int TH, int U, int MINB>
 static cudaError_t launch_bwd_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                            const float* raylen, const float* gout, float* g_src, float* g_tgt,
                                            float* g_raylen, float* g_vol, int B, int H, int W, int slab, float shift,
-                                           float eps, int stop_grad, cudaStream_t stream)
+                                           float eps, int stop_grad, cudaStream_t stream,
+                                           PoseRays pr = PoseRays{nullptr, nullptr, nullptr, nullptr})
 {
     const int n_slabs = (dims.d[0] + slab - 1) / slab;
     const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
@@ -309,7 +350,7 @@ static cudaError_t launch_bwd_slab_variant(const float* vol, VolDims dims, const
     if (e == cudaSuccess && g_raylen) e = cudaMemsetAsync(g_raylen, 0, sizeof(float) * n, stream);
     if (e != cudaSuccess) return e;
     siddon_bwd_slab_kernel<TW, TH, U, MINB><<<(unsigned)blocks, TW * TH, 0, stream>>>(
-        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, slab, shift, eps, stop_grad);
+        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, H, W, slab, shift, eps, stop_grad, pr);
     return cudaGetLastError();
 }
 
@@ -350,6 +391,85 @@ static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const flo
     else
         siddon_fwd_grid_kernel<TW, TH, U, LEAN><<<grid, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, H, W, shift,
                                                                               eps);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pose-in entry points: rays generated in-kernel (PoseRays), gradients reduced to the 3x4 matrices.
+// ---------------------------------------------------------------------------------------------------
+cudaError_t launch_siddon_fwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                   const float* rows, const float* cols, float* out, int B, int H, int W, float shift,
+                                   float eps, cudaStream_t stream)
+{
+    return launch_slab_variant<16, 16, 4>(vol, dims, src, nullptr, nullptr, out, B, H, W, 32, shift, eps, stream,
+                                          PoseRays{G, Wd, rows, cols});
+}
+
+// g_G[b][a][k] = sum_n g_tgt[b][n][a] * p_k(n),  g_Wd[b][a][k] = sum_n g_raylen[b][n] * delta_a(n)/L(n) * p_k(n),
+// p(n) = (cols[w], rows[h], 1, 1): the chain rule through the in-kernel ray generation of make_ray().
+__global__ void __launch_bounds__(256) pose_grad_reduce_kernel(const float* __restrict__ g_tgt,
+                                                                const float* __restrict__ g_raylen,
+                                                                const float* __restrict__ Wd,
+                                                                const float* __restrict__ rows,
+                                                                const float* __restrict__ cols, float* __restrict__ g_G,
+                                                                float* __restrict__ g_Wd, int H, int W)
+{
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    const int64_t N = (int64_t)H * W;
+    float acc[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) acc[i] = 0.0f;
+    const float* wd = Wd + b * 12;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(n / W), w = (int)(n % W);
+        const float c = __ldg(cols + w), r = __ldg(rows + h);
+        const int64_t ray = (int64_t)b * N + n;
+        float dl[3], l2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dl[a] = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), r, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+            l2 = fmaf(dl[a], dl[a], l2);
+        }
+        const float gl = g_raylen ? __ldg(g_raylen + ray) * rsqrtf(fmaxf(l2, 1e-30f)) : 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float gt = __ldg(g_tgt + ray * 3 + a), u = gl * dl[a];
+            acc[a * 3 + 0] = fmaf(gt, c, acc[a * 3 + 0]);
+            acc[a * 3 + 1] = fmaf(gt, r, acc[a * 3 + 1]);
+            acc[a * 3 + 2] += gt;
+            acc[9 + a * 3 + 0] = fmaf(u, c, acc[9 + a * 3 + 0]);
+            acc[9 + a * 3 + 1] = fmaf(u, r, acc[9 + a * 3 + 1]);
+            acc[9 + a * 3 + 2] += u;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+        const float tot = block_sum(acc[i], red);
+        if (threadIdx.x == 0) {
+            float* dst = (i < 9 ? g_G : g_Wd) + b * 12;
+            const int a = (i % 9) / 3, k = i % 3;
+            atomicAdd(dst + a * 4 + k, tot);
+            if (k == 2) atomicAdd(dst + a * 4 + 3, tot);  // the homogeneous 1 multiplies column 3 as well
+        }
+    }
+}
+
+cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                   const float* rows, const float* cols, const float* gout, float* g_src, float* g_G,
+                                   float* g_Wd, float* g_vol, float* ws_tgt, float* ws_len, int B, int H, int W, float shift,
+                                   float eps, int stop_grad, cudaStream_t stream)
+{
+    cudaError_t e = launch_bwd_slab_variant<16, 8, 4, 8>(vol, dims, src, nullptr, nullptr, gout, g_src, ws_tgt,
+                                                        stop_grad ? nullptr : ws_len, g_vol, B, H, W, 64, shift, eps,
+                                                        stop_grad, stream, PoseRays{G, Wd, rows, cols});
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(g_G, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_Wd, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e != cudaSuccess) return e;
+    const int chunks = (int)min((int64_t)64, ((int64_t)H * W + 255) / 256);
+    pose_grad_reduce_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>(ws_tgt, stop_grad ? nullptr : ws_len, Wd,
+                                                                                   rows, cols, g_G, g_Wd, H, W);
     return cudaGetLastError();
 }
 

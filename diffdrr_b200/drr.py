@@ -18,7 +18,7 @@ from torch.utils.checkpoint import checkpoint
 
 from .detector import Detector
 from .pose import RigidTransform, convert
-from .renderers import Siddon, Trilinear
+from .renderers import Siddon, Trilinear, siddon_pose_render
 
 
 class DRR(nn.Module):
@@ -109,6 +109,8 @@ class DRR(nn.Module):
             pose = args[0]
         else:
             pose = convert(*args, parameterization=parameterization, convention=convention, degrees=degrees)
+        if self._pose_in_ok(mask_to_channels, kwargs):
+            return self.reshape_transform(self._render_pose_in(pose, calibration), batch_size=len(pose))
         source, target = self.detector(pose, calibration)
         if self.checkpoint_gradients:
             # kept for API parity; the fused autograd.Function saves inputs only, so this changes nothing memory-wise
@@ -116,6 +118,31 @@ class DRR(nn.Module):
         else:
             img = self.render(self.density, source, target, mask_to_channels, **kwargs)
         return self.reshape_transform(img, batch_size=len(pose))
+
+    # ---- fused pose-in path ------------------------------------------------------------------
+    def _pose_in_ok(self, mask_to_channels, kwargs) -> bool:
+        """True when the whole pose -> rays -> Siddon chain can run as ONE kernel with in-kernel ray generation."""
+        r = self.renderer
+        return (isinstance(r, Siddon) and r.mode == "nearest" and r.reducefn == "sum"
+                and not r.filter_intersections_outside_volume and not mask_to_channels
+                and not kwargs.get("align_corners", False) and kwargs.get("mask") is None
+                and self.detector.n_subsample is None and self.patch_size is None
+                and self.density.is_cuda and self.density.dtype == torch.float32 and self.density.dim() == 3
+                and self.density.numel() < 2**31 - 1)
+
+    def _render_pose_in(self, pose: RigidTransform, calibration: RigidTransform | None):
+        """detector.forward (detector.py:144-154) + ray lengths / affine_inverse (drr.py:201-205) collapsed into two
+        3x4 matrices per pose; the rays themselves are generated inside the CUDA kernel."""
+        det = self.detector
+        calib = det._calibration if calibration is None else calibration.matrix
+        M = pose.matrix @ det._reorient            # canonical C-arm frame -> world   (reorient.compose(extrinsic))
+        T = M @ calib                              # ... including the intrinsic scaling of the detector plane
+        A_inv = self._affine_inverse               # world -> voxel index
+        G = (A_inv @ T)[:, :3, :]
+        src = (A_inv @ M)[:, :3, 3]                # the canonical source is the origin
+        Wd = torch.cat([T[:, :3, :3], (T[:, :3, 3] - M[:, :3, 3]).unsqueeze(-1)], dim=-1)  # target - source, world
+        grid = det.target.view(det.height, det.width, 3)
+        return siddon_pose_render(self.renderer, self.density, src, G, Wd, grid[:, 0, 1], grid[0, :, 0])
 
     def render(self, density: torch.Tensor, source: torch.Tensor, target: torch.Tensor, mask_to_channels: bool = False,
                **kwargs):

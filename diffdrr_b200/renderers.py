@@ -104,6 +104,46 @@ class _SiddonFunction(torch.autograd.Function):
                 None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
 
 
+class _SiddonPoseFunction(torch.autograd.Function):
+    """Siddon line integrals of the full detector grid with the rays generated IN the kernel from per-pose 3x4 matrices
+    (include/b200drr.h: b200drr_siddon_fwd_pose / _bwd_pose); gradients come back as matrices, no (B,N,3) tensors."""
+
+    @staticmethod
+    def forward(ctx, volume, src, G, Wd, rows, cols, voxel_shift, eps, stop_grad):
+        vol = volume.contiguous()
+        B, H, W = G.shape[0], rows.numel(), cols.numel()
+        src, G, Wd = src.contiguous().float(), G.contiguous().float(), Wd.contiguous().float()
+        rows, cols = rows.contiguous().float(), cols.contiguous().float()
+        out = torch.empty(B, H * W, dtype=torch.float32, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(_lib.load().b200drr_siddon_fwd_pose(_ptr(vol), *vol.shape, _ptr(src), _ptr(G), _ptr(Wd), _ptr(rows),
+                                                           _ptr(cols), _ptr(out), B, H, W, voxel_shift, eps, _stream()),
+                       "b200drr_siddon_fwd_pose")
+        ctx.save_for_backward(vol, src, G, Wd, rows, cols)
+        ctx.cfg = (voxel_shift, eps, stop_grad)
+        return out.view(B, 1, H * W)
+
+    @staticmethod
+    def backward(ctx, gout):
+        vol, src, G, Wd, rows, cols = ctx.saved_tensors
+        voxel_shift, eps, stop_grad = ctx.cfg
+        B, H, W = G.shape[0], rows.numel(), cols.numel()
+        dev = vol.device
+        gout = gout.reshape(B, H * W).contiguous().float()
+        g_src = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        g_G = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+        g_Wd = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+        ws_tgt = torch.empty(B, H * W, 3, dtype=torch.float32, device=dev)
+        ws_len = torch.empty(B, H * W, dtype=torch.float32, device=dev)
+        g_vol = torch.zeros_like(vol) if (ctx.needs_input_grad[0] and not stop_grad) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_siddon_bwd_pose(_ptr(vol), *vol.shape, _ptr(src), _ptr(G), _ptr(Wd), _ptr(rows),
+                                                           _ptr(cols), _ptr(gout), _ptr(g_src), _ptr(g_G), _ptr(g_Wd),
+                                                           _ptr(g_vol), _ptr(ws_tgt), _ptr(ws_len), B, H, W, voxel_shift,
+                                                           eps, int(stop_grad), _stream()), "b200drr_siddon_bwd_pose")
+        return g_vol, g_src, g_G, g_Wd, None, None, None, None, None
+
+
 class _TrilinearFunction(torch.autograd.Function):
     """out (B,1,N) = fixed-step trilinear line integrals for the range alpha_range = [alphamin, alphamax]."""
 
@@ -204,6 +244,12 @@ class Siddon(torch.nn.Module):
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
                                      bool(self.stop_gradients_through_grid_sample), self.detector_shape)
+
+
+def siddon_pose_render(renderer, volume, src, G, Wd, rows, cols):
+    """Fused pose-in rendering for a `Siddon` module with default options (used by DRR.forward); -> (B, 1, H*W)."""
+    return _SiddonPoseFunction.apply(volume, src, G, Wd, rows, cols, float(renderer.voxel_shift), float(renderer.eps),
+                                     bool(renderer.stop_gradients_through_grid_sample))
 
 
 def _get_alpha_minmax(source, target, dims, voxel_shift, eps):

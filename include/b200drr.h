@@ -89,6 +89,29 @@ int b200drr_siddon_bwd_grid(const float *vol, int D0, int D1, int D2, const floa
                             int variant, void *stream);
 
 /*
+ * "Pose-in" Siddon: the rays of the full H x W detector grid are generated inside the kernel from two 3x4 matrices
+ * per pose, replacing Detector.forward (detector.py:144-154) + the ray-length / affine_inverse lines of DRR.render
+ * (drr.py:201-205) + Siddon.forward, so no (B, N, 3) tensor exists in HBM:
+ *   target_voxel(h, w) = G[b]  . (cols[w], rows[h], 1, 1)      G  = affine_inverse . extrinsic . reorient . calibration
+ *   raylen(h, w)       = |Wd[b] . (cols[w], rows[h], 1, 1)|     Wd = extrinsic . reorient . calibration, source subtracted
+ *   src [B][3] = source in voxel coordinates; rows [H] / cols [W] = canonical detector coordinates (detector.py:114-126)
+ * out [B][H*W].  Same line integrals as b200drr_siddon_fwd(reduce=0, align_corners=0) on those rays.
+ */
+int b200drr_siddon_fwd_pose(const float *vol, int D0, int D1, int D2, const float *src, const float *G, const float *Wd,
+                            const float *rows, const float *cols, float *out, int B, int H, int W, float voxel_shift,
+                            float eps, void *stream);
+
+/*
+ * Backward of b200drr_siddon_fwd_pose: g_src [B][3], g_G [B][3][4], g_Wd [B][3][4] overwritten; g_vol accumulated into
+ * (NULL = not wanted).  ws_tgt [B][H*W][3] and ws_len [B][H*W] are caller-provided scratch (per-ray gradients before
+ * they are reduced to the matrices).  stop_grad as in b200drr_siddon_bwd.
+ */
+int b200drr_siddon_bwd_pose(const float *vol, int D0, int D1, int D2, const float *src, const float *G, const float *Wd,
+                            const float *rows, const float *cols, const float *gout, float *g_src, float *g_G,
+                            float *g_Wd, float *g_vol, float *ws_tgt, float *ws_len, int B, int H, int W,
+                            float voxel_shift, float eps, int stop_grad, void *stream);
+
+/*
  * Trilinear forward: replaces Trilinear.forward with mask=None (renderers.py:205-240) for a given
  * sampling range.  alpha_range is a DEVICE pointer to {alphamin, alphamax} (so that the range computed
  * on the device by _get_alpha_minmax, renderers.py:124-140,221-223, needs no host round trip).
