@@ -548,19 +548,19 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, con
         for (int j = 0; j < U; ++j) v[j] = ldg(vol + offs[j]);
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if (axprev < 3) {  // a real crossing led into voxel j (false only for the padding steps after the exit)
-                const float coef = vprev - v[j];
+            // crossing (axprev, aprev) led into voxel j; after the exit the padding steps carry axprev == 3 (matches no
+            // axis) and len == 0, so they fall through without a branch
+            const float coef = vprev - v[j];
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
-                    if (a == axprev) {
-                        A[a] = fmaf(coef, aprev, A[a]);
-                        C[a] += coef;
-                    }
-                acc = fmaf(len[j], v[j], acc);
-                if (g_vol) red_add(g_vol + offs[j], gL * len[j]);
-                vprev = v[j];
-                any = true;
-            }
+            for (int a = 0; a < 3; ++a)
+                if (a == axprev) {
+                    A[a] = fmaf(coef, aprev, A[a]);
+                    C[a] += coef;
+                }
+            acc = fmaf(len[j], v[j], acc);
+            if (g_vol && len[j] != 0.0f) red_add(g_vol + offs[j], gL * len[j]);
+            any = any || (axprev < 3);
+            vprev = v[j];
             axprev = ax[j];
             aprev = aend[j];
         }

@@ -291,7 +291,6 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const flo
                                                                  float* __restrict__ g_vol, int B, int H, int W, int slab,
                                                                  float shift, float eps, int stop_grad, PoseRays pr)
 {
-    __shared__ float red[32];
     constexpr int WX = TW / 8;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
     const int tiles = tiles_x * tiles_y;
@@ -325,10 +324,12 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const flo
         if (g_raylen && !stop_grad && acc != 0.0f) red_add(g_raylen + r, g * acc);
     }
     if (g_src) {
+        // warp-level reduction + one atomic per warp: no block barrier, so warps whose rays finish early retire
+        // instead of waiting for the slowest warp of the CTA (ncu: 19 % of stalls were on that barrier)
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float tot = block_sum(gs[a], red);
-            if (threadIdx.x == 0 && tot != 0.0f) atomicAdd(g_src + b * 3 + a, tot);
+            const float tot = warp_sum(gs[a]);
+            if ((threadIdx.x & 31) == 0 && tot != 0.0f) atomicAdd(g_src + b * 3 + a, tot);
         }
     }
 }
