@@ -120,10 +120,9 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
         const float a1 = plane_alpha_acc(ray, a, (float)hi_v[a], shift);
         lo[a] = fminf(a0, a1);
         a_hi = fminf(a_hi, fmaxf(a0, a1));
-        if (lo[a] > w.a_in) {
-            w.a_in = lo[a];
-            w.entry_axis = a;
-        }
+        const bool better = lo[a] > w.a_in;
+        w.a_in = better ? lo[a] : w.a_in;
+        w.entry_axis = better ? a : w.entry_axis;
     }
     w.hit = w.a_in < a_hi;  // false for NaN as well
     w.a_out = INFINITY;
@@ -131,24 +130,18 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
     for (int a = 0; a < 3; ++a) {
         const bool fwd = ray.d[a] > 0.0f;
         w.sti[a] = fwd ? 1 : -1;
-        int i;
-        if (lo[a] >= w.a_in) {
-            i = fwd ? lo_v[a] : hi_v[a] - 1;  // entering through a face of this axis
-        } else {
-            const float q = fmaf(w.a_in, ray.d[a], ray.s[a] + shift);
-            i = (int)floorf(q);
-            i = i < lo_v[a] ? lo_v[a] : (i > hi_v[a] - 1 ? hi_v[a] - 1 : i);
-            // Make the start voxel consistent with the ORDER of the crossing alphas (floor() of a position that sits
-            // within round-off of a plane is a coin toss): the plane behind must have alpha < a_in, and a plane that
-            // ties with the entry face counts as not crossed yet (the face has the lower axis index for slab cuts,
-            // which reproduces the crossing order of the unsplit walk and hence its gradient attribution).
-            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
-            if (plane_alpha_acc(ray, a, (float)behind, shift) >= w.a_in) {
-                if (fwd ? i > lo_v[a] : i < hi_v[a] - 1) i -= w.sti[a];
-            } else if (plane_alpha_acc(ray, a, (float)ahead, shift) < w.a_in) {
-                if (fwd ? i < hi_v[a] - 1 : i > lo_v[a]) i += w.sti[a];
-            }
-        }
+        const int lo_i = lo_v[a], hi_i = hi_v[a] - 1;
+        int i = (int)floorf(fmaf(w.a_in, ray.d[a], ray.s[a] + shift));
+        i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
+        // Make the start voxel consistent with the ORDER of the crossing alphas (floor() of a position that sits
+        // within round-off of a plane is a coin toss): the plane behind must have alpha < a_in, and a plane that
+        // ties with the entry face counts as not crossed yet.  Straight-line selects, no branches.
+        const float a_behind = plane_alpha_acc(ray, a, (float)(fwd ? i : i + 1), shift);
+        const float a_ahead = plane_alpha_acc(ray, a, (float)(fwd ? i + 1 : i), shift);
+        const bool back = (a_behind >= w.a_in) && (fwd ? i > lo_i : i < hi_i);
+        const bool ahead = !(a_behind >= w.a_in) && (a_ahead < w.a_in) && (fwd ? i < hi_i : i > lo_i);
+        i += back ? -w.sti[a] : (ahead ? w.sti[a] : 0);
+        i = (lo[a] >= w.a_in) ? (fwd ? lo_i : hi_i) : i;  // entering through a face of this axis
         w.idx[a] = i;
         w.p0[a] = (float)(fwd ? i + 1 : i);
         w.nx[a] = fwd ? (float)hi_v[a] - w.p0[a] : w.p0[a] - (float)lo_v[a];
@@ -187,20 +180,18 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
     float pref[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        // straight-line (select-only) version of: floor the entry position, then move one voxel back/forward if the
+        // plane behind is not strictly before av_in / the plane ahead is already before it
         const bool fwd = w.sti[a] > 0;
-        int i;
-        if (vlo[a] >= av_in) {
-            i = fwd ? 0 : dims.d[a] - 1;
-        } else {
-            i = (int)floorf(fmaf(av_in, ray.d[a], ray.s[a] + shift));
-            i = i < 0 ? 0 : (i > dims.d[a] - 1 ? dims.d[a] - 1 : i);
-            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
-            if (plane_alpha_acc(ray, a, (float)behind, shift) >= av_in) {
-                if (fwd ? i > 0 : i < dims.d[a] - 1) i -= w.sti[a];
-            } else if (plane_alpha_acc(ray, a, (float)ahead, shift) < av_in) {
-                if (fwd ? i < dims.d[a] - 1 : i > 0) i += w.sti[a];
-            }
-        }
+        const int hi_i = dims.d[a] - 1;
+        int i = (int)floorf(fmaf(av_in, ray.d[a], ray.s[a] + shift));
+        i = i < 0 ? 0 : (i > hi_i ? hi_i : i);
+        const float a_behind = plane_alpha_acc(ray, a, (float)(fwd ? i : i + 1), shift);
+        const float a_ahead = plane_alpha_acc(ray, a, (float)(fwd ? i + 1 : i), shift);
+        const bool back = (a_behind >= av_in) && (fwd ? i > 0 : i < hi_i);
+        const bool ahead = !(a_behind >= av_in) && (a_ahead < av_in) && (fwd ? i < hi_i : i > 0);
+        i += back ? -w.sti[a] : (ahead ? w.sti[a] : 0);
+        i = (vlo[a] >= av_in) ? (fwd ? 0 : hi_i) : i;  // entering through a face of this axis
         pref[a] = (float)(fwd ? i + 1 : i);
         w.a0[a] = plane_alpha_acc(ray, a, pref[a], shift);
     }
@@ -215,10 +206,9 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
         const float a0 = fmaf(((float)lo_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
         const float a1 = fmaf(((float)hi_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
         lo[a] = fminf(a0, a1);
-        if (lo[a] > w.a_in) {
-            w.a_in = lo[a];
-            w.entry_axis = a;
-        }
+        const bool better = lo[a] > w.a_in;
+        w.a_in = better ? lo[a] : w.a_in;
+        w.entry_axis = better ? a : w.entry_axis;
         w.a_out = fminf(w.a_out, fmaxf(a0, a1));
     }
     // a_in == a_out is a (zero-length) hit here: the voxel touched still takes part in the crossing bookkeeping
@@ -227,19 +217,15 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
     for (int a = 0; a < 3; ++a) {
         const bool fwd = w.sti[a] > 0;
         const float sg = (float)w.sti[a];
-        int i;
-        if (lo[a] >= w.a_in) {
-            i = fwd ? lo_v[a] : hi_v[a] - 1;
-        } else {
-            i = (int)floorf(fmaf(w.a_in, ray.d[a], ray.s[a] + shift));
-            i = i < lo_v[a] ? lo_v[a] : (i > hi_v[a] - 1 ? hi_v[a] - 1 : i);
-            const int behind = fwd ? i : i + 1, ahead = fwd ? i + 1 : i;
-            if (fmaf(((float)behind - pref[a]) * sg, w.da[a], w.a0[a]) >= w.a_in) {
-                if (fwd ? i > lo_v[a] : i < hi_v[a] - 1) i -= w.sti[a];
-            } else if (fmaf(((float)ahead - pref[a]) * sg, w.da[a], w.a0[a]) < w.a_in) {
-                if (fwd ? i < hi_v[a] - 1 : i > lo_v[a]) i += w.sti[a];
-            }
-        }
+        const int lo_i = lo_v[a], hi_i = hi_v[a] - 1;
+        int i = (int)floorf(fmaf(w.a_in, ray.d[a], ray.s[a] + shift));
+        i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
+        const float a_behind = fmaf(((float)(fwd ? i : i + 1) - pref[a]) * sg, w.da[a], w.a0[a]);
+        const float a_ahead = fmaf(((float)(fwd ? i + 1 : i) - pref[a]) * sg, w.da[a], w.a0[a]);
+        const bool back = (a_behind >= w.a_in) && (fwd ? i > lo_i : i < hi_i);
+        const bool ahead = !(a_behind >= w.a_in) && (a_ahead < w.a_in) && (fwd ? i < hi_i : i > lo_i);
+        i += back ? -w.sti[a] : (ahead ? w.sti[a] : 0);
+        i = (lo[a] >= w.a_in) ? (fwd ? lo_i : hi_i) : i;
         w.idx[a] = i;
         w.p0[a] = (float)(fwd ? i + 1 : i);
         w.nf[a] = (w.p0[a] - pref[a]) * sg;                                     // crossings already behind us
@@ -517,12 +503,38 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
     return len;
 }
 
+// A[ax] += coef * alpha;  C[ax] += coef   for ax in {0,1,2} (nothing for ax == 3), without branches.
+B200_HD void axis_accumulate(int ax, float coef, float alpha, float& A0, float& A1, float& A2, float& C0, float& C1,
+                             float& C2)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred q0, q1, q2;\n\t"
+        "setp.eq.s32 q0, %6, 0;\n\t"
+        "setp.eq.s32 q1, %6, 1;\n\t"
+        "setp.eq.s32 q2, %6, 2;\n\t"
+        "@q0 fma.rn.f32 %0, %7, %8, %0;\n\t"
+        "@q1 fma.rn.f32 %1, %7, %8, %1;\n\t"
+        "@q2 fma.rn.f32 %2, %7, %8, %2;\n\t"
+        "@q0 add.f32 %3, %3, %7;\n\t"
+        "@q1 add.f32 %4, %4, %7;\n\t"
+        "@q2 add.f32 %5, %5, %7;\n\t"
+        "}"
+        : "+f"(A0), "+f"(A1), "+f"(A2), "+f"(C0), "+f"(C1), "+f"(C2)
+        : "r"(ax), "f"(coef), "f"(alpha));
+#else
+    if (ax == 0) { A0 = fmaf(coef, alpha, A0); C0 += coef; }
+    if (ax == 1) { A1 = fmaf(coef, alpha, A1); C1 += coef; }
+    if (ax == 2) { A2 = fmaf(coef, alpha, A2); C2 += coef; }
+#endif
+}
+
 // Backward of one ray restricted to the sub-box [lo, hi) (closed form, see siddon_ray_bwd below for the algebra).
 // Crossing m between voxel values (before, after) on axis a at alpha contributes coef = before - after to
 //   A_a += coef * alpha,  C_a += coef;  box faces count as crossings against 0, which telescopes correctly when a
 // ray is split into slabs (the two halves of an interior face add up to the true coefficient).
 // Returns sum_j v_j len_j; adds gL*len_j to g_vol[voxel_j] when g_vol != nullptr.  A, C are accumulated INTO.
-template <int U>
+template <int U, bool WANT_VOL>
 B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
                                       int st1, int st2, const Ray& ray, float shift, float gL, float* g_vol, float A[3],
                                       float C[3])
@@ -532,6 +544,7 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, con
     LeanConst k;
     LeanState s;
     lean_init(w, st0, st1, st2, s, k);
+    float A0 = 0.0f, A1 = 0.0f, A2 = 0.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
     float acc = 0.0f, vprev = 0.0f, aprev = w.a_in;
     int axprev = w.entry_axis;
     bool any = false;
@@ -550,15 +563,11 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, con
         for (int j = 0; j < U; ++j) {
             // crossing (axprev, aprev) led into voxel j; after the exit the padding steps carry axprev == 3 (matches no
             // axis) and len == 0, so they fall through without a branch
-            const float coef = vprev - v[j];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                if (a == axprev) {
-                    A[a] = fmaf(coef, aprev, A[a]);
-                    C[a] += coef;
-                }
+            axis_accumulate(axprev, vprev - v[j], aprev, A0, A1, A2, C0, C1, C2);
             acc = fmaf(len[j], v[j], acc);
-            if (g_vol && len[j] != 0.0f) red_add(g_vol + offs[j], gL * len[j]);
+            if (WANT_VOL) {
+                if (len[j] != 0.0f) red_add(g_vol + offs[j], gL * len[j]);
+            }
             any = any || (axprev < 3);
             vprev = v[j];
             axprev = ax[j];
@@ -567,41 +576,36 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, con
     }
     if (!any) {  // the box is only touched (a_in == a_out, e.g. the ray enters the volume exactly on a slab face)
         const float v0 = ldg(vol + s.off);
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (a == w.entry_axis) {
-                A[a] = fmaf(-v0, w.a_in, A[a]);
-                C[a] -= v0;
-            }
+        axis_accumulate(w.entry_axis, -v0, w.a_in, A0, A1, A2, C0, C1, C2);
         vprev = v0;
     }
     // Tail: crossings that TIE with the exit alpha are taken lowest axis first (stable-sort order) until the first
     // boundary plane is met; interior planes among them lead through zero-length voxels that only matter for how the
     // exit coefficient is split between the axes.  (Regular detector grids hit voxel edges exactly, so this is common.)
-    const float an[3] = {s.an0, s.an1, s.an2}, nf[3] = {s.nf0, s.nf1, s.nf2};
-    const int so[3] = {k.so0, k.so1, k.so2};
     int ax_exit = 3;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        if (ax_exit == 3 && an[a] <= k.a_out) {
-            if (nf[a] == w.nx[a]) {
-                ax_exit = a;  // this axis' boundary plane: the ray leaves the box through it
-            } else {
-                s.off += so[a];
-                const float vmid = ldg(vol + s.off);
-                const float coef = vprev - vmid;
-                A[a] = fmaf(coef, k.a_out, A[a]);
-                C[a] += coef;
-                vprev = vmid;
-            }
+    {
+        const bool t0 = s.an0 <= k.a_out, t1 = s.an1 <= k.a_out, t2 = s.an2 <= k.a_out;
+        const bool b0 = s.nf0 == w.nx[0], b1 = s.nf1 == w.nx[1], b2 = s.nf2 == w.nx[2];
+        if (t0 && b0) ax_exit = 0;
+        if (ax_exit == 3 && t0) {  // interior plane of axis 0 at the exit alpha
+            s.off += k.so0;
+            const float vm = ldg(vol + s.off);
+            axis_accumulate(0, vprev - vm, k.a_out, A0, A1, A2, C0, C1, C2);
+            vprev = vm;
         }
-    if (ax_exit == 3) ax_exit = (an[0] <= an[1] && an[0] <= an[2]) ? 0 : (an[1] <= an[2] ? 1 : 2);
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        if (a == ax_exit) {
-            A[a] = fmaf(vprev, k.a_out, A[a]);
-            C[a] += vprev;
+        if (ax_exit == 3 && t1 && b1) ax_exit = 1;
+        if (ax_exit == 3 && t1) {
+            s.off += k.so1;
+            const float vm = ldg(vol + s.off);
+            axis_accumulate(1, vprev - vm, k.a_out, A0, A1, A2, C0, C1, C2);
+            vprev = vm;
         }
+        if (ax_exit == 3 && t2 && b2) ax_exit = 2;
+        if (ax_exit == 3) ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
+    }
+    axis_accumulate(ax_exit, vprev, k.a_out, A0, A1, A2, C0, C1, C2);
+    A[0] += A0; A[1] += A1; A[2] += A2;
+    C[0] += C0; C[1] += C1; C[2] += C2;
     return acc;
 }
 

@@ -132,8 +132,8 @@ void emu_siddon_bwd_lean(const float* vol, int D0, int D1, int D2, const float* 
             for (int sl = 0; sl < n_slabs; ++sl) {
                 const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
                 const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
-                acc += siddon_ray_bwd_lean_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, gL,
-                                                  stop_grad ? nullptr : g_vol, A, C);
+                acc += stop_grad ? siddon_ray_bwd_lean_box<4, false>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, gL, nullptr, A, C)
+                                 : siddon_ray_bwd_lean_box<4, true>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, gL, g_vol, A, C);
             }
             for (int a = 0; a < 3; ++a) {
                 g_tgt[r * 3 + a] = -gL * A[a] * ray.inv[a];
