@@ -40,6 +40,10 @@ DET = 256
 METRIC = "DRRs/sec fwd+bwd (512^3 CT -> 256^2 det)"
 WORKLOAD = "siddon fwd+bwd(pose), 512^3 fp32 CT -> 256^2 detector"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the default workload
+# (16 poses, 512^3 -> 256^2): profiles/r01_fwd_slab_B16_ncu_summary.txt and gpurun capture of the backward kernel.
+# Only quoted when the run uses that workload; otherwise null.
+NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9}
 
 
 def parse():
@@ -314,7 +318,7 @@ def run_ours(args, rank, local_rank, world):
                 "path": "DRR(rot, xyz) -> (img*w).sum().backward(); pinned host pose in; image stack + loss + pose grads out"},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s", "frac": dom[1] / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
+                     "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if (B, D, args.det) == (16, VOL, DET) else None, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
         "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
                          "algorithmic_bytes_per_launch": fwd_bytes, "drr_per_s_fwd_only": B / (fwd_ms * 1e-3)},
         "roofline_bwd": {"kernel": "siddon_bwd_slab_kernel", "achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms_per_launch": bwd_ms,

@@ -11,9 +11,10 @@ from diffdrr_b200.pose import convert  # noqa: E402
 from diffdrr_b200.renderers import _ptr, _stream, siddon_visits  # noqa: E402
 
 D, H, B = 512, 256, int(os.environ.get("B", 16))
+D1, D2 = int(os.environ.get("D1", D)), int(os.environ.get("D2", D))  # non-power-of-two pitches (bank-conflict experiment)
 dev = torch.device("cuda:0")
 lib = _lib.load()
-vol = torch.rand(D, D, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+vol = torch.rand(D, D1, D2, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
 subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
 subj.volume.affine = synthetic.make_affine(D)
 drr = DRR(subj, **synthetic.detector_kwargs(H)).to(dev)
@@ -24,7 +25,8 @@ with torch.no_grad():
     src = drr.affine_inverse(src).reshape(B, 3).contiguous()
     tgt = drr.affine_inverse(tgt).contiguous()
 N = H * H
-visits = int(siddon_visits((D, D, D), src, tgt).sum())
+visits = int(siddon_visits((D, D1, D2), src, tgt).sum())
+print("dims", (D, D1, D2), "visits/ray", visits / (B * N))
 gbytes = (4 * visits + 20 * B * N) / 1e9
 peak = 6570.9
 
@@ -43,14 +45,14 @@ def timeit(fn, iters=5):
 
 ref = torch.empty(B, N, device=dev)
 def base():
-    _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(ref), B, N, 0.5, 1e-8, 0, 0, _stream()), "fwd")
+    _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(ref), B, N, 0.5, 1e-8, 0, 0, _stream()), "fwd")
 ms = timeit(base)
 print(f"baseline linear       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
 variants = [int(v) for v in os.environ.get("VARIANTS", "0,15").split(",")]
 for v in variants:
     out = torch.zeros(B, N, device=dev)
     def run():
-        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, v, _stream()), "grid")
+        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, v, _stream()), "grid")
     try:
         ms = timeit(run)
     except Exception as e:  # unknown variant
@@ -63,14 +65,14 @@ for v in variants:
 gout = torch.rand(B, N, device=dev)
 g_src0, g_tgt0, g_len0 = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
 def bbase():
-    _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src0), _ptr(g_tgt0), _ptr(g_len0), None, B, N, 0.5, 1e-8, 0, 0, _stream()), "bwd")
+    _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src0), _ptr(g_tgt0), _ptr(g_len0), None, B, N, 0.5, 1e-8, 0, 0, _stream()), "bwd")
 bbytes = (4 * visits + 36 * B * N) / 1e9
 ms = timeit(bbase, 3)
 print(f"bwd baseline linear   : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {bbytes / ms * 1e3:8.1f} GB/s  {bbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak")
 for v in [int(x) for x in os.environ.get("BVARIANTS", "0,1,2,3,4,5,6,7,8,9").split(",")]:
     g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
     def run():
-        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, B, H, H, 0.5, 1e-8, 0, v, _stream()), "bwd_grid")
+        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, B, H, H, 0.5, 1e-8, 0, v, _stream()), "bwd_grid")
     ms = timeit(run)
     e = [float((a - b).abs().max() / b.abs().max()) for a, b in ((g_src, g_src0), (g_tgt, g_tgt0), (g_len, g_len0))]
     print(f"bwd grid variant {v:2d}   : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {bbytes / ms * 1e3:8.1f} GB/s  {bbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff src/tgt/len {e[0]:.1e} {e[1]:.1e} {e[2]:.1e}")

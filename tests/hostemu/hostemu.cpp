@@ -190,10 +190,28 @@ void emu_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float* sr
 // Emulates the lock-step lean walk of one warp = WX x WY pixel patch and counts, per walk step, how many distinct
 // sectors and lines the 32 lanes touch.  strides (st0,st1,st2) describe the volume layout being evaluated.
 #include <set>
+// layout < 0: linear with strides (st0,st1,st2).  layout = 1: bricked, 128-B line = 4x4x2 voxels (axes 0,1,2), 32-B
+// sector = 2x2x2.  layout = 2: line = 2x4x4, sector 2x2x2.  layout = 3: line = 4x2x4.  out[4] = distinct sectors
+// touched by the warp over the whole item (a lower bound on its L1 fills).
+static long brick_addr(int layout, int D1, int D2, int i0, int i1, int i2)
+{
+    int b0, b1, b2;  // log2 of the line extent per axis
+    if (layout == 1) { b0 = 2; b1 = 2; b2 = 1; } else if (layout == 2) { b0 = 1; b1 = 2; b2 = 2; } else { b0 = 2; b1 = 1; b2 = 2; }
+    const long n1 = (D1 + (1 << b1) - 1) >> b1, n2 = (D2 + (1 << b2) - 1) >> b2;
+    const long line = (((long)(i0 >> b0)) * n1 + (i1 >> b1)) * n2 + (i2 >> b2);
+    // sector = which 2x2x2 sub-brick inside the line; word = position inside the sector
+    const int s0 = (i0 & ((1 << b0) - 1)) >> 1, s1 = (i1 & ((1 << b1) - 1)) >> 1, s2 = (i2 & ((1 << b2) - 1)) >> 1;
+    const int sector = (s0 * (b1 > 1 ? 2 : 1) + s1) * (b2 > 1 ? 2 : 1) + s2;
+    const int word = (i0 & 1) * 4 + (i1 & 1) * 2 + (i2 & 1);
+    return line * 32 + sector * 8 + word;
+}
+
 extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const float* tgt, int B, int H, int W,
                                  int WX, int WY, int slab, long st0, long st1, long st2, float shift, float eps,
-                                 int sample_every, double* out /* [4]: steps, lane-visits, sectors, lines */)
+                                 int sample_every, double* out /* [5]: steps, lane-visits, sectors, lines, item sectors */)
 {
+    const int layout = st2 < 0 ? (int)(-st2) : -1;
+    double item_sectors = 0;
     const VolDims dims = mk(D0, D1, D2);
     double steps = 0, visits = 0, sectors = 0, lines = 0;
     const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
@@ -218,12 +236,15 @@ extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const
                         acur[l] = w[l].a_in;
                         alive += live[l];
                     }
+                    std::set<long> item_sec;
                     while (alive > 0) {
                         std::set<long> sec, lin;
                         for (int l = 0; l < n; ++l) {
                             if (!live[l]) continue;
-                            const long off = w[l].idx[0] * st0 + w[l].idx[1] * st1 + w[l].idx[2] * st2;
+                            const long off = layout < 0 ? w[l].idx[0] * st0 + w[l].idx[1] * st1 + w[l].idx[2] * st2
+                                                        : brick_addr(layout, D1, D2, w[l].idx[0], w[l].idx[1], w[l].idx[2]);
                             sec.insert(off >> 3);
+                            item_sec.insert(off >> 3);
                             lin.insert(off >> 5);
                             visits += 1;
                             const float anext = fminf(fminf(w[l].an[0], w[l].an[1]), w[l].an[2]);
@@ -239,7 +260,8 @@ extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const
                         sectors += sec.size();
                         lines += lin.size();
                     }
+                    item_sectors += item_sec.size();
                 }
             }
-    out[0] = steps; out[1] = visits; out[2] = sectors; out[3] = lines;
+    out[0] = steps; out[1] = visits; out[2] = sectors; out[3] = lines; out[4] = item_sectors;
 }
