@@ -167,6 +167,29 @@ int b200drr_siddon_bwd_pose(const float* vol, int D0, int D1, int D2, const floa
                                       ws_len, B, H, W, voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
+                            const float* tgt, const float* raylen, float* out, int B, int64_t N, int C, float voxel_shift,
+                            float eps, void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || C <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, out, B, N, C, voxel_shift, eps,
+                                      (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
+                               const float* tgt, const float* raylen, float* out, int B, int64_t N, int C,
+                               float voxel_shift, float eps, int n_points, const float* alpha_range, int align_corners,
+                               void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) ||
+        C <= 0 || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, out, B, N, C, voxel_shift, eps,
+                                         n_points, alpha_range, align_corners != 0, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_visits(int D0, int D1, int D2, const float* src, const float* tgt, int32_t* visits, int B,
                           int64_t N, float voxel_shift, float eps, void* stream)
 {

@@ -49,4 +49,12 @@ cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* 
                                    float* g_Wd, float* g_vol, float* ws_tgt, float* ws_len, int B, int H, int W, float shift,
                                    float eps, int stop_grad, cudaStream_t stream);
 
+cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
+                                   cudaStream_t stream);
+cudaError_t launch_trilinear_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src,
+                                      const float* tgt, const float* raylen, float* out, int B, int64_t N, int C,
+                                      float shift, float eps, int n_points, const float* alpha_range, int align_corners,
+                                      cudaStream_t stream);
+
 }  // namespace b200drr

@@ -503,6 +503,56 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
     return len;
 }
 
+// mask_to_channels (reference renderers.py:77-89): the same lean walk, but every segment's term goes to the channel
+// given by the label volume at the same voxel.  Labels are piecewise constant along a ray, so the walk keeps a running
+// sum per label RUN and flushes it to out[label] when the label changes (few flushes per ray; each (pose, ray) column of
+// `out` belongs to exactly one thread, so a plain += suffices).  `out_n` points at out[b][0][n]; channels are `cstride`
+// floats apart.  Labels outside [0, C) are dropped (the reference's scatter_add_ would raise).
+template <int U>
+B200_HD void siddon_ray_lean_mask(const float* vol, const float* mask, const VolDims& dims, const Ray& ray, float shift,
+                                  float L, float* out_n, int64_t cstride, int C)
+{
+    const int lo_v[3] = {0, 0, 0};
+    const Walk w = start_walk_box(ray, lo_v, dims.d, shift);
+    if (!w.hit) return;
+    LeanConst k;
+    LeanState s;
+    lean_init(w, dims.d[1] * dims.d[2], dims.d[2], 1, s, k);
+    int cur = -1;
+    float run = 0.0f;
+    while (s.acur < k.a_out) {
+        float len[U], v[U], lab[U];
+        int offs[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            offs[j] = s.off;
+            len[j] = lean_step(s, k);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            v[j] = ldg(vol + offs[j]);
+            lab[j] = ldg(mask + offs[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int c = (int)lab[j];
+            if (c != cur) {
+                if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += L * run;
+                cur = c;
+                run = 0.0f;
+            }
+            run = fmaf(len[j], v[j], run);
+        }
+    }
+    if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += L * run;
+}
+
+// Trilinear with a label mask (reference renderers.py:242-252): density sampled trilinearly, label sampled NEAREST at
+// the same point (round-half-even per axis, zero padding -> label 0).  `scale` = raylen * step.
+B200_HD void trilinear_ray_fwd_mask(const float* vol, const float* mask, const VolDims& dims, const Ray& ray, float shift,
+                                    int P, float amin, float amax, int align_corners, float scale, float* out_n,
+                                    int64_t cstride, int C);
+
 // A[ax] += coef * alpha;  C[ax] += coef   for ax in {0,1,2} (nothing for ax == 3), without branches.
 B200_HD void axis_accumulate(int ax, float coef, float alpha, float& A0, float& A1, float& A2, float& C0, float& C1,
                              float& C2)
@@ -805,6 +855,43 @@ B200_HD float trilinear_ray_fwd(const float* vol, const VolDims& dims, const Ray
     // samples skipped by sample_range are exact zeros: they take part in a max
     if (reduce != 0 && (m_lo > 0 || m_hi < P - 1 || !have)) acc = have ? fmaxf(acc, 0.0f) : 0.0f;
     return acc;
+}
+
+B200_HD void trilinear_ray_fwd_mask(const float* vol, const float* mask, const VolDims& dims, const Ray& ray, float shift,
+                                    int P, float amin, float amax, int align_corners, float scale, float* out_n,
+                                    int64_t cstride, int C)
+{
+    const PixLine pl = make_pixline(ray, dims, shift, align_corners);
+    const float range = amax - amin;
+    const float lstep = 1.0f / (float)(P - 1);
+    int m_lo, m_hi;
+    sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    int cur = -1;
+    float run = 0.0f;
+    for (int m = m_lo; m <= m_hi; ++m) {
+        const float alpha = add_rn(mul_rn(linspace01(m, P, lstep), range), amin);
+        float pix[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
+        if (outside_padded(pix, dims)) continue;
+        const float val = lerp8(gather8(vol, dims, pix));
+        bool inb = true;
+        int64_t flat = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float rr = rintf(pix[a]);
+            inb = inb && rr >= 0.0f && rr < (float)dims.d[a];
+            flat = flat * dims.d[a] + (inb ? (int64_t)rr : 0);
+        }
+        const int c = inb ? (int)ldg(mask + flat) : 0;
+        if (c != cur) {
+            if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += scale * run;
+            cur = c;
+            run = 0.0f;
+        }
+        run += val;
+    }
+    if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += scale * run;
 }
 
 struct TriGrad {

@@ -529,6 +529,33 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
 #undef V
 }
 
+// mask_to_channels forward: out [B][C][N], zero-filled by the launcher; one thread per ray owns out[b][:][n].
+__global__ void __launch_bounds__(kThreads) siddon_fwd_mask_kernel(const float* __restrict__ vol,
+                                                                   const float* __restrict__ mask, VolDims dims,
+                                                                   const float* __restrict__ src,
+                                                                   const float* __restrict__ tgt,
+                                                                   const float* __restrict__ raylen, float* out, int64_t N,
+                                                                   int C, float shift, float eps)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int b = blockIdx.y;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    siddon_ray_lean_mask<4>(vol, mask, dims, ray, shift, __ldg(raylen + r), out + (int64_t)b * C * N + n, N, C);
+}
+
+cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
+                                   cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * N, stream);
+    if (e != cudaSuccess) return e;
+    siddon_fwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps);
+    return cudaGetLastError();
+}
+
 static inline dim3 ray_grid(int B, int64_t N) { return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1); }
 
 cudaError_t launch_siddon_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,

@@ -203,6 +203,38 @@ cudaError_t launch_trilinear_bwd_grid(const float* vol, VolDims dims, const floa
 #undef TB
 }
 
+__global__ void __launch_bounds__(kThreads) trilinear_fwd_mask_kernel(const float* __restrict__ vol,
+                                                                      const float* __restrict__ mask, VolDims dims,
+                                                                      const float* __restrict__ src,
+                                                                      const float* __restrict__ tgt,
+                                                                      const float* __restrict__ raylen, float* out,
+                                                                      int64_t N, int C, float shift, float eps, int P,
+                                                                      const float* __restrict__ alpha_range,
+                                                                      int align_corners)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int b = blockIdx.y;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+    const float step = (amax - amin) / (float)(P - 1);
+    trilinear_ray_fwd_mask(vol, mask, dims, ray, shift, P, amin, amax, align_corners, __ldg(raylen + r) * step,
+                           out + (int64_t)b * C * N + n, N, C);
+}
+
+cudaError_t launch_trilinear_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src,
+                                      const float* tgt, const float* raylen, float* out, int B, int64_t N, int C,
+                                      float shift, float eps, int n_points, const float* alpha_range, int align_corners,
+                                      cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * N, stream);
+    if (e != cudaSuccess) return e;
+    trilinear_fwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps, n_points, alpha_range, align_corners);
+    return cudaGetLastError();
+}
+
 static inline dim3 ray_grid(int B, int64_t N) { return dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1); }
 
 cudaError_t launch_trilinear_fwd(const float* vol, VolDims dims, const float* src, const float* tgt,

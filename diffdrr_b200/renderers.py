@@ -203,6 +203,37 @@ class _TrilinearFunction(torch.autograd.Function):
                 None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None)
 
 
+def _mask_channels(mask: torch.Tensor) -> int:
+    """Number of label channels, as the reference computes it (renderers.py:81; one host sync per call)."""
+    return int(mask.max().item() + 1)
+
+
+def _render_mask(kind, volume, mask, source, target, img, voxel_shift, eps, n_points=None, alpha_range=None,
+                 align_corners=False):
+    """mask_to_channels forward through b200drr_*_fwd_mask -> (B, C, N).  Not differentiable (yet)."""
+    B, N = _check_inputs(volume, source, target, img)
+    if any(t.requires_grad for t in (volume, source, target, img)) and torch.is_grad_enabled():
+        raise NotImplementedError("backward through mask_to_channels rendering is not implemented in diffdrr_b200; "
+                                  "call it under torch.no_grad()")
+    if not mask.is_cuda or mask.shape != volume.shape:
+        raise ValueError("mask must be a CUDA label volume with the shape of the density volume")
+    vol, msk = volume.contiguous(), mask.contiguous().float()
+    src, tgt, raylen = source.reshape(B, 3).contiguous(), target.contiguous(), img.reshape(B, N).contiguous()
+    C = _mask_channels(msk)
+    out = torch.empty(B, C, N, dtype=torch.float32, device=vol.device)
+    lib = _lib.load()
+    with torch.cuda.device(vol.device):
+        if kind == "siddon":
+            _lib.check(lib.b200drr_siddon_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                   _ptr(out), B, N, C, voxel_shift, eps, _stream()), "b200drr_siddon_fwd_mask")
+        else:
+            ar = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
+            _lib.check(lib.b200drr_trilinear_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                      _ptr(out), B, N, C, voxel_shift, eps, int(n_points), _ptr(ar),
+                                                      int(align_corners), _stream()), "b200drr_trilinear_fwd_mask")
+    return out
+
+
 def _reduce_code(reducefn):
     if isinstance(reducefn, str) and reducefn in _REDUCE:
         return _REDUCE[reducefn]
@@ -240,7 +271,9 @@ class Siddon(torch.nn.Module):
             raise NotImplementedError("filter_intersections_outside_volume=True is broken in the reference and "
                                       "unnecessary here: the fused walk already clips to the volume")
         if mask is not None:
-            raise NotImplementedError("mask_to_channels rendering is not implemented yet in diffdrr_b200")
+            if align_corners or _reduce_code(self.reducefn) != 0:
+                raise NotImplementedError("mask_to_channels is implemented for reducefn='sum', align_corners=False")
+            return _render_mask("siddon", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps))
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
                                      bool(self.stop_gradients_through_grid_sample), self.detector_shape)
@@ -282,8 +315,8 @@ class Trilinear(torch.nn.Module):
                 alphamax=None):
         if self.mode != "bilinear":
             raise NotImplementedError("Trilinear kernels implement mode='bilinear' (the reference default) only")
-        if mask is not None:
-            raise NotImplementedError("mask_to_channels rendering is not implemented yet in diffdrr_b200")
+        if mask is not None and _reduce_code(self.reducefn) != 0:
+            raise NotImplementedError("mask_to_channels is implemented for reducefn='sum'")
         if alphamin is None or alphamax is None:
             # batch-global sampling range over whatever rays are in this call (quirk Q3), differentiable torch ops
             dims = torch.tensor(volume.shape, device=source.device, dtype=source.dtype)
@@ -291,6 +324,9 @@ class Trilinear(torch.nn.Module):
             alphamin, alphamax = amin.min(), amax.max()
         alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=torch.float32, device=volume.device),
                                    torch.as_tensor(alphamax, dtype=torch.float32, device=volume.device)])
+        if mask is not None:
+            return _render_mask("trilinear", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps),
+                                n_points=n_points, alpha_range=alpha_range, align_corners=align_corners)
         return _TrilinearFunction.apply(volume, source, target, img, alpha_range, float(self.voxel_shift), float(self.eps),
                                         int(n_points), _reduce_code(self.reducefn), bool(align_corners),
                                         self.detector_shape)

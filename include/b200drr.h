@@ -146,6 +146,19 @@ int b200drr_trilinear_bwd_grid(const float *vol, int D0, int D1, int D2, const f
                                int n_points, const float *alpha_range, int variant, void *stream);
 
 /*
+ * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored
+ * as fp32 (as DRR registers it, drr.py:86-91); every segment / sample contributes to channel label(voxel), sampled
+ * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.  Forward only.
+ */
+int b200drr_siddon_fwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                            const float *tgt, const float *raylen, float *out, int B, int64_t N, int C,
+                            float voxel_shift, float eps, void *stream);
+int b200drr_trilinear_fwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                               const float *tgt, const float *raylen, float *out, int B, int64_t N, int C,
+                               float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
+                               void *stream);
+
+/*
  * Per-ray voxel-visit count of the Siddon walk (number of voxels the line crosses inside the volume),
  * the unit of the ALGORITHMIC byte count used for roofline accounting: visits [B][N]
  * int32.  Measurement helper; not part of the reference surface.

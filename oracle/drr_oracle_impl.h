@@ -117,6 +117,42 @@ void FN(oracle_siddon_fwd)(const REAL *vol, int D0, int D1, int D2, const REAL *
     }
 }
 
+/* renderers.py:77-89 (Siddon.forward with a label mask, "mask_to_channels"): every segment's term is routed to the
+ * channel given by the nearest-sampled label at the same midpoint (zero padding -> label 0): out [B][C][N]. */
+void FN(oracle_siddon_fwd_mask)(const REAL *vol, const REAL *mask, int D0, int D1, int D2, const REAL *src,
+                                const REAL *tgt, const REAL *raylen, REAL *out, int B, long N, int C, REAL shift,
+                                REAL eps, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const int M = D0 + D1 + D2 + 3;
+    memset(out, 0, sizeof(REAL) * (size_t)B * C * N);
+#pragma omp parallel
+    {
+        REAL *alpha = (REAL *)malloc(sizeof(REAL) * (size_t)M);
+#pragma omp for schedule(dynamic, 64)
+        for (long r = 0; r < (long)B * N; ++r) {
+            const int b = (int)(r / N);
+            const long n = r % N;
+            REAL s[3], d[3];
+            for (int a = 0; a < 3; ++a) {
+                s[a] = src[b * 3 + a];
+                d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+            }
+            FN(sorted_alphas)(dims, s, d, shift, alpha, NULL, NULL);
+            const REAL L = raylen[r];
+            for (int j = 0; j + 1 < M; ++j) {
+                REAL amid = (alpha[j] + alpha[j + 1]) / (REAL)2;
+                long idx = FN(nearest_index)(amid, s, d, shift, dims, align_corners);
+                if (idx < 0) continue; /* density 0, label 0: adds 0 to channel 0 */
+                long c = (long)mask[idx];
+                if (c < 0 || c >= C) continue;
+                out[((long)b * C + c) * N + n] += (L * vol[idx]) * (alpha[j + 1] - alpha[j]);
+            }
+        }
+        free(alpha);
+    }
+}
+
 /* Autograd of Siddon.forward restated in closed form (checked against the
  * reference's own autograd through the tests/golden siddon fixtures):
  *   dI/dalpha_m = L * (v_{m-1} - v_m)            (v_{-1} = v_{M-1} = 0; nearest sampling has no
@@ -287,6 +323,43 @@ void FN(oracle_trilinear_fwd)(const REAL *vol, int D0, int D1, int D2, const REA
             else if (m == 0 || term > acc) acc = term;
         }
         out[r] = acc;
+    }
+}
+
+/* renderers.py:242-252 (Trilinear.forward with a label mask): the label is sampled with mode="nearest" at the SAME
+ * point as the trilinear density sample. */
+void FN(oracle_trilinear_fwd_mask)(const REAL *vol, const REAL *mask, int D0, int D1, int D2, const REAL *src,
+                                   const REAL *tgt, const REAL *raylen, REAL *out, int B, long N, int C, REAL shift,
+                                   REAL eps, int n_points, REAL alphamin, REAL alphamax, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const REAL step = (alphamax - alphamin) / (REAL)(n_points - 1);
+    memset(out, 0, sizeof(REAL) * (size_t)B * C * N);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < (long)B * N; ++r) {
+        const int b = (int)(r / N);
+        const long n = r % N;
+        REAL s[3], d[3];
+        for (int a = 0; a < 3; ++a) {
+            s[a] = src[b * 3 + a];
+            d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+        }
+        const REAL L = raylen[r];
+        for (int m = 0; m < n_points; ++m) {
+            REAL alpha = FN(linspace01)(m, n_points) * (alphamax - alphamin) + alphamin;
+            REAL pix[3];
+            long c = 0, flat = 0;
+            int inb = 1;
+            for (int a = 0; a < 3; ++a) {
+                pix[a] = FN(pix_at)(alpha, s[a], d[a], shift, dims[a], align_corners);
+                REAL rr = (REAL)nearbyint((double)pix[a]);
+                if (!(rr >= 0 && rr < (REAL)dims[a])) inb = 0;
+                flat = flat * dims[a] + (long)(inb ? rr : 0);
+            }
+            if (inb) c = (long)mask[flat];
+            if (c < 0 || c >= C) continue;
+            out[((long)b * C + c) * N + n] += (L * FN(trilerp)(vol, dims, pix, NULL, NULL, NULL)) * step;
+        }
     }
 }
 

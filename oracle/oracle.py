@@ -72,6 +72,33 @@ def siddon_fwd(vol, src, tgt, raylen, voxel_shift=0.5, eps=1e-8, reduce="sum", a
     return out
 
 
+def siddon_fwd_mask(vol, mask, src, tgt, raylen, n_channels, voxel_shift=0.5, eps=1e-8, align_corners=False, dtype=np.float32):
+    """mask_to_channels rendering: (B, C, N)."""
+    vol, mask, src, tgt, raylen = _prep(dtype, vol, mask, src, tgt, raylen)
+    B, N = tgt.shape[0], tgt.shape[1]
+    out = np.empty((B, n_channels, N), dtype=dtype)
+    R = _real(dtype)
+    getattr(lib(), "oracle_siddon_fwd_mask_" + _suf(dtype))(
+        _p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out), ctypes.c_int(B),
+        ctypes.c_long(N), ctypes.c_int(n_channels), R(voxel_shift), R(eps), ctypes.c_int(bool(align_corners)))
+    return out
+
+
+def trilinear_fwd_mask(vol, mask, src, tgt, raylen, n_channels, n_points=500, alphamin=None, alphamax=None, voxel_shift=0.5,
+                       eps=1e-8, align_corners=False, dtype=np.float32):
+    vol, mask, src, tgt, raylen = _prep(dtype, vol, mask, src, tgt, raylen)
+    B, N = tgt.shape[0], tgt.shape[1]
+    if alphamin is None or alphamax is None:
+        alphamin, alphamax = alpha_minmax(vol.shape, src, tgt, voxel_shift, eps, dtype)
+    out = np.empty((B, n_channels, N), dtype=dtype)
+    R = _real(dtype)
+    getattr(lib(), "oracle_trilinear_fwd_mask_" + _suf(dtype))(
+        _p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out), ctypes.c_int(B),
+        ctypes.c_long(N), ctypes.c_int(n_channels), R(voxel_shift), R(eps), ctypes.c_int(n_points), R(alphamin),
+        R(alphamax), ctypes.c_int(bool(align_corners)))
+    return out
+
+
 def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, align_corners=False,
                want_vol=True, dtype=np.float64):
     """Returns dict(g_source (B,1,3), g_target (B,N,3), g_raylen (B,1,N), g_volume (D0,D1,D2)|None)."""

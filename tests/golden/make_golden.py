@@ -175,6 +175,20 @@ def main():
     renderer_case("siddon_nc_axis", RefSiddon, vol_nc, src, tgt, ln)
     renderer_case("trilinear_nc_axis", RefTrilinear, vol_nc, src, tgt, ln, fwd_kw=dict(n_points=200))
 
+    # mask_to_channels (renderers.py:77-89, 242-252): per-label channels from a label volume
+    i0, i1, i2 = np.meshgrid(np.arange(24), np.arange(32), np.arange(40), indexing="ij")
+    labels = ((i0 * 3) // 24 + 2 * ((i2 * 2) // 40) + ((i1 > 20) & (i0 > 10))).astype(np.float32)  # values 0..4
+    np.savez_compressed(os.path.join(HERE, "labels_nc.npz"), labels=labels)
+    mask_t = torch.from_numpy(labels)
+    for tag, cls, fkw in (("siddon_nc_b4_mask", RefSiddon, {}), ("trilinear_nc_b4_mask", RefTrilinear, dict(n_points=110))):
+        rec = {"source": s.numpy(), "target": t.numpy(), "raylen": l.numpy(), "volume_key": np.str_("nc")}
+        for dt_tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            out = cls()(torch.from_numpy(vol_nc).to(dt), s.to(dt), t.to(dt), l.to(dt), mask=mask_t.to(dt), **fkw)
+            rec["img_" + dt_tag] = out.numpy()
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **rec)
+        print(f"{tag}: shape {rec['img_f64'].shape} f32-vs-f64 "
+              f"{np.abs(rec['img_f32'] - rec['img_f64']).max() / np.abs(rec['img_f64']).max():.2e}")
+
     # ---- BASELINE config[0]: 64^3 -> 64^2, 1 pose (volume regenerated from its seed at test time) -------
     vol64 = synthetic.make_volume(64, "rand", seed=0)
     rot1, xyz1 = synthetic.make_poses(1)

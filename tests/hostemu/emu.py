@@ -112,3 +112,24 @@ def trilinear_bwd(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, vox
                             ctypes.c_float(alphamin), ctypes.c_float(alphamax), ctypes.c_int(bool(align_corners)))
     return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=float(g_ar[0]),
                 g_alphamax=float(g_ar[1]))
+
+
+def siddon_fwd_mask(vol, mask, src, tgt, raylen, C, voxel_shift=0.5, eps=1e-8):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    mask = _f(mask)
+    out = np.empty((B, C, N), np.float32)
+    lib().emu_siddon_fwd_mask(_p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                              ctypes.c_int(B), ctypes.c_long(N), ctypes.c_int(C), ctypes.c_float(voxel_shift), ctypes.c_float(eps))
+    return out
+
+
+def trilinear_fwd_mask(vol, mask, src, tgt, raylen, C, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8,
+                       align_corners=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    mask = _f(mask)
+    out = np.empty((B, C, N), np.float32)
+    lib().emu_trilinear_fwd_mask(_p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                                 ctypes.c_int(B), ctypes.c_long(N), ctypes.c_int(C), ctypes.c_float(voxel_shift),
+                                 ctypes.c_float(eps), ctypes.c_int(n_points), ctypes.c_float(alphamin),
+                                 ctypes.c_float(alphamax), ctypes.c_int(bool(align_corners)))
+    return out

@@ -143,6 +143,35 @@ void emu_siddon_bwd_lean(const float* vol, int D0, int D1, int D2, const float* 
         }
 }
 
+void emu_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                         const float* raylen, float* out, int B, long N, int C, float shift, float eps)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    std::memset(out, 0, sizeof(float) * (size_t)B * C * N);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            siddon_ray_lean_mask<4>(vol, mask, dims, ray, shift, raylen[r], out + (long)b * C * N + n, N, C);
+        }
+}
+
+void emu_trilinear_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
+                            const float* tgt, const float* raylen, float* out, int B, long N, int C, float shift, float eps,
+                            int P, float amin, float amax, int align_corners)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const float step = (amax - amin) / (float)(P - 1);
+    std::memset(out, 0, sizeof(float) * (size_t)B * C * N);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            trilinear_ray_fwd_mask(vol, mask, dims, ray, shift, P, amin, amax, align_corners, raylen[r] * step,
+                                   out + (long)b * C * N + n, N, C);
+        }
+}
+
 void emu_trilinear_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, float* out, int B, long N, float shift, float eps, int P, float amin,
                        float amax, int reduce, int align_corners)

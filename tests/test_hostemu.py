@@ -160,3 +160,17 @@ def test_random_rays_vs_oracle(seed, shape):
     nz = oracle.siddon_fwd(ones, src, tgt, np.ones_like(raylen), dtype=np.float64)[:, 0]
     assert ((visits > 0) == (nz > 1e-9)).mean() > 0.99
     assert visits.max() <= sum(shape) and visits.min() >= 0
+
+
+def test_mask_to_channels():
+    import os
+    from conftest import GOLDEN
+    labels = np.load(os.path.join(GOLDEN, "labels_nc.npz"))["labels"]
+    g = load_golden("siddon_nc_b4_mask")
+    C = g["img_f64"].shape[1]
+    out = emu.siddon_fwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], C)
+    assert relerr(out, g["img_f64"]) < IMG_TOL
+    g = load_golden("trilinear_nc_b4_mask")
+    amin, amax = oracle.alpha_minmax(g["volume"].shape, g["source"], g["target"], 0.5, 1e-8, np.float32)
+    out = emu.trilinear_fwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], C, 110, amin, amax)
+    assert relerr(out, g["img_f64"]) < IMG_TOL

@@ -2,7 +2,9 @@
 import numpy as np
 import pytest
 
-from conftest import load_golden, relerr
+import os
+
+from conftest import GOLDEN, load_golden, relerr
 from oracle import oracle
 
 SIDDON = [
@@ -113,6 +115,17 @@ def test_trilinear_backward_matches_reference_autograd(name, kw, auto):
         assert relerr(g_src, g["g_source_f64"]) < 1e-9
     assert relerr(out["g_raylen"], g["g_raylen_f64"]) < 1e-9
     assert relerr(out["g_volume"], g["g_volume_f64"]) < 1e-9
+
+
+def test_mask_to_channels_matches_reference():
+    labels = np.load(os.path.join(GOLDEN, "labels_nc.npz"))["labels"]
+    for name, fn, kw in (("siddon_nc_b4_mask", oracle.siddon_fwd_mask, {}),
+                         ("trilinear_nc_b4_mask", oracle.trilinear_fwd_mask, dict(n_points=110))):
+        g = load_golden(name)
+        C = g["img_f64"].shape[1]
+        for tag, dtype, tol in (("f32", np.float32, 2e-5), ("f64", np.float64, 1e-10)):
+            out = fn(g["volume"], labels, g["source"], g["target"], g["raylen"], C, dtype=dtype, **kw)
+            assert relerr(out, g["img_" + tag]) < tol, (name, tag)
 
 
 def test_oracle_threads():
