@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL)
     ap.add_argument("--det", type=int, default=DET)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="report the eager end-to-end step only")
     return ap.parse_args()
 
 
@@ -287,13 +288,68 @@ def run_ours(args, rank, local_rank, world):
         e2e_step()
     e_end.record(stream)
     barrier()
-    e2e_ms_total = e_start.elapsed_time(e_end)
+    e2e_eager_ms_total = e_start.elapsed_time(e_end)
+
+    # ---- the same end-to-end step captured ONCE in a CUDA graph and replayed (streams + graphs, no tracing compiler):
+    # pinned-host pose -> H2D -> DRR(rot, xyz) -> loss -> backward -> D2H of image stack / loss / pose gradients.
+    # The host buffers are re-read by every replay, so each step can carry new poses.  (Single GPU only: NCCL
+    # collectives are kept out of the capture.)
+    e2e_ms_total, e2e_mode = e2e_eager_ms_total, "eager"
+    if world == 1 and not args.no_graph:
+        try:
+            rot_d = torch.zeros(B, 3, device=dev, requires_grad=True)
+            xyz_d = torch.zeros(B, 3, device=dev, requires_grad=True)
+            rot_d.grad, xyz_d.grad = torch.zeros_like(rot_d), torch.zeros_like(xyz_d)
+
+            def graph_body():
+                with torch.no_grad():
+                    rot_d.copy_(rot_h, non_blocking=True)
+                    xyz_d.copy_(xyz_h, non_blocking=True)
+                    rot_d.grad.zero_()
+                    xyz_d.grad.zero_()
+                img = drr(rot_d, xyz_d, parameterization="euler_angles", convention="ZXY")
+                loss = (img * w).sum()
+                loss.backward()
+                img_h.copy_(img.detach(), non_blocking=True)
+                grad_h[0].copy_(rot_d.grad, non_blocking=True)
+                grad_h[1].copy_(xyz_d.grad, non_blocking=True)
+                loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    graph_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            ref_img = img_h.clone()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_body()
+
+            def graph_step():
+                graph.replay()
+                torch.cuda.current_stream().synchronize()  # the user reads the result every step
+
+            for _ in range(args.warmup):
+                graph_step()
+            assert torch.allclose(img_h, ref_img, rtol=1e-4, atol=1e-3), "graph replay changed the images"
+            g_start, g_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            g_start.record(stream)
+            for _ in range(args.steps):
+                graph_step()
+            g_end.record(stream)
+            torch.cuda.synchronize()
+            e2e_ms_total, e2e_mode = g_start.elapsed_time(g_end), "cuda-graph replay of the public-API step"
+        except Exception as exc:  # capture is an optimisation of the launch path only; never hide the eager number
+            e2e_mode = f"eager (graph capture failed: {type(exc).__name__})"
 
     # ---- max over ranks -------------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, e2e_ms_total, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total, fwd_ms, bwd_ms = (float(x) for x in stats.tolist())
+    ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total = (float(x) for x in stats.tolist())
     if rank != 0:
         return
 
@@ -312,7 +368,8 @@ def run_ours(args, rank, local_rank, world):
                    "global_batch": B * world, "renderer": "siddon", "parallelism": f"pose-sharded dp{world}",
                    "l2": f"inputs > L2 ({4 * D ** 3 / 1e6:.0f} MB volume vs 126 MB L2); no explicit flush",
                    "mean_visits_per_ray": tot_visits / (B * N)},
-        "e2e": {"value": e2e_value, "unit": "DRRs/s", "ms_per_step": e2e_ms_total / args.steps,
+        "e2e": {"value": e2e_value, "unit": "DRRs/s", "ms_per_step": e2e_ms_total / args.steps, "mode": e2e_mode,
+                "eager_value": total_drr / (e2e_eager_ms_total * 1e-3), "eager_ms_per_step": e2e_eager_ms_total / args.steps,
                 "h2d_bytes_per_step": int(rot_h.numel() + xyz_h.numel()) * 4,
                 "d2h_bytes_per_step": int(img_h.numel() + grad_h.numel() + loss_h.numel()) * 4,
                 "path": "DRR(rot, xyz) -> (img*w).sum().backward(); pinned host pose in; image stack + loss + pose grads out"},

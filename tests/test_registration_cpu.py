@@ -1,0 +1,40 @@
+"""CPU checks of the path's callers: NCC loss and the Registration wrapper."""
+import torch
+
+from diffdrr_b200 import NormalizedCrossCorrelation2d, Registration, synthetic
+from diffdrr_b200.drr import DRR
+
+
+def _ncc_reference(x1, x2, eps=1e-5):
+    """Formula of reference diffdrr/metrics.py:29-44 (patch_size=None), restated for the test."""
+    def norm(x):
+        mu = x.mean(dim=[-1, -2], keepdim=True)
+        var = x.var(dim=[-1, -2], keepdim=True, correction=0) + eps
+        return (x - mu) / var.sqrt()
+    _, c, h, w = x1.shape
+    return torch.einsum("b...,b...->b", norm(x1), norm(x2)) / (c * h * w)
+
+
+def test_ncc_matches_reference_formula_and_bounds():
+    g = torch.Generator().manual_seed(0)
+    x1, x2 = torch.randn(5, 1, 17, 23, generator=g), torch.randn(5, 1, 17, 23, generator=g)
+    ncc = NormalizedCrossCorrelation2d()
+    assert torch.allclose(ncc(x1, x2), _ncc_reference(x1, x2), atol=1e-6)
+    assert torch.allclose(ncc(x1, 3.0 * x1 + 2.0), torch.ones(5), atol=1e-3)      # invariant to affine intensity maps
+    assert torch.allclose(ncc(x1, -x1), -torch.ones(5), atol=1e-3)
+    x1.requires_grad_(True)
+    ncc(x1, x2).sum().backward()
+    assert torch.isfinite(x1.grad).all()
+
+
+def test_registration_module_holds_pose_parameters():
+    vol = synthetic.make_volume(8, "smooth")
+    drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(6))
+    rot, xyz = synthetic.make_poses(1)
+    reg = Registration(drr, rot.clone(), xyz.clone(), "euler_angles", "ZXY")
+    names = dict(reg.named_parameters())
+    assert set(names) == {"_rotation", "_translation"} and reg.rotation is names["_rotation"]
+    pose = reg.pose
+    assert pose.matrix.shape == (1, 4, 4) and pose.matrix.requires_grad
+    # camera centre = R @ t (reference pose.py:149-157): for rot = 0 it is the translation itself
+    assert torch.allclose(pose.matrix[0, :3, 3], xyz[0])
