@@ -13,6 +13,9 @@
 #define B200_HD __host__ __device__ __forceinline__
 #else
 #define B200_HD inline
+struct float4 {  // host emulation only (tests/hostemu): the CUDA headers provide it for device builds
+    float x, y, z, w;
+};
 #endif
 
 namespace b200drr {

@@ -811,6 +811,40 @@ B200_HD Corner8 gather8(const float* vol, const VolDims& dims, const float pix[3
     return k;
 }
 
+// Gather policies for the trilinear marchers: 8 scalar loads from the plain volume, or one 32-byte read from the
+// packed-corner copy (see trilinear_ray_fwd_packed).
+struct GatherPlain {
+    const float* vol;
+    B200_HD Corner8 operator()(const VolDims& dims, const float pix[3]) const { return gather8(vol, dims, pix); }
+};
+
+struct GatherPacked {
+    const float4* packed;
+    B200_HD Corner8 operator()(const VolDims& dims, const float pix[3]) const
+    {
+        Corner8 k;
+        int i0[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float fl = floorf(pix[a]);
+            k.f[a] = pix[a] - fl;
+            i0[a] = (int)fl + 1;  // the packed array starts at base index -1
+        }
+        const int64_t p1 = dims.d[2] + 1, p0 = (int64_t)(dims.d[1] + 1) * p1;
+        const float4* cell = packed + 2 * ((int64_t)i0[0] * p0 + (int64_t)i0[1] * p1 + i0[2]);
+#if defined(__CUDA_ARCH__)
+        const float4 lo = __ldg(cell), hi = __ldg(cell + 1);
+#else
+        const float4 lo = cell[0], hi = cell[1];
+#endif
+        k.v[0] = lo.x; k.v[1] = lo.y; k.v[2] = lo.z; k.v[3] = lo.w;
+        k.v[4] = hi.x; k.v[5] = hi.y; k.v[6] = hi.z; k.v[7] = hi.w;
+        k.base = 0;
+        k.mask = 0u;  // no per-corner addresses: the packed path never scatters a volume gradient
+        return k;
+    }
+};
+
 B200_HD bool outside_padded(const float pix[3], const VolDims& dims)
 {
     return pix[0] <= -1.0f || pix[1] <= -1.0f || pix[2] <= -1.0f || pix[0] >= (float)dims.d[0] ||
@@ -894,6 +928,30 @@ B200_HD void trilinear_ray_fwd_mask(const float* vol, const float* mask, const V
     if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += scale * run;
 }
 
+// ---- packed-corner volume: packed[(i0+1)][(i1+1)][(i2+1)][8] holds the 8 corner values of the interpolation cell
+// whose base voxel is (i0, i1, i2), i in [-1, D-1], zero padding included, corner c = o0 | o1<<1 | o2<<2.  One sample is
+// then ONE aligned 32-byte read (two LDG.128) instead of 8 scalar gathers -- exactly the 32 algorithmic bytes/sample.
+B200_HD float trilinear_ray_fwd_packed(const float4* packed, const VolDims& dims, const Ray& ray, float shift, int P,
+                                       float amin, float amax)
+{
+    const PixLine pl = make_pixline(ray, dims, shift, 0);
+    const float range = amax - amin;
+    const float lstep = 1.0f / (float)(P - 1);
+    int m_lo, m_hi;
+    sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    const GatherPacked gather{packed};
+    float acc = 0.0f;
+    for (int m = m_lo; m <= m_hi; ++m) {
+        const float alpha = add_rn(mul_rn(linspace01(m, P, lstep), range), amin);
+        float pix[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
+        if (outside_padded(pix, dims)) continue;
+        acc += lerp8(gather(dims, pix));
+    }
+    return acc;
+}
+
 struct TriGrad {
     float gs[3], gt[3];  // d/d source, d/d target  (already scaled by g L step)
     float sumV;          // sum of sampled values
@@ -904,8 +962,9 @@ struct TriGrad {
 //   g_s = g L step sum (1-alpha_m) G_m ka,  g_t = g L step sum alpha_m G_m ka,  g_L = g step sum V_m,
 //   g_amin = g L [-sum V/(P-1) + step sum (1-lin_m) G_m.dp],  g_amax = g L [+sum V/(P-1) + step sum lin_m G_m.dp],
 //   g_V[corner] += g L step w_corner.
-B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, int P, float amin,
-                                  float amax, int align_corners, float g, float L, float* g_vol)
+template <class Gather>
+B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, const Ray& ray, float shift, int P,
+                                    float amin, float amax, int align_corners, float g, float L, float* g_vol)
 {
     const PixLine pl = make_pixline(ray, dims, shift, align_corners);
     const float range = amax - amin;
@@ -922,7 +981,7 @@ B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const R
 #pragma unroll
         for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
         if (outside_padded(pix, dims)) continue;
-        const Corner8 k = gather8(vol, dims, pix);
+        const Corner8 k = gather(dims, pix);
         const float f0 = k.f[0], f1 = k.f[1], f2 = k.f[2];
         const float e0 = 1.0f - f0, e1 = 1.0f - f1, e2 = 1.0f - f2;
         const float c00 = fmaf(f2, k.v[4] - k.v[0], k.v[0]), c10 = fmaf(f2, k.v[5] - k.v[1], k.v[1]);
@@ -963,6 +1022,18 @@ B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const R
     out.ga0 = -gLv + gLs * E0;
     out.ga1 = gLv + gLs * E1;
     return out;
+}
+
+B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, int P, float amin,
+                                  float amax, int align_corners, float g, float L, float* g_vol)
+{
+    return trilinear_ray_bwd_g(GatherPlain{vol}, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol);
+}
+
+B200_HD TriGrad trilinear_ray_bwd_packed(const float4* packed, const VolDims& dims, const Ray& ray, float shift, int P,
+                                         float amin, float amax, float g, float L)
+{
+    return trilinear_ray_bwd_g(GatherPacked{packed}, dims, ray, shift, P, amin, amax, 0, g, L, nullptr);
 }
 
 }  // namespace b200drr

@@ -148,10 +148,13 @@ class _TrilinearFunction(torch.autograd.Function):
     """out (B,1,N) = fixed-step trilinear line integrals for the range alpha_range = [alphamin, alphamax]."""
 
     @staticmethod
-    def forward(ctx, volume, source, target, img, alpha_range, voxel_shift, eps, n_points, reduce, align_corners, grid):
+    def forward(ctx, volume, source, target, img, alpha_range, voxel_shift, eps, n_points, reduce, align_corners, grid,
+                packed):
         B, N = _check_inputs(volume, source, target, img)
         if grid is not None and (grid[0] * grid[1] != N or reduce != 0 or align_corners):
             grid = None
+        if grid is None:
+            packed = None
         vol = volume.contiguous()
         src = source.reshape(B, 3).contiguous()
         tgt = target.contiguous()
@@ -160,7 +163,11 @@ class _TrilinearFunction(torch.autograd.Function):
         out = torch.empty(B, N, dtype=torch.float32, device=vol.device)
         lib = _lib.load()
         with torch.cuda.device(vol.device):
-            if grid is not None:
+            if packed is not None:
+                _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                            _ptr(out), B, grid[0], grid[1], voxel_shift, eps, n_points,
+                                                            _ptr(arange), _stream()), "b200drr_trilinear_fwd_packed")
+            elif grid is not None:
                 _lib.check(lib.b200drr_trilinear_fwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
                                                           B, grid[0], grid[1], voxel_shift, eps, n_points, _ptr(arange), 1,
                                                           _stream()), "b200drr_trilinear_fwd_grid")
@@ -169,6 +176,7 @@ class _TrilinearFunction(torch.autograd.Function):
                                                      voxel_shift, eps, n_points, _ptr(arange), reduce, int(align_corners),
                                                      _stream()), "b200drr_trilinear_fwd")
         ctx.save_for_backward(vol, src, tgt, raylen, arange)
+        ctx.packed = packed
         ctx.cfg = (voxel_shift, eps, n_points, reduce, align_corners, tuple(source.shape), tuple(img.shape), grid)
         return out.view(B, 1, N)
 
@@ -189,7 +197,12 @@ class _TrilinearFunction(torch.autograd.Function):
         g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
         lib = _lib.load()
         with torch.cuda.device(dev):
-            if grid is not None:
+            if ctx.packed is not None and g_vol is None:
+                _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(ctx.packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                            _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B,
+                                                            grid[0], grid[1], voxel_shift, eps, n_points, _ptr(arange),
+                                                            _stream()), "b200drr_trilinear_bwd_packed")
+            elif grid is not None:
                 _lib.check(lib.b200drr_trilinear_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                           _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol),
                                                           _ptr(g_ar), B, grid[0], grid[1], voxel_shift, eps, n_points,
@@ -200,7 +213,7 @@ class _TrilinearFunction(torch.autograd.Function):
                                                      voxel_shift, eps, n_points, _ptr(arange), int(align_corners), _stream()),
                            "b200drr_trilinear_bwd")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
-                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None)
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None)
 
 
 def _mask_channels(mask: torch.Tensor) -> int:
@@ -307,9 +320,33 @@ class Trilinear(torch.nn.Module):
         self.voxel_shift = voxel_shift
         self.eps = eps
         self.detector_shape = None  # (H, W) when the rays are the full row-major detector grid (set by DRR.render)
+        # Packed-corner copy of a STATIC volume (8x its size, include/b200drr.h: b200drr_pack_corners): one 32-byte read
+        # per sample instead of 8 gathers.  Built lazily, re-built when the volume tensor changes, skipped when the
+        # volume is being optimised (requires_grad) or the copy would exceed `pack_corners_max_bytes`.
+        self.pack_corners = True
+        self.pack_corners_max_bytes = 24 * 2**30
+        self._packed = None
+        self._packed_key = None
 
     def dims(self, volume):
         return torch.tensor(volume.shape).to(volume)
+
+    def _packed_volume(self, volume):
+        if (not self.pack_corners or volume.requires_grad or not volume.is_cuda or volume.dtype != torch.float32
+                or volume.dim() != 3):
+            return None
+        lib = _lib.load()
+        n = int(lib.b200drr_packed_volume_floats(*volume.shape))
+        if n * 4 > self.pack_corners_max_bytes:
+            return None
+        key = (volume.data_ptr(), volume._version, tuple(volume.shape), volume.device)
+        if self._packed is None or self._packed_key != key:
+            vol = volume.contiguous()
+            packed = torch.empty(n, dtype=torch.float32, device=vol.device)
+            with torch.cuda.device(vol.device):
+                _lib.check(lib.b200drr_pack_corners(_ptr(vol), *vol.shape, _ptr(packed), _stream()), "b200drr_pack_corners")
+            self._packed, self._packed_key = packed, key
+        return self._packed
 
     def forward(self, volume, source, target, img, n_points=500, align_corners=False, mask=None, alphamin=None,
                 alphamax=None):
@@ -329,7 +366,8 @@ class Trilinear(torch.nn.Module):
                                 n_points=n_points, alpha_range=alpha_range, align_corners=align_corners)
         return _TrilinearFunction.apply(volume, source, target, img, alpha_range, float(self.voxel_shift), float(self.eps),
                                         int(n_points), _reduce_code(self.reducefn), bool(align_corners),
-                                        self.detector_shape)
+                                        self.detector_shape,
+                                        self._packed_volume(volume) if self.detector_shape is not None else None)
 
 
 def siddon_visits(volume_shape, source, target, voxel_shift: float = 0.5, eps: float = 1e-8) -> torch.Tensor:

@@ -146,6 +146,26 @@ int b200drr_trilinear_bwd_grid(const float *vol, int D0, int D1, int D2, const f
                                int n_points, const float *alpha_range, int variant, void *stream);
 
 /*
+ * Packed-corner trilinear path.  b200drr_pack_corners writes, for every interpolation cell with base voxel
+ * (i0,i1,i2), i in [-1, D-1], its 8 zero-padded corner values contiguously:
+ *   packed[(i0+1)][(i1+1)][(i2+1)][c] = V[i0+o0][i1+o1][i2+o2],  c = o0 | o1<<1 | o2<<2
+ * into a caller-allocated buffer of b200drr_packed_volume_floats(D0,D1,D2) floats (8x the volume; 32-byte aligned).
+ * b200drr_trilinear_fwd_packed / _bwd_packed then read ONE aligned 32-byte cell per sample (the algorithmic byte
+ * count) instead of 8 scalar gathers; same results as the *_grid entry points (reduce="sum", align_corners=0).
+ * The packed path produces no volume gradient (use b200drr_trilinear_bwd[_grid] when the volume is being optimised)
+ * and must be re-packed whenever the volume changes.
+ */
+int64_t b200drr_packed_volume_floats(int D0, int D1, int D2);
+int b200drr_pack_corners(const float *vol, int D0, int D1, int D2, float *packed, void *stream);
+int b200drr_trilinear_fwd_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
+                                 const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
+                                 int n_points, const float *alpha_range, void *stream);
+int b200drr_trilinear_bwd_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
+                                 const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                                 float *g_alpha_range, int B, int H, int W, float voxel_shift, float eps, int n_points,
+                                 const float *alpha_range, void *stream);
+
+/*
  * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored
  * as fp32 (as DRR registers it, drr.py:86-91); every segment / sample contributes to channel label(voxel), sampled
  * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.  Forward only.

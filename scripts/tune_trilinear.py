@@ -33,6 +33,9 @@ with torch.no_grad():
             cnt += int(((pix > -1) & (pix < D)).all(-1).sum())
 gb = cnt * 32 / 1e9
 print(f"in-volume samples {cnt / (B * N * P):.3f} of all; algorithmic {gb:.2f} GB fwd")
+out = torch.empty(B, N, device=dev)
+gout = torch.rand(B, N, device=dev)
+g_src, g_tgt, g_len, g_ar = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev), torch.zeros(2, device=dev)
 def timeit(fn, iters=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -40,16 +43,27 @@ def timeit(fn, iters=3):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-out = torch.empty(B, N, device=dev)
-gout = torch.rand(B, N, device=dev)
-g_src, g_tgt, g_len, g_ar = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev), torch.zeros(2, device=dev)
+packed = None
+def get_packed():
+    """(D+1)^3 x 8 packed-corner volume (b200drr_pack_corners)."""
+    global packed
+    if packed is None:
+        packed = torch.empty(int(lib.b200drr_packed_volume_floats(D, D, D)), device=dev)
+        t = timeit(lambda: _lib.check(lib.b200drr_pack_corners(_ptr(vol), D, D, D, _ptr(packed), _stream()), "pack"), 2)
+        print(f"pack_corners: {t:.3f} ms for {packed.numel() * 4 / 1e9:.2f} GB")
+    return packed
 for variant in [int(v) for v in os.environ.get("VARIANTS", "-1").split(",")]:
     def fwd():
         if variant < 0:
             _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N, 0.5, 1e-8, P, _ptr(ar), 0, 0, _stream()), "tri fwd")
+        elif variant >= 10:
+            _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), _stream()), "tri fwd packed")
         else:
             _lib.check(lib.b200drr_trilinear_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), variant, _stream()), "tri fwd grid")
     def bwd():
+        if variant >= 10:
+            _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), _stream()), "tri bwd packed")
+            return
         if variant < 0:
             _lib.check(lib.b200drr_trilinear_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, _ptr(g_ar), B, N, 0.5, 1e-8, P, _ptr(ar), 0, _stream()), "tri bwd")
         else:

@@ -172,6 +172,54 @@ void emu_trilinear_fwd_mask(const float* vol, const float* mask, int D0, int D1,
         }
 }
 
+// packed-corner path: host replica of pack_corners_kernel + the packed marchers
+static std::vector<float4> pack_host(const float* vol, const VolDims& dims)
+{
+    const long n1 = dims.d[1] + 1, n2 = dims.d[2] + 1;
+    std::vector<float4> packed(2 * (size_t)(dims.d[0] + 1) * n1 * n2);
+    for (int i0 = -1; i0 < dims.d[0]; ++i0)
+        for (int i1 = -1; i1 < dims.d[1]; ++i1)
+            for (int i2 = -1; i2 < dims.d[2]; ++i2) {
+                float v[8];
+                for (int k = 0; k < 8; ++k) {
+                    const int x = i0 + (k & 1), y = i1 + ((k >> 1) & 1), z = i2 + ((k >> 2) & 1);
+                    const bool inb = x >= 0 && x < dims.d[0] && y >= 0 && y < dims.d[1] && z >= 0 && z < dims.d[2];
+                    v[k] = inb ? vol[((long)x * dims.d[1] + y) * dims.d[2] + z] : 0.0f;
+                }
+                const size_t c = ((size_t)(i0 + 1) * n1 + (i1 + 1)) * n2 + (i2 + 1);
+                packed[2 * c] = float4{v[0], v[1], v[2], v[3]};
+                packed[2 * c + 1] = float4{v[4], v[5], v[6], v[7]};
+            }
+    return packed;
+}
+
+void emu_trilinear_packed(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                          const float* gout, float* out, float* g_src, float* g_tgt, float* g_raylen, float* g_alpha_range,
+                          int B, long N, float shift, float eps, int P, float amin, float amax)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const std::vector<float4> packed = pack_host(vol, dims);
+    const float step = (amax - amin) / (float)(P - 1);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    double ga0 = 0, ga1 = 0;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            out[r] = trilinear_ray_fwd_packed(packed.data(), dims, ray, shift, P, amin, amax) * (raylen[r] * step);
+            const TriGrad tg = trilinear_ray_bwd_packed(packed.data(), dims, ray, shift, P, amin, amax, gout[r], raylen[r]);
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = tg.gt[a];
+                g_src[b * 3 + a] += tg.gs[a];
+            }
+            g_raylen[r] = gout[r] * step * tg.sumV;
+            ga0 += tg.ga0;
+            ga1 += tg.ga1;
+        }
+    g_alpha_range[0] = (float)ga0;
+    g_alpha_range[1] = (float)ga1;
+}
+
 void emu_trilinear_fwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, float* out, int B, long N, float shift, float eps, int P, float amin,
                        float amax, int reduce, int align_corners)

@@ -190,3 +190,37 @@ def test_pose_in_path_matches_ray_tensor_path():
     assert relerr(res[0][0].cpu().numpy(), res[1][0].cpu().numpy()) < 2e-5
     assert relerr(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 1e-3
     assert relerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-3
+
+
+def test_trilinear_packed_corner_path():
+    """Packed-corner kernels (one 32-byte read per sample) == scalar-gather kernels; a volume that requires grad takes
+    the gather path and gets its gradient; an in-place volume update invalidates the packed copy."""
+    from diffdrr_b200 import DRR, Trilinear, synthetic
+    vol = synthetic.make_volume((72, 96, 80), "phantom", seed=11)
+    drr = DRR(synthetic.make_subject(vol), sdd=1020.0, height=64, width=72, delx=3.0, renderer="trilinear").to(DEV)
+    rot0, xyz0 = synthetic.make_poses(3, seed=8)
+    w = torch.rand(3, 1, 64, 72, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    res = []
+    for packed in (True, False):
+        drr.renderer.pack_corners = packed
+        rot, xyz = rot0.to(DEV).requires_grad_(True), xyz0.to(DEV).requires_grad_(True)
+        img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY", n_points=180)
+        (img * w).sum().backward()
+        res.append((img.detach(), rot.grad, xyz.grad))
+        assert (drr.renderer._packed is not None) == packed or not packed
+    assert torch.equal(res[0][0], res[1][0])
+    assert relerr(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 1e-5
+    assert relerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-5
+    drr.renderer.pack_corners = True
+    with torch.no_grad():
+        before = drr(rot0.to(DEV), xyz0.to(DEV), parameterization="euler_angles", convention="ZXY", n_points=180)
+        drr.density.mul_(2.0)  # in-place update bumps the tensor version -> the packed copy is rebuilt
+        after = drr(rot0.to(DEV), xyz0.to(DEV), parameterization="euler_angles", convention="ZXY", n_points=180)
+    assert relerr(after.cpu().numpy(), 2.0 * before.cpu().numpy()) < 1e-6
+    # reconstruction mode: the volume is a parameter -> gather path, volume gradient present
+    from diffdrr_b200.pose import convert
+    dens = drr.density.clone().requires_grad_(True)
+    src, tgt = drr.detector(convert(rot0.to(DEV), xyz0.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
+    out = drr.render(dens, src, tgt, n_points=60)
+    out.sum().backward()
+    assert dens.grad is not None and float(dens.grad.abs().sum()) > 0

@@ -174,3 +174,18 @@ def test_mask_to_channels():
     amin, amax = oracle.alpha_minmax(g["volume"].shape, g["source"], g["target"], 0.5, 1e-8, np.float32)
     out = emu.trilinear_fwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], C, 110, amin, amax)
     assert relerr(out, g["img_f64"]) < IMG_TOL
+
+
+@pytest.mark.parametrize("name,kw", [("trilinear_nc_b4", dict(n_points=160)), ("trilinear_nc_inside", dict(n_points=150)),
+                                     ("trilinear_nc_axis", dict(n_points=200)), ("trilinear_nc_b4_shift0", dict(n_points=120, voxel_shift=0.0))])
+def test_trilinear_packed_corner_path_is_bitwise_the_gather_path(name, kw):
+    g = load_golden(name)
+    amin, amax = _amm(g, kw)
+    a = emu.trilinear_fwd(g["volume"], g["source"], g["target"], g["raylen"], alphamin=amin, alphamax=amax, **kw)
+    ga = emu.trilinear_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], alphamin=amin, alphamax=amax, **kw)
+    b, gb = emu.trilinear_packed(g["volume"], g["source"], g["target"], g["raylen"], g["w"], kw["n_points"], amin, amax,
+                                 voxel_shift=kw.get("voxel_shift", 0.5))
+    assert np.array_equal(a, b)
+    for key in ("g_target", "g_source", "g_raylen"):
+        assert np.array_equal(ga[key], gb[key]), key
+    assert ga["g_alphamin"] == gb["g_alphamin"] and ga["g_alphamax"] == gb["g_alphamax"]
