@@ -204,25 +204,25 @@ int b200drr_pack_corners(const float* vol, int D0, int D1, int D2, float* packed
 
 int b200drr_trilinear_fwd_packed(const float* packed, int D0, int D1, int D2, const float* src, const float* tgt,
                                  const float* raylen, float* out, int B, int H, int W, float voxel_shift, float eps,
-                                 int n_points, const float* alpha_range, void* stream)
+                                 int n_points, const float* alpha_range, int slab, void* stream)
 {
-    if (!packed || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) ||
+    if (!packed || slab < 0 || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) ||
         bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0 || n_points < 2)
         return B200DRR_EINVAL;
     return ret(launch_trilinear_fwd_packed(packed, mk(D0, D1, D2), src, tgt, raylen, out, B, H, W, voxel_shift, eps,
-                                           n_points, alpha_range, (cudaStream_t)stream));
+                                           n_points, alpha_range, slab, (cudaStream_t)stream));
 }
 
 int b200drr_trilinear_bwd_packed(const float* packed, int D0, int D1, int D2, const float* src, const float* tgt,
                                  const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                  float* g_alpha_range, int B, int H, int W, float voxel_shift, float eps, int n_points,
-                                 const float* alpha_range, void* stream)
+                                 const float* alpha_range, int slab, void* stream)
 {
-    if (!packed || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) ||
+    if (!packed || slab < 0 || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) ||
         bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0 || n_points < 2)
         return B200DRR_EINVAL;
     return ret(launch_trilinear_bwd_packed(packed, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen,
-                                           g_alpha_range, B, H, W, voxel_shift, eps, n_points, alpha_range,
+                                           g_alpha_range, B, H, W, voxel_shift, eps, n_points, alpha_range, slab,
                                            (cudaStream_t)stream));
 }
 

@@ -60,10 +60,10 @@ cudaError_t launch_trilinear_fwd_mask(const float* vol, const float* mask, VolDi
 cudaError_t launch_pack_corners(const float* vol, VolDims dims, float* packed, cudaStream_t stream);
 cudaError_t launch_trilinear_fwd_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, int B, int H, int W, float shift, float eps,
-                                        int n_points, const float* alpha_range, cudaStream_t stream);
+                                        int n_points, const float* alpha_range, int slab, cudaStream_t stream);
 cudaError_t launch_trilinear_bwd_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, const float* gout, float* g_src, float* g_tgt,
                                         float* g_raylen, float* g_alpha_range, int B, int H, int W, float shift, float eps,
-                                        int n_points, const float* alpha_range, cudaStream_t stream);
+                                        int n_points, const float* alpha_range, int slab, cudaStream_t stream);
 
 }  // namespace b200drr

@@ -768,6 +768,24 @@ B200_HD void sample_range(const PixLine& pl, const VolDims& dims, float amin, fl
     m_hi = (int)fminf((float)(P - 1), fmaxf(f_hi, -1.0f));
 }
 
+// Narrow [m_lo, m_hi] to the samples whose BASE voxel along axis 0 (floor(pix0)) can lie in [s_lo, s_hi): the
+// slab-major trilinear kernels cut the volume into such slabs; the loop re-checks every sample exactly, so each
+// sample is counted by exactly one slab.  One sample of slack on both sides.
+B200_HD void sample_range_slab(const PixLine& pl, float amin, float range, int P, float s_lo, float s_hi, int& m_lo,
+                               int& m_hi)
+{
+    if (!(range > 0.0f) || m_lo > m_hi) return;
+    const float inv = 1.0f / pl.dp[0];
+    const float a0 = (s_lo - pl.p0[0]) * inv, a1 = (s_hi - pl.p0[0]) * inv;
+    const float lo = fminf(a0, a1), hi = fmaxf(a0, a1);
+    if (!(lo <= hi)) return;  // dp0 == 0 (NaN): the ray runs inside one slab, keep the whole range
+    const float scale = (float)(P - 1) / range;
+    const float f_lo = floorf((lo - amin) * scale) - 1.0f, f_hi = ceilf((hi - amin) * scale) + 1.0f;
+    const int n_lo = (int)fmaxf(0.0f, fminf(f_lo, (float)P)), n_hi = (int)fminf((float)(P - 1), fmaxf(f_hi, -1.0f));
+    m_lo = m_lo > n_lo ? m_lo : n_lo;
+    m_hi = m_hi < n_hi ? m_hi : n_hi;
+}
+
 struct Corner8 {
     float v[8];
     float f[3];
@@ -932,13 +950,14 @@ B200_HD void trilinear_ray_fwd_mask(const float* vol, const float* mask, const V
 // whose base voxel is (i0, i1, i2), i in [-1, D-1], zero padding included, corner c = o0 | o1<<1 | o2<<2.  One sample is
 // then ONE aligned 32-byte read (two LDG.128) instead of 8 scalar gathers -- exactly the 32 algorithmic bytes/sample.
 B200_HD float trilinear_ray_fwd_packed(const float4* packed, const VolDims& dims, const Ray& ray, float shift, int P,
-                                       float amin, float amax)
+                                       float amin, float amax, float s_lo = -INFINITY, float s_hi = INFINITY)
 {
     const PixLine pl = make_pixline(ray, dims, shift, 0);
     const float range = amax - amin;
     const float lstep = 1.0f / (float)(P - 1);
     int m_lo, m_hi;
     sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    sample_range_slab(pl, amin, range, P, s_lo, s_hi, m_lo, m_hi);
     const GatherPacked gather{packed};
     float acc = 0.0f;
     for (int m = m_lo; m <= m_hi; ++m) {
@@ -946,7 +965,7 @@ B200_HD float trilinear_ray_fwd_packed(const float4* packed, const VolDims& dims
         float pix[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
-        if (outside_padded(pix, dims)) continue;
+        if (outside_padded(pix, dims) || !(pix[0] >= s_lo && pix[0] < s_hi)) continue;
         acc += lerp8(gather(dims, pix));
     }
     return acc;
@@ -964,7 +983,8 @@ struct TriGrad {
 //   g_V[corner] += g L step w_corner.
 template <class Gather>
 B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, const Ray& ray, float shift, int P,
-                                    float amin, float amax, int align_corners, float g, float L, float* g_vol)
+                                    float amin, float amax, int align_corners, float g, float L, float* g_vol,
+                                    float s_lo = -INFINITY, float s_hi = INFINITY)
 {
     const PixLine pl = make_pixline(ray, dims, shift, align_corners);
     const float range = amax - amin;
@@ -972,6 +992,7 @@ B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, c
     const float lstep = 1.0f / (float)(P - 1);
     int m_lo, m_hi;
     sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    sample_range_slab(pl, amin, range, P, s_lo, s_hi, m_lo, m_hi);
     const float gLs = g * L * step;
     float sumV = 0.0f, S[3] = {0.0f, 0.0f, 0.0f}, T[3] = {0.0f, 0.0f, 0.0f}, E0 = 0.0f, E1 = 0.0f;
     for (int m = m_lo; m <= m_hi; ++m) {
@@ -980,7 +1001,7 @@ B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, c
         float pix[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
-        if (outside_padded(pix, dims)) continue;
+        if (outside_padded(pix, dims) || !(pix[0] >= s_lo && pix[0] < s_hi)) continue;
         const Corner8 k = gather(dims, pix);
         const float f0 = k.f[0], f1 = k.f[1], f2 = k.f[2];
         const float e0 = 1.0f - f0, e1 = 1.0f - f1, e2 = 1.0f - f2;
@@ -1031,9 +1052,10 @@ B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const R
 }
 
 B200_HD TriGrad trilinear_ray_bwd_packed(const float4* packed, const VolDims& dims, const Ray& ray, float shift, int P,
-                                         float amin, float amax, float g, float L)
+                                         float amin, float amax, float g, float L, float s_lo = -INFINITY,
+                                         float s_hi = INFINITY)
 {
-    return trilinear_ray_bwd_g(GatherPacked{packed}, dims, ray, shift, P, amin, amax, 0, g, L, nullptr);
+    return trilinear_ray_bwd_g(GatherPacked{packed}, dims, ray, shift, P, amin, amax, 0, g, L, nullptr, s_lo, s_hi);
 }
 
 }  // namespace b200drr

@@ -220,6 +220,84 @@ __global__ void __launch_bounds__(TW* TH) trilinear_bwd_packed_kernel(
     }
 }
 
+// Slab-major packed kernels: blockIdx.x = (slab, pose, tile) with the slab slowest.  A slab is `slab` planes of base
+// voxels along axis 0 (slab * (D1+1)*(D2+1)*32 bytes of the packed copy, sized to sit in L2), so the poses of a batch
+// share the packed cells through L2 instead of each streaming the 8x volume from HBM.  Partial sums are combined
+// with red.global.add (outputs zero-filled by the launcher).
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) trilinear_fwd_packed_slab_kernel(
+    const float4* __restrict__ packed, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, float* __restrict__ out, int B, int H, int W, int slab, float shift, float eps, int P,
+    const float* __restrict__ alpha_range)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles = tiles_x * ((H + TH - 1) / TH);
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B, sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+    const float step = (amax - amin) / (float)(P - 1);
+    const float s_lo = (float)(sl * slab - 1), s_hi = (float)((sl + 1) * slab - 1);
+    const float part = trilinear_ray_fwd_packed(packed, dims, ray, shift, P, amin, amax, s_lo, s_hi);
+    if (part != 0.0f) red_add(out + r, part * (__ldg(raylen + r) * step));
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW* TH) trilinear_bwd_packed_slab_kernel(
+    const float4* __restrict__ packed, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, const float* __restrict__ gout, float* __restrict__ g_src,
+    float* __restrict__ g_tgt, float* __restrict__ g_raylen, float* __restrict__ g_alpha_range, int B, int H, int W,
+    int slab, float shift, float eps, int P, const float* __restrict__ alpha_range)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles = tiles_x * ((H + TH - 1) / TH);
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B, sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    float gs[3] = {0.0f, 0.0f, 0.0f}, ga0 = 0.0f, ga1 = 0.0f;
+    if (px < W && py < H) {
+        const int64_t r = ((int64_t)b * H + py) * W + px;
+        const Ray ray = load_ray(src, tgt, b, r, eps);
+        const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+        const float step = (amax - amin) / (float)(P - 1);
+        const float L = __ldg(raylen + r), g = __ldg(gout + r);
+        const float s_lo = (float)(sl * slab - 1), s_hi = (float)((sl + 1) * slab - 1);
+        const TriGrad tg = trilinear_ray_bwd_packed(packed, dims, ray, shift, P, amin, amax, g, L, s_lo, s_hi);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            gs[a] = tg.gs[a];
+            if (g_tgt && tg.gt[a] != 0.0f) red_add(g_tgt + r * 3 + a, tg.gt[a]);
+        }
+        if (g_raylen && tg.sumV != 0.0f) red_add(g_raylen + r, g * step * tg.sumV);
+        ga0 = tg.ga0;
+        ga1 = tg.ga1;
+    }
+    // warp-level reductions, one atomic per warp (no block barrier)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float tot = warp_sum(gs[a]);
+        if (g_src && lane == 0 && tot != 0.0f) atomicAdd(g_src + b * 3 + a, tot);
+    }
+    const float t0 = warp_sum(ga0), t1 = warp_sum(ga1);
+    if (g_alpha_range && lane == 0) {
+        if (t0 != 0.0f) atomicAdd(g_alpha_range, t0);
+        if (t1 != 0.0f) atomicAdd(g_alpha_range + 1, t1);
+    }
+}
+
 // packed[(i0+1)][(i1+1)][(i2+1)][c] = V[i0+o0][i1+o1][i2+o2] (0 outside), c = o0 | o1<<1 | o2<<2, i in [-1, D-1].
 __global__ void __launch_bounds__(256) pack_corners_kernel(const float* __restrict__ vol, VolDims dims,
                                                            float4* __restrict__ packed)
@@ -249,8 +327,18 @@ cudaError_t launch_pack_corners(const float* vol, VolDims dims, float* packed, c
 
 cudaError_t launch_trilinear_fwd_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, int B, int H, int W, float shift, float eps,
-                                        int n_points, const float* alpha_range, cudaStream_t stream)
+                                        int n_points, const float* alpha_range, int slab, cudaStream_t stream)
 {
+    if (slab > 0) {
+        const int n_slabs = (dims.d[0] + 1 + slab - 1) / slab;
+        const int64_t blocks = (int64_t)((W + 15) / 16) * ((H + 15) / 16) * B * n_slabs;
+        if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
+        if (e != cudaSuccess) return e;
+        trilinear_fwd_packed_slab_kernel<16, 16><<<(unsigned)blocks, 256, 0, stream>>>(
+            (const float4*)packed, dims, src, tgt, raylen, out, B, H, W, slab, shift, eps, n_points, alpha_range);
+        return cudaGetLastError();
+    }
     const dim3 grid((unsigned)(((W + 15) / 16) * ((H + 15) / 16)), (unsigned)B, 1);
     trilinear_fwd_packed_kernel<16, 16><<<grid, 256, 0, stream>>>((const float4*)packed, dims, src, tgt, raylen, out, H, W,
                                                                    shift, eps, n_points, alpha_range);
@@ -260,11 +348,25 @@ cudaError_t launch_trilinear_fwd_packed(const float* packed, VolDims dims, const
 cudaError_t launch_trilinear_bwd_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, const float* gout, float* g_src, float* g_tgt,
                                         float* g_raylen, float* g_alpha_range, int B, int H, int W, float shift, float eps,
-                                        int n_points, const float* alpha_range, cudaStream_t stream)
+                                        int n_points, const float* alpha_range, int slab, cudaStream_t stream)
 {
     if (g_src) {
         cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
         if (e != cudaSuccess) return e;
+    }
+    if (slab > 0) {
+        const int n_slabs = (dims.d[0] + 1 + slab - 1) / slab;
+        const int64_t blocks = (int64_t)((W + 15) / 16) * ((H + 15) / 16) * B * n_slabs;
+        if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+        const size_t n = (size_t)B * H * W;
+        cudaError_t e = cudaSuccess;
+        if (g_tgt) e = cudaMemsetAsync(g_tgt, 0, sizeof(float) * 3 * n, stream);
+        if (e == cudaSuccess && g_raylen) e = cudaMemsetAsync(g_raylen, 0, sizeof(float) * n, stream);
+        if (e != cudaSuccess) return e;
+        trilinear_bwd_packed_slab_kernel<16, 16><<<(unsigned)blocks, 256, 0, stream>>>(
+            (const float4*)packed, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_alpha_range, B, H, W, slab, shift,
+            eps, n_points, alpha_range);
+        return cudaGetLastError();
     }
     const dim3 grid((unsigned)(((W + 15) / 16) * ((H + 15) / 16)), (unsigned)B, 1);
     trilinear_bwd_packed_kernel<16, 16><<<grid, 256, 0, stream>>>((const float4*)packed, dims, src, tgt, raylen, gout, g_src,

@@ -154,16 +154,19 @@ int b200drr_trilinear_bwd_grid(const float *vol, int D0, int D1, int D2, const f
  * count) instead of 8 scalar gathers; same results as the *_grid entry points (reduce="sum", align_corners=0).
  * The packed path produces no volume gradient (use b200drr_trilinear_bwd[_grid] when the volume is being optimised)
  * and must be re-packed whenever the volume changes.
+ * slab: 0 = one CTA marches whole rays; > 0 = slab-major scheduling over `slab` planes of base voxels along axis 0
+ * (the poses of a batch then share the packed cells through L2; partial sums are combined with red.global.add, so
+ * results agree with slab = 0 to fp32 round-off).
  */
 int64_t b200drr_packed_volume_floats(int D0, int D1, int D2);
 int b200drr_pack_corners(const float *vol, int D0, int D1, int D2, float *packed, void *stream);
 int b200drr_trilinear_fwd_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
                                  const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
-                                 int n_points, const float *alpha_range, void *stream);
+                                 int n_points, const float *alpha_range, int slab, void *stream);
 int b200drr_trilinear_bwd_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
                                  const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
                                  float *g_alpha_range, int B, int H, int W, float voxel_shift, float eps, int n_points,
-                                 const float *alpha_range, void *stream);
+                                 const float *alpha_range, int slab, void *stream);
 
 /*
  * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored

@@ -57,22 +57,20 @@ for variant in [int(v) for v in os.environ.get("VARIANTS", "-1").split(",")]:
         if variant < 0:
             _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N, 0.5, 1e-8, P, _ptr(ar), 0, 0, _stream()), "tri fwd")
         elif variant >= 10:
-            _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), _stream()), "tri fwd packed")
+            _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), max(0, variant - 10), _stream()), "tri fwd packed")
         else:
             _lib.check(lib.b200drr_trilinear_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), variant, _stream()), "tri fwd grid")
     def bwd():
         if variant >= 10:
-            _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), _stream()), "tri bwd packed")
+            _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), max(0, variant - 10), _stream()), "tri bwd packed")
             return
         if variant < 0:
             _lib.check(lib.b200drr_trilinear_bwd(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, _ptr(g_ar), B, N, 0.5, 1e-8, P, _ptr(ar), 0, _stream()), "tri bwd")
         else:
             _lib.check(lib.b200drr_trilinear_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), variant, _stream()), "tri bwd grid")
-    if variant < 0:
-        ref = None
     f = timeit(fwd)
-    if variant < 0:
-        ref = out.clone()
+    if "ref" not in globals():
+        ref = out.clone()  # the first variant in the list is the reference for maxdiff
     err = float((out - ref).abs().max() / ref.abs().max())
-    b_ = timeit(bwd)
+    b_ = timeit(bwd) if not os.environ.get("FWD_ONLY") else float("nan")
     print(f"variant {variant:2d}: fwd {f:8.3f} ms {B / f * 1e3:8.1f} DRR/s {gb / f * 1e3:7.1f} GB/s ({gb / f * 1e3 / 65.709:5.1f}%)   bwd {b_:8.3f} ms   fwd+bwd {B / (f + b_) * 1e3:7.1f} DRR/s  {2 * gb / (f + b_) * 1e3:7.1f} GB/s   maxdiff {err:.1e}")

@@ -135,7 +135,7 @@ def trilinear_fwd_mask(vol, mask, src, tgt, raylen, C, n_points, alphamin, alpha
     return out
 
 
-def trilinear_packed(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8):
+def trilinear_packed(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8, slab=0):
     """Forward + pose-gradient backward through the packed-corner volume; returns (out, grads dict)."""
     vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
     gout = _f(gout)
@@ -144,5 +144,5 @@ def trilinear_packed(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, 
     lib().emu_trilinear_packed(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(out),
                                _p(g_src), _p(g_tgt), _p(g_len), _p(g_ar), ctypes.c_int(B), ctypes.c_long(N),
                                ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(n_points),
-                               ctypes.c_float(alphamin), ctypes.c_float(alphamax))
+                               ctypes.c_float(alphamin), ctypes.c_float(alphamax), ctypes.c_int(slab))
     return out, dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_alphamin=float(g_ar[0]), g_alphamax=float(g_ar[1]))

@@ -195,26 +195,35 @@ static std::vector<float4> pack_host(const float* vol, const VolDims& dims)
 
 void emu_trilinear_packed(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
                           const float* gout, float* out, float* g_src, float* g_tgt, float* g_raylen, float* g_alpha_range,
-                          int B, long N, float shift, float eps, int P, float amin, float amax)
+                          int B, long N, float shift, float eps, int P, float amin, float amax, int slab)
 {
     const VolDims dims = mk(D0, D1, D2);
     const std::vector<float4> packed = pack_host(vol, dims);
     const float step = (amax - amin) / (float)(P - 1);
     std::memset(g_src, 0, sizeof(float) * 3 * B);
+    const int n_slabs = slab > 0 ? (D0 + 1 + slab - 1) / slab : 1;
     double ga0 = 0, ga1 = 0;
     for (int b = 0; b < B; ++b)
         for (long n = 0; n < N; ++n) {
             const long r = (long)b * N + n;
             const Ray ray = load_ray(src, tgt, b, r, eps);
-            out[r] = trilinear_ray_fwd_packed(packed.data(), dims, ray, shift, P, amin, amax) * (raylen[r] * step);
-            const TriGrad tg = trilinear_ray_bwd_packed(packed.data(), dims, ray, shift, P, amin, amax, gout[r], raylen[r]);
-            for (int a = 0; a < 3; ++a) {
-                g_tgt[r * 3 + a] = tg.gt[a];
-                g_src[b * 3 + a] += tg.gs[a];
+            out[r] = 0.0f;
+            g_raylen[r] = 0.0f;
+            for (int a = 0; a < 3; ++a) g_tgt[r * 3 + a] = 0.0f;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const float s_lo = slab > 0 ? (float)(-1 + sl * slab) : -INFINITY;
+                const float s_hi = slab > 0 ? (float)(-1 + (sl + 1) * slab) : INFINITY;
+                out[r] += trilinear_ray_fwd_packed(packed.data(), dims, ray, shift, P, amin, amax, s_lo, s_hi) * (raylen[r] * step);
+                const TriGrad tg =
+                    trilinear_ray_bwd_packed(packed.data(), dims, ray, shift, P, amin, amax, gout[r], raylen[r], s_lo, s_hi);
+                for (int a = 0; a < 3; ++a) {
+                    g_tgt[r * 3 + a] += tg.gt[a];
+                    g_src[b * 3 + a] += tg.gs[a];
+                }
+                g_raylen[r] += gout[r] * step * tg.sumV;
+                ga0 += tg.ga0;
+                ga1 += tg.ga1;
             }
-            g_raylen[r] = gout[r] * step * tg.sumV;
-            ga0 += tg.ga0;
-            ga1 += tg.ga1;
         }
     g_alpha_range[0] = (float)ga0;
     g_alpha_range[1] = (float)ga1;

@@ -212,6 +212,14 @@ def test_trilinear_packed_corner_path():
     assert relerr(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 1e-5
     assert relerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-5
     drr.renderer.pack_corners = True
+    # batch >= 8 switches the forward to slab-major scheduling (partial sums combined with red.global.add)
+    rot8, xyz8 = synthetic.make_poses(9, seed=12)
+    with torch.no_grad():
+        slabbed = drr(rot8.to(DEV), xyz8.to(DEV), parameterization="euler_angles", convention="ZXY", n_points=180)
+        drr.renderer.pack_corners = False
+        plain = drr(rot8.to(DEV), xyz8.to(DEV), parameterization="euler_angles", convention="ZXY", n_points=180)
+        drr.renderer.pack_corners = True
+    assert relerr(slabbed.cpu().numpy(), plain.cpu().numpy()) < 5e-6
     with torch.no_grad():
         before = drr(rot0.to(DEV), xyz0.to(DEV), parameterization="euler_angles", convention="ZXY", n_points=180)
         drr.density.mul_(2.0)  # in-place update bumps the tensor version -> the packed copy is rebuilt

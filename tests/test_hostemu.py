@@ -189,3 +189,16 @@ def test_trilinear_packed_corner_path_is_bitwise_the_gather_path(name, kw):
     for key in ("g_target", "g_source", "g_raylen"):
         assert np.array_equal(ga[key], gb[key]), key
     assert ga["g_alphamin"] == gb["g_alphamin"] and ga["g_alphamax"] == gb["g_alphamax"]
+
+
+@pytest.mark.parametrize("slab", [1, 3, 7])
+def test_trilinear_packed_slab_cut_counts_every_sample_once(slab):
+    """The slab-major trilinear kernels cut the march by the base voxel along axis 0: partial sums must add up."""
+    g = load_golden("trilinear_nc_b4")
+    amin, amax = _amm(g, {})
+    a, ga = emu.trilinear_packed(g["volume"], g["source"], g["target"], g["raylen"], g["w"], 160, amin, amax)
+    b, gb = emu.trilinear_packed(g["volume"], g["source"], g["target"], g["raylen"], g["w"], 160, amin, amax, slab=slab)
+    assert relerr(b, a) < 2e-6
+    for key in ("g_target", "g_source", "g_raylen"):
+        assert relerr(gb[key], ga[key]) < 2e-5, key
+    assert abs(gb["g_alphamin"] - ga["g_alphamin"]) < 1e-4 * abs(ga["g_alphamin"])
