@@ -351,3 +351,63 @@ extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const
             }
     out[0] = steps; out[1] = visits; out[2] = sectors; out[3] = lines; out[4] = item_sectors;
 }
+
+
+// ---- tuning aid: per-lane 16-byte chunk reuse along the MAJOR axis (transposed copy with the major axis fastest) ------
+// For every warp-step counts the lanes that must load a new aligned 4-voxel chunk and the distinct 128-byte lines among
+// those loads.  out: [steps, lane-visits, chunk loads, sum over steps of distinct lines among loading lanes]
+extern "C" void emu_chunk_reuse(int D0, int D1, int D2, const float* src, const float* tgt, int B, int H, int W, int WX, int WY,
+                                int slab, float shift, float eps, int sample_every, double* out)
+{
+    double steps = 0, visits = 0, loads = 0, lines = 0;
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    long warp_id = 0;
+    for (int b = 0; b < B; ++b)
+        for (int ty = 0; ty + WY <= H; ty += WY)
+            for (int tx = 0; tx + WX <= W; tx += WX, ++warp_id) {
+                if (warp_id % sample_every) continue;
+                for (int sl = 0; sl < n_slabs; ++sl) {
+                    const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                    const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                    const int n = WX * WY;
+                    std::vector<Walk> w(n);
+                    std::vector<bool> live(n);
+                    std::vector<long> chunk(n, -1);
+                    std::vector<int> major(n);
+                    int alive = 0;
+                    for (int l = 0; l < n; ++l) {
+                        const long r = ((long)b * H + ty + l / WX) * W + tx + l % WX;
+                        const Ray ray = load_ray(src, tgt, b, r, eps);
+                        w[l] = start_walk_box(ray, lo_v, hi_v, shift);
+                        live[l] = w[l].hit;
+                        alive += live[l];
+                        const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
+                        major[l] = (a0 >= a1 && a0 >= a2) ? 0 : (a1 >= a2 ? 1 : 2);
+                    }
+                    const int dims[3] = {D0, D1, D2};
+                    while (alive > 0) {
+                        std::set<long> lin;
+                        for (int l = 0; l < n; ++l) {
+                            if (!live[l]) continue;
+                            const int m = major[l], u = (m + 1) % 3, v = (m + 2) % 3;
+                            // transposed copy: major axis fastest, then v, then u
+                            const long row = (long)w[l].idx[u] * dims[v] + w[l].idx[v];
+                            const long off = row * dims[m] + w[l].idx[m];
+                            visits += 1;
+                            if ((off >> 2) != chunk[l]) { chunk[l] = off >> 2; loads += 1; lin.insert(off >> 5); }
+                            const float anext = fminf(fminf(w[l].an[0], w[l].an[1]), w[l].an[2]);
+                            if (!(anext < w[l].a_out)) { live[l] = false; --alive; continue; }
+                            for (int a = 0; a < 3; ++a)
+                                if (w[l].an[a] == anext) {
+                                    w[l].idx[a] += w[l].sti[a];
+                                    w[l].nf[a] += 1.0f;
+                                    w[l].an[a] = fmaf(w[l].nf[a], w[l].da[a], w[l].a0[a]);
+                                }
+                        }
+                        steps += 1;
+                        lines += lin.size();
+                    }
+                }
+            }
+    out[0] = steps; out[1] = visits; out[2] = loads; out[3] = lines;
+}
