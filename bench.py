@@ -43,7 +43,8 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the default workload
 # (16 poses, 512^3 -> 256^2): profiles/r01_fwd_slab_B16_ncu_summary.txt and gpurun capture of the backward kernel.
 # Only quoted when the run uses that workload; otherwise null.
-NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9}
+NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9,
+                     "siddon_sens_slab_kernel": None}  # filled from the ncu capture of the fused kernel
 
 
 def parse():
@@ -224,20 +225,35 @@ def run_ours(args, rank, local_rank, world):
 
     stream = torch.cuda.current_stream()
 
+    sens = torch.empty(B, N, 8, device=dev)
+    sens_bytes = 4 * tot_visits + (16 + 4 + 32) * B * N      # voxels + (tgt, raylen) + out + 8 sensitivities per ray
+
     def kernel_step(ev=None):
+        """One training step at kernel level: image + per-ray sensitivities in ONE walk, then the elementwise backward."""
         if ev:
             ev[0].record(stream)
-        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, args.det,
-                                               args.det, 0.5, 1e-8, 0, _stream()), "siddon_fwd_grid")
+        _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
+                                                    _ptr(sens), B, args.det, args.det, 0.5, 1e-8, 0, _stream()),
+                   "siddon_fwd_sens_grid")
         if ev:
             ev[1].record(stream)
-        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src),
-                                               _ptr(g_tgt), _ptr(g_len), None, B, args.det, args.det, 0.5, 1e-8, 0, 0,
-                                               _stream()), "siddon_bwd_grid")
+        _lib.check(lib.b200drr_siddon_bwd_sens(_ptr(sens), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), B, N, 0,
+                                               _stream()), "siddon_bwd_sens")
         if ev:
             ev[2].record(stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)
+
+    def two_walk_step(ev):
+        """The inference forward and the backward WALK (still the path when the volume needs gradients), for the record."""
+        ev[0].record(stream)
+        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, args.det,
+                                               args.det, 0.5, 1e-8, 0, _stream()), "siddon_fwd_grid")
+        ev[1].record(stream)
+        _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src),
+                                               _ptr(g_tgt), _ptr(g_len), None, B, args.det, args.det, 0.5, 1e-8, 0, 0,
+                                               _stream()), "siddon_bwd_grid")
+        ev[2].record(stream)
 
     def barrier():
         if world > 1:
@@ -257,8 +273,15 @@ def run_ours(args, rank, local_rank, world):
         t_end.record(stream)
         barrier()
     ms_total = t_start.elapsed_time(t_end)
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
-    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    sens_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
+    sens_bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    # not part of `value`: the plain forward kernel (inference) and the backward walk, timed the same way
+    events2 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        two_walk_step(events2[k])
+    torch.cuda.synchronize()
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events2[1:] or events2]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events2[1:] or events2]))
 
     # ---- end-to-end leg through the public module, host buffers in and out -----------------------------
     img_h = torch.empty(B, 1, args.det, args.det).pin_memory()
@@ -346,10 +369,11 @@ def run_ours(args, rank, local_rank, world):
             e2e_mode = f"eager (graph capture failed: {type(exc).__name__})"
 
     # ---- max over ranks -------------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total, sens_ms, sens_bwd_ms], device=dev,
+                         dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total = (float(x) for x in stats.tolist())
+    ms_total, e2e_ms_total, fwd_ms, bwd_ms, e2e_eager_ms_total, sens_ms, sens_bwd_ms = (float(x) for x in stats.tolist())
     if rank != 0:
         return
 
@@ -359,7 +383,8 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = total_drr / (e2e_ms_total * 1e-3)
     fwd_gbs = fwd_bytes / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
-    dom = ("siddon_bwd_slab_kernel", bwd_gbs, bwd_bytes, bwd_ms) if bwd_ms >= fwd_ms else ("siddon_fwd_slab_kernel", fwd_gbs, fwd_bytes, fwd_ms)
+    sens_gbs = sens_bytes / (sens_ms * 1e-3) / 1e9
+    dom = ("siddon_sens_slab_kernel", sens_gbs, sens_bytes, sens_ms)  # >95 % of the step
     line = {
         "metric": METRIC, "value": value, "unit": "DRRs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -376,10 +401,13 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s", "frac": dom[1] / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if (B, D, args.det) == (16, VOL, DET) else None, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
+        "step_breakdown_ms": {"siddon_sens_slab_kernel (image + sensitivities, one walk)": sens_ms,
+                              "sens_bwd_kernel (elementwise backward)": sens_bwd_ms},
         "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
                          "algorithmic_bytes_per_launch": fwd_bytes, "drr_per_s_fwd_only": B / (fwd_ms * 1e-3)},
         "roofline_bwd": {"kernel": "siddon_bwd_slab_kernel", "achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms_per_launch": bwd_ms,
-                         "algorithmic_bytes_per_launch": bwd_bytes},
+                         "algorithmic_bytes_per_launch": bwd_bytes,
+                         "note": "two-walk backward; used when the volume needs gradients, not part of the timed step"},
         "clocks": clocks.summary(),
     }
     if not args.no_cpu_baseline and world == 1:

@@ -167,6 +167,47 @@ int b200drr_siddon_bwd_pose(const float* vol, int D0, int D1, int D2, const floa
                                       ws_len, B, H, W, voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_sens_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                                 const float* raylen, float* out, float* sens, int B, int H, int W, float voxel_shift,
+                                 float eps, int variant, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !sens || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 ||
+        W <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_sens_grid(vol, mk(D0, D1, D2), src, tgt, raylen, out, sens, B, H, W, voxel_shift, eps,
+                                           variant, (cudaStream_t)stream));
+}
+
+int b200drr_siddon_fwd_sens_pose(const float* vol, int D0, int D1, int D2, const float* src, const float* G, const float* Wd,
+                                 const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                 float voxel_shift, float eps, void* stream)
+{
+    if (!vol || !src || !G || !Wd || !rows || !cols || !out || !sens || bad_dims(D0, D1, D2) ||
+        bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_sens_pose(vol, mk(D0, D1, D2), src, G, Wd, rows, cols, out, sens, B, H, W, voxel_shift, eps,
+                                           (cudaStream_t)stream));
+}
+
+int b200drr_siddon_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen, int B,
+                            int64_t N, int stop_grad, void* stream)
+{
+    if (!sens || !gout || bad_rays(B, N)) return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_sens(sens, gout, g_src, g_tgt, g_raylen, B, N, stop_grad != 0, (cudaStream_t)stream));
+}
+
+int b200drr_siddon_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows, const float* cols,
+                                 float* g_src, float* g_G, float* g_Wd, int B, int H, int W, int stop_grad, void* stream)
+{
+    if (!sens || !gout || !Wd || !rows || !cols || !g_src || !g_G || !g_Wd || H <= 0 || W <= 0 ||
+        bad_rays(B, (int64_t)H * W))
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_sens_pose(sens, gout, Wd, rows, cols, g_src, g_G, g_Wd, B, H, W, stop_grad != 0,
+                                           (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
                             const float* tgt, const float* raylen, float* out, int B, int64_t N, int C, float voxel_shift,
                             float eps, void* stream)

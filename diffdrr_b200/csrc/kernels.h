@@ -49,6 +49,19 @@ cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* 
                                    float* g_Wd, float* g_vol, float* ws_tgt, float* ws_len, int B, int H, int W, float shift,
                                    float eps, int stop_grad, cudaStream_t stream);
 
+// forward with per-ray end-point sensitivities (sens: 8 floats per ray) and the backward that consumes them
+cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                        const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                        float eps, int variant, cudaStream_t stream);
+cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                        const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                        float shift, float eps, cudaStream_t stream);
+cudaError_t launch_siddon_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                   int B, int64_t N, int stop_grad, cudaStream_t stream);
+cudaError_t launch_siddon_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows,
+                                        const float* cols, float* g_src, float* g_G, float* g_Wd, int B, int H, int W,
+                                        int stop_grad, cudaStream_t stream);
+
 cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
                                    cudaStream_t stream);

@@ -496,6 +496,227 @@ cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward WITH per-ray sensitivities: one walk produces the line integral AND its derivative with respect to the
+// ray's own end points (forward-mode; each pixel depends on one ray only, so the whole Jacobian is 6 numbers per
+// ray).  The crossing coefficients A_a, C_a of the closed-form backward do not depend on the
+// incoming gradient, so they are accumulated here and the backward pass shrinks to an elementwise product with g:
+//   sens[r] = { dI/dt0, dI/dt1, dI/dt2, S = sum v*dalpha,  dI/ds0, dI/ds1, dI/ds2, 0 },   out[r] = L * S.
+// Same slab-major decomposition as siddon_bwd_slab_kernel; partial sums via red.global.add (zero-filled by the launcher).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int TW, int TH, int U, int MINB>
+__global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                  const float* __restrict__ src,
+                                                                  const float* __restrict__ tgt,
+                                                                  const float* __restrict__ raylen, float* __restrict__ out,
+                                                                  float* __restrict__ sens, int B, int H, int W, int slab,
+                                                                  float shift, float eps, PoseRays pr)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    float L;
+    const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    const float S = siddon_ray_bwd_lean_box<U, false>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift,
+                                                      0.0f, nullptr, A, C);
+    float jt[3], js[3];
+    bool any = S != 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float k = L * ray.inv[a];
+        jt[a] = -k * A[a];
+        js[a] = k * (A[a] - C[a]);
+        any = any || jt[a] != 0.0f || js[a] != 0.0f;
+    }
+    if (any) {  // rays that miss this slab (or see only zeros) add nothing
+        red_add4(sens + r * 8, jt[0], jt[1], jt[2], S);
+        red_add4(sens + r * 8 + 4, js[0], js[1], js[2], 0.0f);
+        red_add(out + r, L * S);
+    }
+}
+
+template <int TW, int TH, int U, int MINB>
+static cudaError_t launch_sens_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                            const float* raylen, float* out, float* sens, int B, int H, int W, int slab,
+                                            float shift, float eps, cudaStream_t stream,
+                                            PoseRays pr = PoseRays{nullptr, nullptr, nullptr, nullptr})
+{
+    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
+    if (blocks > INT32_MAX || (int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    const size_t n = (size_t)B * H * W;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 8 * n, stream);
+    if (e != cudaSuccess) return e;
+    siddon_sens_slab_kernel<TW, TH, U, MINB><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens, B,
+                                                                                    H, W, slab, shift, eps, pr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
+                                        const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                        float eps, int variant, cudaStream_t stream)
+{
+#define SV(id, TW, TH, U, SLAB, MINB)                                                                                   \
+    case id:                                                                                                             \
+        return launch_sens_slab_variant<TW, TH, U, MINB>(vol, dims, src, tgt, raylen, out, sens, B, H, W, SLAB, shift, eps, \
+                                                         stream);
+    switch (variant) {
+        SV(0, 16, 8, 4, 64, 8)
+        SV(1, 16, 8, 4, 32, 8)
+        SV(2, 16, 16, 4, 64, 4)
+        SV(3, 16, 16, 4, 32, 4)
+        SV(4, 16, 8, 2, 64, 8)
+        SV(5, 16, 8, 4, 64, 6)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SV
+}
+
+cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
+                                        const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                        float shift, float eps, cudaStream_t stream)
+{
+    return launch_sens_slab_variant<16, 8, 4, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, 64, shift, eps, stream,
+                                                 PoseRays{G, Wd, rows, cols});
+}
+
+// Backward from the saved sensitivities, arbitrary-ray layout: g_tgt = g * dI/dt, g_raylen = g * S, g_src = sum_n g * dI/ds.
+__global__ void __launch_bounds__(256) sens_bwd_kernel(const float4* __restrict__ sens, const float* __restrict__ gout,
+                                                       float* __restrict__ g_src, float* __restrict__ g_tgt,
+                                                       float* __restrict__ g_raylen, int64_t N, int stop_grad)
+{
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    float gs[3] = {0.0f, 0.0f, 0.0f};
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = (int64_t)b * N + n;
+        const float g = __ldg(gout + r);
+        const float4 t = __ldg(sens + r * 2), s = __ldg(sens + r * 2 + 1);
+        if (g_tgt) {
+            g_tgt[r * 3 + 0] = g * t.x;
+            g_tgt[r * 3 + 1] = g * t.y;
+            g_tgt[r * 3 + 2] = g * t.z;
+        }
+        if (g_raylen) g_raylen[r] = stop_grad ? 0.0f : g * t.w;
+        gs[0] = fmaf(g, s.x, gs[0]);
+        gs[1] = fmaf(g, s.y, gs[1]);
+        gs[2] = fmaf(g, s.z, gs[2]);
+    }
+    if (g_src) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tot = block_sum(gs[a], red);
+            if (threadIdx.x == 0) atomicAdd(g_src + b * 3 + a, tot);
+        }
+    }
+}
+
+cudaError_t launch_siddon_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                   int B, int64_t N, int stop_grad, cudaStream_t stream)
+{
+    if (g_src) {
+        const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int chunks = (int)min((int64_t)64, (N + 255) / 256);
+    sens_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const float4*)sens, gout, g_src, g_tgt, g_raylen,
+                                                                           N, stop_grad);
+    return cudaGetLastError();
+}
+
+// Backward from the saved sensitivities, pose-in layout: the chain rule through make_ray() as in
+// pose_grad_reduce_kernel, with g_tgt = g * dI/dt and g_raylen = g * S formed on the fly.
+__global__ void __launch_bounds__(256) sens_bwd_pose_kernel(const float4* __restrict__ sens, const float* __restrict__ gout,
+                                                            const float* __restrict__ Wd, const float* __restrict__ rows,
+                                                            const float* __restrict__ cols, float* __restrict__ g_src,
+                                                            float* __restrict__ g_G, float* __restrict__ g_Wd, int H, int W,
+                                                            int stop_grad)
+{
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    const int64_t N = (int64_t)H * W;
+    float acc[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acc[i] = 0.0f;
+    const float* wd = Wd + b * 12;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(n / W), w = (int)(n % W);
+        const float c = __ldg(cols + w), r = __ldg(rows + h);
+        const int64_t ray = (int64_t)b * N + n;
+        const float g = __ldg(gout + ray);
+        const float4 t = __ldg(sens + ray * 2), s = __ldg(sens + ray * 2 + 1);
+        float dl[3], l2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dl[a] = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), r, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+            l2 = fmaf(dl[a], dl[a], l2);
+        }
+        const float gl = stop_grad ? 0.0f : g * t.w * rsqrtf(fmaxf(l2, 1e-30f));
+        const float gt[3] = {g * t.x, g * t.y, g * t.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float u = gl * dl[a];
+            acc[a * 3 + 0] = fmaf(gt[a], c, acc[a * 3 + 0]);
+            acc[a * 3 + 1] = fmaf(gt[a], r, acc[a * 3 + 1]);
+            acc[a * 3 + 2] += gt[a];
+            acc[9 + a * 3 + 0] = fmaf(u, c, acc[9 + a * 3 + 0]);
+            acc[9 + a * 3 + 1] = fmaf(u, r, acc[9 + a * 3 + 1]);
+            acc[9 + a * 3 + 2] += u;
+        }
+        acc[18] = fmaf(g, s.x, acc[18]);
+        acc[19] = fmaf(g, s.y, acc[19]);
+        acc[20] = fmaf(g, s.z, acc[20]);
+    }
+#pragma unroll
+    for (int i = 0; i < 21; ++i) {
+        const float tot = block_sum(acc[i], red);
+        if (threadIdx.x == 0) {
+            if (i >= 18) {
+                atomicAdd(g_src + b * 3 + (i - 18), tot);
+            } else {
+                float* dst = (i < 9 ? g_G : g_Wd) + b * 12;
+                const int a = (i % 9) / 3, k = i % 3;
+                atomicAdd(dst + a * 4 + k, tot);
+                if (k == 2) atomicAdd(dst + a * 4 + 3, tot);  // the homogeneous 1 multiplies column 3 as well
+            }
+        }
+    }
+}
+
+cudaError_t launch_siddon_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows,
+                                        const float* cols, float* g_src, float* g_G, float* g_Wd, int B, int H, int W,
+                                        int stop_grad, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_G, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_Wd, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e != cudaSuccess) return e;
+    const int chunks = (int)min((int64_t)64, ((int64_t)H * W + 255) / 256);
+    sens_bwd_pose_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const float4*)sens, gout, Wd, rows, cols,
+                                                                                g_src, g_G, g_Wd, H, W, stop_grad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int H, int W, float shift, float eps,
                                    int variant, cudaStream_t stream)

@@ -51,6 +51,17 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Training-step fast path: when only the ray end points need gradients, the forward walk also accumulates the per-ray
+# sensitivities and the backward pass is elementwise (one walk per step instead of two).  Module-level switch for A/B tests.
+_FUSED_SENSITIVITIES = True
+
+
+def _wants_sens(needs_input_grad, stop_grad) -> bool:
+    """inputs 1..3 are the ray-defining tensors; input 0 is the volume (its gradient needs the backward walk)."""
+    need_vol = needs_input_grad[0] and not stop_grad
+    return any(needs_input_grad[1:4]) and not need_vol
+
+
 class _SiddonFunction(torch.autograd.Function):
     """out (B,1,N) = Siddon line integrals; backward = closed-form kernel (include/b200drr.h)."""
 
@@ -66,8 +77,17 @@ class _SiddonFunction(torch.autograd.Function):
         if grid is not None and (grid[0] * grid[1] != N or reduce != 0 or align_corners or vol.numel() >= 2**31 - 1):
             grid = None
         lib = _lib.load()
+        # Ray gradients wanted and no volume gradient: ONE walk yields the image and the 6 per-ray sensitivities, and the
+        # backward is elementwise (include/b200drr.h: b200drr_siddon_fwd_sens_grid / _bwd_sens).
+        sens = None
+        if grid is not None and _FUSED_SENSITIVITIES and _wants_sens(ctx.needs_input_grad, stop_grad):
+            sens = torch.empty(B, N, 8, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
-            if grid is not None:
+            if sens is not None:
+                _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                            _ptr(out), _ptr(sens), B, grid[0], grid[1], voxel_shift, eps, 0,
+                                                            _stream()), "b200drr_siddon_fwd_sens_grid")
+            elif grid is not None:
                 _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
                                                        B, grid[0], grid[1], voxel_shift, eps, 0, _stream()),
                            "b200drr_siddon_fwd_grid")
@@ -75,14 +95,31 @@ class _SiddonFunction(torch.autograd.Function):
                 _lib.check(lib.b200drr_siddon_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B,
                                                   N, voxel_shift, eps, reduce, int(align_corners), _stream()),
                            "b200drr_siddon_fwd")
-        ctx.save_for_backward(vol, src, tgt, raylen)
+        if sens is not None:
+            ctx.save_for_backward(sens)
+        else:
+            ctx.save_for_backward(vol, src, tgt, raylen)
+        ctx.fused = sens is not None
         ctx.cfg = (voxel_shift, eps, reduce, align_corners, stop_grad, tuple(source.shape), tuple(img.shape), grid)
         return out.view(B, 1, N)
 
     @staticmethod
     def backward(ctx, gout):
-        vol, src, tgt, raylen = ctx.saved_tensors
         voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape, grid = ctx.cfg
+        if ctx.fused:
+            (sens,) = ctx.saved_tensors
+            B, N = sens.shape[0], sens.shape[1]
+            _, need_src, need_tgt, need_len = ctx.needs_input_grad[:4]
+            gout = gout.reshape(B, N).contiguous().float()
+            g_src = torch.empty(B, 3, dtype=torch.float32, device=sens.device) if need_src else None
+            g_tgt = torch.empty(B, N, 3, dtype=torch.float32, device=sens.device) if need_tgt else None
+            g_len = torch.empty(B, N, dtype=torch.float32, device=sens.device) if (need_len and not stop_grad) else None
+            with torch.cuda.device(sens.device):
+                _lib.check(_lib.load().b200drr_siddon_bwd_sens(_ptr(sens), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len),
+                                                               B, N, int(stop_grad), _stream()), "b200drr_siddon_bwd_sens")
+            return (None, None if g_src is None else g_src.view(src_shape), g_tgt,
+                    None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
+        vol, src, tgt, raylen = ctx.saved_tensors
         if reduce != 0:
             raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
         if align_corners:
@@ -121,18 +158,40 @@ class _SiddonPoseFunction(torch.autograd.Function):
         src, G, Wd = src.contiguous().float(), G.contiguous().float(), Wd.contiguous().float()
         rows, cols = rows.contiguous().float(), cols.contiguous().float()
         out = torch.empty(B, H * W, dtype=torch.float32, device=vol.device)
+        ctx.fused = _FUSED_SENSITIVITIES and _wants_sens(ctx.needs_input_grad, stop_grad)
+        ctx.cfg = (voxel_shift, eps, stop_grad)
         with torch.cuda.device(vol.device):
+            if ctx.fused:  # one walk: image + per-ray sensitivities; backward is elementwise
+                sens = torch.empty(B, H * W, 8, dtype=torch.float32, device=vol.device)
+                _lib.check(_lib.load().b200drr_siddon_fwd_sens_pose(_ptr(vol), *vol.shape, _ptr(src), _ptr(G), _ptr(Wd),
+                                                                    _ptr(rows), _ptr(cols), _ptr(out), _ptr(sens), B, H, W,
+                                                                    voxel_shift, eps, _stream()),
+                           "b200drr_siddon_fwd_sens_pose")
+                ctx.save_for_backward(sens, Wd, rows, cols)
+                return out.view(B, 1, H * W)
             _lib.check(_lib.load().b200drr_siddon_fwd_pose(_ptr(vol), *vol.shape, _ptr(src), _ptr(G), _ptr(Wd), _ptr(rows),
                                                            _ptr(cols), _ptr(out), B, H, W, voxel_shift, eps, _stream()),
                        "b200drr_siddon_fwd_pose")
         ctx.save_for_backward(vol, src, G, Wd, rows, cols)
-        ctx.cfg = (voxel_shift, eps, stop_grad)
         return out.view(B, 1, H * W)
 
     @staticmethod
     def backward(ctx, gout):
-        vol, src, G, Wd, rows, cols = ctx.saved_tensors
         voxel_shift, eps, stop_grad = ctx.cfg
+        if ctx.fused:
+            sens, Wd, rows, cols = ctx.saved_tensors
+            B, H, W = Wd.shape[0], rows.numel(), cols.numel()
+            dev = sens.device
+            gout = gout.reshape(B, H * W).contiguous().float()
+            g_src = torch.empty(B, 3, dtype=torch.float32, device=dev)
+            g_G = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+            g_Wd = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().b200drr_siddon_bwd_sens_pose(_ptr(sens), _ptr(gout), _ptr(Wd), _ptr(rows), _ptr(cols),
+                                                                    _ptr(g_src), _ptr(g_G), _ptr(g_Wd), B, H, W,
+                                                                    int(stop_grad), _stream()), "b200drr_siddon_bwd_sens_pose")
+            return None, g_src, g_G, g_Wd, None, None, None, None, None
+        vol, src, G, Wd, rows, cols = ctx.saved_tensors
         B, H, W = G.shape[0], rows.numel(), cols.numel()
         dev = vol.device
         gout = gout.reshape(B, H * W).contiguous().float()

@@ -112,6 +112,33 @@ int b200drr_siddon_bwd_pose(const float *vol, int D0, int D1, int D2, const floa
                             float voxel_shift, float eps, int stop_grad, void *stream);
 
 /*
+ * Siddon forward WITH per-ray sensitivities (the training-step fast path).  Every pixel depends on ONE ray, so the whole
+ * Jacobian of Siddon.forward (renderers.py:40-86) w.r.t. the ray end points is 6 numbers per ray, and the crossing
+ * coefficients of the closed-form backward do not depend on the incoming gradient: ONE walk yields
+ *   out  [B][H*W]     the same line integrals as b200drr_siddon_fwd_grid
+ *   sens [B][H*W][8]  { dI/dtgt0, dI/dtgt1, dI/dtgt2, S = out/raylen, dI/dsrc0, dI/dsrc1, dI/dsrc2, 0 }
+ * and autograd's backward (what torch derives for renderers.py:40-86 given g = dLoss/dout) is the elementwise
+ * b200drr_siddon_bwd_sens below.  Replaces a forward walk + a backward walk by one.  No volume gradient on this path
+ * (use b200drr_siddon_bwd_grid when the volume requires grad).  variant 0 = tuned default.
+ */
+int b200drr_siddon_fwd_sens_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                                 const float *raylen, float *out, float *sens, int B, int H, int W, float voxel_shift,
+                                 float eps, int variant, void *stream);
+
+/* g_tgt [B][N][3] = g * dI/dtgt, g_raylen [B][N] = g * S (0 when stop_grad), g_src [B][3] = sum_n g * dI/dsrc;
+ * any of the three may be NULL. */
+int b200drr_siddon_bwd_sens(const float *sens, const float *gout, float *g_src, float *g_tgt, float *g_raylen, int B,
+                            int64_t N, int stop_grad, void *stream);
+
+/* Pose-in forms (rays generated in-kernel as in b200drr_siddon_fwd_pose; gradients reduced to the 3x4 matrices). */
+int b200drr_siddon_fwd_sens_pose(const float *vol, int D0, int D1, int D2, const float *src, const float *G,
+                                 const float *Wd, const float *rows, const float *cols, float *out, float *sens, int B,
+                                 int H, int W, float voxel_shift, float eps, void *stream);
+int b200drr_siddon_bwd_sens_pose(const float *sens, const float *gout, const float *Wd, const float *rows,
+                                 const float *cols, float *g_src, float *g_G, float *g_Wd, int B, int H, int W,
+                                 int stop_grad, void *stream);
+
+/*
  * Trilinear forward: replaces Trilinear.forward with mask=None (renderers.py:205-240) for a given
  * sampling range.  alpha_range is a DEVICE pointer to {alphamin, alphamax} (so that the range computed
  * on the device by _get_alpha_minmax, renderers.py:124-140,221-223, needs no host round trip).

@@ -353,6 +353,81 @@ extern "C" void emu_warp_sectors(int D0, int D1, int D2, const float* src, const
 }
 
 
+// ---- tuning aid: the lean walk with the lanes of a warp re-synchronised every K planes of the (common) major axis ----
+// K = 1 reproduces the request pattern of the plane-synchronous walk (1..3 requests per plane: all lanes, then the
+// lanes with one minor crossing, then those with two).  out: [steps, lane-visits, sectors, lines]
+extern "C" void emu_warp_sectors_sync(int D0, int D1, int D2, const float* src, const float* tgt, int B, int H, int W,
+                                      int WX, int WY, int slab, int K, float shift, float eps, int sample_every, double* out)
+{
+    double steps = 0, visits = 0, sectors = 0, lines = 0;
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    const long st0 = (long)D1 * D2, st1 = D2;
+    long warp_id = 0;
+    for (int b = 0; b < B; ++b)
+        for (int ty = 0; ty + WY <= H; ty += WY)
+            for (int tx = 0; tx + WX <= W; tx += WX, ++warp_id) {
+                if (warp_id % sample_every) continue;
+                for (int sl = 0; sl < n_slabs; ++sl) {
+                    const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                    const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                    const int n = WX * WY;
+                    std::vector<Walk> w(n);
+                    std::vector<bool> live(n);
+                    std::vector<int> major(n);
+                    int alive = 0;
+                    for (int l = 0; l < n; ++l) {
+                        const long r = ((long)b * H + ty + l / WX) * W + tx + l % WX;
+                        const Ray ray = load_ray(src, tgt, b, r, eps);
+                        w[l] = start_walk_box(ray, lo_v, hi_v, shift);
+                        live[l] = w[l].hit;
+                        alive += live[l];
+                        const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
+                        major[l] = (a0 >= a1 && a0 >= a2) ? 0 : (a1 >= a2 ? 1 : 2);
+                    }
+                    while (alive > 0) {
+                        // the chunk the warp is working on = that of the most lagging live lane
+                        int m = -1, dir = 0;
+                        bool uniform = K > 0;
+                        for (int l = 0; l < n && uniform; ++l) {
+                            if (!live[l]) continue;
+                            if (m < 0) { m = major[l]; dir = w[l].sti[m]; }
+                            else if (major[l] != m || w[l].sti[m] != dir) uniform = false;
+                        }
+                        int target = 0;
+                        if (uniform) {
+                            bool first = true;
+                            for (int l = 0; l < n; ++l) {
+                                if (!live[l]) continue;
+                                const int c = w[l].idx[m] / K;
+                                if (first || (dir > 0 ? c < target : c > target)) { target = c; first = false; }
+                            }
+                        }
+                        std::set<long> sec, lin;
+                        for (int l = 0; l < n; ++l) {
+                            if (!live[l]) continue;
+                            if (uniform && w[l].idx[m] / K != target) continue;  // waits for the others
+                            const long off = w[l].idx[0] * st0 + w[l].idx[1] * st1 + w[l].idx[2];
+                            sec.insert(off >> 3);
+                            lin.insert(off >> 5);
+                            visits += 1;
+                            const float anext = fminf(fminf(w[l].an[0], w[l].an[1]), w[l].an[2]);
+                            if (!(anext < w[l].a_out)) { live[l] = false; --alive; continue; }
+                            for (int a = 0; a < 3; ++a)
+                                if (w[l].an[a] == anext) {
+                                    w[l].idx[a] += w[l].sti[a];
+                                    w[l].nf[a] += 1.0f;
+                                    w[l].an[a] = fmaf(w[l].nf[a], w[l].da[a], w[l].a0[a]);
+                                }
+                        }
+                        steps += 1;
+                        sectors += sec.size();
+                        lines += lin.size();
+                    }
+                }
+            }
+    out[0] = steps; out[1] = visits; out[2] = sectors; out[3] = lines;
+}
+
 // ---- tuning aid: per-lane 16-byte chunk reuse along the MAJOR axis (transposed copy with the major axis fastest) ------
 // For every warp-step counts the lanes that must load a new aligned 4-voxel chunk and the distinct 128-byte lines among
 // those loads.  out: [steps, lane-visits, chunk loads, sum over steps of distinct lines among loading lanes]

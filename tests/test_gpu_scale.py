@@ -232,3 +232,48 @@ def test_trilinear_packed_corner_path():
     out = drr.render(dens, src, tgt, n_points=60)
     out.sum().backward()
     assert dens.grad is not None and float(dens.grad.abs().sum()) > 0
+
+
+def test_fused_sensitivities_match_two_walk_backward():
+    """Training-step fast path (one walk: image + per-ray sensitivities, elementwise backward) against the two-walk
+    path (forward kernel + backward walk) it replaces: images, pose gradients, ray-tensor gradients, stop-gradient flag;
+    and a volume that requires grad must still get its gradient (two-walk path)."""
+    from diffdrr_b200 import DRR, Siddon, renderers, synthetic
+    from diffdrr_b200.pose import convert
+    vol = synthetic.make_volume((112, 128, 96), "smooth", seed=13)
+    rot0, xyz0 = synthetic.make_poses(3, seed=8)
+    w = torch.rand(3, 1, 88, 72, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    for stop in (False, True):
+        drr = DRR(synthetic.make_subject(vol), sdd=1020.0, height=88, width=72, delx=2.5, dely=3.0, x0=5.0,
+                  stop_gradients_through_grid_sample=stop).to(DEV)
+        res = []
+        for fused in (True, False):
+            renderers._FUSED_SENSITIVITIES = fused
+            try:
+                rot, xyz = rot0.to(DEV).requires_grad_(True), xyz0.to(DEV).requires_grad_(True)
+                img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY")     # pose-in kernels
+                (img * w).sum().backward()
+                src, tgt = drr.detector(convert(rot0.to(DEV), xyz0.to(DEV), parameterization="euler_angles",
+                                                convention="ZXY"), None)
+                s, t_ = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+                img2 = drr.render(drr.density, s, t_)                                           # detector-grid kernels
+                (img2.view(3, 1, 88, 72) * w).sum().backward()
+                res.append((img.detach(), rot.grad, xyz.grad, img2.detach(), s.grad, t_.grad))
+            finally:
+                renderers._FUSED_SENSITIVITIES = True
+        for a, b, tol in zip(res[0], res[1], (2e-6, 2e-5, 2e-5, 2e-6, 2e-5, 2e-5)):
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < tol
+    # volume gradient requested -> backward walk; pose gradients identical to the fused ones
+    sid = Siddon()
+    sid.detector_shape = (88, 72)
+    aff = drr.affine_inverse
+    raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+    sv, tv = aff(src).detach(), aff(tgt).detach()
+    outs = []
+    for need_vol in (False, True):
+        v = drr.density.clone().requires_grad_(need_vol)
+        t_ = tv.clone().requires_grad_(True)
+        (sid(v, sv, t_, raylen).view(3, 1, 88, 72) * w).sum().backward()
+        outs.append(t_.grad)
+        assert (v.grad is not None) == need_vol
+    assert relerr(outs[0].cpu().numpy(), outs[1].cpu().numpy()) < 2e-5
