@@ -579,6 +579,174 @@ B200_HD void axis_accumulate(int ax, float coef, float alpha, float& A0, float& 
 #endif
 }
 
+// ---- two-axis bookkeeping for the sensitivities walk ---------------------------------------------------------------
+// Over one box the crossing coefficients telescope:  sum_a C_a = 0  and  sum_a A_a = sum_j v_j len_j  (Abel summation,
+// box faces counted against 0).  So only TWO axes need per-crossing accumulation; the third follows from the totals.
+// The derived axis is the ray's MAJOR axis M (most crossings -> most work saved; and its gradient is divided by the
+// largest |d|, so the subtraction costs no accuracy).  LOCAL axis index: 0 = first minor axis, 1 = second, 2 = neither.
+template <int M>
+struct MinorAxes {
+    static constexpr int U = M == 0 ? 1 : 0;
+    static constexpr int V = M == 2 ? 1 : 2;
+    B200_HD static int local(int axis) { return axis == U ? 0 : (axis == V ? 1 : 2); }
+};
+
+// lean_step_ax with the crossing reported as a LOCAL index of MinorAxes<M>; same sequential tie order (lowest axis
+// first).  If the minimum is below the exit alpha and neither axis 0 nor axis 1 attains it, axis 2 does -- no third compare.
+#define B200_LEAN_STEP_UV_ASM(PV, PU)                                                                                  \
+    asm("{\n\t"                                                                                                    \
+        ".reg .pred q, p0, p1, p2;\n\t"                                                                             \
+        ".reg .f32 nx;\n\t"                                                                                         \
+        "min.f32 nx, %0, %1, %2;\n\t"                                                                               \
+        "sub.f32 %8, nx, %6;\n\t"                                                                                   \
+        "mov.f32 %6, nx;\n\t"                                                                                       \
+        "setp.lt.f32 q, nx, %10;\n\t"                                                                               \
+        "setp.eq.and.f32 p0, %0, nx, q;\n\t"                                                                        \
+        "setp.eq.and.f32 p1, %1, nx, q;\n\t"                                                                        \
+        "and.pred p1, p1, !p0;\n\t"                                                                                 \
+        "or.pred p2, p0, p1;\n\t"                                                                                   \
+        "and.pred p2, q, !p2;\n\t"                                                                                  \
+        "selp.s32 %9, 1, 2, " PV ";\n\t"                                                                            \
+        "selp.s32 %9, 0, %9, " PU ";\n\t"                                                                           \
+        "@p0 add.f32 %3, %3, 0f3F800000;\n\t"                                                                       \
+        "@p1 add.f32 %4, %4, 0f3F800000;\n\t"                                                                       \
+        "@p2 add.f32 %5, %5, 0f3F800000;\n\t"                                                                       \
+        "@p0 fma.rn.f32 %0, %3, %11, %14;\n\t"                                                                      \
+        "@p1 fma.rn.f32 %1, %4, %12, %15;\n\t"                                                                      \
+        "@p2 fma.rn.f32 %2, %5, %13, %16;\n\t"                                                                      \
+        "@p0 add.s32 %7, %7, %17;\n\t"                                                                              \
+        "@p1 add.s32 %7, %7, %18;\n\t"                                                                              \
+        "@p2 add.s32 %7, %7, %19;\n\t"                                                                              \
+        "}"                                                                                                         \
+        : "+f"(s.an0), "+f"(s.an1), "+f"(s.an2), "+f"(s.nf0), "+f"(s.nf1), "+f"(s.nf2), "+f"(s.acur), "+r"(s.off),  \
+          "=f"(len), "=r"(ax)                                                                                       \
+        : "f"(k.a_out), "f"(k.da0), "f"(k.da1), "f"(k.da2), "f"(k.a00), "f"(k.a01), "f"(k.a02), "r"(k.so0),         \
+          "r"(k.so1), "r"(k.so2))
+
+template <int M>
+B200_HD float lean_step_uv(LeanState& s, const LeanConst& k, int& ax)
+{
+    float len;
+#if defined(__CUDA_ARCH__)
+    if (M == 0) B200_LEAN_STEP_UV_ASM("p2", "p1");       // minor axes (1, 2)
+    else if (M == 1) B200_LEAN_STEP_UV_ASM("p2", "p0");  // minor axes (0, 2)
+    else B200_LEAN_STEP_UV_ASM("p1", "p0");              // minor axes (0, 1)
+#else
+    int axis;
+    len = lean_step_ax(s, k, axis);
+    ax = MinorAxes<M>::local(axis);
+#endif
+    return len;
+}
+
+// Au += coef*alpha, Cu += coef for LOCAL index 0; (Av, Cv) for 1; nothing for 2.
+B200_HD void minor_accumulate(int ax, float coef, float alpha, float& Au, float& Av, float& Cu, float& Cv)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred q0, q1;\n\t"
+        "setp.eq.s32 q0, %4, 0;\n\t"
+        "setp.eq.s32 q1, %4, 1;\n\t"
+        "@q0 fma.rn.f32 %0, %5, %6, %0;\n\t"
+        "@q1 fma.rn.f32 %1, %5, %6, %1;\n\t"
+        "@q0 add.f32 %2, %2, %5;\n\t"
+        "@q1 add.f32 %3, %3, %5;\n\t"
+        "}"
+        : "+f"(Au), "+f"(Av), "+f"(Cu), "+f"(Cv)
+        : "r"(ax), "f"(coef), "f"(alpha));
+#else
+    if (ax == 0) { Au = fmaf(coef, alpha, Au); Cu += coef; }
+    if (ax == 1) { Av = fmaf(coef, alpha, Av); Cv += coef; }
+#endif
+}
+
+// The sensitivities walk of one ray restricted to a box, for a ray whose major axis is M: same walk, tie order and
+// tail as siddon_ray_bwd_lean_box, two accumulated axes + the telescoping identities.  A, C accumulated INTO.
+template <int U, int M>
+B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
+                                    int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
+{
+    using Ax = MinorAxes<M>;
+    const Walk w = start_walk_frame(ray, dims, lo_v, hi_v, shift);
+    if (!w.hit) return 0.0f;
+    LeanConst k;
+    LeanState s;
+    lean_init(w, st0, st1, st2, s, k);
+    float Au = 0.0f, Av = 0.0f, Cu = 0.0f, Cv = 0.0f;
+    float acc = 0.0f, vprev = 0.0f, aprev = w.a_in;
+    int axprev = Ax::local(w.entry_axis);
+    const bool any = s.acur < k.a_out;  // false: the box is only touched (a_in == a_out)
+    while (s.acur < k.a_out) {
+        float aend[U], v[U];
+        int offs[U], ax[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            offs[j] = s.off;
+            (void)lean_step_uv<M>(s, k, ax[j]);
+            aend[j] = s.acur;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = ldg(vol + offs[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            // crossing (axprev, aprev) led into voxel j; padding steps after the exit carry local index 2 and length 0.
+            // The segment length is re-formed from the two alphas (same subtraction the step did) instead of being kept
+            // in a register across the loads: U fewer live registers.
+            minor_accumulate(axprev, vprev - v[j], aprev, Au, Av, Cu, Cv);
+            acc = fmaf(aend[j] - aprev, v[j], acc);
+            vprev = v[j];
+            axprev = ax[j];
+            aprev = aend[j];
+        }
+    }
+    if (!any) {
+        const float v0 = ldg(vol + s.off);
+        minor_accumulate(Ax::local(w.entry_axis), -v0, w.a_in, Au, Av, Cu, Cv);
+        vprev = v0;
+    }
+    // Tail: identical to siddon_ray_bwd_lean_box (ties with the exit alpha, lowest axis first)
+    int ax_exit = 3;
+    {
+        const bool t0 = s.an0 <= k.a_out, t1 = s.an1 <= k.a_out, t2 = s.an2 <= k.a_out;
+        const bool b0 = s.nf0 == w.nx[0], b1 = s.nf1 == w.nx[1], b2 = s.nf2 == w.nx[2];
+        if (t0 && b0) ax_exit = 0;
+        if (ax_exit == 3 && t0) {
+            s.off += k.so0;
+            const float vm = ldg(vol + s.off);
+            minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+            vprev = vm;
+        }
+        if (ax_exit == 3 && t1 && b1) ax_exit = 1;
+        if (ax_exit == 3 && t1) {
+            s.off += k.so1;
+            const float vm = ldg(vol + s.off);
+            minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+            vprev = vm;
+        }
+        if (ax_exit == 3 && t2 && b2) ax_exit = 2;
+        if (ax_exit == 3) ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
+    }
+    minor_accumulate(Ax::local(ax_exit), vprev, k.a_out, Au, Av, Cu, Cv);
+    A[Ax::U] += Au;
+    A[Ax::V] += Av;
+    A[M] += acc - Au - Av;  // sum_a A_a = sum_j v_j len_j over the box
+    C[Ax::U] += Cu;
+    C[Ax::V] += Cv;
+    C[M] -= Cu + Cv;        // sum_a C_a = 0 over the box
+    return acc;
+}
+
+// Dispatch on the ray's major axis (uniform per warp except for rays near a 45-degree direction).
+template <int U>
+B200_HD float siddon_ray_sens_box(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
+                                  int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
+{
+    const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
+    if (a0 >= a1 && a0 >= a2) return siddon_ray_sens_box_m<U, 0>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    if (a1 >= a2) return siddon_ray_sens_box_m<U, 1>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    return siddon_ray_sens_box_m<U, 2>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+}
+
 // Backward of one ray restricted to the sub-box [lo, hi) (closed form, see siddon_ray_bwd below for the algebra).
 // Crossing m between voxel values (before, after) on axis a at alpha contributes coef = before - after to
 //   A_a += coef * alpha,  C_a += coef;  box faces count as crossings against 0, which telescopes correctly when a

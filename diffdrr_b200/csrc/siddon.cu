@@ -536,8 +536,7 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const fl
     const int lo_v[3] = {sl * slab, 0, 0};
     const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
     float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
-    const float S = siddon_ray_bwd_lean_box<U, false>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift,
-                                                      0.0f, nullptr, A, C);
+    const float S = siddon_ray_sens_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
     float jt[3], js[3];
     bool any = S != 0.0f;
 #pragma unroll
@@ -581,12 +580,28 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
         return launch_sens_slab_variant<TW, TH, U, MINB>(vol, dims, src, tgt, raylen, out, sens, B, H, W, SLAB, shift, eps, \
                                                          stream);
     switch (variant) {
-        SV(0, 16, 8, 4, 64, 8)
+        SV(0, 16, 8, 8, 48, 8)  // tuned default (profiles/r01_tune_sens.log)
+        SV(22, 16, 8, 4, 64, 8)
         SV(1, 16, 8, 4, 32, 8)
         SV(2, 16, 16, 4, 64, 4)
         SV(3, 16, 16, 4, 32, 4)
         SV(4, 16, 8, 2, 64, 8)
         SV(5, 16, 8, 4, 64, 6)
+        SV(6, 16, 16, 4, 128, 4)
+        SV(7, 16, 8, 4, 128, 8)
+        SV(8, 16, 8, 6, 64, 6)
+        SV(9, 16, 8, 8, 64, 4)
+        SV(10, 8, 8, 4, 64, 16)
+        SV(11, 16, 16, 2, 64, 4)
+        SV(12, 16, 8, 4, 64, 10)
+        SV(13, 16, 8, 8, 32, 4)
+        SV(14, 16, 8, 8, 32, 8)
+        SV(15, 16, 8, 6, 32, 8)
+        SV(16, 16, 8, 8, 16, 8)
+        SV(17, 16, 16, 8, 32, 4)
+        SV(18, 16, 8, 12, 32, 4)
+        SV(20, 16, 16, 8, 32, 3)
+        SV(21, 8, 8, 8, 32, 16)
         default: return cudaErrorInvalidValue;
     }
 #undef SV
@@ -596,7 +611,7 @@ cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const fl
                                         const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
                                         float shift, float eps, cudaStream_t stream)
 {
-    return launch_sens_slab_variant<16, 8, 4, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, 64, shift, eps, stream,
+    return launch_sens_slab_variant<16, 8, 8, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, 48, shift, eps, stream,
                                                  PoseRays{G, Wd, rows, cols});
 }
 

@@ -61,6 +61,28 @@ for v in variants:
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"grid variant {v:2d}       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")
 
+# ---- forward + sensitivities (training-step fast path) variants ----------------------------------------------------
+if os.environ.get("SVARIANTS"):
+    gout_s = torch.rand(B, N, device=dev)
+    g_src0, g_tgt0, g_len0 = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
+    _lib.check(lib.b200drr_siddon_bwd(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout_s), _ptr(g_src0), _ptr(g_tgt0), _ptr(g_len0), None, B, N, 0.5, 1e-8, 0, 0, _stream()), "bwd")
+    sbytes = (4 * visits + 52 * B * N) / 1e9
+    for v in [int(x) for x in os.environ["SVARIANTS"].split(",")]:
+        out, sens = torch.empty(B, N, device=dev), torch.empty(B, N, 8, device=dev)
+        g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
+        def run():
+            _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), D, D1, D2, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), _ptr(sens), B, H, H, 0.5, 1e-8, v, _stream()), "sens")
+        try:
+            ms = timeit(run)
+        except Exception as e:
+            print(f"sens variant {v}: {e}")
+            continue
+        _lib.check(lib.b200drr_siddon_bwd_sens(_ptr(sens), _ptr(gout_s), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), B, N, 0, _stream()), "bwd_sens")
+        e = [float((a - b).abs().max() / b.abs().max()) for a, b in ((out, ref), (g_src, g_src0), (g_tgt, g_tgt0), (g_len, g_len0))]
+        print(f"sens variant {v:2d}       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {sbytes / ms * 1e3:8.1f} GB/s  {sbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff img/src/tgt/len {e[0]:.1e} {e[1]:.1e} {e[2]:.1e} {e[3]:.1e}")
+    if os.environ.get("SENS_ONLY"):
+        sys.exit(0)
+
 # ---- backward variants ----------------------------------------------------------------------------------------
 gout = torch.rand(B, N, device=dev)
 g_src0, g_tgt0, g_len0 = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)

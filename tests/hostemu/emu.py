@@ -88,6 +88,18 @@ def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad
     return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
 
 
+def siddon_sens(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, slab=0):
+    """Fused forward + sensitivities + elementwise backward (the training-step fast path)."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    gout = _f(gout)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, out = np.zeros((B, 1, N), np.float32), np.zeros((B, 1, N), np.float32)
+    lib().emu_siddon_sens(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
+                          _p(g_tgt), _p(g_len), _p(out), ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift),
+                          ctypes.c_float(eps), ctypes.c_int(bool(stop_grad)), ctypes.c_int(slab))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, img=out)
+
+
 def trilinear_fwd(vol, src, tgt, raylen, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8, reduce="sum",
                   align_corners=False):
     vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)

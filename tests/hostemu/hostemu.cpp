@@ -143,6 +143,43 @@ void emu_siddon_bwd_lean(const float* vol, int D0, int D1, int D2, const float* 
         }
 }
 
+// The training-step fast path: per-ray sensitivities from the two-axis walk (ray_math.cuh: siddon_ray_sens_box), then the
+// elementwise backward exactly as sens_bwd_kernel forms it.  slab <= 0: whole volume.
+void emu_siddon_sens(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                     const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* out, int B, long N, float shift,
+                     float eps, int stop_grad, int slab)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            const float L = raylen[r];
+            float sens[8] = {0, 0, 0, 0, 0, 0, 0, 0}, img = 0;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                float A[3] = {0, 0, 0}, C[3] = {0, 0, 0};
+                const float S = siddon_ray_sens_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C);
+                for (int a = 0; a < 3; ++a) {
+                    const float k = L * ray.inv[a];
+                    sens[a] += -k * A[a];
+                    sens[4 + a] += k * (A[a] - C[a]);
+                }
+                sens[3] += S;
+                img += L * S;
+            }
+            out[r] = img;
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = gout[r] * sens[a];
+                g_src[b * 3 + a] += gout[r] * sens[4 + a];
+            }
+            g_raylen[r] = stop_grad ? 0.0f : gout[r] * sens[3];
+        }
+}
+
 void emu_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
                          const float* raylen, float* out, int B, long N, int C, float shift, float eps)
 {

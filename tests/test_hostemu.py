@@ -104,6 +104,30 @@ def test_siddon_backward(name, kw, lean_slab):
 
 
 @pytest.mark.parametrize("name,kw", [
+    ("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)), ("siddon_nc_b4_ragged", {}),
+    ("siddon_nc_b4_stopgrad", dict(stop_grad=True)), ("siddon_nc_inside", {}), ("siddon_nc_axis", {}),
+])
+@pytest.mark.parametrize("slab", [0, 5])
+def test_siddon_sensitivities_walk(name, kw, slab):
+    """Training-step fast path: one walk -> image + per-ray end-point sensitivities (two accumulated axes, the major axis
+    from the telescoping identities), backward = sensitivities x upstream gradient.  Same bar as the backward walk."""
+    g = load_golden(name)
+    out = emu.siddon_sens(g["volume"], g["source"], g["target"], g["raylen"], g["w"], slab=slab, **kw)
+    assert relerr(out["img"], g["img_f64"]) < IMG_TOL
+    if name != "siddon_nc_axis":  # exactly axis-aligned rays: gradients depend on how exact alpha ties are ordered
+        assert relerr(out["g_target"], g["g_target_f64"]) < _grad_tol(g, "g_target")
+        assert relerr(out["g_source"], g["g_source_f64"]) < _grad_tol(g, "g_source")
+    if kw.get("stop_grad"):
+        assert not out["g_raylen"].any()
+    else:
+        assert relerr(out["g_raylen"], g["g_raylen_f64"]) < _grad_tol(g, "g_raylen")
+    # and against the three-axis backward walk it replaces
+    ref = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], lean_slab=slab, **kw)
+    assert relerr(out["g_target"], ref["g_target"]) < 2e-5
+    assert relerr(out["g_source"], ref["g_source"]) < 2e-5
+
+
+@pytest.mark.parametrize("name,kw", [
     ("trilinear_nc_b4_alpha", dict(n_points=100, alphamin=0.62, alphamax=0.97)),
     ("trilinear_nc_b4", dict(n_points=160)),
     ("trilinear_nc_b4_ragged", dict(n_points=77)),
