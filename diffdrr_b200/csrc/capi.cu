@@ -208,6 +208,24 @@ int b200drr_siddon_bwd_sens_pose(const float* sens, const float* gout, const flo
                                            (cudaStream_t)stream));
 }
 
+int b200drr_trilinear_fwd_sens_packed(const float* packed, int D0, int D1, int D2, const float* src, const float* tgt,
+                                      const float* raylen, float* out, float* sens, int B, int H, int W, float voxel_shift,
+                                      float eps, int n_points, const float* alpha_range, int slab, void* stream)
+{
+    if (!packed || !src || !tgt || !raylen || !out || !sens || !alpha_range || bad_dims(D0, D1, D2) ||
+        bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0 || n_points < 2 || slab < 0)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_sens_packed(packed, mk(D0, D1, D2), src, tgt, raylen, out, sens, B, H, W, voxel_shift, eps,
+                                                n_points, alpha_range, slab, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                               float* g_alpha_range, int B, int64_t N, void* stream)
+{
+    if (!sens || !gout || bad_rays(B, N)) return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd_sens(sens, gout, g_src, g_tgt, g_raylen, g_alpha_range, B, N, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
                             const float* tgt, const float* raylen, float* out, int B, int64_t N, int C, float voxel_shift,
                             float eps, void* stream)

@@ -62,6 +62,13 @@ cudaError_t launch_siddon_bwd_sens_pose(const float* sens, const float* gout, co
                                         const float* cols, float* g_src, float* g_G, float* g_Wd, int B, int H, int W,
                                         int stop_grad, cudaStream_t stream);
 
+cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
+                                             const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                             float eps, int n_points, const float* alpha_range, int slab,
+                                             cudaStream_t stream);
+cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                      float* g_alpha_range, int B, int64_t N, cudaStream_t stream);
+
 cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
                                    cudaStream_t stream);

@@ -375,6 +375,134 @@ cudaError_t launch_trilinear_bwd_packed(const float* packed, VolDims dims, const
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward WITH per-ray sensitivities from the packed copy (the training-step fast path; siddon.cu has the Siddon
+// twin).  Every sample's 8 corners are in registers anyway, so the interpolant's gradient costs no extra traffic, and
+// everything the closed-form backward accumulates is linear in the upstream gradient g.  One march with g = 1 yields
+//   out[r] = L * step * sum V     and     sens[r] = { dI/dtgt[3], step*sum V | dI/dsrc[3], dI/dalphamin | dI/dalphamax, 0, 0, 0 }
+// and the backward pass is the elementwise trilinear_sens_bwd_kernel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int TW, int TH, bool SLAB>
+__global__ void __launch_bounds__(TW* TH) trilinear_sens_packed_kernel(
+    const float4* __restrict__ packed, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, float* __restrict__ out, float* __restrict__ sens, int B, int H, int W, int slab,
+    float shift, float eps, int P, const float* __restrict__ alpha_range)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles = tiles_x * ((H + TH - 1) / TH);
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B, sl = id / B;  // sl == 0 when not slabbed
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+    const float step = (amax - amin) / (float)(P - 1);
+    const float L = __ldg(raylen + r);
+    const float s_lo = SLAB ? (float)(sl * slab - 1) : -INFINITY, s_hi = SLAB ? (float)((sl + 1) * slab - 1) : INFINITY;
+    const TriGrad tg = trilinear_ray_bwd_packed(packed, dims, ray, shift, P, amin, amax, 1.0f, L, s_lo, s_hi);
+    const float sv = step * tg.sumV;
+    float* sr = sens + r * 12;
+    if (SLAB) {
+        if (tg.sumV != 0.0f || tg.gt[0] != 0.0f || tg.gt[1] != 0.0f || tg.gt[2] != 0.0f || tg.ga0 != 0.0f || tg.ga1 != 0.0f) {
+            red_add4(sr, tg.gt[0], tg.gt[1], tg.gt[2], sv);
+            red_add4(sr + 4, tg.gs[0], tg.gs[1], tg.gs[2], tg.ga0);
+            red_add(sr + 8, tg.ga1);
+            red_add(out + r, L * sv);
+        }
+    } else {
+        reinterpret_cast<float4*>(sr)[0] = make_float4(tg.gt[0], tg.gt[1], tg.gt[2], sv);
+        reinterpret_cast<float4*>(sr)[1] = make_float4(tg.gs[0], tg.gs[1], tg.gs[2], tg.ga0);
+        reinterpret_cast<float4*>(sr)[2] = make_float4(tg.ga1, 0.0f, 0.0f, 0.0f);
+        out[r] = L * sv;
+    }
+}
+
+cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
+                                             const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                             float eps, int n_points, const float* alpha_range, int slab,
+                                             cudaStream_t stream)
+{
+    const int64_t tiles = (int64_t)((W + 15) / 16) * ((H + 15) / 16);
+    if (slab > 0) {
+        const int n_slabs = (dims.d[0] + 1 + slab - 1) / slab;
+        const int64_t blocks = tiles * B * n_slabs;
+        if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+        const size_t n = (size_t)B * H * W;
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 12 * n, stream);
+        if (e != cudaSuccess) return e;
+        trilinear_sens_packed_kernel<16, 16, true><<<(unsigned)blocks, 256, 0, stream>>>(
+            (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, slab, shift, eps, n_points, alpha_range);
+        return cudaGetLastError();
+    }
+    if (tiles * B > INT32_MAX) return cudaErrorInvalidValue;
+    trilinear_sens_packed_kernel<16, 16, false><<<(unsigned)(tiles * B), 256, 0, stream>>>(
+        (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, 0, shift, eps, n_points, alpha_range);
+    return cudaGetLastError();
+}
+
+// g_tgt = g * dI/dtgt, g_raylen = g * step*sumV, g_src[b] = sum_n g * dI/dsrc, g_alpha_range += sum g * dI/d(alphamin, alphamax)
+__global__ void __launch_bounds__(256) trilinear_sens_bwd_kernel(const float4* __restrict__ sens, const float* __restrict__ gout,
+                                                                 float* __restrict__ g_src, float* __restrict__ g_tgt,
+                                                                 float* __restrict__ g_raylen,
+                                                                 float* __restrict__ g_alpha_range, int64_t N)
+{
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    float acc[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = (int64_t)b * N + n;
+        const float g = __ldg(gout + r);
+        const float4 t = __ldg(sens + r * 3), s = __ldg(sens + r * 3 + 1), u = __ldg(sens + r * 3 + 2);
+        if (g_tgt) {
+            g_tgt[r * 3 + 0] = g * t.x;
+            g_tgt[r * 3 + 1] = g * t.y;
+            g_tgt[r * 3 + 2] = g * t.z;
+        }
+        if (g_raylen) g_raylen[r] = g * t.w;
+        acc[0] = fmaf(g, s.x, acc[0]);
+        acc[1] = fmaf(g, s.y, acc[1]);
+        acc[2] = fmaf(g, s.z, acc[2]);
+        acc[3] = fmaf(g, s.w, acc[3]);
+        acc[4] = fmaf(g, u.x, acc[4]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float tot = block_sum(acc[i], red);
+        if (threadIdx.x == 0) {
+            if (i < 3) {
+                if (g_src) atomicAdd(g_src + b * 3 + i, tot);
+            } else if (g_alpha_range) {
+                atomicAdd(g_alpha_range + (i - 3), tot);
+            }
+        }
+    }
+}
+
+cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                      float* g_alpha_range, int B, int64_t N, cudaStream_t stream)
+{
+    if (g_src) {
+        const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int chunks = (int)min((int64_t)64, (N + 255) / 256);
+    trilinear_sens_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const float4*)sens, gout, g_src, g_tgt,
+                                                                                     g_raylen, g_alpha_range, N);
+    return cudaGetLastError();
+}
+
 template <int TW, int TH>
 static cudaError_t tri_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                 float* out, int B, int H, int W, float shift, float eps, int P, const float* ar,

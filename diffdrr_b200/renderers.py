@@ -23,6 +23,7 @@ _REDUCE = {"sum": 0, "max": 1}
 # roofline at 64 poses, 59.8 % -> 74.6 % at 16; no gain at 4).  The backward stays one-CTA-per-ray-tile: its per-slab
 # reductions cost more than the L2 sharing returns (measured).
 _PACKED_SLAB_FWD = 16
+_PACKED_SLAB_SENS = 0   # forward+sensitivities march: unslabbed is faster (measured 8.8 vs 9.5-11 ms at 16 poses)
 _PACKED_SLAB_MIN_BATCH = 8
 
 
@@ -227,8 +228,19 @@ class _TrilinearFunction(torch.autograd.Function):
         arange = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
         out = torch.empty(B, N, dtype=torch.float32, device=vol.device)
         lib = _lib.load()
+        # training-step fast path (twin of the Siddon one): ray gradients wanted, static (packed) volume -> one march
+        # yields the image and the per-ray sensitivities; backward is elementwise (b200drr_trilinear_bwd_sens)
+        sens = None
+        if packed is not None and _FUSED_SENSITIVITIES and any(ctx.needs_input_grad[1:5]) and not ctx.needs_input_grad[0]:
+            sens = torch.empty(B, N, 12, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
-            if packed is not None:
+            if sens is not None:
+                _lib.check(lib.b200drr_trilinear_fwd_sens_packed(_ptr(packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                                 _ptr(out), _ptr(sens), B, grid[0], grid[1], voxel_shift, eps,
+                                                                 n_points, _ptr(arange),
+                                                                 _PACKED_SLAB_SENS if B >= _PACKED_SLAB_MIN_BATCH else 0,
+                                                                 _stream()), "b200drr_trilinear_fwd_sens_packed")
+            elif packed is not None:
                 _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                             _ptr(out), B, grid[0], grid[1], voxel_shift, eps, n_points,
                                                             _ptr(arange),
@@ -242,15 +254,34 @@ class _TrilinearFunction(torch.autograd.Function):
                 _lib.check(lib.b200drr_trilinear_fwd(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N,
                                                      voxel_shift, eps, n_points, _ptr(arange), reduce, int(align_corners),
                                                      _stream()), "b200drr_trilinear_fwd")
-        ctx.save_for_backward(vol, src, tgt, raylen, arange)
-        ctx.packed = packed
+        ctx.fused = sens is not None
+        if ctx.fused:
+            ctx.save_for_backward(sens)
+        else:
+            ctx.save_for_backward(vol, src, tgt, raylen, arange)
+        ctx.packed = None if ctx.fused else packed
         ctx.cfg = (voxel_shift, eps, n_points, reduce, align_corners, tuple(source.shape), tuple(img.shape), grid)
         return out.view(B, 1, N)
 
     @staticmethod
     def backward(ctx, gout):
-        vol, src, tgt, raylen, arange = ctx.saved_tensors
         voxel_shift, eps, n_points, reduce, align_corners, src_shape, img_shape, grid = ctx.cfg
+        if ctx.fused:
+            (sens,) = ctx.saved_tensors
+            B, N = sens.shape[0], sens.shape[1]
+            _, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
+            dev = sens.device
+            gout = gout.reshape(B, N).contiguous().float()
+            g_src = torch.empty(B, 3, dtype=torch.float32, device=dev) if need_src else None
+            g_tgt = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if need_tgt else None
+            g_len = torch.empty(B, N, dtype=torch.float32, device=dev) if need_len else None
+            g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().b200drr_trilinear_bwd_sens(_ptr(sens), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len),
+                                                                  _ptr(g_ar), B, N, _stream()), "b200drr_trilinear_bwd_sens")
+            return (None, None if g_src is None else g_src.view(src_shape), g_tgt,
+                    None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None)
+        vol, src, tgt, raylen, arange = ctx.saved_tensors
         if reduce != 0:
             raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
         B, N = tgt.shape[0], tgt.shape[1]

@@ -196,6 +196,21 @@ int b200drr_trilinear_bwd_packed(const float *packed, int D0, int D1, int D2, co
                                  const float *alpha_range, int slab, void *stream);
 
 /*
+ * Trilinear forward WITH per-ray sensitivities from the packed-corner copy (training-step fast path, the twin of
+ * b200drr_siddon_fwd_sens_grid): one march yields out [B][H*W] (== b200drr_trilinear_fwd_packed) and
+ *   sens [B][H*W][12] = { dI/dtgt[3], out/raylen | dI/dsrc[3], dI/dalphamin | dI/dalphamax, 0, 0, 0 }
+ * i.e. everything torch's backward of Trilinear.forward (renderers.py:205-240) needs is linear in g = dLoss/dout, and
+ * b200drr_trilinear_bwd_sens applies it: g_tgt [B][N][3], g_raylen [B][N], g_src [B][3] overwritten (NULL = not wanted),
+ * g_alpha_range [2] ACCUMULATED INTO (caller zero-fills; NULL = not wanted).  slab as in b200drr_trilinear_fwd_packed.
+ */
+int b200drr_trilinear_fwd_sens_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
+                                      const float *raylen, float *out, float *sens, int B, int H, int W,
+                                      float voxel_shift, float eps, int n_points, const float *alpha_range, int slab,
+                                      void *stream);
+int b200drr_trilinear_bwd_sens(const float *sens, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                               float *g_alpha_range, int B, int64_t N, void *stream);
+
+/*
  * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored
  * as fp32 (as DRR registers it, drr.py:86-91); every segment / sample contributes to channel label(voxel), sampled
  * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.  Forward only.

@@ -74,3 +74,22 @@ for variant in [int(v) for v in os.environ.get("VARIANTS", "-1").split(",")]:
     err = float((out - ref).abs().max() / ref.abs().max())
     b_ = timeit(bwd) if not os.environ.get("FWD_ONLY") else float("nan")
     print(f"variant {variant:2d}: fwd {f:8.3f} ms {B / f * 1e3:8.1f} DRR/s {gb / f * 1e3:7.1f} GB/s ({gb / f * 1e3 / 65.709:5.1f}%)   bwd {b_:8.3f} ms   fwd+bwd {B / (f + b_) * 1e3:7.1f} DRR/s  {2 * gb / (f + b_) * 1e3:7.1f} GB/s   maxdiff {err:.1e}")
+
+# ---- forward + sensitivities (one march) + elementwise backward: the training-step fast path ------------------------
+for slab in [int(v) for v in os.environ.get("SENS_SLABS", "").split(",") if v]:
+    sens = torch.empty(B, N, 12, device=dev)
+    out2 = torch.empty(B, N, device=dev)
+    h_src, h_tgt, h_len, h_ar = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev), torch.zeros(2, device=dev)
+    def sens_fwd():
+        _lib.check(lib.b200drr_trilinear_fwd_sens_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out2), _ptr(sens), B, H, H, 0.5, 1e-8, P, _ptr(ar), slab, _stream()), "tri sens")
+    def sens_bwd():
+        h_ar.zero_()
+        _lib.check(lib.b200drr_trilinear_bwd_sens(_ptr(sens), _ptr(gout), _ptr(h_src), _ptr(h_tgt), _ptr(h_len), _ptr(h_ar), B, N, _stream()), "tri bwd sens")
+    f, b_ = timeit(sens_fwd), timeit(sens_bwd)
+    # reference gradients from the two-march packed backward
+    g_ar.zero_()
+    _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B, H, H, 0.5, 1e-8, P, _ptr(ar), 0, _stream()), "tri bwd packed")
+    _lib.check(lib.b200drr_trilinear_fwd_packed(_ptr(get_packed()), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, P, _ptr(ar), 0, _stream()), "tri fwd packed")
+    sens_bwd()
+    e = [float((a - b).abs().max() / b.abs().max()) for a, b in ((out2, out), (h_src, g_src), (h_tgt, g_tgt), (h_len, g_len), (h_ar, g_ar))]
+    print(f"sens slab {slab:3d}: march {f:8.3f} ms ({gb / f * 1e3 / 65.709:5.1f}% of peak on fwd bytes)  bwd {b_:6.3f} ms   fwd+bwd {B / (f + b_) * 1e3:7.1f} DRR/s   maxdiff img/src/tgt/len/ar " + " ".join(f"{x:.1e}" for x in e))
