@@ -5,7 +5,10 @@
 
 A "step" is one pass of the hot path over one batch of synthetic poses: Siddon forward (line integrals of
 `--batch` poses through a 512^3 fp32 volume onto a 256^2 detector) + Siddon backward (gradients w.r.t. the ray
-end points / ray lengths, i.e. the pose-gradient path of 2D/3D registration).  Reported on ONE JSON line:
+end points / ray lengths, i.e. the pose-gradient path of 2D/3D registration).  Since every pixel depends on one ray
+only, the forward walk also accumulates the ray's 6 end-point sensitivities (they do not depend on the upstream
+gradient) and the backward pass is an elementwise kernel: one walk per step instead of two, same outputs.
+Reported on ONE JSON line:
 
   value      whole-job DRRs/s with the rays already resident in HBM (kernels only, CUDA-event timed)
   e2e        the same metric through the public module call `DRR(rot, xyz)` + backward, with the pose parameters
@@ -44,7 +47,7 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # (16 poses, 512^3 -> 256^2): profiles/r01_fwd_slab_B16_ncu_summary.txt and gpurun capture of the backward kernel.
 # Only quoted when the run uses that workload; otherwise null.
 NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9,
-                     "siddon_sens_slab_kernel": None}  # filled from the ncu capture of the fused kernel
+                     "siddon_sens_slab_kernel": 1.38e9 + 0.14e9}
 
 
 def parse():
@@ -216,7 +219,6 @@ def run_ours(args, rank, local_rank, world):
     gout = w.reshape(B, N).contiguous()
     out = torch.empty(B, N, device=dev)
     g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
-    gathered = torch.empty(B * world, N, device=dev) if world > 1 else None
 
     visits = siddon_visits((D, D, D), src, tgt)
     tot_visits = int(visits.sum().item())
@@ -228,8 +230,13 @@ def run_ours(args, rank, local_rank, world):
     sens = torch.empty(B, N, 8, device=dev)
     sens_bytes = 4 * tot_visits + (16 + 4 + 32) * B * N      # voxels + (tgt, raylen) + out + 8 sensitivities per ray
 
+    outs = [out, torch.empty_like(out)] if world > 1 else [out]
+    gathered = [torch.empty(B * world, N, device=dev) for _ in range(2)] if world > 1 else None
+    pending, state = [None, None], {"k": 0}
+
     def kernel_step(ev=None):
         """One training step at kernel level: image + per-ray sensitivities in ONE walk, then the elementwise backward."""
+        out = outs[state["k"] & 1] if world > 1 else outs[0]
         if ev:
             ev[0].record(stream)
         _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
@@ -242,7 +249,19 @@ def run_ours(args, rank, local_rank, world):
         if ev:
             ev[2].record(stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            # double-buffered: the gather of this step's image stack runs on NCCL's stream while the next step walks
+            # (the next step writes the other buffer); a buffer is reused only after its gather has been waited for
+            slot = state["k"] & 1
+            if pending[slot] is not None:
+                pending[slot].wait()
+            pending[slot] = dist.all_gather_into_tensor(gathered[slot], outs[slot], async_op=True)
+            state["k"] += 1
+
+    def drain():
+        for slot in (0, 1):
+            if pending[slot] is not None:
+                pending[slot].wait()
+                pending[slot] = None
 
     def two_walk_step(ev):
         """The inference forward and the backward WALK (still the path when the volume needs gradients), for the record."""
@@ -263,6 +282,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- kernels-only leg (inputs resident in HBM) ------------------------------------------------------
     for _ in range(args.warmup):
         kernel_step()
+    drain()
     events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -270,6 +290,7 @@ def run_ours(args, rank, local_rank, world):
         t_start.record(stream)
         for k in range(args.steps):
             kernel_step(events[k])
+        drain()  # the last gathers complete inside the timed region
         t_end.record(stream)
         barrier()
     ms_total = t_start.elapsed_time(t_end)
@@ -295,7 +316,7 @@ def run_ours(args, rank, local_rank, world):
         loss = (img * w).sum()
         loss.backward()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, img.detach().reshape(B, N))
+            dist.all_gather_into_tensor(gathered[0], img.detach().reshape(B, N))
         img_h.copy_(img.detach(), non_blocking=True)
         grad_h[0].copy_(rot.grad, non_blocking=True)
         grad_h[1].copy_(xyz.grad, non_blocking=True)
@@ -324,16 +345,24 @@ def run_ours(args, rank, local_rank, world):
             xyz_d = torch.zeros(B, 3, device=dev, requires_grad=True)
             rot_d.grad, xyz_d.grad = torch.zeros_like(rot_d), torch.zeros_like(xyz_d)
 
+            copy_stream = torch.cuda.Stream()
+
             def graph_body():
+                main = torch.cuda.current_stream()
                 with torch.no_grad():
                     rot_d.copy_(rot_h, non_blocking=True)
                     xyz_d.copy_(xyz_h, non_blocking=True)
                     rot_d.grad.zero_()
                     xyz_d.grad.zero_()
                 img = drr(rot_d, xyz_d, parameterization="euler_angles", convention="ZXY")
+                # the 4 MB image stack goes back to the host on a second stream while loss + backward run
+                # (a fork/join inside the captured graph)
+                copy_stream.wait_stream(main)
+                with torch.cuda.stream(copy_stream):
+                    img_h.copy_(img.detach(), non_blocking=True)
                 loss = (img * w).sum()
                 loss.backward()
-                img_h.copy_(img.detach(), non_blocking=True)
+                main.wait_stream(copy_stream)
                 grad_h[0].copy_(rot_d.grad, non_blocking=True)
                 grad_h[1].copy_(xyz_d.grad, non_blocking=True)
                 loss_h.copy_(loss.detach().reshape(1), non_blocking=True)

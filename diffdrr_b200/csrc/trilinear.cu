@@ -418,13 +418,13 @@ __global__ void __launch_bounds__(TW* TH) trilinear_sens_packed_kernel(
             red_add4(sr, tg.gt[0], tg.gt[1], tg.gt[2], sv);
             red_add4(sr + 4, tg.gs[0], tg.gs[1], tg.gs[2], tg.ga0);
             red_add(sr + 8, tg.ga1);
-            red_add(out + r, L * sv);
+            red_add(out + r, tg.sumV * (L * step));  // bitwise the forward kernel's expression
         }
     } else {
         reinterpret_cast<float4*>(sr)[0] = make_float4(tg.gt[0], tg.gt[1], tg.gt[2], sv);
         reinterpret_cast<float4*>(sr)[1] = make_float4(tg.gs[0], tg.gs[1], tg.gs[2], tg.ga0);
         reinterpret_cast<float4*>(sr)[2] = make_float4(tg.ga1, 0.0f, 0.0f, 0.0f);
-        out[r] = L * sv;
+        out[r] = tg.sumV * (L * step);  // bitwise the forward kernel's expression
     }
 }
 

@@ -345,6 +345,19 @@ def _render_mask(kind, volume, mask, source, target, img, voxel_shift, eps, n_po
     return out
 
 
+_DIMS_CACHE: dict = {}
+
+
+def _dims_tensor(shape, device, dtype) -> torch.Tensor:
+    """Volume shape as a device tensor, built once per (shape, device, dtype): a host->device copy per call would be a
+    sync point and cannot be captured in a CUDA graph."""
+    key = (tuple(shape), str(device), dtype)
+    t = _DIMS_CACHE.get(key)
+    if t is None:
+        t = _DIMS_CACHE[key] = torch.tensor(tuple(shape), dtype=dtype).to(device)
+    return t
+
+
 def _reduce_code(reducefn):
     if isinstance(reducefn, str) and reducefn in _REDUCE:
         return _REDUCE[reducefn]
@@ -372,7 +385,7 @@ class Siddon(torch.nn.Module):
         self.detector_shape = None
 
     def dims(self, volume):
-        return torch.tensor(volume.shape).to(volume)
+        return _dims_tensor(volume.shape, volume.device, volume.dtype)
 
     def forward(self, volume, source, target, img, align_corners=False, mask=None):
         if self.mode != "nearest":
@@ -427,7 +440,7 @@ class Trilinear(torch.nn.Module):
         self._packed_key = None
 
     def dims(self, volume):
-        return torch.tensor(volume.shape).to(volume)
+        return _dims_tensor(volume.shape, volume.device, volume.dtype)
 
     def _packed_volume(self, volume):
         if (not self.pack_corners or volume.requires_grad or not volume.is_cuda or volume.dtype != torch.float32
@@ -454,7 +467,7 @@ class Trilinear(torch.nn.Module):
             raise NotImplementedError("mask_to_channels is implemented for reducefn='sum'")
         if alphamin is None or alphamax is None:
             # batch-global sampling range over whatever rays are in this call (quirk Q3), differentiable torch ops
-            dims = torch.tensor(volume.shape, device=source.device, dtype=source.dtype)
+            dims = _dims_tensor(volume.shape, source.device, source.dtype)
             amin, amax = _get_alpha_minmax(source, target, dims, self.voxel_shift, self.eps)
             alphamin, alphamax = amin.min(), amax.max()
         alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=torch.float32, device=volume.device),

@@ -14,6 +14,6 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --batch 8 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:siddon -s 2 -c 2 -o $OUT/prof_siddon \
-    python bench.py --steps 1 --warmup 1 --batch 8 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:siddon -s 1 -c 3 -o $OUT/prof_siddon \
+    python bench.py --steps 1 --warmup 1 --batch 16 --no-cpu-baseline --no-graph > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT

@@ -290,14 +290,15 @@ def test_trilinear_fused_sensitivities_match_two_march_backward(B):
     rot0, xyz0 = synthetic.make_poses(B, seed=6)
     w = torch.rand(B, 1, 64, 56, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
     res = []
-    for fused in (True, False):
-        renderers._FUSED_SENSITIVITIES = fused
+    for fused, slab in ((True, 0), (False, 0), (True, 16)):   # slab 16: the slab-major form of the fused march (opt-in)
+        renderers._FUSED_SENSITIVITIES, renderers._PACKED_SLAB_SENS = fused, slab
         try:
             rot, xyz = rot0.to(DEV).requires_grad_(True), xyz0.to(DEV).requires_grad_(True)
             img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY", n_points=150)
             (img * w).sum().backward()
             res.append((img.detach(), rot.grad, xyz.grad))
         finally:
-            renderers._FUSED_SENSITIVITIES = True
-    for a, b, tol in zip(res[0], res[1], (2e-6, 1e-4, 1e-4)):
-        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < tol
+            renderers._FUSED_SENSITIVITIES, renderers._PACKED_SLAB_SENS = True, 0
+    for other, tols in ((res[0], (2e-6, 1e-4, 1e-4)), (res[2], (2e-6, 3e-4, 3e-4))):
+        for a, b, tol in zip(other, res[1], tols):
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < tol
