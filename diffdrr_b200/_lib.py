@@ -72,6 +72,16 @@ _SIGNATURES = {
     "b200drr_trilinear_bwd_sens": (ctypes.c_int, [
         _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64,
         ctypes.c_void_p]),
+    "b200drr_euler_pose_fwd": (ctypes.c_int, [
+        _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, _c_float_p, ctypes.c_int,
+        ctypes.c_void_p]),
+    "b200drr_euler_pose_bwd": (ctypes.c_int, [
+        _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_pose_rays_fwd": (ctypes.c_int, [
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_pose_rays_bwd": (ctypes.c_int, [
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
     "b200drr_siddon_fwd_mask": (ctypes.c_int, [
         _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
         ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),

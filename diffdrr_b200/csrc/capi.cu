@@ -226,6 +226,39 @@ int b200drr_trilinear_bwd_sens(const float* sens, const float* gout, float* g_sr
     return ret(launch_trilinear_bwd_sens(sens, gout, g_src, g_tgt, g_raylen, g_alpha_range, B, N, (cudaStream_t)stream));
 }
 
+static bool bad_axes(int c0, int c1, int c2)
+{
+    return c0 < 0 || c0 > 2 || c1 < 0 || c1 > 2 || c2 < 0 || c2 > 2 || c1 == c0 || c1 == c2;
+}
+
+int b200drr_euler_pose_fwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, float* P, int B,
+                           void* stream)
+{
+    if (!rot || !xyz || !P || B <= 0 || bad_axes(c0, c1, c2)) return B200DRR_EINVAL;
+    return ret(launch_euler_pose_fwd(rot, xyz, c0, c1, c2, scale, P, B, (cudaStream_t)stream));
+}
+
+int b200drr_euler_pose_bwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, const float* gP,
+                           float* g_rot, float* g_xyz, int B, void* stream)
+{
+    if (!rot || !xyz || !gP || B <= 0 || bad_axes(c0, c1, c2)) return B200DRR_EINVAL;
+    return ret(launch_euler_pose_bwd(rot, xyz, c0, c1, c2, scale, gP, g_rot, g_xyz, B, (cudaStream_t)stream));
+}
+
+int b200drr_pose_rays_fwd(const float* P, const float* Q, const float* r, const float* Ainv, float* src, float* G, float* Wd,
+                          int B, void* stream)
+{
+    if (!P || !Q || !r || !Ainv || !src || !G || !Wd || B <= 0) return B200DRR_EINVAL;
+    return ret(launch_pose_rays_fwd(P, Q, r, Ainv, src, G, Wd, B, (cudaStream_t)stream));
+}
+
+int b200drr_pose_rays_bwd(const float* Q, const float* r, const float* Ainv, const float* g_src, const float* g_G,
+                          const float* g_Wd, float* gP, int B, void* stream)
+{
+    if (!Q || !r || !Ainv || !g_src || !g_G || !g_Wd || !gP || B <= 0) return B200DRR_EINVAL;
+    return ret(launch_pose_rays_bwd(Q, r, Ainv, g_src, g_G, g_Wd, gP, B, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
                             const float* tgt, const float* raylen, float* out, int B, int64_t N, int C, float voxel_shift,
                             float eps, void* stream)

@@ -69,6 +69,16 @@ cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, 
 cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                       float* g_alpha_range, int B, int64_t N, cudaStream_t stream);
 
+// per-pose algebra around the pose-in kernels (pose.cu)
+cudaError_t launch_euler_pose_fwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, float* P, int B,
+                                  cudaStream_t stream);
+cudaError_t launch_euler_pose_bwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, const float* gP,
+                                  float* g_rot, float* g_xyz, int B, cudaStream_t stream);
+cudaError_t launch_pose_rays_fwd(const float* P, const float* Q, const float* r, const float* Ainv, float* src, float* G,
+                                 float* Wd, int B, cudaStream_t stream);
+cudaError_t launch_pose_rays_bwd(const float* Q, const float* r, const float* Ainv, const float* g_src, const float* g_G,
+                                 const float* g_Wd, float* gP, int B, cudaStream_t stream);
+
 cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
                                    cudaStream_t stream);

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 from torch.utils.checkpoint import checkpoint
 
+from . import geometry
 from .detector import Detector
 from .pose import RigidTransform, convert
 from .renderers import Siddon, Trilinear, siddon_pose_render
@@ -105,11 +106,18 @@ class DRR(nn.Module):
     def forward(self, *args, parameterization: str = None, convention: str = None, calibration: RigidTransform = None,
                 mask_to_channels: bool = False, degrees: bool = False, **kwargs):
         """SE(3) pose (a RigidTransform, or rotation/translation parameters) -> DRR of shape (B, C, H, W)."""
-        if parameterization is None:
+        fused = self._pose_in_ok(mask_to_channels, kwargs)
+        if (fused and parameterization == "euler_angles" and calibration is None and len(args) == 2
+                and geometry.euler_convention_ok(convention) and all(
+                    torch.is_tensor(a) and a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[-1] == 3
+                    for a in args)):
+            # pose parameters -> pose matrix in one kernel (same algebra as pose.convert)
+            pose = RigidTransform(geometry.euler_pose(args[0], args[1], convention, degrees))
+        elif parameterization is None:
             pose = args[0]
         else:
             pose = convert(*args, parameterization=parameterization, convention=convention, degrees=degrees)
-        if self._pose_in_ok(mask_to_channels, kwargs):
+        if fused:
             return self.reshape_transform(self._render_pose_in(pose, calibration), batch_size=len(pose))
         source, target = self.detector(pose, calibration)
         if self.checkpoint_gradients:
@@ -134,6 +142,12 @@ class DRR(nn.Module):
         """detector.forward (detector.py:144-154) + ray lengths / affine_inverse (drr.py:201-205) collapsed into two
         3x4 matrices per pose; the rays themselves are generated inside the CUDA kernel."""
         det = self.detector
+        grid = det.target.view(det.height, det.width, 3)
+        if calibration is None and pose.matrix.dtype == torch.float32:
+            # the whole composition below as one kernel per direction (include/b200drr.h: b200drr_pose_rays_fwd/_bwd)
+            Q, r, Ainv = self._pose_constants()
+            src, G, Wd = geometry.pose_rays(pose.matrix, Q, r, Ainv)
+            return siddon_pose_render(self.renderer, self.density, src, G, Wd, grid[:, 0, 1], grid[0, :, 0])
         calib = det._calibration if calibration is None else calibration.matrix
         M = pose.matrix @ det._reorient            # canonical C-arm frame -> world   (reorient.compose(extrinsic))
         T = M @ calib                              # ... including the intrinsic scaling of the detector plane
@@ -141,8 +155,24 @@ class DRR(nn.Module):
         G = (A_inv @ T)[:, :3, :]
         src = (A_inv @ M)[:, :3, 3]                # the canonical source is the origin
         Wd = torch.cat([T[:, :3, :3], (T[:, :3, 3] - M[:, :3, 3]).unsqueeze(-1)], dim=-1)  # target - source, world
-        grid = det.target.view(det.height, det.width, 3)
         return siddon_pose_render(self.renderer, self.density, src, G, Wd, grid[:, 0, 1], grid[0, :, 0])
+
+    def _pose_constants(self):
+        """Q = reorient . calibration, r = reorient[:, 3], Ainv = affine_inverse as contiguous device tensors, rebuilt only
+        when the detector / affine buffers change (set_intrinsics_, .to(device))."""
+        det = self.detector
+        key = (det._calibration.data_ptr(), det._calibration._version, det._reorient.data_ptr(), det._reorient._version,
+               self._affine_inverse.data_ptr(), self._affine_inverse._version)
+        cached = getattr(self, "_pose_consts", None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                reorient = det._reorient.reshape(4, 4).float()
+                Q = (reorient @ det._calibration.reshape(4, 4).float()).contiguous()
+                r = reorient[:, 3].contiguous()
+                Ainv = self._affine_inverse.reshape(4, 4).float().contiguous()
+            cached = (key, (Q, r, Ainv))
+            object.__setattr__(self, "_pose_consts", cached)
+        return cached[1]
 
     def render(self, density: torch.Tensor, source: torch.Tensor, target: torch.Tensor, mask_to_channels: bool = False,
                **kwargs):

@@ -139,6 +139,26 @@ int b200drr_siddon_bwd_sens_pose(const float *sens, const float *gout, const flo
                                  int stop_grad, void *stream);
 
 /*
+ * Per-pose algebra either side of the pose-in entry points, one thread per pose (replaces ~95 tiny ATen kernels per
+ * training step; everything is [B] x a few floats):
+ *   b200drr_euler_pose_fwd: reference pose.py `convert(rot, xyz, parameterization="euler_angles", convention)`:
+ *     R = R_c0(a0) R_c1(a1) R_c2(a2) (c = 0/1/2 for X/Y/Z; angles = rot * scale, scale = pi/180 for degrees=True),
+ *     P [B][4][4] = [[R, R.xyz], [0 0 0 1]].   _bwd: gP -> g_rot [B][3], g_xyz [B][3] (either may be NULL).
+ *   b200drr_pose_rays_fwd: detector.py:144-154 + drr.py:201-205 collapsed into the inputs of b200drr_siddon_fwd_pose:
+ *     T = P.Q, G = Ainv.T (rows 0..2), src = Ainv.(P.r), Wd = [T[:3,:3] | T[:3,3] - (P.r)[:3]] with
+ *     Q [4][4] = reorient . calibration, r [4] = reorient[:, 3], Ainv [4][4] = affine_inverse (all row-major, device).
+ *     _bwd: (g_src, g_G, g_Wd) -> gP [B][4][4].
+ */
+int b200drr_euler_pose_fwd(const float *rot, const float *xyz, int c0, int c1, int c2, float scale, float *P, int B,
+                           void *stream);
+int b200drr_euler_pose_bwd(const float *rot, const float *xyz, int c0, int c1, int c2, float scale, const float *gP,
+                           float *g_rot, float *g_xyz, int B, void *stream);
+int b200drr_pose_rays_fwd(const float *P, const float *Q, const float *r, const float *Ainv, float *src, float *G,
+                          float *Wd, int B, void *stream);
+int b200drr_pose_rays_bwd(const float *Q, const float *r, const float *Ainv, const float *g_src, const float *g_G,
+                          const float *g_Wd, float *gP, int B, void *stream);
+
+/*
  * Trilinear forward: replaces Trilinear.forward with mask=None (renderers.py:205-240) for a given
  * sampling range.  alpha_range is a DEVICE pointer to {alphamin, alphamax} (so that the range computed
  * on the device by _get_alpha_minmax, renderers.py:124-140,221-223, needs no host round trip).

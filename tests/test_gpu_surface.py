@@ -56,8 +56,8 @@ def test_calibration_override_and_intrinsics_editing(setup):
         a = _drr(vol, delx=5.0, dely=3.5, x0=6.0, y0=-3.0)(rot, xyz, **kw)
         drr = _drr(vol)
         calib = torch.tensor([[5.0, 0, 0, 6.0], [0, 3.5, 0, -3.0], [0, 0, 1020.0, 0], [0, 0, 0, 1.0]], device=DEV)
-        b = drr(rot, xyz, calibration=RigidTransform(calib), **kw)
-        assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+        b = drr(rot, xyz, calibration=RigidTransform(calib), **kw)   # override -> torch algebra; default -> pose kernels
+        assert relerr(b.cpu().numpy(), a.cpu().numpy()) < 2e-5
         drr.set_intrinsics_(delx=5.0, dely=3.5, x0=6.0, y0=-3.0)
         c = drr(rot, xyz, **kw)
         assert relerr(c.cpu().numpy(), a.cpu().numpy()) < 1e-6
@@ -93,3 +93,59 @@ def test_stop_gradient_flag_through_every_path(setup):
     drr(rot, xyz, parameterization="euler_angles", convention="ZXY").sum().backward()
     # analytically the ray length is pose-invariant (Q7), so both must agree up to that numerically tiny term
     assert relerr(grads[0].cpu().numpy(), rot.grad.cpu().numpy()) < 1e-3
+
+
+def test_pose_algebra_kernels_match_torch_ops():
+    """b200drr_euler_pose_* / b200drr_pose_rays_* (one thread per pose) against the torch ops they replace inside
+    DRR.forward: pose.convert(euler_angles) for every valid axis convention, and the detector/affine composition of
+    DRR._render_pose_in; values and gradients."""
+    from itertools import permutations, product
+
+    from diffdrr_b200 import DRR, geometry, synthetic
+    from diffdrr_b200.pose import convert
+    g = torch.Generator(device=DEV).manual_seed(11)
+    B = 5
+    rot0 = (torch.rand(B, 3, device=DEV, generator=g) * 2 - 1) * 1.2
+    xyz0 = (torch.rand(B, 3, device=DEV, generator=g) * 2 - 1) * 300
+    w = torch.rand(B, 4, 4, device=DEV, generator=g)
+    conventions = ["".join(p) for p in permutations("XYZ")] + [a + b + a for a, b in product("XYZ", "XYZ") if a != b]
+    assert len(conventions) == 12
+    for conv in conventions:
+        for degrees in (False, True):
+            scale = 180.0 / torch.pi if degrees else 1.0
+            outs = []
+            for fn in ("kernel", "torch"):
+                rot, xyz = (rot0 * scale).clone().requires_grad_(True), xyz0.clone().requires_grad_(True)
+                P = (geometry.euler_pose(rot, xyz, conv, degrees) if fn == "kernel" else
+                     convert(rot, xyz, parameterization="euler_angles", convention=conv, degrees=degrees).matrix)
+                (P * w).sum().backward()
+                outs.append((P.detach(), rot.grad, xyz.grad))
+            assert float((outs[0][0] - outs[1][0]).abs().max()) < 1e-4 * 300          # |translation| up to ~500
+            assert relerr(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < 2e-5, (conv, degrees)
+            assert relerr(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy()) < 2e-5, (conv, degrees)
+    # pose matrix -> (src, G, Wd)
+    vol = synthetic.make_volume((24, 28, 20), "smooth", seed=2)
+    drr = DRR(synthetic.make_subject(vol), sdd=1020.0, height=12, width=10, delx=4.0, dely=4.5, x0=7.0, y0=-3.0).to(DEV)
+    P0 = convert(rot0, xyz0, parameterization="euler_angles", convention="ZXY").matrix
+    ws, wg, ww = torch.rand(B, 3, device=DEV, generator=g), torch.rand(B, 3, 4, device=DEV, generator=g), \
+        torch.rand(B, 3, 4, device=DEV, generator=g)
+    outs = []
+    for fn in ("kernel", "torch"):
+        P = P0.clone().requires_grad_(True)
+        if fn == "kernel":
+            src, G, Wd = geometry.pose_rays(P, *drr._pose_constants())
+        else:
+            det = drr.detector
+            M = P @ det._reorient
+            T = M @ det._calibration
+            G = (drr._affine_inverse @ T)[:, :3, :]
+            src = (drr._affine_inverse @ M)[:, :3, 3]
+            Wd = torch.cat([T[:, :3, :3], (T[:, :3, 3] - M[:, :3, 3]).unsqueeze(-1)], dim=-1)
+        ((src * ws).sum() + (G * wg).sum() + (Wd * ww).sum()).backward()
+        outs.append((src.detach(), G.detach(), Wd.detach(), P.grad))
+    for a, b in zip(outs[0], outs[1]):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    # set_intrinsics_ must invalidate the cached constants
+    q_before = drr._pose_constants()[0].clone()
+    drr.set_intrinsics_(delx=2.0)
+    assert not torch.equal(drr._pose_constants()[0], q_before)
