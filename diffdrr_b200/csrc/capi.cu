@@ -167,6 +167,16 @@ int b200drr_siddon_bwd_pose(const float* vol, int D0, int D1, int D2, const floa
                                       ws_len, B, H, W, voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_sens(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                            const float* raylen, float* out, float* sens, int B, int64_t N, float voxel_shift, float eps,
+                            void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !sens || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_sens(vol, mk(D0, D1, D2), src, tgt, raylen, out, sens, B, N, voxel_shift, eps,
+                                      (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_sens_grid(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                                  const float* raylen, float* out, float* sens, int B, int H, int W, float voxel_shift,
                                  float eps, int variant, void* stream)

@@ -50,6 +50,8 @@ cudaError_t launch_siddon_bwd_pose(const float* vol, VolDims dims, const float* 
                                    float eps, int stop_grad, cudaStream_t stream);
 
 // forward with per-ray end-point sensitivities (sens: 8 floats per ray) and the backward that consumes them
+cudaError_t launch_siddon_fwd_sens(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                   float* out, float* sens, int B, int64_t N, float shift, float eps, cudaStream_t stream);
 cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                         float eps, int variant, cudaStream_t stream);

@@ -832,6 +832,44 @@ cudaError_t launch_siddon_visits(VolDims dims, const float* src, const float* tg
     return cudaGetLastError();
 }
 
+// Forward with sensitivities for ARBITRARY ray sets (sub-sampled / patched / user rays): one thread per ray over the
+// whole volume, plain stores (no slabs, so no partial sums).  Volumes too large for 32-bit offsets are refused.
+__global__ void __launch_bounds__(kThreads) siddon_sens_kernel(const float* __restrict__ vol, VolDims dims,
+                                                               const float* __restrict__ src, const float* __restrict__ tgt,
+                                                               const float* __restrict__ raylen, float* __restrict__ out,
+                                                               float* __restrict__ sens, int64_t N, float shift, float eps)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int b = blockIdx.y;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float L = __ldg(raylen + r);
+    const int lo_v[3] = {0, 0, 0};
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    const float S = siddon_ray_sens_box<4>(vol, dims, lo_v, dims.d, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
+    float4 t, s4;
+    t.x = -L * ray.inv[0] * A[0];
+    t.y = -L * ray.inv[1] * A[1];
+    t.z = -L * ray.inv[2] * A[2];
+    t.w = S;
+    s4.x = L * ray.inv[0] * (A[0] - C[0]);
+    s4.y = L * ray.inv[1] * (A[1] - C[1]);
+    s4.z = L * ray.inv[2] * (A[2] - C[2]);
+    s4.w = 0.0f;
+    reinterpret_cast<float4*>(sens)[r * 2] = t;
+    reinterpret_cast<float4*>(sens)[r * 2 + 1] = s4;
+    out[r] = L * S;
+}
+
+cudaError_t launch_siddon_fwd_sens(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                   float* out, float* sens, int B, int64_t N, float shift, float eps, cudaStream_t stream)
+{
+    if ((int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    siddon_sens_kernel<<<ray_grid(B, N), kThreads, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens, N, shift, eps);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_siddon_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,
                               const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                               float* g_vol, int B, int64_t N, float shift, float eps, int stop_grad,

@@ -1,4 +1,5 @@
-"""Multi-GPU rendering: poses shard across ranks, the volume is replicated, ONE gather of the image stack.
+"""Multi-GPU rendering: poses (or, for small batches, detector rows) shard across ranks, the volume is replicated,
+ONE gather of the image stack.
 
 The reference has no distributed code.  Every ray is independent given the volume, so the only
 exchange step of the path is assembling the image stack: `all_gather_into_tensor` over NCCL (NVLink/NVSwitch),
@@ -86,16 +87,104 @@ def global_alpha_range(alphamin: torch.Tensor, alphamax: torch.Tensor, group=Non
     return alphamin, alphamax
 
 
-def render_sharded(drr, *pose_args, group=None, gather: bool = True, **kwargs):
-    """`drr(*pose_args, **kwargs)` with the pose batch sharded over the ranks of `group`.
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """Identity whose backward all-reduces (SUM) the gradient: pose parameters are replicated on every rank while each
+    rank differentiates only its own rays, so the true gradient is the sum of the per-rank partials."""
 
-    Every rank passes the FULL pose batch (rotation, translation tensors or a RigidTransform); it renders only its
-    contiguous slice and, with gather=True, returns the full (B, C, H, W) stack.  Gradients flow to the local slice.
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        total = grad.contiguous().clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.group)
+        return total, None
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """(B, C, h_local, W) row blocks (balanced contiguous split of H, shard_bounds) -> (B, C, H, W) on every rank;
+    backward keeps this rank's rows of the gradient."""
+
+    @staticmethod
+    def forward(ctx, local, height, group):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        B, C, h, W = local.shape
+        per = -(-height // world)
+        padded = local if h == per else torch.cat([local, local.new_zeros(B, C, per - h, W)], dim=2)
+        flat = local.new_empty(world * B, C, per, W)  # rank-major concatenation along dim 0
+        dist.all_gather_into_tensor(flat, padded.contiguous(), group=group)
+        out = flat.view(world, B, C, per, W)
+        blocks = []
+        for r in range(world):
+            lo, hi = shard_bounds(height, r, world)
+            blocks.append(out[r, :, :, :hi - lo])
+        ctx.span = shard_bounds(height, rank, world)
+        return torch.cat(blocks, dim=2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad[:, :, ctx.span[0]:ctx.span[1]].contiguous(), None, None
+
+
+def render_ray_sharded(drr, *pose_args, group=None, gather: bool = True, **kwargs):
+    """`drr(*pose_args, **kwargs)` with the DETECTOR ROWS sharded over the ranks (the partitioning for
+    batches smaller than the GPU count, e.g. the B = 1 registration loop).  Every rank holds the full pose batch, renders
+    a contiguous block of rows of every pose and (gather=True) returns the full (B, C, H, W) stack.  Pose gradients are
+    summed over the ranks in backward, so after `loss.backward()` every rank holds the full gradient, exactly as on
+    one GPU.  Trilinear's batch-global alpha range is computed from the full ray set on every rank (no collective)."""
+    from .pose import RigidTransform, convert
+    from .renderers import Trilinear, _dims_tensor, _get_alpha_minmax
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return drr(*pose_args, **kwargs)
+    det = drr.detector
+    if det.n_subsample is not None or drr.patch_size is not None or not drr.reshape:
+        raise NotImplementedError("ray sharding needs the full, reshaped detector grid (no p_subsample / patch_size)")
+    kwargs = dict(kwargs)
+    parameterization, convention = kwargs.pop("parameterization", None), kwargs.pop("convention", None)
+    degrees, calibration = kwargs.pop("degrees", False), kwargs.pop("calibration", None)
+    mask_to_channels = kwargs.pop("mask_to_channels", False)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if parameterization is None:
+        pose = RigidTransform(_SumGradAcrossRanks.apply(pose_args[0].matrix, group))
+    else:
+        pose = convert(*(_SumGradAcrossRanks.apply(a, group) for a in pose_args), parameterization=parameterization,
+                       convention=convention, degrees=degrees)
+    H, W, B = det.height, det.width, len(pose)
+    h0, h1 = shard_bounds(H, rank, world)
+    if drr._pose_in_ok(mask_to_channels, kwargs):
+        img = drr._render_pose_in(pose, calibration, rows=(h0, h1))
+    else:
+        source, target = det(pose, calibration)
+        if isinstance(drr.renderer, Trilinear) and kwargs.get("alphamin") is None:
+            s_v, t_v = drr.affine_inverse(source), drr.affine_inverse(target)
+            amin, amax = _get_alpha_minmax(s_v, t_v, _dims_tensor(drr.density.shape, s_v.device, s_v.dtype),
+                                           drr.renderer.voxel_shift, drr.renderer.eps)
+            kwargs.update(alphamin=amin.min(), alphamax=amax.max())  # quirk Q3: the range of ALL rays of the call
+        img = drr.render(drr.density, source, target[:, h0 * W:h1 * W].contiguous(), mask_to_channels,
+                         grid_shape=(h1 - h0, W), **kwargs)
+    img = img.view(B, -1, h1 - h0, W)
+    return _AllGatherRows.apply(img, H, group) if gather else img
+
+
+def render_sharded(drr, *pose_args, group=None, gather: bool = True, shard: str = "auto", **kwargs):
+    """`drr(*pose_args, **kwargs)` sharded over the ranks of `group`.
+
+    shard="poses": every rank passes the FULL pose batch (rotation, translation tensors or a RigidTransform), renders only
+    its contiguous slice of poses and, with gather=True, returns the full (B, C, H, W) stack; gradients flow to the local
+    slice.  shard="rays": `render_ray_sharded` (detector rows split, pose gradients summed over ranks).
+    shard="auto": poses when the batch has at least one pose per rank, rays otherwise.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return drr(*pose_args, **kwargs)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     batch = len(pose_args[0])
+    if shard not in ("auto", "poses", "rays"):
+        raise ValueError("shard must be 'auto', 'poses' or 'rays'")
+    if shard == "rays" or (shard == "auto" and batch < world):
+        return render_ray_sharded(drr, *pose_args, group=group, gather=gather, **kwargs)
     lo, hi = shard_bounds(batch, rank, world)
     local_args = tuple(a[lo:hi] for a in pose_args)
     from .renderers import Trilinear, _get_alpha_minmax

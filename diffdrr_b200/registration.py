@@ -23,7 +23,10 @@ class Registration(nn.Module):
         self.convention = convention
 
     def forward(self, **kwargs):
-        return self.drr(self.pose, **kwargs)
+        # same pose as `self.drr(self.pose)` (registration.py:34-35); handing DRR.forward the parameters lets it run the
+        # parameter -> pose-matrix algebra as one kernel on its fused path
+        return self.drr(self._rotation, self._translation, parameterization=self.parameterization,
+                        convention=self.convention, **kwargs)
 
     @property
     def pose(self):

@@ -81,10 +81,15 @@ class _SiddonFunction(torch.autograd.Function):
         # Ray gradients wanted and no volume gradient: ONE walk yields the image and the 6 per-ray sensitivities, and the
         # backward is elementwise (include/b200drr.h: b200drr_siddon_fwd_sens_grid / _bwd_sens).
         sens = None
-        if grid is not None and _FUSED_SENSITIVITIES and _wants_sens(ctx.needs_input_grad, stop_grad):
+        if (_FUSED_SENSITIVITIES and _wants_sens(ctx.needs_input_grad, stop_grad) and reduce == 0 and not align_corners
+                and vol.numel() < 2**31 - 1):
             sens = torch.empty(B, N, 8, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
-            if sens is not None:
+            if sens is not None and grid is None:   # arbitrary ray set (sub-sampled / patched / user rays)
+                _lib.check(lib.b200drr_siddon_fwd_sens(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
+                                                       _ptr(sens), B, N, voxel_shift, eps, _stream()),
+                           "b200drr_siddon_fwd_sens")
+            elif sens is not None:
                 _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                             _ptr(out), _ptr(sens), B, grid[0], grid[1], voxel_shift, eps, 0,
                                                             _stream()), "b200drr_siddon_fwd_sens_grid")

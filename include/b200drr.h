@@ -121,6 +121,9 @@ int b200drr_siddon_bwd_pose(const float *vol, int D0, int D1, int D2, const floa
  * b200drr_siddon_bwd_sens below.  Replaces a forward walk + a backward walk by one.  No volume gradient on this path
  * (use b200drr_siddon_bwd_grid when the volume requires grad).  variant 0 = tuned default.
  */
+int b200drr_siddon_fwd_sens(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                            const float *raylen, float *out, float *sens, int B, int64_t N, float voxel_shift, float eps,
+                            void *stream); /* arbitrary ray sets (sub-sampled / patched rays); same out / sens layout */
 int b200drr_siddon_fwd_sens_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
                                  const float *raylen, float *out, float *sens, int B, int H, int W, float voxel_shift,
                                  float eps, int variant, void *stream);

@@ -35,6 +35,20 @@ for renderer, kw in (("siddon", {}), ("trilinear", dict(n_points=150))):
     good = e_img < 1e-5 and e_gr < 1e-3 and e_gx < 1e-3 and outside == 0.0
     ok &= good
     print(f"[rank {rank}] {renderer}: image err {e_img:.2e}, grad err rot {e_gr:.2e} xyz {e_gx:.2e}, grads outside shard {outside} -> {'OK' if good else 'FAIL'}", flush=True)
+    # ray sharding (detector rows split, every rank ends with the FULL pose gradient): the B < #GPUs partitioning
+    for nb in (1, 3):
+        r3, x3 = rot[:nb].to(dev).requires_grad_(True), xyz[:nb].to(dev).requires_grad_(True)
+        ref3 = drr(r3, x3, parameterization="euler_angles", convention="ZXY", **kw)
+        (ref3 * w[:nb]).sum().backward()
+        r4, x4 = rot[:nb].to(dev).requires_grad_(True), xyz[:nb].to(dev).requires_grad_(True)
+        out3 = render_sharded(drr, r4, x4, shard="rays", parameterization="euler_angles", convention="ZXY", **kw)
+        (out3 * w[:nb]).sum().backward()
+        e_img = float((out3 - ref3).abs().max() / ref3.abs().max())
+        e_gr = float((r4.grad - r3.grad).abs().max() / r3.grad.abs().max())
+        e_gx = float((x4.grad - x3.grad).abs().max() / x3.grad.abs().max())
+        good = e_img < 1e-5 and e_gr < 1e-3 and e_gx < 1e-3
+        ok &= good
+        print(f"[rank {rank}] {renderer} ray-sharded B={nb}: image err {e_img:.2e}, grad err rot {e_gr:.2e} xyz {e_gx:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

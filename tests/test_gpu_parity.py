@@ -69,6 +69,27 @@ def test_siddon_backward_golden(name, kw):
 
 
 @pytest.mark.parametrize("name,kw", [
+    ("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)), ("siddon_nc_b4_ragged", {}),
+    ("siddon_nc_b4_stopgrad", dict(stop_grad=True)), ("siddon_nc_inside", {}),
+])
+def test_siddon_ray_gradients_only_golden(name, kw):
+    """Only the ray tensors require grad (registration): the binding takes the one-walk forward-with-sensitivities entry
+    (b200drr_siddon_fwd_sens for arbitrary ray sets) + the elementwise backward.  Same goldens, same bar."""
+    g = load_golden(name)
+    mod, fkw = _siddon(kw)
+    v, s, tg, l = t(g["volume"]), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+    out = mod(v, s, tg, l, **fkw)
+    assert relerr(out.detach().cpu().numpy(), g["img_f64"]) < 1e-4
+    (out * t(g["w"])).sum().backward()
+    assert relerr(tg.grad.cpu().numpy(), g["g_target_f64"]) < grad_tol(g, "g_target")
+    assert relerr(s.grad.cpu().numpy(), g["g_source_f64"]) < grad_tol(g, "g_source")
+    if kw.get("stop_grad"):
+        assert l.grad is None or not l.grad.any()
+    else:
+        assert relerr(l.grad.cpu().numpy(), g["g_raylen_f64"]) < grad_tol(g, "g_raylen")
+
+
+@pytest.mark.parametrize("name,kw", [
     ("trilinear_nc_b4", dict(n_points=160)),
     ("trilinear_nc_b4_alpha", dict(n_points=100, alphamin=0.62, alphamax=0.97)),
     ("trilinear_nc_b4_ragged", dict(n_points=77)),

@@ -55,3 +55,59 @@ def _worker(rank, world, port, batch):
 def test_gather_and_range_world2(batch):
     port = 29500 + (os.getpid() % 2000) + batch
     mp.spawn(_worker, args=(2, port, batch), nprocs=2, join=True)
+
+
+class _StubRenderer(torch.nn.Module):
+    """CPU stand-in for the CUDA renderers: a smooth, per-ray-independent function of (source, target, raylen) plus the
+    batch-global term Trilinear has (alphamin/alphamax kwargs), so that sharding mistakes change the result."""
+
+    voxel_shift, eps = 0.5, 1e-8
+    detector_shape = None
+
+    def forward(self, volume, source, target, img, alphamin=None, alphamax=None, **kw):
+        d = (target - source) * 1e-2
+        val = torch.sin(d).sum(-1) + 0.1 * torch.cos(target * 1e-2).prod(-1)
+        out = val.unsqueeze(1) * img * 1e-3
+        if alphamin is not None:
+            out = out * (1.0 + alphamin) + alphamax
+        return out
+
+
+def _ray_worker(rank, world, port, batch, height):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diffdrr_b200 import DRR, synthetic
+        from diffdrr_b200.parallel import render_sharded
+        vol = torch.zeros(8, 8, 8)
+        drr = DRR(synthetic.make_subject(vol), sdd=1020.0, height=height, width=6, delx=4.0)
+        drr.renderer = _StubRenderer()
+        rot0, xyz0 = synthetic.make_poses(batch, seed=3)
+        w = torch.linspace(0.5, 1.5, batch * height * 6).reshape(batch, 1, height, 6)
+        kw = dict(parameterization="euler_angles", convention="ZXY")
+        rot, xyz = rot0.clone().requires_grad_(True), xyz0.clone().requires_grad_(True)
+        ref = drr(rot, xyz, **kw)
+        (ref * w).sum().backward()
+        r2, x2 = rot0.clone().requires_grad_(True), xyz0.clone().requires_grad_(True)
+        out = render_sharded(drr, r2, x2, shard="rays", **kw)
+        assert out.shape == ref.shape and torch.allclose(out, ref, rtol=1e-6, atol=1e-7), "ray-sharded image differs"
+        (out * w).sum().backward()
+        # every rank ends up with the FULL pose gradient (partials summed in backward)
+        assert torch.allclose(r2.grad, rot.grad, rtol=1e-4, atol=1e-6) and torch.allclose(x2.grad, xyz.grad, rtol=1e-4, atol=1e-7)
+        # "auto" picks rays when there are fewer poses than ranks, poses otherwise
+        auto = render_sharded(drr, rot0, xyz0, **kw)
+        assert torch.allclose(auto, ref.detach(), rtol=1e-6, atol=1e-7)
+        # local block only
+        blk = render_sharded(drr, rot0, xyz0, shard="rays", gather=False, **kw)
+        lo, hi = shard_bounds(height, rank, world)
+        assert torch.allclose(blk, ref.detach()[:, :, lo:hi], rtol=1e-6, atol=1e-7)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch,height", [(1, 7), (3, 8)])
+def test_ray_sharding_world2(batch, height):
+    """Detector rows split over 2 gloo ranks (ragged when H is odd): gathered image == unsharded, pose gradients summed."""
+    port = 31500 + (os.getpid() % 2000) + batch
+    mp.spawn(_ray_worker, args=(2, port, batch, height), nprocs=2, join=True)
