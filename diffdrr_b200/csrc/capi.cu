@@ -218,6 +218,18 @@ int b200drr_siddon_bwd_sens_pose(const float* sens, const float* gout, const flo
                                            (cudaStream_t)stream));
 }
 
+int b200drr_trilinear_fwd_sens(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                               const float* raylen, float* out, float* sens, int B, int64_t N, int H, int W,
+                               float voxel_shift, float eps, int n_points, const float* alpha_range, int align_corners,
+                               void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !sens || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) ||
+        n_points < 2 || H < 0 || W < 0 || (H > 0 && ((int64_t)H * W != N || align_corners)))
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_sens(vol, mk(D0, D1, D2), src, tgt, raylen, out, sens, B, N, H, W, voxel_shift, eps,
+                                         n_points, alpha_range, align_corners != 0, (cudaStream_t)stream));
+}
+
 int b200drr_trilinear_fwd_sens_packed(const float* packed, int D0, int D1, int D2, const float* src, const float* tgt,
                                       const float* raylen, float* out, float* sens, int B, int H, int W, float voxel_shift,
                                       float eps, int n_points, const float* alpha_range, int slab, void* stream)

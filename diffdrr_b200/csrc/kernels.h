@@ -64,6 +64,9 @@ cudaError_t launch_siddon_bwd_sens_pose(const float* sens, const float* gout, co
                                         const float* cols, float* g_src, float* g_G, float* g_Wd, int B, int H, int W,
                                         int stop_grad, cudaStream_t stream);
 
+cudaError_t launch_trilinear_fwd_sens(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      float* out, float* sens, int B, int64_t N, int H, int W, float shift, float eps,
+                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                              const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                              float eps, int n_points, const float* alpha_range, int slab,

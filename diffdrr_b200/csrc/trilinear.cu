@@ -428,6 +428,56 @@ __global__ void __launch_bounds__(TW* TH) trilinear_sens_packed_kernel(
     }
 }
 
+// Forward with sensitivities from the PLAIN volume (8 scalar gathers per sample): arbitrary ray sets (H == 0: ray n of
+// pose b, one thread per ray in row order) or the full detector grid (H > 0: 16x16 pixel tiles, 8x4 ray bundle per warp).
+// Same sens layout as the packed kernel; align_corners supported (arbitrary-ray form only).
+__global__ void __launch_bounds__(256) trilinear_sens_kernel(const float* __restrict__ vol, VolDims dims,
+                                                             const float* __restrict__ src, const float* __restrict__ tgt,
+                                                             const float* __restrict__ raylen, float* __restrict__ out,
+                                                             float* __restrict__ sens, int64_t N, int H, int W, float shift,
+                                                             float eps, int P, const float* __restrict__ alpha_range,
+                                                             int align_corners)
+{
+    const int b = blockIdx.y;
+    int64_t n;
+    if (H > 0) {
+        const int tiles_x = (W + 15) / 16;
+        const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int px = tile_x * 16 + (warp % 2) * 8 + (lane & 7);
+        const int py = tile_y * 16 + (warp / 2) * 4 + (lane >> 3);
+        if (px >= W || py >= H) return;
+        n = (int64_t)py * W + px;
+    } else {
+        n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= N) return;
+    }
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+    const float step = (amax - amin) / (float)(P - 1);
+    const float L = __ldg(raylen + r);
+    const TriGrad tg = trilinear_ray_bwd(vol, dims, ray, shift, P, amin, amax, align_corners, 1.0f, L, nullptr);
+    float* sr = sens + r * 12;
+    reinterpret_cast<float4*>(sr)[0] = make_float4(tg.gt[0], tg.gt[1], tg.gt[2], step * tg.sumV);
+    reinterpret_cast<float4*>(sr)[1] = make_float4(tg.gs[0], tg.gs[1], tg.gs[2], tg.ga0);
+    reinterpret_cast<float4*>(sr)[2] = make_float4(tg.ga1, 0.0f, 0.0f, 0.0f);
+    out[r] = tg.sumV * (L * step);  // bitwise the forward kernels' expression
+}
+
+cudaError_t launch_trilinear_fwd_sens(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      float* out, float* sens, int B, int64_t N, int H, int W, float shift, float eps,
+                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream)
+{
+    if (H > 0 && ((int64_t)H * W != N || align_corners)) return cudaErrorInvalidValue;
+    const int64_t blocks = H > 0 ? (int64_t)((W + 15) / 16) * ((H + 15) / 16) : (N + 255) / 256;
+    if (blocks > INT32_MAX || B > 65535) return cudaErrorInvalidValue;
+    trilinear_sens_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens, N, H,
+                                                                                 W, shift, eps, n_points, alpha_range,
+                                                                                 align_corners);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                              const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                              float eps, int n_points, const float* alpha_range, int slab,

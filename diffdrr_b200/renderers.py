@@ -236,10 +236,15 @@ class _TrilinearFunction(torch.autograd.Function):
         # training-step fast path (twin of the Siddon one): ray gradients wanted, static (packed) volume -> one march
         # yields the image and the per-ray sensitivities; backward is elementwise (b200drr_trilinear_bwd_sens)
         sens = None
-        if packed is not None and _FUSED_SENSITIVITIES and any(ctx.needs_input_grad[1:5]) and not ctx.needs_input_grad[0]:
+        if _FUSED_SENSITIVITIES and reduce == 0 and any(ctx.needs_input_grad[1:5]) and not ctx.needs_input_grad[0]:
             sens = torch.empty(B, N, 12, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
-            if sens is not None:
+            if sens is not None and packed is None:   # plain volume: arbitrary ray sets, or the grid without a packed copy
+                h, w_ = grid if grid is not None else (0, 0)
+                _lib.check(lib.b200drr_trilinear_fwd_sens(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
+                                                          _ptr(sens), B, N, h, w_, voxel_shift, eps, n_points, _ptr(arange),
+                                                          int(align_corners), _stream()), "b200drr_trilinear_fwd_sens")
+            elif sens is not None:
                 _lib.check(lib.b200drr_trilinear_fwd_sens_packed(_ptr(packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                                  _ptr(out), _ptr(sens), B, grid[0], grid[1], voxel_shift, eps,
                                                                  n_points, _ptr(arange),

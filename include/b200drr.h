@@ -226,6 +226,10 @@ int b200drr_trilinear_bwd_packed(const float *packed, int D0, int D1, int D2, co
  * b200drr_trilinear_bwd_sens applies it: g_tgt [B][N][3], g_raylen [B][N], g_src [B][3] overwritten (NULL = not wanted),
  * g_alpha_range [2] ACCUMULATED INTO (caller zero-fills; NULL = not wanted).  slab as in b200drr_trilinear_fwd_packed.
  */
+int b200drr_trilinear_fwd_sens(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                               const float *raylen, float *out, float *sens, int B, int64_t N, int H, int W,
+                               float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
+                               void *stream); /* from the plain volume: H = W = 0 arbitrary rays, else N == H*W grid tiles */
 int b200drr_trilinear_fwd_sens_packed(const float *packed, int D0, int D1, int D2, const float *src, const float *tgt,
                                       const float *raylen, float *out, float *sens, int B, int H, int W,
                                       float voxel_shift, float eps, int n_points, const float *alpha_range, int slab,

@@ -109,6 +109,26 @@ def test_trilinear_backward_golden(name, kw):
     assert relerr(v.grad.cpu().numpy(), g["g_volume_f64"]) < grad_tol(g, "g_volume")
 
 
+@pytest.mark.parametrize("name,kw", [
+    ("trilinear_nc_b4", dict(n_points=160)),
+    ("trilinear_nc_b4_alpha", dict(n_points=100, alphamin=0.62, alphamax=0.97)),
+    ("trilinear_nc_b4_ragged", dict(n_points=77)),
+    ("trilinear_nc_b4_shift0", dict(n_points=120, voxel_shift=0.0)),
+])
+def test_trilinear_ray_gradients_only_golden(name, kw):
+    """Only the ray tensors require grad: one march (b200drr_trilinear_fwd_sens, arbitrary ray set) + elementwise
+    backward, incl. the arg-min/arg-max branch of the batch-global alpha range.  Same goldens, same bar."""
+    g = load_golden(name)
+    mod, fkw = _trilinear(kw)
+    v, s, tg, l = t(g["volume"]), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+    out = mod(v, s, tg, l, **fkw)
+    assert relerr(out.detach().cpu().numpy(), g["img_f64"]) < 1e-4
+    (out * t(g["w"])).sum().backward()
+    assert relerr(tg.grad.cpu().numpy(), g["g_target_f64"]) < grad_tol(g, "g_target", 1e-3)
+    assert relerr(s.grad.cpu().numpy(), g["g_source_f64"]) < grad_tol(g, "g_source", 1e-3)
+    assert relerr(l.grad.cpu().numpy(), g["g_raylen_f64"]) < grad_tol(g, "g_raylen")
+
+
 @pytest.mark.parametrize("name,renderer,fkw", [
     ("drr_siddon_b4", "siddon", {}), ("drr_trilinear_b4", "trilinear", dict(n_points=200)),
     ("drr_siddon_b1_patch", "siddon", {}),
