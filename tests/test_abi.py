@@ -35,6 +35,25 @@ def test_argument_validation_without_gpu(lib):
     assert lib.b200drr_siddon_fwd(None, 4, 4, 4, None, None, None, None, 1, 1, 0.5, 1e-8, 0, 0, None) == -1
     assert lib.b200drr_trilinear_fwd(None, 4, 4, 4, None, None, None, None, 1, 1, 0.5, 1e-8, 1, None, 0, 0, None) == -1
     assert lib.b200drr_siddon_visits(0, 4, 4, None, None, None, 1, 1, 0.5, 1e-8, None) == -1
+    # every entry point taking pointers rejects an all-NULL call with B200DRR_EINVAL instead of touching CUDA
+    n = None
+    assert lib.b200drr_siddon_fwd_sens(n, 4, 4, 4, n, n, n, n, n, 1, 1, 0.5, 1e-8, n) == -1
+    assert lib.b200drr_siddon_fwd_sens_grid(n, 4, 4, 4, n, n, n, n, n, 1, 2, 2, 0.5, 1e-8, 0, n) == -1
+    assert lib.b200drr_siddon_fwd_sens_pose(n, 4, 4, 4, n, n, n, n, n, n, n, 1, 2, 2, 0.5, 1e-8, n) == -1
+    assert lib.b200drr_siddon_bwd_sens(n, n, n, n, n, 1, 4, 0, n) == -1
+    assert lib.b200drr_siddon_bwd_sens_pose(n, n, n, n, n, n, n, n, 1, 2, 2, 0, n) == -1
+    assert lib.b200drr_trilinear_fwd_sens(n, 4, 4, 4, n, n, n, n, n, 1, 4, 0, 0, 0.5, 1e-8, 10, n, 0, n) == -1
+    assert lib.b200drr_trilinear_fwd_sens_packed(n, 4, 4, 4, n, n, n, n, n, 1, 2, 2, 0.5, 1e-8, 10, n, 0, n) == -1
+    assert lib.b200drr_trilinear_bwd_sens(n, n, n, n, n, n, 1, 4, n) == -1
+    assert lib.b200drr_euler_pose_fwd(n, n, 2, 0, 1, 1.0, n, 1, n) == -1
+    assert lib.b200drr_euler_pose_bwd(n, n, 2, 0, 1, 1.0, n, n, n, 1, n) == -1
+    assert lib.b200drr_pose_rays_fwd(n, n, n, n, n, n, n, 1, n) == -1
+    assert lib.b200drr_pose_rays_bwd(n, n, n, n, n, n, n, 1, n) == -1
+    # bad Euler axis triple (middle axis repeated / out of range) is refused even with valid-looking pointers
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.b200drr_euler_pose_fwd(p, p, 0, 0, 1, 1.0, p, 1, n) == -1
+    assert lib.b200drr_euler_pose_fwd(p, p, 0, 3, 1, 1.0, p, 1, n) == -1
     assert b"invalid argument" in lib.b200drr_error_string(-1)
     assert b"unsupported" in lib.b200drr_error_string(-2)
     assert lib.b200drr_error_string(0) == b"success"
