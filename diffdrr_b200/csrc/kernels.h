@@ -74,6 +74,15 @@ cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, 
 cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                       float* g_alpha_range, int B, int64_t N, cudaStream_t stream);
 
+cudaError_t launch_siddon_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
+                                   const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                   float* g_vol, int B, int64_t N, int C, float shift, float eps, int stop_grad,
+                                   cudaStream_t stream);
+cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                      float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
+                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
+
 // per-pose algebra around the pose-in kernels (pose.cu)
 cudaError_t launch_euler_pose_fwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, float* P, int B,
                                   cudaStream_t stream);

@@ -832,8 +832,35 @@ B200_HD float siddon_ray_bwd_lean_box(const float* vol, const VolDims& dims, con
 // Per axis accumulate A_a = sum coef*alpha, C_a = sum coef with coef = v_before - v_after; then
 //   g_t[a] = -g L A_a / d_a,   g_s[a] = g L (A_a - C_a) / d_a.
 // Returns sum_j v_j len_j (for g_raylen); g_vol[voxel_j] += gL * len_j when g_vol != nullptr.
-B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, float gL, float* g_vol,
-                             float gs[3], float gt[3])
+// `fetch(off, gj)` returns the EFFECTIVE voxel value gj * V[off] and the per-voxel upstream factor gj: 1 for the plain
+// renderer; with a label mask (mask_to_channels, renderers.py:77-89) gj = gout[b][label(off)][n], the gradient of the
+// channel the segment was scattered to -- everything else is unchanged (v_j -> g_j v_j, g = 1).
+struct FetchPlain {
+    const float* vol;
+    B200_HD float operator()(int64_t off, float& gj) const
+    {
+        gj = 1.0f;
+        return ldg(vol + off);
+    }
+};
+
+struct FetchMasked {
+    const float* vol;
+    const float* mask;
+    const float* gch;  // gout[b][0][n]; channels are cstride floats apart
+    int64_t cstride;
+    int C;
+    B200_HD float operator()(int64_t off, float& gj) const
+    {
+        const int c = (int)ldg(mask + off);
+        gj = (unsigned)c < (unsigned)C ? ldg(gch + (int64_t)c * cstride) : 0.0f;
+        return gj * ldg(vol + off);
+    }
+};
+
+template <class Fetch>
+B200_HD float siddon_ray_bwd_f(const Fetch& fetch, const VolDims& dims, const Ray& ray, float shift, float gL, float* g_vol,
+                               float gs[3], float gt[3])
 {
     Walk w = start_walk(ray, dims, shift);
     float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
@@ -846,7 +873,8 @@ B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& r
         int axis_in = w.entry_axis;
         bool inside = true;
         while (inside) {
-            const float v = ldg(vol + off);
+            float gj;
+            const float v = fetch(off, gj);
             const float coef = vprev - v;  // crossing into this voxel at acur through axis_in
 #pragma unroll
             for (int a = 0; a < 3; ++a)
@@ -857,7 +885,7 @@ B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& r
             const float anext = fminf(fminf(w.an[0], w.an[1]), w.an[2]);
             const float len = anext - acur;
             acc = fmaf(len, v, acc);
-            if (g_vol) red_add(g_vol + off, gL * len);
+            if (g_vol) red_add(g_vol + off, (gL * gj) * len);
             acur = anext;
             vprev = v;
             axis_in = step_walk(w, dims, anext, off, so, inside);
@@ -876,6 +904,12 @@ B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& r
         gs[a] = gL * (A[a] - C[a]) * ray.inv[a];
     }
     return acc;
+}
+
+B200_HD float siddon_ray_bwd(const float* vol, const VolDims& dims, const Ray& ray, float shift, float gL, float* g_vol,
+                             float gs[3], float gt[3])
+{
+    return siddon_ray_bwd_f(FetchPlain{vol}, dims, ray, shift, gL, g_vol, gs, gt);
 }
 
 // ===================================================================================================
@@ -1149,10 +1183,37 @@ struct TriGrad {
 //   g_s = g L step sum (1-alpha_m) G_m ka,  g_t = g L step sum alpha_m G_m ka,  g_L = g step sum V_m,
 //   g_amin = g L [-sum V/(P-1) + step sum (1-lin_m) G_m.dp],  g_amax = g L [+sum V/(P-1) + step sum lin_m G_m.dp],
 //   g_V[corner] += g L step w_corner.
-template <class Gather>
+// Per-sample upstream factor: 1 for the plain renderer; with a label mask (renderers.py:242-252) the gradient of the
+// channel the sample was scattered to, label sampled NEAREST at the sample point (zero padding -> label 0).
+struct SampleGradOne {
+    B200_HD float operator()(const VolDims&, const float*) const { return 1.0f; }
+};
+
+struct SampleGradMasked {
+    const float* mask;
+    const float* gch;  // gout[b][0][n]; channels are cstride floats apart
+    int64_t cstride;
+    int C;
+    B200_HD float operator()(const VolDims& dims, const float pix[3]) const
+    {
+        bool inb = true;
+        int64_t flat = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float rr = rintf(pix[a]);
+            inb = inb && rr >= 0.0f && rr < (float)dims.d[a];
+            flat = flat * dims.d[a] + (inb ? (int64_t)rr : 0);
+        }
+        const int c = inb ? (int)ldg(mask + flat) : 0;
+        return (unsigned)c < (unsigned)C ? ldg(gch + (int64_t)c * cstride) : 0.0f;
+    }
+};
+
+template <class Gather, class SampleGrad = SampleGradOne>
 B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, const Ray& ray, float shift, int P,
                                     float amin, float amax, int align_corners, float g, float L, float* g_vol,
-                                    float s_lo = -INFINITY, float s_hi = INFINITY)
+                                    float s_lo = -INFINITY, float s_hi = INFINITY,
+                                    const SampleGrad& sample_grad = SampleGrad())
 {
     const PixLine pl = make_pixline(ray, dims, shift, align_corners);
     const float range = amax - amin;
@@ -1176,12 +1237,13 @@ B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, c
         const float c00 = fmaf(f2, k.v[4] - k.v[0], k.v[0]), c10 = fmaf(f2, k.v[5] - k.v[1], k.v[1]);
         const float c01 = fmaf(f2, k.v[6] - k.v[2], k.v[2]), c11 = fmaf(f2, k.v[7] - k.v[3], k.v[3]);
         const float c0 = fmaf(f1, c01 - c00, c00), c1 = fmaf(f1, c11 - c10, c10);
-        sumV += fmaf(f0, c1 - c0, c0);
+        const float gm = sample_grad(dims, pix);  // == 1.0f exactly for the plain renderer (products below are exact)
+        sumV += gm * fmaf(f0, c1 - c0, c0);
         float G[3];
-        G[0] = c1 - c0;
-        G[1] = e0 * (c01 - c00) + f0 * (c11 - c10);
-        G[2] = e0 * (e1 * (k.v[4] - k.v[0]) + f1 * (k.v[6] - k.v[2])) +
-               f0 * (e1 * (k.v[5] - k.v[1]) + f1 * (k.v[7] - k.v[3]));
+        G[0] = gm * (c1 - c0);
+        G[1] = gm * (e0 * (c01 - c00) + f0 * (c11 - c10));
+        G[2] = gm * (e0 * (e1 * (k.v[4] - k.v[0]) + f1 * (k.v[6] - k.v[2])) +
+                     f0 * (e1 * (k.v[5] - k.v[1]) + f1 * (k.v[7] - k.v[3])));
         float Gd = 0.0f;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -1196,7 +1258,7 @@ B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, c
             for (int c = 0; c < 8; ++c)
                 if (k.mask & (1u << c)) {
                     const float w = ((c & 1) ? f0 : e0) * (((c >> 1) & 1) ? f1 : e1) * (((c >> 2) & 1) ? f2 : e2);
-                    red_add(g_vol + k.base + corner_off(dims, c), gLs * w);
+                    red_add(g_vol + k.base + corner_off(dims, c), (gLs * gm) * w);
                 }
         }
     }

@@ -478,6 +478,67 @@ cudaError_t launch_trilinear_fwd_sens(const float* vol, VolDims dims, const floa
     return cudaGetLastError();
 }
 
+// mask_to_channels backward (autograd of renderers.py:242-252): gout [B][C][N]; sample m carries the gradient of the
+// channel its nearest label routed it to.  g_alpha_range accumulated into (caller zero-fills).
+__global__ void __launch_bounds__(kThreads) trilinear_bwd_mask_kernel(
+    const float* __restrict__ vol, const float* __restrict__ mask, VolDims dims, const float* __restrict__ src,
+    const float* __restrict__ tgt, const float* __restrict__ raylen, const float* __restrict__ gout,
+    float* __restrict__ g_src, float* __restrict__ g_tgt, float* __restrict__ g_raylen, float* __restrict__ g_vol,
+    float* __restrict__ g_alpha_range, int64_t N, int C, float shift, float eps, int P,
+    const float* __restrict__ alpha_range, int align_corners)
+{
+    __shared__ float red[32];
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    float gs[3] = {0.0f, 0.0f, 0.0f}, ga0 = 0.0f, ga1 = 0.0f;
+    if (n < N) {
+        const int64_t r = (int64_t)b * N + n;
+        const Ray ray = load_ray(src, tgt, b, r, eps);
+        const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
+        const float step = (amax - amin) / (float)(P - 1);
+        const float L = __ldg(raylen + r);
+        const SampleGradMasked sg{mask, gout + (int64_t)b * C * N + n, N, C};
+        const TriGrad tg = trilinear_ray_bwd_g(GatherPlain{vol}, dims, ray, shift, P, amin, amax, align_corners, 1.0f, L,
+                                               g_vol, -INFINITY, INFINITY, sg);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            gs[a] = tg.gs[a];
+            if (g_tgt) g_tgt[r * 3 + a] = tg.gt[a];
+        }
+        if (g_raylen) g_raylen[r] = step * tg.sumV;
+        ga0 = tg.ga0;
+        ga1 = tg.ga1;
+    }
+    if (g_src) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tot = block_sum(gs[a], red);
+            if (threadIdx.x == 0) atomicAdd(g_src + b * 3 + a, tot);
+        }
+    }
+    if (g_alpha_range) {
+        const float t0 = block_sum(ga0, red);
+        if (threadIdx.x == 0) atomicAdd(g_alpha_range, t0);
+        const float t1 = block_sum(ga1, red);
+        if (threadIdx.x == 0) atomicAdd(g_alpha_range + 1, t1);
+    }
+}
+
+cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                      float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
+                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream)
+{
+    if (g_src) {
+        const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+        if (e != cudaSuccess) return e;
+    }
+    trilinear_bwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, g_alpha_range, N, C, shift, eps, n_points,
+        alpha_range, align_corners);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
                                              const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                              float eps, int n_points, const float* alpha_range, int slab,

@@ -329,30 +329,76 @@ def _mask_channels(mask: torch.Tensor) -> int:
     return int(mask.max().item() + 1)
 
 
+class _MaskFunction(torch.autograd.Function):
+    """mask_to_channels rendering (B, C, N) through b200drr_*_fwd_mask; backward = b200drr_*_bwd_mask (the per-segment /
+    per-sample upstream gradient is the gradient of the channel the label routed it to)."""
+
+    @staticmethod
+    def forward(ctx, volume, source, target, img, alpha_range, mask, kind, voxel_shift, eps, n_points, align_corners,
+                stop_grad, C):
+        B, N = _check_inputs(volume, source, target, img)
+        vol, msk = volume.contiguous(), mask
+        src, tgt, raylen = source.reshape(B, 3).contiguous(), target.contiguous(), img.reshape(B, N).contiguous()
+        out = torch.empty(B, C, N, dtype=torch.float32, device=vol.device)
+        lib = _lib.load()
+        ar = None
+        with torch.cuda.device(vol.device):
+            if kind == "siddon":
+                _lib.check(lib.b200drr_siddon_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                       _ptr(out), B, N, C, voxel_shift, eps, _stream()),
+                           "b200drr_siddon_fwd_mask")
+            else:
+                ar = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
+                _lib.check(lib.b200drr_trilinear_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),
+                                                          _ptr(raylen), _ptr(out), B, N, C, voxel_shift, eps, int(n_points),
+                                                          _ptr(ar), int(align_corners), _stream()),
+                           "b200drr_trilinear_fwd_mask")
+        ctx.save_for_backward(vol, msk, src, tgt, raylen, ar)
+        ctx.cfg = (kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, tuple(source.shape), tuple(img.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        vol, msk, src, tgt, raylen, ar = ctx.saved_tensors
+        kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, src_shape, img_shape = ctx.cfg
+        B, N = tgt.shape[0], tgt.shape[1]
+        need_vol, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
+        dev = vol.device
+        gout = gout.reshape(B, C, N).contiguous().float()
+        g_src = torch.empty(B, 3, dtype=torch.float32, device=dev) if need_src else None
+        g_tgt = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if need_tgt else None
+        g_len = torch.empty(B, N, dtype=torch.float32, device=dev) if (need_len and not stop_grad) else None
+        g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
+        g_ar = None
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            if kind == "siddon":
+                _lib.check(lib.b200drr_siddon_bwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                       _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, C,
+                                                       voxel_shift, eps, int(stop_grad), _stream()), "b200drr_siddon_bwd_mask")
+            else:
+                g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
+                _lib.check(lib.b200drr_trilinear_bwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),
+                                                          _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len),
+                                                          _ptr(g_vol), _ptr(g_ar), B, N, C, voxel_shift, eps, int(n_points),
+                                                          _ptr(ar), int(align_corners), _stream()),
+                           "b200drr_trilinear_bwd_mask")
+        return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None, None)
+
+
 def _render_mask(kind, volume, mask, source, target, img, voxel_shift, eps, n_points=None, alpha_range=None,
-                 align_corners=False):
-    """mask_to_channels forward through b200drr_*_fwd_mask -> (B, C, N).  Not differentiable (yet)."""
-    B, N = _check_inputs(volume, source, target, img)
-    if any(t.requires_grad for t in (volume, source, target, img)) and torch.is_grad_enabled():
-        raise NotImplementedError("backward through mask_to_channels rendering is not implemented in diffdrr_b200; "
-                                  "call it under torch.no_grad()")
+                 align_corners=False, stop_grad=False):
+    """mask_to_channels rendering -> (B, C, N), differentiable w.r.t. volume, rays, ray lengths (and the trilinear
+    sampling range)."""
     if not mask.is_cuda or mask.shape != volume.shape:
         raise ValueError("mask must be a CUDA label volume with the shape of the density volume")
-    vol, msk = volume.contiguous(), mask.contiguous().float()
-    src, tgt, raylen = source.reshape(B, 3).contiguous(), target.contiguous(), img.reshape(B, N).contiguous()
-    C = _mask_channels(msk)
-    out = torch.empty(B, C, N, dtype=torch.float32, device=vol.device)
-    lib = _lib.load()
-    with torch.cuda.device(vol.device):
-        if kind == "siddon":
-            _lib.check(lib.b200drr_siddon_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
-                                                   _ptr(out), B, N, C, voxel_shift, eps, _stream()), "b200drr_siddon_fwd_mask")
-        else:
-            ar = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
-            _lib.check(lib.b200drr_trilinear_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
-                                                      _ptr(out), B, N, C, voxel_shift, eps, int(n_points), _ptr(ar),
-                                                      int(align_corners), _stream()), "b200drr_trilinear_fwd_mask")
-    return out
+    msk = mask.detach().contiguous().float()
+    if alpha_range is None:
+        alpha_range = torch.zeros(2, dtype=torch.float32, device=volume.device)
+    return _MaskFunction.apply(volume, source, target, img, alpha_range, msk, kind, float(voxel_shift), float(eps),
+                               0 if n_points is None else int(n_points), bool(align_corners), bool(stop_grad),
+                               _mask_channels(msk))
 
 
 _DIMS_CACHE: dict = {}
@@ -407,7 +453,8 @@ class Siddon(torch.nn.Module):
         if mask is not None:
             if align_corners or _reduce_code(self.reducefn) != 0:
                 raise NotImplementedError("mask_to_channels is implemented for reducefn='sum', align_corners=False")
-            return _render_mask("siddon", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps))
+            return _render_mask("siddon", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps),
+                                stop_grad=self.stop_gradients_through_grid_sample)
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
                                      bool(self.stop_gradients_through_grid_sample), self.detector_shape)

@@ -240,13 +240,29 @@ int b200drr_trilinear_bwd_sens(const float *sens, const float *gout, float *g_sr
 /*
  * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored
  * as fp32 (as DRR registers it, drr.py:86-91); every segment / sample contributes to channel label(voxel), sampled
- * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.  Forward only.
+ * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.
  */
 int b200drr_siddon_fwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
                             const float *tgt, const float *raylen, float *out, int B, int64_t N, int C,
                             float voxel_shift, float eps, void *stream);
 int b200drr_trilinear_fwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
                                const float *tgt, const float *raylen, float *out, int B, int64_t N, int C,
+                               float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
+                               void *stream);
+
+/*
+ * mask_to_channels backward = what autograd derives for the scatter_add_ routing above: gout [B][C][N]; the segment /
+ * sample routed to channel c carries gout[b][c][n], otherwise the closed forms of b200drr_siddon_bwd /
+ * b200drr_trilinear_bwd.  Output conventions as there (g_src/g_tgt/g_raylen overwritten, g_vol and g_alpha_range
+ * accumulated into, any may be NULL).
+ */
+int b200drr_siddon_bwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                            const float *tgt, const float *raylen, const float *gout, float *g_src, float *g_tgt,
+                            float *g_raylen, float *g_vol, int B, int64_t N, int C, float voxel_shift, float eps,
+                            int stop_grad, void *stream);
+int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                               const float *tgt, const float *raylen, const float *gout, float *g_src, float *g_tgt,
+                               float *g_raylen, float *g_vol, float *g_alpha_range, int B, int64_t N, int C,
                                float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
                                void *stream);
 

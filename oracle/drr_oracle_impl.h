@@ -222,6 +222,76 @@ void FN(oracle_siddon_bwd)(const REAL *vol, int D0, int D1, int D2, const REAL *
     }
 }
 
+/* Autograd of Siddon.forward WITH a label mask (renderers.py:77-89): the scatter_add_ routes segment j to channel
+ * c_j = label at the segment's voxel, so the upstream gradient of segment j is g_j = gout[b][c_j][n] and everything
+ * above holds with v_j replaced by g_j v_j and g = 1:
+ *   dLoss/dalpha_m = L (g_{m-1} v_{m-1} - g_m v_m),  dLoss/dL = sum_j g_j v_j len_j,  dLoss/dV[voxel_j] += g_j L len_j.
+ * gout is [B][C][N]; labels outside [0, C) carry no gradient (the forward drops them). */
+void FN(oracle_siddon_bwd_mask)(const REAL *vol, const REAL *mask, int D0, int D1, int D2, const REAL *src, const REAL *tgt,
+                                const REAL *raylen, const REAL *gout, REAL *g_src, REAL *g_tgt, REAL *g_raylen,
+                                REAL *g_vol, int B, long N, int C, REAL shift, REAL eps, int stop_grad, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const int M = D0 + D1 + D2 + 3;
+    if (g_src) memset(g_src, 0, sizeof(REAL) * (size_t)B * 3);
+#pragma omp parallel
+    {
+        REAL *alpha = (REAL *)malloc(sizeof(REAL) * (size_t)M);
+        int *axis = (int *)malloc(sizeof(int) * (size_t)M);
+        REAL *v = (REAL *)malloc(sizeof(REAL) * (size_t)(M + 1));
+#pragma omp for schedule(dynamic, 64)
+        for (long r = 0; r < (long)B * N; ++r) {
+            const int b = (int)(r / N);
+            const long n = r % N;
+            REAL s[3], d[3];
+            for (int a = 0; a < 3; ++a) {
+                s[a] = src[b * 3 + a];
+                d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+            }
+            FN(sorted_alphas)(dims, s, d, shift, alpha, axis, NULL);
+            const REAL L = raylen[r];
+            REAL gL = 0;
+            for (int j = 0; j + 1 < M; ++j) {
+                REAL amid = (alpha[j] + alpha[j + 1]) / (REAL)2;
+                long idx = FN(nearest_index)(amid, s, d, shift, dims, align_corners);
+                REAL gj = 0;
+                if (idx >= 0) {
+                    long c = (long)mask[idx];
+                    if (c >= 0 && c < C) gj = gout[((long)b * C + c) * N + n];
+                }
+                v[j] = idx < 0 ? (REAL)0 : gj * vol[idx];
+                REAL len = alpha[j + 1] - alpha[j];
+                gL += v[j] * len;
+                if (g_vol && !stop_grad && idx >= 0) {
+                    REAL add = gj * L * len;
+#pragma omp atomic
+                    g_vol[idx] += add;
+                }
+            }
+            REAL gs[3] = {0, 0, 0}, gt[3] = {0, 0, 0};
+            for (int m = 0; m < M; ++m) {
+                REAL vm1 = m > 0 ? v[m - 1] : (REAL)0;
+                REAL vm = m + 1 < M ? v[m] : (REAL)0;
+                REAL c = L * (vm1 - vm);
+                int a = axis[m];
+                gs[a] += c * (alpha[m] - (REAL)1) / d[a];
+                gt[a] += c * (-alpha[m]) / d[a];
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (g_tgt) g_tgt[r * 3 + a] = gt[a];
+                if (g_src) {
+#pragma omp atomic
+                    g_src[b * 3 + a] += gs[a];
+                }
+            }
+            if (g_raylen) g_raylen[r] = stop_grad ? (REAL)0 : gL;
+        }
+        free(alpha);
+        free(axis);
+        free(v);
+    }
+}
+
 /* renderers.py:124-140 (_get_alpha_minmax) followed by the batch-global .min()/.max() of
  * renderers.py:221-223.  Far plane is dims + 1 - shift (quirk Q4). */
 void FN(oracle_alpha_minmax)(const REAL *src, const REAL *tgt, int D0, int D1, int D2, int B, long N,
@@ -428,6 +498,79 @@ void FN(oracle_trilinear_bwd)(const REAL *vol, int D0, int D1, int D2, const REA
         if (g_raylen) g_raylen[r] = g * step * sumV;
         tot_amin += g * L * (-sumV / (REAL)(n_points - 1) + step * ga0);
         tot_amax += g * L * (sumV / (REAL)(n_points - 1) + step * ga1);
+    }
+    if (g_amin) *g_amin = tot_amin;
+    if (g_amax) *g_amax = tot_amax;
+}
+
+/* Autograd of Trilinear.forward WITH a label mask (renderers.py:242-252): sample m goes to channel c_m = nearest label
+ * at the sample point (zero padding -> label 0), so its upstream gradient is g_m = gout[b][c_m][n]; the closed forms
+ * above hold with every per-sample term weighted by g_m (and g = 1). */
+void FN(oracle_trilinear_bwd_mask)(const REAL *vol, const REAL *mask, int D0, int D1, int D2, const REAL *src,
+                                   const REAL *tgt, const REAL *raylen, const REAL *gout, REAL *g_src, REAL *g_tgt,
+                                   REAL *g_raylen, REAL *g_vol, REAL *g_amin, REAL *g_amax, int B, long N, int C, REAL shift,
+                                   REAL eps, int n_points, REAL alphamin, REAL alphamax, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const REAL step = (alphamax - alphamin) / (REAL)(n_points - 1);
+    if (g_src) memset(g_src, 0, sizeof(REAL) * (size_t)B * 3);
+    REAL tot_amin = 0, tot_amax = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : tot_amin, tot_amax)
+    for (long r = 0; r < (long)B * N; ++r) {
+        const int b = (int)(r / N);
+        const long n = r % N;
+        REAL s[3], d[3], scale[3];
+        for (int a = 0; a < 3; ++a) {
+            s[a] = src[b * 3 + a];
+            d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+            scale[a] = align_corners ? (REAL)(dims[a] - 1) / (REAL)dims[a] : (REAL)1;
+        }
+        const REAL L = raylen[r];
+        REAL sumV = 0, gs[3] = {0, 0, 0}, gt[3] = {0, 0, 0}, ga0 = 0, ga1 = 0;
+        for (int m = 0; m < n_points; ++m) {
+            REAL lin = FN(linspace01)(m, n_points);
+            REAL alpha = lin * (alphamax - alphamin) + alphamin;
+            REAL pix[3], G[3], cw[8];
+            long ci[8], c = 0, flat = 0;
+            int inb = 1;
+            for (int a = 0; a < 3; ++a) {
+                pix[a] = FN(pix_at)(alpha, s[a], d[a], shift, dims[a], align_corners);
+                REAL rr = (REAL)nearbyint((double)pix[a]);
+                if (!(rr >= 0 && rr < (REAL)dims[a])) inb = 0;
+                flat = flat * dims[a] + (long)(inb ? rr : 0);
+            }
+            if (inb) c = (long)mask[flat];
+            const REAL g = (c >= 0 && c < C) ? gout[((long)b * C + c) * N + n] : (REAL)0;
+            REAL v = FN(trilerp)(vol, dims, pix, G, ci, cw);
+            sumV += g * v;
+            REAL Gd = 0;
+            for (int a = 0; a < 3; ++a) {
+                G[a] *= scale[a] * g;
+                gs[a] += ((REAL)1 - alpha) * G[a];
+                gt[a] += alpha * G[a];
+                Gd += G[a] * d[a];
+            }
+            ga0 += ((REAL)1 - lin) * Gd;
+            ga1 += lin * Gd;
+            if (g_vol)
+                for (int k = 0; k < 8; ++k)
+                    if (ci[k] >= 0) {
+                        REAL add = g * L * step * cw[k];
+#pragma omp atomic
+                        g_vol[ci[k]] += add;
+                    }
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (g_tgt) g_tgt[r * 3 + a] = L * step * gt[a];
+            if (g_src) {
+                REAL add = L * step * gs[a];
+#pragma omp atomic
+                g_src[b * 3 + a] += add;
+            }
+        }
+        if (g_raylen) g_raylen[r] = step * sumV;
+        tot_amin += L * (-sumV / (REAL)(n_points - 1) + step * ga0);
+        tot_amax += L * (sumV / (REAL)(n_points - 1) + step * ga1);
     }
     if (g_amin) *g_amin = tot_amin;
     if (g_amax) *g_amax = tot_amax;

@@ -161,3 +161,39 @@ def trilinear_bwd(vol, src, tgt, raylen, gout, n_points=500, alphamin=None, alph
         R(eps), ctypes.c_int(n_points), R(alphamin), R(alphamax), ctypes.c_int(bool(align_corners)))
     return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=ga0.value,
                 g_alphamax=ga1.value)
+
+
+def siddon_bwd_mask(vol, mask, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, align_corners=False,
+                    want_vol=True, dtype=np.float64):
+    """Backward of siddon_fwd_mask for gout (B,C,N); same outputs as siddon_bwd."""
+    vol, mask, src, tgt, raylen, gout = _prep(dtype, vol, mask, src, tgt, raylen, gout)
+    B, N, C = tgt.shape[0], tgt.shape[1], gout.shape[1]
+    g_src, g_tgt = np.zeros((B, 1, 3), dtype=dtype), np.zeros((B, N, 3), dtype=dtype)
+    g_len = np.zeros((B, 1, N), dtype=dtype)
+    g_vol = np.zeros(vol.shape, dtype=dtype) if (want_vol and not stop_grad) else None
+    R = _real(dtype)
+    getattr(lib(), "oracle_siddon_bwd_mask_" + _suf(dtype))(
+        _p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src), _p(g_tgt),
+        _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N), ctypes.c_int(C), R(voxel_shift), R(eps),
+        ctypes.c_int(bool(stop_grad)), ctypes.c_int(bool(align_corners)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
+
+
+def trilinear_bwd_mask(vol, mask, src, tgt, raylen, gout, n_points=500, alphamin=None, alphamax=None, voxel_shift=0.5,
+                       eps=1e-8, align_corners=False, want_vol=True, dtype=np.float64):
+    """Backward of trilinear_fwd_mask for gout (B,C,N); same outputs as trilinear_bwd (fixed range + its partials)."""
+    vol, mask, src, tgt, raylen, gout = _prep(dtype, vol, mask, src, tgt, raylen, gout)
+    B, N, C = tgt.shape[0], tgt.shape[1], gout.shape[1]
+    if alphamin is None or alphamax is None:
+        alphamin, alphamax = alpha_minmax(vol.shape, src, tgt, voxel_shift, eps, dtype)
+    g_src, g_tgt = np.zeros((B, 1, 3), dtype=dtype), np.zeros((B, N, 3), dtype=dtype)
+    g_len = np.zeros((B, 1, N), dtype=dtype)
+    g_vol = np.zeros(vol.shape, dtype=dtype) if want_vol else None
+    R = _real(dtype)
+    ga0, ga1 = R(0), R(0)
+    getattr(lib(), "oracle_trilinear_bwd_mask_" + _suf(dtype))(
+        _p(vol), _p(mask), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src), _p(g_tgt),
+        _p(g_len), _p(g_vol), ctypes.byref(ga0), ctypes.byref(ga1), ctypes.c_int(B), ctypes.c_long(N), ctypes.c_int(C),
+        R(voxel_shift), R(eps), ctypes.c_int(n_points), R(alphamin), R(alphamax), ctypes.c_int(bool(align_corners)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=ga0.value,
+                g_alphamax=ga1.value)

@@ -307,6 +307,56 @@ void emu_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float* sr
     g_alpha_range[1] = (float)ga1;
 }
 
+// mask_to_channels backward through the device routines (FetchMasked / SampleGradMasked): gout is [B][C][N]
+void emu_siddon_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                         const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,
+                         int B, long N, int C, float shift, float eps, int stop_grad)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float gs[3], gt[3];
+            const FetchMasked fetch{vol, mask, gout + (long)b * C * N + n, N, C};
+            const float acc = siddon_ray_bwd_f(fetch, dims, ray, shift, raylen[r], stop_grad ? nullptr : g_vol, gs, gt);
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = gt[a];
+                g_src[b * 3 + a] += gs[a];
+            }
+            g_raylen[r] = stop_grad ? 0.0f : acc;
+        }
+}
+
+void emu_trilinear_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                            const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                            float* g_vol, float* g_alpha_range, int B, long N, int C, float shift, float eps, int P,
+                            float amin, float amax, int align_corners)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const float step = (amax - amin) / (float)(P - 1);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    double ga0 = 0, ga1 = 0;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            const SampleGradMasked sg{mask, gout + (long)b * C * N + n, N, C};
+            const TriGrad tg = trilinear_ray_bwd_g(GatherPlain{vol}, dims, ray, shift, P, amin, amax, align_corners, 1.0f,
+                                                   raylen[r], g_vol, -INFINITY, INFINITY, sg);
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = tg.gt[a];
+                g_src[b * 3 + a] += tg.gs[a];
+            }
+            g_raylen[r] = step * tg.sumV;
+            ga0 += tg.ga0;
+            ga1 += tg.ga1;
+        }
+    g_alpha_range[0] = (float)ga0;
+    g_alpha_range[1] = (float)ga1;
+}
+
 }  // extern "C"
 
 // ---- access-pattern analysis (tuning aid): distinct 32-byte sectors / 128-byte lines per warp-wide gather ----------

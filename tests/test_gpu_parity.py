@@ -177,6 +177,33 @@ def test_mask_to_channels_golden():
     assert relerr(ch.sum(1, keepdim=True).cpu().numpy(), full.cpu().numpy()) < 2e-5
 
 
+def test_mask_to_channels_backward_golden():
+    """Autograd through mask_to_channels rendering (b200drr_*_bwd_mask) against the reference's own autograd of the
+    scatter_add_ routing (tests/golden/make_golden_mask_grads.py): loss = sum(w * img), img (B, C, N)."""
+    import os
+    from conftest import GOLDEN
+    from diffdrr_b200 import Siddon, Trilinear
+    labels = np.load(os.path.join(GOLDEN, "labels_nc.npz"))["labels"]
+    for name, mod, fkw, floor in (("siddon_nc_b4_mask", Siddon(), {}, 1e-4),
+                                  ("trilinear_nc_b4_mask", Trilinear(), dict(n_points=110), 1e-3)):
+        g = load_golden(name)
+        gg = np.load(os.path.join(GOLDEN, name + "_grad.npz"))
+        v, s, tg, l = t(g["volume"], True), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+        out = mod(v, s, tg, l, mask=t(labels), **fkw)
+        assert relerr(out.detach().cpu().numpy(), g["img_f64"]) < IMG_TOL
+        (out * t(gg["w"])).sum().backward()
+        for key, x in (("g_target", tg), ("g_source", s), ("g_raylen", l), ("g_volume", v)):
+            tol = max(floor if key in ("g_target", "g_source") else 1e-4, 2.0 * relerr(gg[key + "_f32"], gg[key + "_f64"]))
+            assert relerr(x.grad.cpu().numpy(), gg[key + "_f64"]) < tol, (name, key)
+    # stop_gradients_through_grid_sample: no volume / ray-length gradient, ray gradients unchanged
+    g = load_golden("siddon_nc_b4_mask")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_mask_grad.npz"))
+    v, s, tg, l = t(g["volume"], True), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+    (Siddon(stop_gradients_through_grid_sample=True)(v, s, tg, l, mask=t(labels)) * t(gg["w"])).sum().backward()
+    assert v.grad is None and l.grad is None
+    assert relerr(tg.grad.cpu().numpy(), gg["g_target_f64"]) < 1e-4
+
+
 def test_unsupported_options_raise():
     from diffdrr_b200 import Siddon, Trilinear
     g = load_golden("siddon_nc_axis")
@@ -187,8 +214,8 @@ def test_unsupported_options_raise():
         Siddon(mode="bilinear")(*args)
     with pytest.raises(NotImplementedError):
         Siddon(reducefn=lambda x: x.mean(-1))(*args)
-    with pytest.raises(NotImplementedError):  # mask rendering is forward-only
-        Siddon()(args[0], args[1].clone().requires_grad_(True), *args[2:], mask=torch.zeros_like(args[0]))
+    with pytest.raises(NotImplementedError):  # mask rendering: reducefn="sum", align_corners=False only
+        Siddon()(*args, align_corners=True, mask=torch.zeros_like(args[0]))
     with pytest.raises(NotImplementedError):
         Siddon()(args[0].double(), *args[1:])
     out = Siddon(reducefn="max")(args[0], args[1].requires_grad_(True), *args[2:])

@@ -200,6 +200,33 @@ def test_mask_to_channels():
     assert relerr(out, g["img_f64"]) < IMG_TOL
 
 
+def test_mask_to_channels_backward():
+    """Device backward routines with the per-voxel / per-sample channel gradient (FetchMasked, SampleGradMasked) against
+    the fp64 oracle, which is pinned to the reference's autograd (tests/test_oracle.py)."""
+    import os
+    from conftest import GOLDEN
+    labels = np.load(os.path.join(GOLDEN, "labels_nc.npz"))["labels"]
+    g = load_golden("siddon_nc_b4_mask")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_mask_grad.npz"))
+    out = emu.siddon_bwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], gg["w"])
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        tol = max(1e-4, 2.0 * relerr(gg[key + "_f32"], gg[key + "_f64"]))
+        assert relerr(out[key], gg[key + "_f64"]) < tol, key
+    g = load_golden("trilinear_nc_b4_mask")
+    gg = np.load(os.path.join(GOLDEN, "trilinear_nc_b4_mask_grad.npz"))
+    amin, amax = oracle.alpha_minmax(g["volume"].shape, g["source"], g["target"], 0.5, 1e-8, np.float32)
+    out = emu.trilinear_bwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], gg["w"], 110, amin, amax)
+    ref = oracle.trilinear_bwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], gg["w"], n_points=110,
+                                    alphamin=amin, alphamax=amax, dtype=np.float64)
+    for key in ("g_target", "g_source"):  # fixed-range partials: against the oracle at the same (fp32) range
+        assert relerr(out[key], ref[key]) < 1e-3, key   # fp32 sums of voxel differences (SURVEY 8c)
+    for key in ("g_raylen", "g_volume"):  # no range chain: straight against the reference's fp64 autograd
+        assert relerr(out[key], gg[key + "_f64"]) < max(1e-4, 2.0 * relerr(gg[key + "_f32"], gg[key + "_f64"])), key
+    scale = max(abs(ref["g_alphamin"]), abs(ref["g_alphamax"]))
+    assert abs(out["g_alphamin"] - ref["g_alphamin"]) < 5e-3 * scale
+    assert abs(out["g_alphamax"] - ref["g_alphamax"]) < 5e-3 * scale
+
+
 @pytest.mark.parametrize("name,kw", [("trilinear_nc_b4", dict(n_points=160)), ("trilinear_nc_inside", dict(n_points=150)),
                                      ("trilinear_nc_axis", dict(n_points=200)), ("trilinear_nc_b4_shift0", dict(n_points=120, voxel_shift=0.0))])
 def test_trilinear_packed_corner_path_is_bitwise_the_gather_path(name, kw):

@@ -128,5 +128,25 @@ def test_mask_to_channels_matches_reference():
             assert relerr(out, g["img_" + tag]) < tol, (name, tag)
 
 
+def test_mask_to_channels_backward_matches_reference_autograd():
+    """Gradients of loss = sum(w * img) with img (B,C,N) through the reference's scatter_add_ routing
+    (tests/golden/make_golden_mask_grads.py) against the closed form with per-segment upstream gradients."""
+    labels = np.load(os.path.join(GOLDEN, "labels_nc.npz"))["labels"]
+    g = load_golden("siddon_nc_b4_mask")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_mask_grad.npz"))
+    out = oracle.siddon_bwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], gg["w"], dtype=np.float64)
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < 1e-9, key
+    g = load_golden("trilinear_nc_b4_mask")
+    gg = np.load(os.path.join(GOLDEN, "trilinear_nc_b4_mask_grad.npz"))
+    out = oracle.trilinear_bwd_mask(g["volume"], labels, g["source"], g["target"], g["raylen"], gg["w"], n_points=110,
+                                    dtype=np.float64)
+    es, et = _minmax_chain(g, out, 0.5)   # the batch-global alpha range came from the rays
+    assert relerr(out["g_target"] + et, gg["g_target_f64"]) < 1e-9
+    assert relerr(out["g_source"] + es, gg["g_source_f64"]) < 1e-9
+    assert relerr(out["g_raylen"], gg["g_raylen_f64"]) < 1e-9
+    assert relerr(out["g_volume"], gg["g_volume_f64"]) < 1e-9
+
+
 def test_oracle_threads():
     assert oracle.max_threads() >= 1
