@@ -580,7 +580,8 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
         return launch_sens_slab_variant<TW, TH, U, MINB>(vol, dims, src, tgt, raylen, out, sens, B, H, W, SLAB, shift, eps, \
                                                          stream);
     switch (variant) {
-        SV(0, 16, 8, 8, 48, 8)  // tuned default (profiles/r01_tune_sens.log)
+        SV(0, 8, 16, 8, 48, 8)  // tuned default (profiles/r01_tune_sens.log)
+        SV(32, 16, 8, 8, 48, 8)
         SV(22, 16, 8, 4, 64, 8)
         SV(1, 16, 8, 4, 32, 8)
         SV(2, 16, 16, 4, 64, 4)
@@ -601,6 +602,14 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
         SV(17, 16, 16, 8, 32, 4)
         SV(18, 16, 8, 12, 32, 4)
         SV(20, 16, 16, 8, 32, 3)
+        SV(24, 32, 4, 8, 48, 8)
+        SV(25, 16, 8, 8, 40, 8)
+        SV(26, 16, 8, 8, 56, 8)
+        SV(27, 16, 4, 8, 48, 16)
+        SV(28, 8, 8, 8, 48, 16)
+        SV(29, 16, 8, 6, 48, 8)
+        SV(30, 16, 8, 10, 48, 6)
+        SV(31, 32, 8, 8, 48, 4)
         SV(21, 8, 8, 8, 32, 16)
         default: return cudaErrorInvalidValue;
     }
@@ -611,7 +620,7 @@ cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const fl
                                         const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
                                         float shift, float eps, cudaStream_t stream)
 {
-    return launch_sens_slab_variant<16, 8, 8, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, 48, shift, eps, stream,
+    return launch_sens_slab_variant<8, 16, 8, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, 48, shift, eps, stream,
                                                  PoseRays{G, Wd, rows, cols});
 }
 
