@@ -127,7 +127,8 @@ class B200DRRError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # B200DRR_LIB: an alternative build of the same C ABI (kernel A/B experiments from scripts/); default = the in-tree build
+    return os.environ.get("B200DRR_LIB") or _build.LIB_PATH
 
 
 def load():

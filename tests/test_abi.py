@@ -109,3 +109,19 @@ def test_drr_module_surface_on_cpu():
     world = drr2.inverse_projection(pose, px.clone())
     back = drr2.perspective_projection(pose, world)
     assert torch.allclose(back, px, atol=1e-3)
+
+
+def test_render_grid_shape_is_validated_on_cpu():
+    """`DRR.render(grid_shape=...)` (row-block hint used by ray sharding) refuses anything but whole detector rows."""
+    vol = synthetic.make_volume(16, "phantom")
+    drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(12))
+    src, tgt = torch.zeros(1, 1, 3), torch.zeros(1, 24, 3)
+    with pytest.raises(ValueError, match="grid_shape"):
+        drr.render(drr.density, src, tgt, grid_shape=(2, 11))      # wrong width
+    with pytest.raises(ValueError, match="grid_shape"):
+        drr.render(drr.density, src, tgt, grid_shape=(3, 12))      # 36 rays declared, 24 given
+    sub = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(12), p_subsample=0.5)
+    with pytest.raises(ValueError, match="grid_shape"):
+        sub.render(sub.density, src, tgt, grid_shape=(2, 12))      # sub-sampled detector has no row blocks
+    from diffdrr_b200.parallel import render_sharded
+    assert render_sharded.__kwdefaults__["shard"] == "auto"
