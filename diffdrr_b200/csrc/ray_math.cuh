@@ -101,6 +101,25 @@ struct Walk {
 // fma(p, 1/d, -(shift+s)/d) cancels two huge terms there and loses ~1e-2 voxel along the ray).
 B200_HD float plane_alpha_acc(const Ray& ray, int a, float p, float shift) { return ((p - shift) - ray.s[a]) * ray.inv[a]; }
 
+// Conservative pre-test for the slab-major kernels (a ray crosses only 1-3 of the ~11 slabs; the rest of its threads
+// used to pay the full walk set-up just to find that out): true ONLY when the line certainly stays clear of the box
+// [lo, hi), with a margin three orders above fp32 rounding, so every borderline ray still goes through
+// the exact set-up, which alone decides hits.  inf / NaN alphas compare false (never skipped).
+B200_HD bool box_surely_missed(const Ray& ray, const int lo_v[3], const int hi_v[3], float shift)
+{
+    float a_in = -INFINITY, a_out = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float a0 = plane_alpha_acc(ray, a, (float)lo_v[a], shift), a1 = plane_alpha_acc(ray, a, (float)hi_v[a], shift);
+        a_in = fmaxf(a_in, fminf(a0, a1));
+        a_out = fminf(a_out, fmaxf(a0, a1));
+    }
+    // alphas carry ~1e-7 relative rounding; 1e-4 of their magnitude is three orders above that and still a fraction of a
+    // voxel (one voxel is ~7e-4 in alpha at 512^3)
+    const float margin = 1e-4f * (1.0f + fabsf(a_in) + fabsf(a_out));
+    return a_in > a_out + margin;
+}
+
 // Walk restricted to the sub-box of voxels [lo_a, hi_a) per axis (planes lo_a .. hi_a); the whole volume is
 // lo = 0, hi = dims.  Splitting a ray at voxel planes is exact: every Siddon segment ends on a plane anyway.
 // Crossing alphas are generated as fma(n, |1/d|, alpha_first) from an integer crossing count n (never

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __
     const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
     const int lo_v[3] = {sl * slab, 0, 0};
     const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;  // most (ray, slab) pairs: skip the walk set-up
     const float part = siddon_ray_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
     if (part != 0.0f) red_add(out + r, L * part);
 }
@@ -535,6 +536,7 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const fl
     const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
     const int lo_v[3] = {sl * slab, 0, 0};
     const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;  // most (ray, slab) pairs: skip the walk set-up
     float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
     const float S = siddon_ray_sens_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
     float jt[3], js[3];

@@ -161,6 +161,7 @@ void emu_siddon_sens(const float* vol, int D0, int D1, int D2, const float* src,
             for (int sl = 0; sl < n_slabs; ++sl) {
                 const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
                 const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                if (slab > 0 && box_surely_missed(ray, lo_v, hi_v, shift)) continue;  // as the slab kernels do
                 float A[3] = {0, 0, 0}, C[3] = {0, 0, 0};
                 const float S = siddon_ray_sens_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C);
                 for (int a = 0; a < 3; ++a) {
@@ -305,6 +306,31 @@ void emu_trilinear_bwd(const float* vol, int D0, int D1, int D2, const float* sr
         }
     g_alpha_range[0] = (float)ga0;
     g_alpha_range[1] = (float)ga1;
+}
+
+// box_surely_missed (pre-test of the slab-major kernels) against the exact set-ups it short-cuts:
+// out = {(ray, slab) pairs, pairs skipped, pairs skipped although an exact set-up reports a hit (must be 0), exact hits}
+void emu_box_pretest(int D0, int D1, int D2, const float* src, const float* tgt, int B, long N, int slab, float shift,
+                     float eps, double* out)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const int n_slabs = (D0 + slab - 1) / slab;
+    double pairs = 0, skipped = 0, wrong = 0, hits = 0;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const Ray ray = load_ray(src, tgt, b, (long)b * N + n, eps);
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {sl * slab, 0, 0};
+                const int hi_v[3] = {std::min(D0, (sl + 1) * slab), D1, D2};
+                const bool hit = start_walk_box(ray, lo_v, hi_v, shift).hit || start_walk_frame(ray, dims, lo_v, hi_v, shift).hit;
+                const bool skip = box_surely_missed(ray, lo_v, hi_v, shift);
+                pairs += 1;
+                skipped += skip;
+                hits += hit;
+                wrong += (skip && hit);
+            }
+        }
+    out[0] = pairs; out[1] = skipped; out[2] = wrong; out[3] = hits;
 }
 
 // mask_to_channels backward through the device routines (FetchMasked / SampleGradMasked): gout is [B][C][N]

@@ -4,7 +4,7 @@ parity tests (tests/test_gpu_*.py) run the CUDA build of the same source through
 import numpy as np
 import pytest
 
-from conftest import load_golden, relerr
+from conftest import ROOT, load_golden, relerr
 from hostemu import emu
 from oracle import oracle
 from test_oracle import SIDDON, TRILINEAR
@@ -273,3 +273,32 @@ def test_sensitivities_walk_random_rays(seed, shape, slab):
             assert not out[key].any()
         else:
             assert np.abs(out[key] - ref[key]).max() / scale < 5e-5, key
+
+
+@pytest.mark.parametrize("case", ["golden", "random", "bench"])
+def test_slab_miss_pretest_never_drops_a_hit(case):
+    """The slab-major kernels skip the walk set-up for (ray, slab) pairs that `box_surely_missed` rejects: it must never
+    reject a pair the exact set-up would walk, and it should catch most of the misses (that is its point)."""
+    import ctypes
+    from hostemu.emu import _f, _p, lib
+    if case == "golden":
+        g = load_golden("siddon_nc_b4")
+        shape, src, tgt, slab = g["volume"].shape, g["source"], g["target"], 5
+    elif case == "random":
+        shape, slab = (40, 56, 48), 7
+        _, src, tgt, _ = _random_case(9, shape, B=4, N=500)
+    else:  # rays of the metric's configuration (512^3 -> 256^2), a strided sample of 3 poses, 48-plane slabs
+        import sys
+        sys.path.insert(0, ROOT)
+        from bench import make_host_rays
+        src, tgt, _ = make_host_rays(512, 256, 3, seed=0)
+        shape, slab = (512, 512, 512), 48
+        tgt = tgt[:, ::37]
+    src, tgt = _f(np.asarray(src).reshape(len(tgt), 3)), _f(tgt)
+    out = np.zeros(4)
+    lib().emu_box_pretest(*map(ctypes.c_int, shape), _p(src), _p(tgt), ctypes.c_int(tgt.shape[0]), ctypes.c_long(tgt.shape[1]),
+                          ctypes.c_int(slab), ctypes.c_float(0.5), ctypes.c_float(1e-8), _p(out))
+    pairs, skipped, wrong, hits = out
+    assert wrong == 0, f"{int(wrong)} (ray, slab) pairs skipped although the exact set-up walks them"
+    assert skipped + hits <= pairs
+    assert skipped >= 0.9 * (pairs - hits), "the pre-test should reject nearly every true miss"
