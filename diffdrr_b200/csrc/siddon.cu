@@ -334,10 +334,12 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_bwd_slab_kernel(const flo
         const float gL = g * L;
         float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
         const bool want_vol = g_vol != nullptr && !stop_grad;
-        const float acc = want_vol ? siddon_ray_bwd_lean_box<U, true>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1,
-                                                                      ray, shift, gL, g_vol, A, C)
-                                   : siddon_ray_bwd_lean_box<U, false>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1,
-                                                                       ray, shift, gL, nullptr, A, C);
+        float acc = 0.0f;
+        if (!box_surely_missed(ray, lo_v, hi_v, shift))  // most (ray, slab) pairs are misses: skip the walk set-up
+            acc = want_vol ? siddon_ray_bwd_lean_box<U, true>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray,
+                                                              shift, gL, g_vol, A, C)
+                           : siddon_ray_bwd_lean_box<U, false>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray,
+                                                               shift, gL, nullptr, A, C);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const float gt = -gL * A[a] * ray.inv[a];
