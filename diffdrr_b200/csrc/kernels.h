@@ -31,7 +31,8 @@ cudaError_t launch_trilinear_fwd(const float* vol, VolDims dims, const float* sr
 cudaError_t launch_trilinear_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,
                                  const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                  float* g_vol, float* g_alpha_range, int B, int64_t N, float shift, float eps,
-                                 int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
+                                 int n_points, const float* alpha_range, int align_corners, cudaStream_t stream,
+                                 int reduce = 0);
 
 cudaError_t launch_trilinear_fwd_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                       const float* raylen, float* out, int B, int H, int W, float shift, float eps,
@@ -74,6 +75,10 @@ cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, 
 cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                       float* g_alpha_range, int B, int64_t N, cudaStream_t stream);
 
+cudaError_t launch_siddon_bwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,
+                                      int64_t N, float shift, float eps, int stop_grad, int reduce, int align_corners,
+                                      cudaStream_t stream);
 cudaError_t launch_siddon_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                    float* g_vol, int B, int64_t N, int C, float shift, float eps, int stop_grad,

@@ -73,6 +73,117 @@ B200_HD float siddon_ray_general(const float* vol, const VolDims& dims, const Ra
     return acc;
 }
 
+// Backward of the general walk (reducefn "sum" with align_corners=True, or reducefn "max"): the same plane-by-plane
+// pop, closed form of SURVEY.md 8a-G.  "max": only the FIRST maximal segment carries gradient (torch.max returns the
+// first maximal index): +L v at its exit crossing, -L v at its entry crossing.  gL = g * L.
+// Returns sum_j v_j len_j ("sum") or v* len* ("max") for the ray-length gradient; g_vol accumulated into when non-null.
+B200_HD float siddon_ray_general_bwd(const float* vol, const VolDims& dims, const Ray& ray, float L, float gL, float shift,
+                                     int reduce, int align_corners, float* g_vol, float gs[3], float gt[3])
+{
+    int pos[3], stp[3], left[3];
+    float head[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = ray.d[a] > 0.0f;
+        pos[a] = fwd ? 0 : dims.d[a];
+        stp[a] = fwd ? 1 : -1;
+        left[a] = dims.d[a] + 1;
+        head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+    }
+    const int M = dims.d[0] + dims.d[1] + dims.d[2] + 3;
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    float sumvl = 0.0f, aprev = 0.0f, vbefore = 0.0f;
+    int axprev = 0;
+    // "max" bookkeeping
+    bool first = true;
+    float tbest = 0.0f, vbest = 0.0f, a0best = 0.0f, a1best = 0.0f;
+    int ax0best = 0, ax1best = 0;
+    int64_t offbest = -1;
+    for (int m = 0; m < M; ++m) {
+        const float h0 = left[0] > 0 ? head[0] : INFINITY;
+        const float h1 = left[1] > 0 ? head[1] : INFINITY;
+        const float h2 = left[2] > 0 ? head[2] : INFINITY;
+        const float acur = fminf(fminf(h0, h1), h2);
+        const int best = (left[0] > 0 && h0 == acur) ? 0 : ((left[1] > 0 && h1 == acur) ? 1 : 2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == best) {
+                pos[a] += stp[a];
+                left[a] -= 1;
+                if (left[a] > 0) head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+            }
+        if (m > 0) {
+            const float amid = (aprev + acur) / 2.0f;
+            bool inb = true;
+            int64_t off = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = add_rn(ray.s[a], mul_rn(amid, ray.d[a]));
+                const float gn = 2.0f * (x + shift) / (float)dims.d[a] - 1.0f;
+                const float rr = rintf(unnormalize(gn, dims.d[a], align_corners));
+                inb = inb && (rr >= 0.0f) && (rr < (float)dims.d[a]);
+                off = off * dims.d[a] + (inb ? (int64_t)rr : 0);
+            }
+            const float v = inb ? ldg(vol + off) : 0.0f;
+            const float len = acur - aprev;
+            if (reduce == 0) {
+                const float coef = vbefore - v;  // crossing m-1 (axis axprev, alpha aprev) separates the two segments
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (a == axprev) {
+                        A[a] = fmaf(coef, aprev, A[a]);
+                        C[a] += coef;
+                    }
+                sumvl = fmaf(v, len, sumvl);
+                if (g_vol && inb) red_add(g_vol + off, gL * len);
+                vbefore = v;
+            } else {
+                const float term = mul_rn(mul_rn(L, v), len);
+                if (first || term > tbest) {
+                    tbest = term;
+                    vbest = v;
+                    a0best = aprev;
+                    ax0best = axprev;
+                    a1best = acur;
+                    ax1best = best;
+                    offbest = inb ? off : -1;
+                }
+                first = false;
+            }
+        }
+        aprev = acur;
+        axprev = best;
+    }
+    if (reduce == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == axprev) {  // last crossing: v_last -> 0
+                A[a] = fmaf(vbefore, aprev, A[a]);
+                C[a] += vbefore;
+            }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (a == ax1best) {
+                A[a] = fmaf(vbest, a1best, A[a]);
+                C[a] += vbest;
+            }
+            if (a == ax0best) {
+                A[a] = fmaf(-vbest, a0best, A[a]);
+                C[a] -= vbest;
+            }
+        }
+        sumvl = vbest * (a1best - a0best);
+        if (g_vol && offbest >= 0) red_add(g_vol + offbest, gL * (a1best - a0best));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        gt[a] = -gL * A[a] * ray.inv[a];
+        gs[a] = gL * (A[a] - C[a]) * ray.inv[a];
+    }
+    return sumvl;
+}
+
 // ===================================================================================================
 // Siddon, fast walk (align_corners = False): clipped to the volume's box, incremental voxel index.
 // In "plane space" q = x + shift, voxel k of axis a spans q in [k, k+1] and the reference's plane i
@@ -1232,7 +1343,7 @@ template <class Gather, class SampleGrad = SampleGradOne>
 B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, const Ray& ray, float shift, int P,
                                     float amin, float amax, int align_corners, float g, float L, float* g_vol,
                                     float s_lo = -INFINITY, float s_hi = INFINITY,
-                                    const SampleGrad& sample_grad = SampleGrad())
+                                    const SampleGrad& sample_grad = SampleGrad(), int m_only = -1)
 {
     const PixLine pl = make_pixline(ray, dims, shift, align_corners);
     const float range = amax - amin;
@@ -1241,6 +1352,10 @@ B200_HD TriGrad trilinear_ray_bwd_g(const Gather& gather, const VolDims& dims, c
     int m_lo, m_hi;
     sample_range(pl, dims, amin, range, P, m_lo, m_hi);
     sample_range_slab(pl, amin, range, P, s_lo, s_hi, m_lo, m_hi);
+    if (m_only != -1) {  // reducefn="max": the gradient of ONE sample (m_only < -1: none at all)
+        m_lo = m_lo > m_only ? m_lo : m_only;
+        m_hi = m_only < -1 ? m_lo - 1 : (m_hi < m_only ? m_hi : m_only);
+    }
     const float gLs = g * L * step;
     float sumV = 0.0f, S[3] = {0.0f, 0.0f, 0.0f}, T[3] = {0.0f, 0.0f, 0.0f}, E0 = 0.0f, E1 = 0.0f;
     for (int m = m_lo; m <= m_hi; ++m) {
@@ -1298,6 +1413,39 @@ B200_HD TriGrad trilinear_ray_bwd(const float* vol, const VolDims& dims, const R
                                   float amax, int align_corners, float g, float L, float* g_vol)
 {
     return trilinear_ray_bwd_g(GatherPlain{vol}, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol);
+}
+
+// reducefn="max" (renderers.py:175-183 on Trilinear.forward): I = max_m (L V_m) step; the gradient flows through the
+// FIRST maximal sample only (torch.max).  Samples skipped by sample_range are exact zeros and take part in the max: if
+// one of them is the (first) maximum nothing has a gradient.  L, step > 0, so the order of the terms is that of V_m.
+B200_HD TriGrad trilinear_ray_bwd_max(const float* vol, const VolDims& dims, const Ray& ray, float shift, int P, float amin,
+                                      float amax, int align_corners, float g, float L, float* g_vol)
+{
+    const PixLine pl = make_pixline(ray, dims, shift, align_corners);
+    const float range = amax - amin;
+    const float lstep = 1.0f / (float)(P - 1);
+    int m_lo, m_hi;
+    sample_range(pl, dims, amin, range, P, m_lo, m_hi);
+    int mbest = -2;  // -2: a skipped (zero, gradient-free) sample holds the maximum
+    float best = 0.0f;
+    bool have = m_lo > 0;  // samples before m_lo are zeros and come first
+    for (int m = m_lo; m <= m_hi; ++m) {
+        const float alpha = add_rn(mul_rn(linspace01(m, P, lstep), range), amin);
+        float pix[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pix[a] = fmaf(alpha, pl.dp[a], pl.p0[a]);
+        float val = 0.0f;
+        if (!outside_padded(pix, dims)) val = lerp8(gather8(vol, dims, pix));
+        if (!have || val > best) {
+            best = val;
+            mbest = m;
+        }
+        have = true;
+    }
+    if (have && m_hi < P - 1 && best < 0.0f) mbest = -2;  // a trailing zero beats an all-negative march
+    if (!have) mbest = -2;
+    return trilinear_ray_bwd_g(GatherPlain{vol}, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol, -INFINITY,
+                               INFINITY, SampleGradOne(), mbest);
 }
 
 B200_HD TriGrad trilinear_ray_bwd_packed(const float4* packed, const VolDims& dims, const Ray& ray, float shift, int P,

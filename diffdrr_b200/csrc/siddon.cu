@@ -835,6 +835,53 @@ cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims 
     return cudaGetLastError();
 }
 
+// Backward for the options the fast kernels do not cover: reducefn="max" and/or align_corners=True (general walk).
+__global__ void __launch_bounds__(kThreads) siddon_bwd_general_kernel(
+    const float* __restrict__ vol, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, const float* __restrict__ gout, float* __restrict__ g_src, float* __restrict__ g_tgt,
+    float* __restrict__ g_raylen, float* __restrict__ g_vol, int64_t N, float shift, float eps, int stop_grad, int reduce,
+    int align_corners)
+{
+    __shared__ float red[32];
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    float gs[3] = {0.0f, 0.0f, 0.0f};
+    if (n < N) {
+        const int64_t r = (int64_t)b * N + n;
+        const Ray ray = load_ray(src, tgt, b, r, eps);
+        const float L = __ldg(raylen + r), g = __ldg(gout + r);
+        float gt[3];
+        const float acc = siddon_ray_general_bwd(vol, dims, ray, L, g * L, shift, reduce, align_corners,
+                                                 stop_grad ? nullptr : g_vol, gs, gt);
+        if (g_tgt) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) g_tgt[r * 3 + a] = gt[a];
+        }
+        if (g_raylen) g_raylen[r] = stop_grad ? 0.0f : g * acc;
+    }
+    if (g_src) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tot = block_sum(gs[a], red);
+            if (threadIdx.x == 0) atomicAdd(g_src + b * 3 + a, tot);
+        }
+    }
+}
+
+cudaError_t launch_siddon_bwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,
+                                      int64_t N, float shift, float eps, int stop_grad, int reduce, int align_corners,
+                                      cudaStream_t stream)
+{
+    if (g_src) {
+        const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+        if (e != cudaSuccess) return e;
+    }
+    siddon_bwd_general_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
+        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, N, shift, eps, stop_grad, reduce, align_corners);
+    return cudaGetLastError();
+}
+
 // mask_to_channels backward (autograd of renderers.py:77-89): gout [B][C][N]; the segment in voxel j receives the
 // gradient of the channel it was scattered to, g_j = gout[b][label_j][n], i.e. the closed-form walk with v_j -> g_j v_j.
 __global__ void __launch_bounds__(kThreads) siddon_bwd_mask_kernel(

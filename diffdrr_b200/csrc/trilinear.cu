@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kThreads) trilinear_bwd_kernel(
     const float* __restrict__ raylen, const float* __restrict__ gout, float* __restrict__ g_src,
     float* __restrict__ g_tgt, float* __restrict__ g_raylen, float* __restrict__ g_vol,
     float* __restrict__ g_alpha_range, int64_t N, float shift, float eps, int P,
-    const float* __restrict__ alpha_range, int align_corners)
+    const float* __restrict__ alpha_range, int align_corners, int reduce)
 {
     __shared__ float red[32];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(kThreads) trilinear_bwd_kernel(
         const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
         const float step = (amax - amin) / (float)(P - 1);
         const float L = __ldg(raylen + r), g = __ldg(gout + r);
-        const TriGrad tg = trilinear_ray_bwd(vol, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol);
+        const TriGrad tg = reduce == 0
+                               ? trilinear_ray_bwd(vol, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol)
+                               : trilinear_ray_bwd_max(vol, dims, ray, shift, P, amin, amax, align_corners, g, L, g_vol);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             gs[a] = tg.gs[a];
@@ -717,7 +719,8 @@ cudaError_t launch_trilinear_fwd(const float* vol, VolDims dims, const float* sr
 cudaError_t launch_trilinear_bwd(const float* vol, VolDims dims, const float* src, const float* tgt,
                                  const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                  float* g_vol, float* g_alpha_range, int B, int64_t N, float shift, float eps,
-                                 int n_points, const float* alpha_range, int align_corners, cudaStream_t stream)
+                                 int n_points, const float* alpha_range, int align_corners, cudaStream_t stream,
+                                 int reduce)
 {
     if (g_src) {
         cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
@@ -725,7 +728,7 @@ cudaError_t launch_trilinear_bwd(const float* vol, VolDims dims, const float* sr
     }
     trilinear_bwd_kernel<<<ray_grid(B, N), kThreads, 0, stream>>>(vol, dims, src, tgt, raylen, gout, g_src, g_tgt,
                                                                   g_raylen, g_vol, g_alpha_range, N, shift, eps,
-                                                                  n_points, alpha_range, align_corners);
+                                                                  n_points, alpha_range, align_corners, reduce);
     return cudaGetLastError();
 }
 

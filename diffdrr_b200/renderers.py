@@ -126,10 +126,6 @@ class _SiddonFunction(torch.autograd.Function):
             return (None, None if g_src is None else g_src.view(src_shape), g_tgt,
                     None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
         vol, src, tgt, raylen = ctx.saved_tensors
-        if reduce != 0:
-            raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
-        if align_corners:
-            raise NotImplementedError("backward with align_corners=True is not implemented for the Siddon kernels")
         B, N = tgt.shape[0], tgt.shape[1]
         need_vol, need_src, need_tgt, need_len = ctx.needs_input_grad[:4]
         gout = gout.reshape(B, N).contiguous().float()
@@ -139,7 +135,12 @@ class _SiddonFunction(torch.autograd.Function):
         g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
         lib = _lib.load()
         with torch.cuda.device(vol.device):
-            if grid is not None:
+            if reduce != 0 or align_corners:  # options outside the fast kernels: plane-by-plane general walk
+                _lib.check(lib.b200drr_siddon_bwd_general(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                          _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift,
+                                                          eps, int(stop_grad), reduce, int(align_corners), _stream()),
+                           "b200drr_siddon_bwd_general")
+            elif grid is not None:
                 _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
                                                        _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, grid[0], grid[1],
                                                        voxel_shift, eps, int(stop_grad), 0, _stream()),
@@ -292,8 +293,6 @@ class _TrilinearFunction(torch.autograd.Function):
             return (None, None if g_src is None else g_src.view(src_shape), g_tgt,
                     None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None)
         vol, src, tgt, raylen, arange = ctx.saved_tensors
-        if reduce != 0:
-            raise NotImplementedError("backward through reducefn='max' is not implemented in diffdrr_b200")
         B, N = tgt.shape[0], tgt.shape[1]
         need_vol, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
         gout = gout.reshape(B, N).contiguous().float()
@@ -305,7 +304,12 @@ class _TrilinearFunction(torch.autograd.Function):
         g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
         lib = _lib.load()
         with torch.cuda.device(dev):
-            if ctx.packed is not None and g_vol is None:
+            if reduce != 0:  # reducefn="max": the first maximal sample carries the gradient
+                _lib.check(lib.b200drr_trilinear_bwd_max(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                         _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), _ptr(g_ar), B, N,
+                                                         voxel_shift, eps, n_points, _ptr(arange), int(align_corners),
+                                                         _stream()), "b200drr_trilinear_bwd_max")
+            elif ctx.packed is not None and g_vol is None:
                 _lib.check(lib.b200drr_trilinear_bwd_packed(_ptr(ctx.packed), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                             _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_ar), B,
                                                             grid[0], grid[1], voxel_shift, eps, n_points, _ptr(arange),

@@ -251,6 +251,21 @@ int b200drr_trilinear_fwd_mask(const float *vol, const float *mask, int D0, int 
                                void *stream);
 
 /*
+ * Backward for the renderer options outside the fast kernels (reference renderers.py:175-183 `reduce`, :40/:161
+ * align_corners): Siddon with reducefn="max" (reduce = 1: the first maximal segment carries the whole gradient, as
+ * torch.max does) and/or align_corners=1, through the plane-by-plane general walk; Trilinear with reducefn="max" (first
+ * maximal sample).  Output conventions of b200drr_siddon_bwd / b200drr_trilinear_bwd.
+ */
+int b200drr_siddon_bwd_general(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                               const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                               float *g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int reduce,
+                               int align_corners, void *stream);
+int b200drr_trilinear_bwd_max(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                              const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
+                              float *g_vol, float *g_alpha_range, int B, int64_t N, float voxel_shift, float eps,
+                              int n_points, const float *alpha_range, int align_corners, void *stream);
+
+/*
  * mask_to_channels backward = what autograd derives for the scatter_add_ routing above: gout [B][C][N]; the segment /
  * sample routed to channel c carries gout[b][c][n], otherwise the closed forms of b200drr_siddon_bwd /
  * b200drr_trilinear_bwd.  Output conventions as there (g_src/g_tgt/g_raylen overwritten, g_vol and g_alpha_range

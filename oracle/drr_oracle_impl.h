@@ -292,6 +292,73 @@ void FN(oracle_siddon_bwd_mask)(const REAL *vol, const REAL *mask, int D0, int D
     }
 }
 
+/* Autograd of Siddon.forward with reducefn="max" (renderers.py:175-183: img.max(dim=-1).values): only the FIRST maximal
+ * segment j* carries gradient (torch.max returns the first maximal index):
+ *   dI/dalpha_{j*+1} = +L v,  dI/dalpha_{j*} = -L v,  dI/dL = v len,  dI/dV[voxel] = L len   (v, len of segment j*). */
+void FN(oracle_siddon_bwd_max)(const REAL *vol, int D0, int D1, int D2, const REAL *src, const REAL *tgt,
+                               const REAL *raylen, const REAL *gout, REAL *g_src, REAL *g_tgt, REAL *g_raylen,
+                               REAL *g_vol, int B, long N, REAL shift, REAL eps, int stop_grad, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const int M = D0 + D1 + D2 + 3;
+    if (g_src) memset(g_src, 0, sizeof(REAL) * (size_t)B * 3);
+#pragma omp parallel
+    {
+        REAL *alpha = (REAL *)malloc(sizeof(REAL) * (size_t)M);
+        int *axis = (int *)malloc(sizeof(int) * (size_t)M);
+#pragma omp for schedule(dynamic, 64)
+        for (long r = 0; r < (long)B * N; ++r) {
+            const int b = (int)(r / N);
+            REAL s[3], d[3];
+            for (int a = 0; a < 3; ++a) {
+                s[a] = src[b * 3 + a];
+                d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+            }
+            FN(sorted_alphas)(dims, s, d, shift, alpha, axis, NULL);
+            const REAL L = raylen[r], g = gout[r];
+            int jbest = 0;
+            long ibest = -1;
+            REAL tbest = 0, vbest = 0;
+            for (int j = 0; j + 1 < M; ++j) {
+                REAL amid = (alpha[j] + alpha[j + 1]) / (REAL)2;
+                long idx = FN(nearest_index)(amid, s, d, shift, dims, align_corners);
+                REAL v = idx < 0 ? (REAL)0 : vol[idx];
+                REAL term = (L * v) * (alpha[j + 1] - alpha[j]);
+                if (j == 0 || term > tbest) {
+                    tbest = term;
+                    jbest = j;
+                    vbest = v;
+                    ibest = idx;
+                }
+            }
+            const REAL len = alpha[jbest + 1] - alpha[jbest];
+            REAL gs[3] = {0, 0, 0}, gt[3] = {0, 0, 0};
+            for (int e = 0; e < 2; ++e) {
+                const int m = jbest + e;
+                const REAL c = (e ? (REAL)1 : (REAL)-1) * g * L * vbest;
+                const int a = axis[m];
+                gs[a] += c * (alpha[m] - (REAL)1) / d[a];
+                gt[a] += c * (-alpha[m]) / d[a];
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (g_tgt) g_tgt[r * 3 + a] = gt[a];
+                if (g_src) {
+#pragma omp atomic
+                    g_src[b * 3 + a] += gs[a];
+                }
+            }
+            if (g_raylen) g_raylen[r] = stop_grad ? (REAL)0 : g * vbest * len;
+            if (g_vol && !stop_grad && ibest >= 0) {
+                REAL add = g * L * len;
+#pragma omp atomic
+                g_vol[ibest] += add;
+            }
+        }
+        free(alpha);
+        free(axis);
+    }
+}
+
 /* renderers.py:124-140 (_get_alpha_minmax) followed by the batch-global .min()/.max() of
  * renderers.py:221-223.  Far plane is dims + 1 - shift (quirk Q4). */
 void FN(oracle_alpha_minmax)(const REAL *src, const REAL *tgt, int D0, int D1, int D2, int B, long N,
@@ -498,6 +565,71 @@ void FN(oracle_trilinear_bwd)(const REAL *vol, int D0, int D1, int D2, const REA
         if (g_raylen) g_raylen[r] = g * step * sumV;
         tot_amin += g * L * (-sumV / (REAL)(n_points - 1) + step * ga0);
         tot_amax += g * L * (sumV / (REAL)(n_points - 1) + step * ga1);
+    }
+    if (g_amin) *g_amin = tot_amin;
+    if (g_amax) *g_amax = tot_amax;
+}
+
+/* Autograd of Trilinear.forward with reducefn="max": I = max_m (L V_m) step, gradient through the FIRST maximal sample m*
+ * only; the closed forms of oracle_trilinear_bwd with every sum over m replaced by its m* term. */
+void FN(oracle_trilinear_bwd_max)(const REAL *vol, int D0, int D1, int D2, const REAL *src, const REAL *tgt,
+                                  const REAL *raylen, const REAL *gout, REAL *g_src, REAL *g_tgt, REAL *g_raylen,
+                                  REAL *g_vol, REAL *g_amin, REAL *g_amax, int B, long N, REAL shift, REAL eps,
+                                  int n_points, REAL alphamin, REAL alphamax, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const REAL step = (alphamax - alphamin) / (REAL)(n_points - 1);
+    if (g_src) memset(g_src, 0, sizeof(REAL) * (size_t)B * 3);
+    REAL tot_amin = 0, tot_amax = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : tot_amin, tot_amax)
+    for (long r = 0; r < (long)B * N; ++r) {
+        const int b = (int)(r / N);
+        REAL s[3], d[3], scale[3];
+        for (int a = 0; a < 3; ++a) {
+            s[a] = src[b * 3 + a];
+            d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+            scale[a] = align_corners ? (REAL)(dims[a] - 1) / (REAL)dims[a] : (REAL)1;
+        }
+        const REAL L = raylen[r], g = gout[r];
+        int mbest = 0;
+        REAL tbest = 0;
+        for (int m = 0; m < n_points; ++m) {
+            REAL alpha = FN(linspace01)(m, n_points) * (alphamax - alphamin) + alphamin;
+            REAL pix[3];
+            for (int a = 0; a < 3; ++a) pix[a] = FN(pix_at)(alpha, s[a], d[a], shift, dims[a], align_corners);
+            REAL term = (L * FN(trilerp)(vol, dims, pix, NULL, NULL, NULL)) * step;
+            if (m == 0 || term > tbest) {
+                tbest = term;
+                mbest = m;
+            }
+        }
+        const REAL lin = FN(linspace01)(mbest, n_points);
+        const REAL alpha = lin * (alphamax - alphamin) + alphamin;
+        REAL pix[3], G[3], cw[8];
+        long ci[8];
+        for (int a = 0; a < 3; ++a) pix[a] = FN(pix_at)(alpha, s[a], d[a], shift, dims[a], align_corners);
+        const REAL v = FN(trilerp)(vol, dims, pix, G, ci, cw);
+        REAL Gd = 0;
+        for (int a = 0; a < 3; ++a) {
+            G[a] *= scale[a];
+            Gd += G[a] * d[a];
+            if (g_tgt) g_tgt[r * 3 + a] = g * L * step * alpha * G[a];
+            if (g_src) {
+                REAL add = g * L * step * ((REAL)1 - alpha) * G[a];
+#pragma omp atomic
+                g_src[b * 3 + a] += add;
+            }
+        }
+        if (g_vol)
+            for (int k = 0; k < 8; ++k)
+                if (ci[k] >= 0) {
+                    REAL add = g * L * step * cw[k];
+#pragma omp atomic
+                    g_vol[ci[k]] += add;
+                }
+        if (g_raylen) g_raylen[r] = g * step * v;
+        tot_amin += g * L * (-v / (REAL)(n_points - 1) + step * ((REAL)1 - lin) * Gd);
+        tot_amax += g * L * (v / (REAL)(n_points - 1) + step * lin * Gd);
     }
     if (g_amin) *g_amin = tot_amin;
     if (g_amax) *g_amax = tot_amax;

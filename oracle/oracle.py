@@ -100,7 +100,7 @@ def trilinear_fwd_mask(vol, mask, src, tgt, raylen, n_channels, n_points=500, al
 
 
 def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, align_corners=False,
-               want_vol=True, dtype=np.float64):
+               want_vol=True, dtype=np.float64, reduce="sum"):
     """Returns dict(g_source (B,1,3), g_target (B,N,3), g_raylen (B,1,N), g_volume (D0,D1,D2)|None)."""
     vol, src, tgt, raylen, gout = _prep(dtype, vol, src, tgt, raylen, gout)
     B, N = tgt.shape[0], tgt.shape[1]
@@ -109,7 +109,7 @@ def siddon_bwd(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad
     g_len = np.zeros((B, 1, N), dtype=dtype)
     g_vol = np.zeros(vol.shape, dtype=dtype) if (want_vol and not stop_grad) else None
     R = _real(dtype)
-    getattr(lib(), "oracle_siddon_bwd_" + _suf(dtype))(
+    getattr(lib(), ("oracle_siddon_bwd_max_" if reduce == "max" else "oracle_siddon_bwd_") + _suf(dtype))(
         _p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src), _p(g_tgt),
         _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N), R(voxel_shift), R(eps), ctypes.c_int(bool(stop_grad)),
         ctypes.c_int(bool(align_corners)))
@@ -143,7 +143,7 @@ def trilinear_fwd(vol, src, tgt, raylen, n_points=500, alphamin=None, alphamax=N
 
 
 def trilinear_bwd(vol, src, tgt, raylen, gout, n_points=500, alphamin=None, alphamax=None, voxel_shift=0.5, eps=1e-8,
-                  align_corners=False, want_vol=True, dtype=np.float64):
+                  align_corners=False, want_vol=True, dtype=np.float64, reduce="sum"):
     """Gradients for FIXED alphamin/alphamax plus the partials g_alphamin/g_alphamax (scalars)."""
     vol, src, tgt, raylen, gout = _prep(dtype, vol, src, tgt, raylen, gout)
     B, N = tgt.shape[0], tgt.shape[1]
@@ -155,7 +155,7 @@ def trilinear_bwd(vol, src, tgt, raylen, gout, n_points=500, alphamin=None, alph
     g_vol = np.zeros(vol.shape, dtype=dtype) if want_vol else None
     R = _real(dtype)
     ga0, ga1 = R(0), R(0)
-    getattr(lib(), "oracle_trilinear_bwd_" + _suf(dtype))(
+    getattr(lib(), ("oracle_trilinear_bwd_max_" if reduce == "max" else "oracle_trilinear_bwd_") + _suf(dtype))(
         _p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src), _p(g_tgt),
         _p(g_len), _p(g_vol), ctypes.byref(ga0), ctypes.byref(ga1), ctypes.c_int(B), ctypes.c_long(N), R(voxel_shift),
         R(eps), ctypes.c_int(n_points), R(alphamin), R(alphamax), ctypes.c_int(bool(align_corners)))

@@ -147,6 +147,34 @@ def trilinear_fwd_mask(vol, mask, src, tgt, raylen, C, n_points, alphamin, alpha
     return out
 
 
+def siddon_bwd_general(vol, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False, reduce="sum",
+                       align_corners=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    gout = _f(gout)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
+    lib().emu_siddon_bwd_general(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
+                                 _p(g_tgt), _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N),
+                                 ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(bool(stop_grad)),
+                                 ctypes.c_int({"sum": 0, "max": 1}[reduce]), ctypes.c_int(bool(align_corners)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
+
+
+def trilinear_bwd_max(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, voxel_shift=0.5, eps=1e-8,
+                      align_corners=False):
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    gout = _f(gout)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
+    g_ar = np.zeros(2, np.float32)
+    lib().emu_trilinear_bwd_max(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src),
+                                _p(g_tgt), _p(g_len), _p(g_vol), _p(g_ar), ctypes.c_int(B), ctypes.c_long(N),
+                                ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(n_points),
+                                ctypes.c_float(alphamin), ctypes.c_float(alphamax), ctypes.c_int(bool(align_corners)))
+    return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=float(g_ar[0]),
+                g_alphamax=float(g_ar[1]))
+
+
 def siddon_bwd_mask(vol, mask, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False):
     vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
     mask, gout = _f(mask), _f(gout)

@@ -333,6 +333,55 @@ void emu_box_pretest(int D0, int D1, int D2, const float* src, const float* tgt,
     out[0] = pairs; out[1] = skipped; out[2] = wrong; out[3] = hits;
 }
 
+// Backward of the general walk (reduce "sum"/"max", align_corners) and trilinear reduce="max" through the device routines
+void emu_siddon_bwd_general(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                            const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B, long N,
+                            float shift, float eps, int stop_grad, int reduce, int align_corners)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float gs[3], gt[3];
+            const float acc = siddon_ray_general_bwd(vol, dims, ray, raylen[r], gout[r] * raylen[r], shift, reduce,
+                                                     align_corners, stop_grad ? nullptr : g_vol, gs, gt);
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = gt[a];
+                g_src[b * 3 + a] += gs[a];
+            }
+            g_raylen[r] = stop_grad ? 0.0f : gout[r] * acc;
+        }
+}
+
+void emu_trilinear_bwd_max(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                           const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,
+                           float* g_alpha_range, int B, long N, float shift, float eps, int P, float amin, float amax,
+                           int align_corners)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const float step = (amax - amin) / (float)(P - 1);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    double ga0 = 0, ga1 = 0;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            const TriGrad tg =
+                trilinear_ray_bwd_max(vol, dims, ray, shift, P, amin, amax, align_corners, gout[r], raylen[r], g_vol);
+            for (int a = 0; a < 3; ++a) {
+                g_tgt[r * 3 + a] = tg.gt[a];
+                g_src[b * 3 + a] += tg.gs[a];
+            }
+            g_raylen[r] = gout[r] * step * tg.sumV;
+            ga0 += tg.ga0;
+            ga1 += tg.ga1;
+        }
+    g_alpha_range[0] = (float)ga0;
+    g_alpha_range[1] = (float)ga1;
+}
+
 // mask_to_channels backward through the device routines (FetchMasked / SampleGradMasked): gout is [B][C][N]
 void emu_siddon_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
                          const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,

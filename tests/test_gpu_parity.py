@@ -204,6 +204,27 @@ def test_mask_to_channels_backward_golden():
     assert relerr(tg.grad.cpu().numpy(), gg["g_target_f64"]) < 1e-4
 
 
+def test_option_backward_golden():
+    """Autograd through the options outside the fast kernels -- Siddon align_corners=True, reducefn="max" on both
+    renderers -- against the reference's own autograd (tests/golden/make_golden_extra_grads.py)."""
+    import os
+    from conftest import GOLDEN
+    from diffdrr_b200 import Siddon, Trilinear
+    cases = (("siddon_nc_b4_ac", Siddon(), dict(align_corners=True), 1e-4),
+             ("siddon_nc_b4_max", Siddon(reducefn="max"), {}, 1e-4),
+             ("trilinear_nc_b4_max", Trilinear(reducefn="max"), dict(n_points=96), 1e-3))
+    for name, mod, fkw, floor in cases:
+        g = load_golden(name)
+        gg = np.load(os.path.join(GOLDEN, name + "_grad.npz"))
+        v, s, tg, l = t(g["volume"], True), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+        out = mod(v, s, tg, l, **fkw)
+        assert relerr(out.detach().cpu().numpy(), g["img_f64"]) < IMG_TOL
+        (out * t(g["w"])).sum().backward()
+        for key, x in (("g_target", tg), ("g_source", s), ("g_raylen", l), ("g_volume", v)):
+            tol = max(floor if key in ("g_target", "g_source") else 1e-4, 2.0 * relerr(gg[key + "_f32"], gg[key + "_f64"]))
+            assert relerr(x.grad.cpu().numpy(), gg[key + "_f64"]) < tol, (name, key)
+
+
 def test_unsupported_options_raise():
     from diffdrr_b200 import Siddon, Trilinear
     g = load_golden("siddon_nc_axis")
@@ -218,6 +239,3 @@ def test_unsupported_options_raise():
         Siddon()(*args, align_corners=True, mask=torch.zeros_like(args[0]))
     with pytest.raises(NotImplementedError):
         Siddon()(args[0].double(), *args[1:])
-    out = Siddon(reducefn="max")(args[0], args[1].requires_grad_(True), *args[2:])
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()

@@ -302,3 +302,40 @@ def test_slab_miss_pretest_never_drops_a_hit(case):
     assert wrong == 0, f"{int(wrong)} (ray, slab) pairs skipped although the exact set-up walks them"
     assert skipped + hits <= pairs
     assert skipped >= 0.9 * (pairs - hits), "the pre-test should reject nearly every true miss"
+
+
+def test_option_backward_general_walk_and_max():
+    """Device backward of the general walk (align_corners=True; reducefn="max") and of trilinear reducefn="max" against
+    the reference's autograd (tests/golden/*_grad.npz) resp. the fp64 oracle pinned to it."""
+    import os
+    from conftest import GOLDEN
+
+    def tol(gg, key, floor=1e-4):
+        return max(floor, 2.0 * relerr(gg[key + "_f32"], gg[key + "_f64"]))
+    g = load_golden("siddon_nc_b4_ac")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_ac_grad.npz"))
+    out = emu.siddon_bwd_general(g["volume"], g["source"], g["target"], g["raylen"], g["w"], align_corners=True)
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < tol(gg, key), ("ac", key)
+    # align_corners=False through the general walk == the fast backward walk's goldens
+    g = load_golden("siddon_nc_b4")
+    out = emu.siddon_bwd_general(g["volume"], g["source"], g["target"], g["raylen"], g["w"])
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], g[key + "_f64"]) < tol(g, key), ("plain", key)
+    g = load_golden("siddon_nc_b4_max")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_max_grad.npz"))
+    out = emu.siddon_bwd_general(g["volume"], g["source"], g["target"], g["raylen"], g["w"], reduce="max")
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < tol(gg, key), ("max", key)
+    g = load_golden("trilinear_nc_b4_max")
+    gg = np.load(os.path.join(GOLDEN, "trilinear_nc_b4_max_grad.npz"))
+    amin, amax = oracle.alpha_minmax(g["volume"].shape, g["source"], g["target"], 0.5, 1e-8, np.float32)
+    out = emu.trilinear_bwd_max(g["volume"], g["source"], g["target"], g["raylen"], g["w"], 96, amin, amax)
+    ref = oracle.trilinear_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], n_points=96, alphamin=amin,
+                               alphamax=amax, reduce="max", dtype=np.float64)
+    for key in ("g_target", "g_source"):
+        assert relerr(out[key], ref[key]) < 1e-3, ("tri max", key)
+    for key in ("g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < tol(gg, key), ("tri max", key)
+    scale = max(abs(ref["g_alphamin"]), abs(ref["g_alphamax"]))
+    assert abs(out["g_alphamin"] - ref["g_alphamin"]) < 5e-3 * scale and abs(out["g_alphamax"] - ref["g_alphamax"]) < 5e-3 * scale

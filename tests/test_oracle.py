@@ -148,5 +148,29 @@ def test_mask_to_channels_backward_matches_reference_autograd():
     assert relerr(out["g_volume"], gg["g_volume_f64"]) < 1e-9
 
 
+def test_option_backward_matches_reference_autograd():
+    """reducefn="max" (both renderers) and Siddon align_corners=True: the reference's autograd for these options
+    (tests/golden/make_golden_extra_grads.py) against the oracle's closed forms."""
+    g = load_golden("siddon_nc_b4_ac")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_ac_grad.npz"))
+    out = oracle.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], align_corners=True, dtype=np.float64)
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < 1e-9, ("ac", key)
+    g = load_golden("siddon_nc_b4_max")
+    gg = np.load(os.path.join(GOLDEN, "siddon_nc_b4_max_grad.npz"))
+    out = oracle.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], reduce="max", dtype=np.float64)
+    for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+        assert relerr(out[key], gg[key + "_f64"]) < 1e-9, ("siddon max", key)
+    g = load_golden("trilinear_nc_b4_max")
+    gg = np.load(os.path.join(GOLDEN, "trilinear_nc_b4_max_grad.npz"))
+    out = oracle.trilinear_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], n_points=96, reduce="max",
+                               dtype=np.float64)
+    es, et = _minmax_chain(g, out, 0.5)
+    assert relerr(out["g_target"] + et, gg["g_target_f64"]) < 1e-9
+    assert relerr(out["g_source"] + es, gg["g_source_f64"]) < 1e-9
+    assert relerr(out["g_raylen"], gg["g_raylen_f64"]) < 1e-9
+    assert relerr(out["g_volume"], gg["g_volume_f64"]) < 1e-9
+
+
 def test_oracle_threads():
     assert oracle.max_threads() >= 1
