@@ -307,12 +307,26 @@ int b200drr_trilinear_fwd_mask(const float* vol, const float* mask, int D0, int 
 int b200drr_siddon_bwd_general(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                                const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int reduce,
-                               int align_corners, void* stream)
+                               int align_corners, int mode, void* stream)
 {
-    if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1)
+    if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1 ||
+        mode < 0 || mode > 1)
         return B200DRR_EINVAL;
+    if (mode == 1 && reduce != 0) return B200DRR_EUNSUPPORTED;
     return ret(launch_siddon_bwd_general(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, N,
-                                         voxel_shift, eps, stop_grad != 0, reduce, align_corners != 0, (cudaStream_t)stream));
+                                         voxel_shift, eps, stop_grad != 0, reduce, align_corners != 0, mode,
+                                         (cudaStream_t)stream));
+}
+
+int b200drr_siddon_fwd_general(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                               const float* raylen, float* out, int B, int64_t N, float voxel_shift, float eps, int reduce,
+                               int align_corners, int mode, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1 ||
+        mode < 0 || mode > 1)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd_general(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, reduce,
+                                         align_corners != 0, mode, (cudaStream_t)stream));
 }
 
 int b200drr_trilinear_bwd_max(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,

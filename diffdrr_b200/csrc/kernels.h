@@ -78,7 +78,10 @@ cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, floa
 cudaError_t launch_siddon_bwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                       const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,
                                       int64_t N, float shift, float eps, int stop_grad, int reduce, int align_corners,
-                                      cudaStream_t stream);
+                                      int mode, cudaStream_t stream);
+cudaError_t launch_siddon_fwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      float* out, int B, int64_t N, float shift, float eps, int reduce, int align_corners,
+                                      int mode, cudaStream_t stream);
 cudaError_t launch_siddon_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                    float* g_vol, int B, int64_t N, int C, float shift, float eps, int stop_grad,

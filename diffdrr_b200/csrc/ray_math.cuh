@@ -1455,4 +1455,127 @@ B200_HD TriGrad trilinear_ray_bwd_packed(const float4* packed, const VolDims& di
     return trilinear_ray_bwd_g(GatherPacked{packed}, dims, ray, shift, P, amin, amax, 0, g, L, nullptr, s_lo, s_hi);
 }
 
+// ===================================================================================================
+// Siddon with mode="bilinear" (reference renderers.py:18,66): the density of a segment is the TRILINEAR interpolant T at the
+// segment midpoint instead of the nearest voxel; everything else is the general plane-by-plane walk above.  Slow path.
+//   I = L sum_j len_j T(x_j)                    (reduce "max": max_j instead of sum_j, forward only)
+// GRAD (reduce "sum"): closed-form backward, pinned to the reference's autograd through the oracle:
+//   dI/dalpha_m = L [ (T_{m-1} - T_m) + (len_{m-1} G_{m-1}.d + len_m G_m.d)/2 ],  G = grad T w.r.t. x
+//   dI/ds += L sum_j len_j (1 - abar_j) G_j,  dI/dt += L sum_j len_j abar_j G_j,  dI/dL = sum_j len_j T_j,
+//   dI/dV[corner] += L len_j w_corner.   stop_grad (stop_gradients_through_grid_sample): T is a constant, only the
+//   (T_{m-1} - T_m) terms remain.  gs/gt come back already multiplied by g; returns the image value; sum_tl = sum len T.
+// ===================================================================================================
+template <bool GRAD>
+B200_HD float siddon_ray_bilinear(const float* vol, const VolDims& dims, const Ray& ray, float L, float shift, int reduce,
+                                  int align_corners, float g, bool stop_grad, float* g_vol, float gs[3], float gt[3],
+                                  float& sum_tl)
+{
+    int pos[3], stp[3], left[3];
+    float head[3], ka[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = ray.d[a] > 0.0f;
+        pos[a] = fwd ? 0 : dims.d[a];
+        stp[a] = fwd ? 1 : -1;
+        left[a] = dims.d[a] + 1;
+        head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+        ka[a] = align_corners ? (float)(dims.d[a] - 1) / (float)dims.d[a] : 1.0f;
+    }
+    const int M = dims.d[0] + dims.d[1] + dims.d[2] + 3;
+    const float gL = g * L;
+    float acc = 0.0f, aprev = 0.0f;
+    bool first = true;
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f}, S[3] = {0.0f, 0.0f, 0.0f}, Tt[3] = {0.0f, 0.0f, 0.0f};
+    float Tprev = 0.0f, hprev = 0.0f;  // value and len*G.d/2 of the segment before the previous crossing
+    int axprev = 0;
+    sum_tl = 0.0f;
+    for (int m = 0; m < M; ++m) {
+        const float h0 = left[0] > 0 ? head[0] : INFINITY;
+        const float h1 = left[1] > 0 ? head[1] : INFINITY;
+        const float h2 = left[2] > 0 ? head[2] : INFINITY;
+        const float acur = fminf(fminf(h0, h1), h2);
+        const int best = (left[0] > 0 && h0 == acur) ? 0 : ((left[1] > 0 && h1 == acur) ? 1 : 2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a == best) {
+                pos[a] += stp[a];
+                left[a] -= 1;
+                if (left[a] > 0) head[a] = plane_alpha(ray, a, (float)pos[a], shift);
+            }
+        if (m > 0) {
+            const float amid = (aprev + acur) / 2.0f, len = acur - aprev;
+            float pix[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x = add_rn(ray.s[a], mul_rn(amid, ray.d[a]));
+                pix[a] = unnormalize(2.0f * (x + shift) / (float)dims.d[a] - 1.0f, dims.d[a], align_corners);
+            }
+            float T = 0.0f, half = 0.0f;
+            if (!outside_padded(pix, dims)) {
+                const Corner8 k = gather8(vol, dims, pix);
+                const float f0 = k.f[0], f1 = k.f[1], f2 = k.f[2];
+                const float e0 = 1.0f - f0, e1 = 1.0f - f1, e2 = 1.0f - f2;
+                const float c00 = fmaf(f2, k.v[4] - k.v[0], k.v[0]), c10 = fmaf(f2, k.v[5] - k.v[1], k.v[1]);
+                const float c01 = fmaf(f2, k.v[6] - k.v[2], k.v[2]), c11 = fmaf(f2, k.v[7] - k.v[3], k.v[3]);
+                const float c0 = fmaf(f1, c01 - c00, c00), c1 = fmaf(f1, c11 - c10, c10);
+                T = fmaf(f0, c1 - c0, c0);
+                if (GRAD && !stop_grad) {
+                    float G[3];
+                    G[0] = (c1 - c0) * ka[0];
+                    G[1] = (e0 * (c01 - c00) + f0 * (c11 - c10)) * ka[1];
+                    G[2] = (e0 * (e1 * (k.v[4] - k.v[0]) + f1 * (k.v[6] - k.v[2])) +
+                            f0 * (e1 * (k.v[5] - k.v[1]) + f1 * (k.v[7] - k.v[3]))) * ka[2];
+                    float Gd = 0.0f;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        S[a] = fmaf(len * (1.0f - amid), G[a], S[a]);
+                        Tt[a] = fmaf(len * amid, G[a], Tt[a]);
+                        Gd = fmaf(G[a], ray.d[a], Gd);
+                    }
+                    half = 0.5f * len * Gd;
+                    if (g_vol) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (k.mask & (1u << c)) {
+                                const float w = ((c & 1) ? f0 : e0) * (((c >> 1) & 1) ? f1 : e1) * (((c >> 2) & 1) ? f2 : e2);
+                                red_add(g_vol + k.base + corner_off(dims, c), gL * len * w);
+                            }
+                    }
+                }
+            }
+            const float term = mul_rn(mul_rn(L, T), len);
+            if (reduce == 0) acc = add_rn(acc, term);
+            else if (first || term > acc) acc = term;
+            first = false;
+            if (GRAD) {
+                sum_tl = fmaf(T, len, sum_tl);
+                const float coef = (Tprev - T) + (hprev + half);  // crossing m-1 (axis axprev, alpha aprev)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (a == axprev) {
+                        A[a] = fmaf(coef, aprev, A[a]);
+                        C[a] += coef;
+                    }
+                Tprev = T;
+                hprev = half;
+            }
+        }
+        aprev = acur;
+        axprev = best;
+    }
+    if (GRAD) {
+        const float coef = Tprev + hprev;  // last crossing: T_last -> 0
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (a == axprev) {
+                A[a] = fmaf(coef, aprev, A[a]);
+                C[a] += coef;
+            }
+            gt[a] = gL * (Tt[a] - A[a] * ray.inv[a]);
+            gs[a] = gL * (S[a] + (A[a] - C[a]) * ray.inv[a]);
+        }
+    }
+    return acc;
+}
+
 }  // namespace b200drr

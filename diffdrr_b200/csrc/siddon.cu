@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_general_kernel(
     const float* __restrict__ vol, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
     const float* __restrict__ raylen, const float* __restrict__ gout, float* __restrict__ g_src, float* __restrict__ g_tgt,
     float* __restrict__ g_raylen, float* __restrict__ g_vol, int64_t N, float shift, float eps, int stop_grad, int reduce,
-    int align_corners)
+    int align_corners, int mode)
 {
     __shared__ float red[32];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -851,8 +851,13 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_general_kernel(
         const Ray ray = load_ray(src, tgt, b, r, eps);
         const float L = __ldg(raylen + r), g = __ldg(gout + r);
         float gt[3];
-        const float acc = siddon_ray_general_bwd(vol, dims, ray, L, g * L, shift, reduce, align_corners,
-                                                 stop_grad ? nullptr : g_vol, gs, gt);
+        float acc;
+        if (mode == 0)
+            acc = siddon_ray_general_bwd(vol, dims, ray, L, g * L, shift, reduce, align_corners, stop_grad ? nullptr : g_vol,
+                                         gs, gt);
+        else  // mode="bilinear" (reduce "sum"): trilinear sampling at the segment midpoints
+            siddon_ray_bilinear<true>(vol, dims, ray, L, shift, 0, align_corners, g, stop_grad != 0,
+                                      stop_grad ? nullptr : g_vol, gs, gt, acc);
         if (g_tgt) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) g_tgt[r * 3 + a] = gt[a];
@@ -871,14 +876,48 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_general_kernel(
 cudaError_t launch_siddon_bwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                       const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,
                                       int64_t N, float shift, float eps, int stop_grad, int reduce, int align_corners,
-                                      cudaStream_t stream)
+                                      int mode, cudaStream_t stream)
 {
+    if (mode != 0 && reduce != 0) return cudaErrorNotSupported;
     if (g_src) {
         const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
         if (e != cudaSuccess) return e;
     }
     siddon_bwd_general_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
-        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, N, shift, eps, stop_grad, reduce, align_corners);
+        vol, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, N, shift, eps, stop_grad, reduce, align_corners,
+        mode);
+    return cudaGetLastError();
+}
+
+// Forward of the general walk with the sampling mode selectable (0 = nearest: the reference default, 1 = bilinear).
+__global__ void __launch_bounds__(kThreads) siddon_fwd_bilinear_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                       const float* __restrict__ src,
+                                                                       const float* __restrict__ tgt,
+                                                                       const float* __restrict__ raylen,
+                                                                       float* __restrict__ out, int64_t N, float shift,
+                                                                       float eps, int reduce, int align_corners)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int b = blockIdx.y;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    float gs[3], gt[3], sum_tl;
+    out[r] = siddon_ray_bilinear<false>(vol, dims, ray, __ldg(raylen + r), shift, reduce, align_corners, 0.0f, true, nullptr,
+                                        gs, gt, sum_tl);
+}
+
+cudaError_t launch_siddon_fwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                      float* out, int B, int64_t N, float shift, float eps, int reduce, int align_corners,
+                                      int mode, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1);
+    if (mode == 0)
+        siddon_fwd_general_kernel<<<grid, kThreads, 0, stream>>>(vol, dims, src, tgt, raylen, out, N, shift, eps, reduce,
+                                                                 align_corners);
+    else
+        siddon_fwd_bilinear_kernel<<<grid, kThreads, 0, stream>>>(vol, dims, src, tgt, raylen, out, N, shift, eps, reduce,
+                                                                  align_corners);
     return cudaGetLastError();
 }
 

@@ -138,7 +138,7 @@ class _SiddonFunction(torch.autograd.Function):
             if reduce != 0 or align_corners:  # options outside the fast kernels: plane-by-plane general walk
                 _lib.check(lib.b200drr_siddon_bwd_general(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
                                                           _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift,
-                                                          eps, int(stop_grad), reduce, int(align_corners), _stream()),
+                                                          eps, int(stop_grad), reduce, int(align_corners), 0, _stream()),
                            "b200drr_siddon_bwd_general")
             elif grid is not None:
                 _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
@@ -152,6 +152,47 @@ class _SiddonFunction(torch.autograd.Function):
                            "b200drr_siddon_bwd")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
                 None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
+
+
+class _SiddonBilinearFunction(torch.autograd.Function):
+    """Siddon(mode="bilinear") (reference renderers.py:18,66): trilinear sampling at the segment midpoints through the general
+    walk (include/b200drr.h: b200drr_siddon_fwd_general / _bwd_general with mode = 1)."""
+
+    @staticmethod
+    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad):
+        B, N = _check_inputs(volume, source, target, img)
+        vol, src, tgt = volume.contiguous(), source.reshape(B, 3).contiguous(), target.contiguous()
+        raylen = img.reshape(B, N).contiguous()
+        out = torch.empty(B, N, dtype=torch.float32, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(_lib.load().b200drr_siddon_fwd_general(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                              _ptr(out), B, N, voxel_shift, eps, reduce, int(align_corners), 1,
+                                                              _stream()), "b200drr_siddon_fwd_general")
+        ctx.save_for_backward(vol, src, tgt, raylen)
+        ctx.cfg = (voxel_shift, eps, reduce, align_corners, stop_grad, tuple(source.shape), tuple(img.shape))
+        return out.view(B, 1, N)
+
+    @staticmethod
+    def backward(ctx, gout):
+        vol, src, tgt, raylen = ctx.saved_tensors
+        voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape = ctx.cfg
+        if reduce != 0:
+            raise NotImplementedError("backward through Siddon(mode='bilinear', reducefn='max') is not implemented")
+        B, N = tgt.shape[0], tgt.shape[1]
+        need_vol, need_src, need_tgt, need_len = ctx.needs_input_grad[:4]
+        gout = gout.reshape(B, N).contiguous().float()
+        dev = vol.device
+        g_src = torch.empty(B, 3, dtype=torch.float32, device=dev) if need_src else None
+        g_tgt = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if need_tgt else None
+        g_len = torch.empty(B, N, dtype=torch.float32, device=dev) if (need_len and not stop_grad) else None
+        g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_siddon_bwd_general(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                              _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B,
+                                                              N, voxel_shift, eps, int(stop_grad), 0, int(align_corners), 1,
+                                                              _stream()), "b200drr_siddon_bwd_general")
+        return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
+                None if g_len is None else g_len.view(img_shape), None, None, None, None, None)
 
 
 class _SiddonPoseFunction(torch.autograd.Function):
@@ -448,8 +489,8 @@ class Siddon(torch.nn.Module):
         return _dims_tensor(volume.shape, volume.device, volume.dtype)
 
     def forward(self, volume, source, target, img, align_corners=False, mask=None):
-        if self.mode != "nearest":
-            raise NotImplementedError("Siddon kernels implement mode='nearest' (the reference default) only")
+        if self.mode not in ("nearest", "bilinear"):
+            raise ValueError(f"mode must be 'nearest' or 'bilinear', not {self.mode!r}")
         if self.filter_intersections_outside_volume:
             # the reference crashes on this flag (renderers.py:118 calls _get_alpha_minmax with too few arguments)
             raise NotImplementedError("filter_intersections_outside_volume=True is broken in the reference and "
@@ -457,8 +498,14 @@ class Siddon(torch.nn.Module):
         if mask is not None:
             if align_corners or _reduce_code(self.reducefn) != 0:
                 raise NotImplementedError("mask_to_channels is implemented for reducefn='sum', align_corners=False")
+            if self.mode != "nearest":
+                raise NotImplementedError("mask_to_channels is implemented for mode='nearest'")
             return _render_mask("siddon", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps),
                                 stop_grad=self.stop_gradients_through_grid_sample)
+        if self.mode == "bilinear":  # trilinear sampling at the segment midpoints: general walk (slow path)
+            return _SiddonBilinearFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
+                                                 _reduce_code(self.reducefn), bool(align_corners),
+                                                 bool(self.stop_gradients_through_grid_sample))
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
                                      bool(self.stop_gradients_through_grid_sample), self.detector_shape)

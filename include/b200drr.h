@@ -259,7 +259,14 @@ int b200drr_trilinear_fwd_mask(const float *vol, const float *mask, int D0, int 
 int b200drr_siddon_bwd_general(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
                                const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
                                float *g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int reduce,
-                               int align_corners, void *stream);
+                               int align_corners, int mode, void *stream);
+/* General walk with the Siddon sampling mode selectable (reference renderers.py:18,66): mode 0 = "nearest" (same result as
+ * b200drr_siddon_fwd), mode 1 = "bilinear" = trilinear interpolation at the segment midpoints.  The backward above takes
+ * the same `mode` (bilinear: reduce = 0 only, B200DRR_EUNSUPPORTED otherwise; stop_grad then drops the interpolant's
+ * gradient terms exactly like stop_gradients_through_grid_sample). */
+int b200drr_siddon_fwd_general(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                               const float *raylen, float *out, int B, int64_t N, float voxel_shift, float eps, int reduce,
+                               int align_corners, int mode, void *stream);
 int b200drr_trilinear_bwd_max(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
                               const float *raylen, const float *gout, float *g_src, float *g_tgt, float *g_raylen,
                               float *g_vol, float *g_alpha_range, int B, int64_t N, float voxel_shift, float eps,

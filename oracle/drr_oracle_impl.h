@@ -570,6 +570,93 @@ void FN(oracle_trilinear_bwd)(const REAL *vol, int D0, int D1, int D2, const REA
     if (g_amax) *g_amax = tot_amax;
 }
 
+/* renderers.py:34-76 with mode="bilinear" (renderers.py:18,66 -> grid_sample(mode="bilinear")): the density of segment j
+ * is the trilinear interpolant T at the segment MIDPOINT x_j = s + abar_j d, abar_j = (alpha_j + alpha_{j+1})/2:
+ *   I = L sum_j len_j T(x_j).
+ * Backward (closed form; stop_grad restates stop_gradients_through_grid_sample=True, i.e. T is a constant):
+ *   dI/dalpha_m = L [ (T_{m-1} - T_m) + (len_{m-1} G_{m-1}.d + len_m G_m.d)/2 ],  G = grad T w.r.t. x (x dpix/dx)
+ *   dI/ds = sum_m dI/dalpha_m dalpha_m/ds + L sum_j len_j (1 - abar_j) G_j,   dI/dt likewise with abar_j
+ *   dI/dL = sum_j len_j T_j,   dI/dV[corner] += L len_j w_corner.
+ * g_* == NULL everywhere: forward only (out [B][N]).  reduce must be 0 (sum). */
+void FN(oracle_siddon_bilinear)(const REAL *vol, int D0, int D1, int D2, const REAL *src, const REAL *tgt,
+                                const REAL *raylen, const REAL *gout, REAL *out, REAL *g_src, REAL *g_tgt, REAL *g_raylen,
+                                REAL *g_vol, int B, long N, REAL shift, REAL eps, int stop_grad, int align_corners)
+{
+    const int dims[3] = {D0, D1, D2};
+    const int M = D0 + D1 + D2 + 3;
+    if (g_src) memset(g_src, 0, sizeof(REAL) * (size_t)B * 3);
+#pragma omp parallel
+    {
+        REAL *alpha = (REAL *)malloc(sizeof(REAL) * (size_t)M);
+        int *axis = (int *)malloc(sizeof(int) * (size_t)M);
+        REAL *T = (REAL *)malloc(sizeof(REAL) * (size_t)(M + 1));
+        REAL *Gd = (REAL *)malloc(sizeof(REAL) * (size_t)(M + 1));
+#pragma omp for schedule(dynamic, 64)
+        for (long r = 0; r < (long)B * N; ++r) {
+            const int b = (int)(r / N);
+            REAL s[3], d[3], scale[3];
+            for (int a = 0; a < 3; ++a) {
+                s[a] = src[b * 3 + a];
+                d[a] = (tgt[r * 3 + a] - s[a]) + eps;
+                scale[a] = align_corners ? (REAL)(dims[a] - 1) / (REAL)dims[a] : (REAL)1;
+            }
+            FN(sorted_alphas)(dims, s, d, shift, alpha, axis, NULL);
+            const REAL L = raylen[r], g = gout ? gout[r] : (REAL)0;
+            REAL acc = 0, sumTL = 0, gs[3] = {0, 0, 0}, gt[3] = {0, 0, 0};
+            for (int j = 0; j + 1 < M; ++j) {
+                const REAL amid = (alpha[j] + alpha[j + 1]) / (REAL)2, len = alpha[j + 1] - alpha[j];
+                REAL pix[3], G[3], cw[8];
+                long ci[8];
+                for (int a = 0; a < 3; ++a) pix[a] = FN(pix_at)(amid, s[a], d[a], shift, dims[a], align_corners);
+                T[j] = FN(trilerp)(vol, dims, pix, G, ci, cw);
+                acc += (L * T[j]) * len;
+                sumTL += T[j] * len;
+                Gd[j] = 0;
+                for (int a = 0; a < 3; ++a) {
+                    G[a] *= scale[a];
+                    Gd[j] += G[a] * d[a];
+                    if (!stop_grad) { /* direct dependence of the midpoint on s and t */
+                        gs[a] += g * L * len * ((REAL)1 - amid) * G[a];
+                        gt[a] += g * L * len * amid * G[a];
+                    }
+                }
+                if (g_vol && !stop_grad)
+                    for (int k = 0; k < 8; ++k)
+                        if (ci[k] >= 0) {
+                            REAL add = g * L * len * cw[k];
+#pragma omp atomic
+                            g_vol[ci[k]] += add;
+                        }
+            }
+            if (out) out[r] = acc;
+            for (int m = 0; m < M; ++m) {
+                const REAL Tm1 = m > 0 ? T[m - 1] : (REAL)0, Tm = m + 1 < M ? T[m] : (REAL)0;
+                REAL c = Tm1 - Tm;
+                if (!stop_grad) {
+                    if (m > 0) c += (alpha[m] - alpha[m - 1]) * Gd[m - 1] / (REAL)2;
+                    if (m + 1 < M) c += (alpha[m + 1] - alpha[m]) * Gd[m] / (REAL)2;
+                }
+                c *= g * L;
+                const int a = axis[m];
+                gs[a] += c * (alpha[m] - (REAL)1) / d[a];
+                gt[a] += c * (-alpha[m]) / d[a];
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (g_tgt) g_tgt[r * 3 + a] = gt[a];
+                if (g_src) {
+#pragma omp atomic
+                    g_src[b * 3 + a] += gs[a];
+                }
+            }
+            if (g_raylen) g_raylen[r] = stop_grad ? (REAL)0 : g * sumTL;
+        }
+        free(alpha);
+        free(axis);
+        free(T);
+        free(Gd);
+    }
+}
+
 /* Autograd of Trilinear.forward with reducefn="max": I = max_m (L V_m) step, gradient through the FIRST maximal sample m*
  * only; the closed forms of oracle_trilinear_bwd with every sum over m replaced by its m* term. */
 void FN(oracle_trilinear_bwd_max)(const REAL *vol, int D0, int D1, int D2, const REAL *src, const REAL *tgt,

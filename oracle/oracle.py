@@ -197,3 +197,25 @@ def trilinear_bwd_mask(vol, mask, src, tgt, raylen, gout, n_points=500, alphamin
         R(voxel_shift), R(eps), ctypes.c_int(n_points), R(alphamin), R(alphamax), ctypes.c_int(bool(align_corners)))
     return dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol, g_alphamin=ga0.value,
                 g_alphamax=ga1.value)
+
+
+def siddon_bilinear(vol, src, tgt, raylen, gout=None, voxel_shift=0.5, eps=1e-8, stop_grad=False, align_corners=False,
+                    dtype=np.float64):
+    """Siddon with mode="bilinear": image (B,1,N) and, when gout is given, the gradients dict of siddon_bwd."""
+    if gout is None:
+        vol, src, tgt, raylen = _prep(dtype, vol, src, tgt, raylen)
+    else:
+        vol, src, tgt, raylen, gout = _prep(dtype, vol, src, tgt, raylen, gout)
+    B, N = tgt.shape[0], tgt.shape[1]
+    out = np.zeros((B, 1, N), dtype=dtype)
+    grads = gout is not None
+    g_src = np.zeros((B, 1, 3), dtype=dtype) if grads else None
+    g_tgt = np.zeros((B, N, 3), dtype=dtype) if grads else None
+    g_len = np.zeros((B, 1, N), dtype=dtype) if grads else None
+    g_vol = np.zeros(vol.shape, dtype=dtype) if (grads and not stop_grad) else None
+    R = _real(dtype)
+    getattr(lib(), "oracle_siddon_bilinear_" + _suf(dtype))(
+        _p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(out), _p(g_src), _p(g_tgt),
+        _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N), R(voxel_shift), R(eps), ctypes.c_int(bool(stop_grad)),
+        ctypes.c_int(bool(align_corners)))
+    return dict(img=out, g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)

@@ -50,3 +50,25 @@ if __name__ == "__main__":
         path = os.path.join(HERE, tag + "_grad.npz")
         np.savez_compressed(path, **rec)
         print(tag, {k: float(np.abs(v).max()) for k, v in rec.items() if k.endswith("f64")}, f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+    # Siddon with mode="bilinear" (renderers.py:18,66: trilinear sampling at the segment midpoints), with and without
+    # stop_gradients_through_grid_sample; rays and weights of siddon_nc_b4; full records (no forward golden existed)
+    g = np.load(os.path.join(HERE, "siddon_nc_b4.npz"))
+    for tag, ctor in (("siddon_nc_b4_bilinear", dict(mode="bilinear")),
+                      ("siddon_nc_b4_bilinear_stopgrad", dict(mode="bilinear", stop_gradients_through_grid_sample=True))):
+        rec = {k: g[k] for k in ("source", "target", "raylen", "w")}
+        rec["volume_key"] = np.str_("nc")
+        for dt_tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            v = torch.from_numpy(vol).to(dt).requires_grad_(True)
+            s = torch.from_numpy(g["source"]).to(dt).requires_grad_(True)
+            t = torch.from_numpy(g["target"]).to(dt).requires_grad_(True)
+            l = torch.from_numpy(g["raylen"]).to(dt).requires_grad_(True)
+            img = RefSiddon(**ctor)(v, s, t, l)
+            rec["img_" + dt_tag] = img.detach().numpy()
+            (img * torch.from_numpy(g["w"]).to(dt)).sum().backward()
+            for name, x in (("g_volume", v), ("g_source", s), ("g_target", t), ("g_raylen", l)):
+                if x.grad is not None:
+                    rec[f"{name}_{dt_tag}"] = x.grad.numpy()
+        path = os.path.join(HERE, tag + ".npz")
+        np.savez_compressed(path, **rec)
+        print(tag, {k: float(np.abs(v).max()) for k, v in rec.items() if k.endswith("f64")}, f"{os.path.getsize(path) / 1024:.0f} KiB")

@@ -175,6 +175,23 @@ def trilinear_bwd_max(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax,
                 g_alphamax=float(g_ar[1]))
 
 
+def siddon_bilinear(vol, src, tgt, raylen, gout=None, voxel_shift=0.5, eps=1e-8, stop_grad=False, reduce="sum",
+                    align_corners=False):
+    """Siddon(mode="bilinear"): dict(img, and with gout the gradients)."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    grads = gout is not None
+    gout = _f(gout) if grads else np.zeros((B, 1, N), np.float32)
+    out = np.zeros((B, 1, N), np.float32)
+    g_src, g_tgt = np.zeros((B, 1, 3), np.float32), np.zeros((B, N, 3), np.float32)
+    g_len, g_vol = np.zeros((B, 1, N), np.float32), np.zeros(vol.shape, np.float32)
+    lib().emu_siddon_bilinear(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(out),
+                              _p(g_src), _p(g_tgt), _p(g_len), _p(g_vol), ctypes.c_int(B), ctypes.c_long(N),
+                              ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(bool(stop_grad)),
+                              ctypes.c_int({"sum": 0, "max": 1}[reduce]), ctypes.c_int(bool(align_corners)),
+                              ctypes.c_int(bool(grads)))
+    return dict(img=out, g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_volume=g_vol)
+
+
 def siddon_bwd_mask(vol, mask, src, tgt, raylen, gout, voxel_shift=0.5, eps=1e-8, stop_grad=False):
     vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
     mask, gout = _f(mask), _f(gout)

@@ -382,6 +382,33 @@ void emu_trilinear_bwd_max(const float* vol, int D0, int D1, int D2, const float
     g_alpha_range[1] = (float)ga1;
 }
 
+// Siddon mode="bilinear" through the device routine: image and (grads != 0) gradients in one call
+void emu_siddon_bilinear(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                         const float* gout, float* out, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,
+                         long N, float shift, float eps, int stop_grad, int reduce, int align_corners, int grads)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    std::memset(g_src, 0, sizeof(float) * 3 * B);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float gs[3] = {0, 0, 0}, gt[3] = {0, 0, 0}, sum_tl = 0;
+            if (grads) {
+                out[r] = siddon_ray_bilinear<true>(vol, dims, ray, raylen[r], shift, 0, align_corners, gout[r], stop_grad != 0,
+                                                   stop_grad ? nullptr : g_vol, gs, gt, sum_tl);
+                for (int a = 0; a < 3; ++a) {
+                    g_tgt[r * 3 + a] = gt[a];
+                    g_src[b * 3 + a] += gs[a];
+                }
+                g_raylen[r] = stop_grad ? 0.0f : gout[r] * sum_tl;
+            } else {
+                out[r] = siddon_ray_bilinear<false>(vol, dims, ray, raylen[r], shift, reduce, align_corners, 0.0f, true, nullptr,
+                                                    gs, gt, sum_tl);
+            }
+        }
+}
+
 // mask_to_channels backward through the device routines (FetchMasked / SampleGradMasked): gout is [B][C][N]
 void emu_siddon_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
                          const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,

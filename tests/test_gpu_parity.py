@@ -225,14 +225,37 @@ def test_option_backward_golden():
             assert relerr(x.grad.cpu().numpy(), gg[key + "_f64"]) < tol, (name, key)
 
 
+@pytest.mark.parametrize("name,stop", [("siddon_nc_b4_bilinear", False), ("siddon_nc_b4_bilinear_stopgrad", True)])
+def test_siddon_bilinear_mode_golden(name, stop):
+    """Siddon(mode="bilinear") -- trilinear sampling at the segment midpoints -- image and autograd against the reference,
+    with and without stop_gradients_through_grid_sample (the flag only matters in this mode: quirk Q6)."""
+    from diffdrr_b200 import Siddon
+    g = load_golden(name)
+    mod = Siddon(mode="bilinear", stop_gradients_through_grid_sample=stop)
+    v, s, tg, l = t(g["volume"], True), t(g["source"], True), t(g["target"], True), t(g["raylen"], True)
+    out = mod(v, s, tg, l)
+    assert relerr(out.detach().cpu().numpy(), g["img_f64"]) < IMG_TOL
+    (out * t(g["w"])).sum().backward()
+    assert relerr(tg.grad.cpu().numpy(), g["g_target_f64"]) < grad_tol(g, "g_target", 1e-3)
+    assert relerr(s.grad.cpu().numpy(), g["g_source_f64"]) < grad_tol(g, "g_source", 1e-3)
+    if stop:
+        assert v.grad is None and l.grad is None
+    else:
+        assert relerr(l.grad.cpu().numpy(), g["g_raylen_f64"]) < grad_tol(g, "g_raylen")
+        assert relerr(v.grad.cpu().numpy(), g["g_volume_f64"]) < grad_tol(g, "g_volume")
+    with torch.no_grad():  # reducefn="max" forward: bounded by the sum on a non-negative volume
+        mx = Siddon(mode="bilinear", reducefn="max")(v, s, tg, l)
+    assert bool((mx <= out.detach() * (1 + 1e-5) + 1e-6).all())
+
+
 def test_unsupported_options_raise():
     from diffdrr_b200 import Siddon, Trilinear
     g = load_golden("siddon_nc_axis")
     args = (t(g["volume"]), t(g["source"]), t(g["target"]), t(g["raylen"]))
     with pytest.raises(NotImplementedError):
         Siddon(filter_intersections_outside_volume=True)(*args)   # quirk Q5: the reference crashes too
-    with pytest.raises(NotImplementedError):
-        Siddon(mode="bilinear")(*args)
+    with pytest.raises(ValueError):
+        Siddon(mode="bicubic")(*args)
     with pytest.raises(NotImplementedError):
         Siddon(reducefn=lambda x: x.mean(-1))(*args)
     with pytest.raises(NotImplementedError):  # mask rendering: reducefn="sum", align_corners=False only

@@ -339,3 +339,20 @@ def test_option_backward_general_walk_and_max():
         assert relerr(out[key], gg[key + "_f64"]) < tol(gg, key), ("tri max", key)
     scale = max(abs(ref["g_alphamin"]), abs(ref["g_alphamax"]))
     assert abs(out["g_alphamin"] - ref["g_alphamin"]) < 5e-3 * scale and abs(out["g_alphamax"] - ref["g_alphamax"]) < 5e-3 * scale
+
+
+@pytest.mark.parametrize("name,stop", [("siddon_nc_b4_bilinear", False), ("siddon_nc_b4_bilinear_stopgrad", True)])
+def test_siddon_bilinear_mode(name, stop):
+    """Siddon(mode="bilinear") device routine: image and closed-form gradients against the reference's autograd."""
+    g = load_golden(name)
+    out = emu.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"], g["w"], stop_grad=stop)
+    assert relerr(out["img"], g["img_f64"]) < IMG_TOL
+    assert relerr(emu.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"])["img"], g["img_f64"]) < IMG_TOL
+    for key in ("g_target", "g_source") + (() if stop else ("g_raylen", "g_volume")):
+        assert relerr(out[key], g[key + "_f64"]) < max(1e-3 if key in ("g_target", "g_source") else 1e-4,
+                                                        2.0 * relerr(g[key + "_f32"], g[key + "_f64"])), key
+    if stop:
+        assert not out["g_volume"].any() and not out["g_raylen"].any()
+    # reducefn="max" forward against the oracle-free identity: max <= sum for non-negative volumes, and > 0 where sum > 0
+    mx = emu.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"], reduce="max")["img"]
+    assert (mx <= out["img"] * (1 + 1e-5) + 1e-6).all() and ((mx > 0) == (out["img"] > 0)).all()

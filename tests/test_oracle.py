@@ -172,5 +172,23 @@ def test_option_backward_matches_reference_autograd():
     assert relerr(out["g_volume"], gg["g_volume_f64"]) < 1e-9
 
 
+@pytest.mark.parametrize("name,stop", [("siddon_nc_b4_bilinear", False), ("siddon_nc_b4_bilinear_stopgrad", True)])
+def test_siddon_bilinear_mode_matches_reference(name, stop):
+    """Siddon(mode="bilinear"): trilinear sampling at the segment midpoints, image and autograd gradients, with and without
+    stop_gradients_through_grid_sample (tests/golden/make_golden_extra_grads.py)."""
+    g = load_golden(name)
+    out = oracle.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"], g["w"], stop_grad=stop, dtype=np.float64)
+    assert relerr(out["img"], g["img_f64"]) < 1e-10
+    assert relerr(oracle.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"], dtype=np.float32)["img"],
+                  g["img_f32"]) < 2e-5
+    assert relerr(out["g_target"], g["g_target_f64"]) < 1e-9
+    assert relerr(out["g_source"], g["g_source_f64"]) < 1e-9
+    if stop:
+        assert "g_volume_f64" not in g and "g_raylen_f64" not in g
+    else:
+        assert relerr(out["g_raylen"], g["g_raylen_f64"]) < 1e-9
+        assert relerr(out["g_volume"], g["g_volume_f64"]) < 1e-9
+
+
 def test_oracle_threads():
     assert oracle.max_threads() >= 1
