@@ -356,3 +356,38 @@ def test_siddon_bilinear_mode(name, stop):
     # reducefn="max" forward against the oracle-free identity: max <= sum for non-negative volumes, and > 0 where sum > 0
     mx = emu.siddon_bilinear(g["volume"], g["source"], g["target"], g["raylen"], reduce="max")["img"]
     assert (mx <= out["img"] * (1 + 1e-5) + 1e-6).all() and ((mx > 0) == (out["img"] > 0)).all()
+
+
+def test_property_random_geometry_lean_and_sensitivity_walks():
+    """Property test (hypothesis): for random small volumes, voxel shifts and ray bundles -- including rays that start inside,
+    graze faces, run along axes or miss -- every production walk agrees with the fp64 oracle on the image, and the
+    one-walk sensitivities agree with the three-axis backward walk, with and without slab cuts."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.tuples(st.integers(1, 12), st.integers(1, 12), st.integers(1, 12)), st.integers(0, 2**31 - 1),
+           st.sampled_from([0.5, 0.0, 0.25]), st.integers(1, 5))
+    def check(shape, seed, shift, slab):
+        rng = np.random.default_rng(seed)
+        vol = rng.random(shape, dtype=np.float32)
+        B, N = 2, 23
+        c = np.array(shape, dtype=np.float64) / 2
+        src = (c + rng.normal(size=(B, 1, 3)) * np.array(shape) * rng.choice([0.2, 1.5, 4.0])).astype(np.float32)
+        tgt = (c + (c - src) * 0.8 + rng.normal(size=(B, N, 3)) * np.array(shape) * 0.7).astype(np.float32)
+        tgt[:, 0] = src[:, 0] + np.array([0.0, 0.0, 7.5], np.float32)       # axis-parallel ray
+        tgt[:, 1, 0] = np.round(tgt[:, 1, 0])                               # lands on a plane coordinate
+        raylen = np.linalg.norm(tgt - src, axis=-1)[:, None, :].astype(np.float32)
+        ref = oracle.siddon_fwd(vol, src, tgt, raylen, voxel_shift=shift, dtype=np.float64)
+        scale = max(np.abs(ref).max(), 1e-6)
+        for out in (emu.siddon_fwd(vol, src, tgt, raylen, voxel_shift=shift),
+                    emu.siddon_fwd_ilp(vol, src, tgt, raylen, unroll=-4, voxel_shift=shift)):
+            assert np.abs(out - ref).max() / scale < 2e-5
+        w = rng.random((B, 1, N), dtype=np.float32)
+        sens = emu.siddon_sens(vol, src, tgt, raylen, w, voxel_shift=shift, slab=slab)
+        bwd = emu.siddon_bwd(vol, src, tgt, raylen, w, voxel_shift=shift, lean_slab=slab)
+        assert np.abs(sens["img"] - ref).max() / scale < 2e-5
+        for key in ("g_target", "g_source", "g_raylen"):
+            s_ = np.abs(bwd[key]).max()
+            assert s_ == 0.0 and not sens[key].any() or np.abs(sens[key] - bwd[key]).max() / s_ < 2e-4, key
+
+    check()
