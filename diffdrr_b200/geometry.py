@@ -12,6 +12,7 @@ from __future__ import annotations
 import math
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .renderers import _ptr, _stream
@@ -40,6 +41,7 @@ class _EulerPoseFunction(torch.autograd.Function):
         return P
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gP):
         rot, xyz = ctx.saved_tensors
         axes, scale = ctx.cfg
@@ -76,6 +78,7 @@ class _PoseRaysFunction(torch.autograd.Function):
         return src, G, Wd
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_src, g_G, g_Wd):
         Q, r, Ainv = ctx.saved_tensors
         B = g_G.shape[0]

@@ -14,6 +14,7 @@ import ctypes
 from typing import Callable
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -110,6 +111,7 @@ class _SiddonFunction(torch.autograd.Function):
         return out.view(B, 1, N)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape, grid = ctx.cfg
         if ctx.fused:
@@ -173,6 +175,7 @@ class _SiddonBilinearFunction(torch.autograd.Function):
         return out.view(B, 1, N)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         vol, src, tgt, raylen = ctx.saved_tensors
         voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape = ctx.cfg
@@ -224,6 +227,7 @@ class _SiddonPoseFunction(torch.autograd.Function):
         return out.view(B, 1, H * W)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         voxel_shift, eps, stop_grad = ctx.cfg
         if ctx.fused:
@@ -316,6 +320,7 @@ class _TrilinearFunction(torch.autograd.Function):
         return out.view(B, 1, N)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         voxel_shift, eps, n_points, reduce, align_corners, src_shape, img_shape, grid = ctx.cfg
         if ctx.fused:
@@ -403,6 +408,7 @@ class _MaskFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         vol, msk, src, tgt, raylen, ar = ctx.saved_tensors
         kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, src_shape, img_shape = ctx.cfg
