@@ -339,7 +339,10 @@ def run_ours(args, rank, local_rank, world):
     # The host buffers are re-read by every replay, so each step can carry new poses.  (Single GPU only: NCCL
     # collectives are kept out of the capture.)
     e2e_ms_total, e2e_mode = e2e_eager_ms_total, "eager"
-    if world == 1 and not args.no_graph:
+    # N > 1: opt-in (B200DRR_BENCH_GRAPH_MULTI=1, not yet measured on a multi-GPU box): the per-rank step is replayed from
+    # its graph and the gather of the image stack is issued after the replay, outside the capture.
+    graph_multi = world > 1 and os.environ.get("B200DRR_BENCH_GRAPH_MULTI") == "1"
+    if (world == 1 or graph_multi) and not args.no_graph:
         try:
             rot_d = torch.zeros(B, 3, device=dev, requires_grad=True)
             xyz_d = torch.zeros(B, 3, device=dev, requires_grad=True)
@@ -366,6 +369,7 @@ def run_ours(args, rank, local_rank, world):
                 grad_h[0].copy_(rot_d.grad, non_blocking=True)
                 grad_h[1].copy_(xyz_d.grad, non_blocking=True)
                 loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+                return img.detach()
 
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -377,22 +381,24 @@ def run_ours(args, rank, local_rank, world):
             ref_img = img_h.clone()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                graph_body()
+                img_static = graph_body()
 
             def graph_step():
                 graph.replay()
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered[0], img_static.reshape(B, N))
                 torch.cuda.current_stream().synchronize()  # the user reads the result every step
 
             for _ in range(args.warmup):
                 graph_step()
             assert torch.allclose(img_h, ref_img, rtol=1e-4, atol=1e-3), "graph replay changed the images"
             g_start, g_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
+            barrier()
             g_start.record(stream)
             for _ in range(args.steps):
                 graph_step()
             g_end.record(stream)
-            torch.cuda.synchronize()
+            barrier()
             e2e_ms_total, e2e_mode = g_start.elapsed_time(g_end), "cuda-graph replay of the public-API step"
         except Exception as exc:  # capture is an optimisation of the launch path only; never hide the eager number
             e2e_mode = f"eager (graph capture failed: {type(exc).__name__})"
