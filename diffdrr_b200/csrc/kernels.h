@@ -91,6 +91,12 @@ cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDi
                                       float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
                                       int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 
+// experiments (b200drr_x_*): chunk-reuse forward over a major-axis-fastest copy
+cudaError_t launch_x_transpose_volume(const float* vol, VolDims dims, int axis, float* out, cudaStream_t stream);
+cudaError_t launch_x_siddon_fwd_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,
+                                      const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                      int variant, cudaStream_t stream);
+
 // per-pose algebra around the pose-in kernels (pose.cu)
 cudaError_t launch_euler_pose_fwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, float* P, int B,
                                   cudaStream_t stream);

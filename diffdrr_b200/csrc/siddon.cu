@@ -229,6 +229,100 @@ static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// EXPERIMENT (opt-in, b200drr_x_*): slab-major forward over a major-axis-fastest copy with per-lane chunk reuse
+// (ray_math.cuh: siddon_ray_lean_box_chunk).  Not on any default path; kept compiled so the next tuning round can time it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_volume_kernel(const float* __restrict__ vol, VolDims dims, int axis,
+                                                               float* __restrict__ out)
+{
+    // out[i_p][i_q][i_axis], (p, q) = the other two axes in ascending order; one thread per OUTPUT element
+    const int64_t total = (int64_t)dims.d[0] * dims.d[1] * dims.d[2];
+    const int p = axis == 0 ? 1 : 0, q = axis == 2 ? 1 : 2;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        int idx[3];
+        idx[axis] = (int)(o % dims.d[axis]);
+        const int64_t t = o / dims.d[axis];
+        idx[q] = (int)(t % dims.d[q]);
+        idx[p] = (int)(t / dims.d[q]);
+        out[o] = __ldg(vol + ((int64_t)idx[0] * dims.d[1] + idx[1]) * dims.d[2] + idx[2]);
+    }
+}
+
+cudaError_t launch_x_transpose_volume(const float* vol, VolDims dims, int axis, float* out, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)dims.d[0] * dims.d[1] * dims.d[2];
+    cudaError_t e = cudaMemsetAsync(out + total, 0, sizeof(float) * 4, stream);  // the padding chunk
+    if (e != cudaSuccess) return e;
+    transpose_volume_kernel<<<148 * 8, 256, 0, stream>>>(vol, dims, axis, out);
+    return cudaGetLastError();
+}
+
+template <int TW, int TH, int U, int CW>
+__global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_chunk_kernel(const float* __restrict__ volT, VolDims dims, int axis,
+                                                                       const float* __restrict__ src,
+                                                                       const float* __restrict__ tgt,
+                                                                       const float* __restrict__ raylen,
+                                                                       float* __restrict__ out, int B, int H, int W, int slab,
+                                                                       float shift, float eps)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;
+    // element strides of the copy whose fastest axis is `axis` (the other two keep their order)
+    const int d0 = dims.d[0], d1 = dims.d[1], d2 = dims.d[2];
+    const int st0 = axis == 0 ? 1 : (axis == 1 ? d1 * d2 : d2 * d1);  // out[i_p][i_q][i_axis], p < q
+    const int st1 = axis == 1 ? 1 : (axis == 0 ? d0 * d2 : d2);
+    const int st2 = axis == 2 ? 1 : (axis == 0 ? d0 : d1);
+    const float part = siddon_ray_lean_box_chunk<U, CW>(volT, lo_v, hi_v, st0, st1, st2, ray, shift);
+    if (part != 0.0f) red_add(out + r, __ldg(raylen + r) * part);
+}
+
+cudaError_t launch_x_siddon_fwd_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,
+                                      const float* raylen, float* out, int B, int H, int W, float shift, float eps,
+                                      int variant, cudaStream_t stream)
+{
+    if ((int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
+    if (e != cudaSuccess) return e;
+#define XC(id, TW, TH, U, CW, SLAB)                                                                                      \
+    case id: {                                                                                                           \
+        const int n_slabs = (dims.d[0] + SLAB - 1) / SLAB;                                                               \
+        const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;                         \
+        if (blocks > INT32_MAX) return cudaErrorInvalidValue;                                                            \
+        siddon_fwd_slab_chunk_kernel<TW, TH, U, CW><<<(unsigned)blocks, TW * TH, 0, stream>>>(                           \
+            volT, dims, axis, src, tgt, raylen, out, B, H, W, SLAB, shift, eps);                                         \
+        return cudaGetLastError();                                                                                       \
+    }
+    switch (variant) {
+        XC(0, 16, 16, 4, 4, 32)
+        XC(1, 16, 16, 4, 2, 32)
+        XC(2, 16, 8, 4, 4, 32)
+        XC(3, 8, 16, 4, 4, 32)
+        XC(4, 16, 16, 2, 4, 32)
+        XC(5, 16, 16, 8, 4, 32)
+        XC(6, 16, 16, 4, 4, 48)
+        XC(7, 8, 16, 8, 2, 48)
+        default: return cudaErrorInvalidValue;
+    }
+#undef XC
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Plane-synchronous slab-major kernel (psync.cuh): same decomposition as siddon_fwd_slab_kernel, but every
 // lane advances one MAJOR-axis plane per iteration and the lanes of a warp are aligned onto the same plane
 // (WarpAlign), so the 8x4 ray bundle gathers from one voxel plane at a time and shares sectors.

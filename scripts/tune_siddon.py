@@ -61,6 +61,24 @@ for v in variants:
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"grid variant {v:2d}       : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")
 
+# ---- EXPERIMENT: chunk-reuse forward over a major-axis-fastest copy (b200drr_x_*), XVARIANTS=0,1,... [XAXIS=1] ------------
+if os.environ.get("XVARIANTS"):
+    axis = int(os.environ.get("XAXIS", 1))  # the bench poses travel along volume axis 1
+    volT = torch.empty(D * D1 * D2 + 4, device=dev)
+    t_ms = timeit(lambda: _lib.check(lib.b200drr_x_transpose_volume(_ptr(vol), D, D1, D2, axis, _ptr(volT), _stream()), "transpose"), 2)
+    print(f"transpose to axis-{axis}-fastest: {t_ms:.3f} ms")
+    for v in [int(x) for x in os.environ["XVARIANTS"].split(",")]:
+        out = torch.zeros(B, N, device=dev)
+        def run():
+            _lib.check(lib.b200drr_x_siddon_fwd_chunk(_ptr(volT), D, D1, D2, axis, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, H, H, 0.5, 1e-8, v, _stream()), "chunk")
+        try:
+            ms = timeit(run)
+        except Exception as e:
+            print(f"chunk variant {v}: {e}")
+            continue
+        err = float((out - ref).abs().max() / ref.abs().max())
+        print(f"chunk variant {v:2d}      : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")
+
 # ---- forward + sensitivities (training-step fast path) variants ----------------------------------------------------
 if os.environ.get("SVARIANTS"):
     gout_s = torch.rand(B, N, device=dev)

@@ -175,6 +175,27 @@ def trilinear_bwd_max(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax,
                 g_alphamax=float(g_ar[1]))
 
 
+def transposed_padded(vol, axis, pad=4):
+    """Copy of `vol` with `axis` fastest (the other two axes keep their order), flattened and padded by `pad` floats."""
+    order = [a for a in range(3) if a != axis] + [axis]
+    flat = np.ascontiguousarray(np.transpose(_f(vol), order)).ravel()
+    return np.concatenate([flat, np.zeros(pad, np.float32)])
+
+
+def siddon_fwd_chunk(vol, src, tgt, raylen, axis, width=4, voxel_shift=0.5, eps=1e-8, slab=0):
+    """EXPERIMENT: chunk-reuse lean walk; returns (chunk result, plain lean walk with the same slab cuts)."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    volT = transposed_padded(vol, axis)
+    out, ref = np.empty((B, 1, N), np.float32), np.empty((B, 1, N), np.float32)
+    lib().emu_siddon_fwd_chunk(_p(volT), *map(ctypes.c_int, vol.shape), ctypes.c_int(axis), ctypes.c_int(width), _p(src),
+                               _p(tgt), _p(raylen), _p(out), ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift),
+                               ctypes.c_float(eps), ctypes.c_int(slab))
+    lib().emu_siddon_fwd_lean_slab(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(ref),
+                                   ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                                   ctypes.c_int(slab))
+    return out, ref
+
+
 def siddon_bilinear(vol, src, tgt, raylen, gout=None, voxel_shift=0.5, eps=1e-8, stop_grad=False, reduce="sum",
                     align_corners=False):
     """Siddon(mode="bilinear"): dict(img, and with gout the gradients)."""

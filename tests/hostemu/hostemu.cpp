@@ -409,6 +409,52 @@ void emu_siddon_bilinear(const float* vol, int D0, int D1, int D2, const float* 
         }
 }
 
+// EXPERIMENT: chunk-reuse lean walk over a transposed (major-axis-fastest), padded copy; slab > 0 cuts axis 0.
+// `axis` = which volume axis is fastest in volT: volT[i_p][i_q][i_axis] with (p, q) the other two axes in ascending order.
+void emu_siddon_fwd_chunk(const float* volT, int D0, int D1, int D2, int axis, int width, const float* src, const float* tgt,
+                          const float* raylen, float* out, int B, long N, float shift, float eps, int slab)
+{
+    const int D[3] = {D0, D1, D2};
+    const int p = axis == 0 ? 1 : 0, q = axis == 2 ? 1 : 2;
+    int st[3];
+    st[axis] = 1;
+    st[q] = D[axis];
+    st[p] = D[axis] * D[q];
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float acc = 0.0f;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                acc += width == 4 ? siddon_ray_lean_box_chunk<4, 4>(volT, lo_v, hi_v, st[0], st[1], st[2], ray, shift)
+                                  : siddon_ray_lean_box_chunk<4, 2>(volT, lo_v, hi_v, st[0], st[1], st[2], ray, shift);
+            }
+            out[r] = raylen[r] * acc;
+        }
+}
+
+// the reference for it: the plain lean walk on the ORIGINAL layout with the same slab cuts
+void emu_siddon_fwd_lean_slab(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                              const float* raylen, float* out, int B, long N, float shift, float eps, int slab)
+{
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            float acc = 0.0f;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                acc += siddon_ray_lean_box<4>(vol, lo_v, hi_v, D1 * D2, D2, 1, ray, shift);
+            }
+            out[r] = raylen[r] * acc;
+        }
+}
+
 // mask_to_channels backward through the device routines (FetchMasked / SampleGradMasked): gout is [B][C][N]
 void emu_siddon_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
                          const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,

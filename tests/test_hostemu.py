@@ -391,3 +391,19 @@ def test_property_random_geometry_lean_and_sensitivity_walks():
             assert s_ == 0.0 and not sens[key].any() or np.abs(sens[key] - bwd[key]).max() / s_ < 2e-4, key
 
     check()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("width,slab", [(4, 0), (2, 0), (4, 5)])
+def test_chunk_reuse_walk_is_bitwise_the_lean_walk(axis, width, slab):
+    """EXPERIMENT kept for the next tuning round (b200drr_x_siddon_fwd_chunk): the lean walk over a major-axis-fastest copy
+    with per-lane chunk reuse reads the same voxels in the same order, so it must equal the plain lean walk bit for bit --
+    for every choice of the fast axis, both chunk widths, with and without slab cuts, on odd-sized volumes."""
+    for name in ("siddon_nc_b4", "siddon_nc_inside", "siddon_nc_axis"):
+        g = load_golden(name)
+        out, ref = emu.siddon_fwd_chunk(g["volume"], g["source"], g["target"], g["raylen"], axis, width, slab=slab)
+        assert np.array_equal(out, ref), name
+        assert relerr(out, g["img_f64"]) < IMG_TOL
+    vol, src, tgt, raylen = _random_case(11, (7, 9, 5), B=2, N=101)
+    out, ref = emu.siddon_fwd_chunk(vol, src, tgt, raylen, axis, width, slab=slab and 3)
+    assert np.array_equal(out, ref)
