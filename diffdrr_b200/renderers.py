@@ -4,7 +4,8 @@ Drop-in for the reference's renderer slot (`DRR.renderer`, reference drr.py:94-1
 `forward` signatures as reference renderers.py:14-42 (Siddon) and 189-216 (Trilinear), same `(B, 1, N)` result.
 The whole `(B, N, M)`-shaped tensor algebra of the reference (plane alphas, sort, midpoints, grid_sample, diff,
 sum) is ONE kernel launch per direction through the C ABI of include/b200drr.h; backward is a closed-form
-kernel (no saved activations: `checkpoint_gradients` is a no-op by construction).
+kernel (no saved activations: `checkpoint_gradients` is a no-op by construction).  When only ray / pose gradients are
+needed the forward kernel also writes each ray's end-point sensitivities (32-48 B per ray) and the backward is elementwise.
 
 There is no CPU / PyTorch fallback: tensors must be CUDA fp32, otherwise the call raises.
 """
