@@ -882,6 +882,12 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         S(17, 16, 8, 4, 8)
         S(18, 16, 8, 4, 128)
         S(19, 32, 8, 4, 32)
+        S(40, 8, 16, 4, 32)
+        S(41, 8, 16, 8, 32)
+        S(42, 8, 16, 4, 48)
+        S(43, 16, 8, 8, 48)
+        S(44, 16, 16, 8, 32)
+        S(45, 8, 16, 6, 32)
 #undef S
 #define P(id, TW, TH, U, SLAB, ALIGN) \
     case id: return launch_psync_variant<TW, TH, U, ALIGN>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
