@@ -383,6 +383,18 @@ int b200drr_x_siddon_fwd_chunk(const float* volT, int D0, int D1, int D2, int ax
                                          (cudaStream_t)stream));
 }
 
+int b200drr_x_siddon_sens_chunk(const float* volT, int D0, int D1, int D2, int axis, const float* src, const float* tgt,
+                                const float* raylen, float* out, float* sens, int B, int H, int W, float voxel_shift,
+                                float eps, int variant, void* stream)
+{
+    if (!volT || !src || !tgt || !raylen || !out || !sens || bad_dims(D0, D1, D2) || axis < 0 || axis > 2 ||
+        bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_x_siddon_sens_chunk(volT, mk(D0, D1, D2), axis, src, tgt, raylen, out, sens, B, H, W, voxel_shift, eps,
+                                          variant, (cudaStream_t)stream));
+}
+
 int64_t b200drr_packed_volume_floats(int D0, int D1, int D2)
 {
     if (bad_dims(D0, D1, D2)) return 0;

@@ -97,6 +97,10 @@ cudaError_t launch_x_siddon_fwd_chunk(const float* volT, VolDims dims, int axis,
                                       const float* raylen, float* out, int B, int H, int W, float shift, float eps,
                                       int variant, cudaStream_t stream);
 
+cudaError_t launch_x_siddon_sens_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,
+                                       const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                       float eps, int variant, cudaStream_t stream);
+
 // per-pose algebra around the pose-in kernels (pose.cu)
 cudaError_t launch_euler_pose_fwd(const float* rot, const float* xyz, int c0, int c1, int c2, float scale, float* P, int B,
                                   cudaStream_t stream);

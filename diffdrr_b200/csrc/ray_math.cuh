@@ -873,13 +873,52 @@ B200_HD void minor_accumulate(int ax, float coef, float alpha, float& Au, float&
 #endif
 }
 
+// How the sensitivities walk fetches its voxels: one scalar load per visit from the volume as stored (production), or --
+// EXPERIMENT, see siddon_ray_lean_box_chunk -- W-voxel chunks from a major-axis-fastest copy, re-used across visits.
+struct LoadPlain {
+    template <int U>
+    B200_HD void batch(const float* vol, const int (&offs)[U], float (&v)[U])
+    {
+#pragma unroll
+        for (int j = 0; j < U; ++j) v[j] = ldg(vol + offs[j]);
+    }
+    B200_HD float at(const float* vol, int off) const { return ldg(vol + off); }
+};
+
+template <int W>
+struct LoadChunk {
+    Chunk<W> cur;
+    int ccur = -1;
+    template <int U>
+    B200_HD void batch(const float* volT, const int (&offs)[U], float (&v)[U])
+    {
+        constexpr int SH = W == 4 ? 2 : 1;
+        Chunk<W> q[U];
+        bool need[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int c = offs[j] >> SH;
+            need[j] = c != (j == 0 ? ccur : (offs[j - 1] >> SH));
+            if (need[j]) q[j] = Chunk<W>::load(volT, c);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (need[j]) cur = q[j];
+            v[j] = cur.pick(offs[j] & (W - 1));
+        }
+        ccur = offs[U - 1] >> SH;
+    }
+    B200_HD float at(const float* volT, int off) const { return ldg(volT + off); }
+};
+
 // The sensitivities walk of one ray restricted to a box, for a ray whose major axis is M: same walk, tie order and
 // tail as siddon_ray_bwd_lean_box, two accumulated axes + the telescoping identities.  A, C accumulated INTO.
-template <int U, int M>
+template <int U, int M, class Load = LoadPlain>
 B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
                                     int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
 {
     using Ax = MinorAxes<M>;
+    Load loader;
     const Walk w = start_walk_frame(ray, dims, lo_v, hi_v, shift);
     if (!w.hit) return 0.0f;
     LeanConst k;
@@ -898,8 +937,7 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
             (void)lean_step_uv<M>(s, k, ax[j]);
             aend[j] = s.acur;
         }
-#pragma unroll
-        for (int j = 0; j < U; ++j) v[j] = ldg(vol + offs[j]);
+        loader.template batch<U>(vol, offs, v);
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             // crossing (axprev, aprev) led into voxel j; padding steps after the exit carry local index 2 and length 0.
@@ -913,7 +951,7 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
         }
     }
     if (!any) {
-        const float v0 = ldg(vol + s.off);
+        const float v0 = loader.at(vol, s.off);
         minor_accumulate(Ax::local(w.entry_axis), -v0, w.a_in, Au, Av, Cu, Cv);
         vprev = v0;
     }
@@ -925,14 +963,14 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
         if (t0 && b0) ax_exit = 0;
         if (ax_exit == 3 && t0) {
             s.off += k.so0;
-            const float vm = ldg(vol + s.off);
+            const float vm = loader.at(vol, s.off);
             minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
             vprev = vm;
         }
         if (ax_exit == 3 && t1 && b1) ax_exit = 1;
         if (ax_exit == 3 && t1) {
             s.off += k.so1;
-            const float vm = ldg(vol + s.off);
+            const float vm = loader.at(vol, s.off);
             minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
             vprev = vm;
         }
@@ -950,14 +988,15 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
 }
 
 // Dispatch on the ray's major axis (uniform per warp except for rays near a 45-degree direction).
-template <int U>
+template <int U, class Load = LoadPlain>
 B200_HD float siddon_ray_sens_box(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
                                   int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
 {
     const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
-    if (a0 >= a1 && a0 >= a2) return siddon_ray_sens_box_m<U, 0>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
-    if (a1 >= a2) return siddon_ray_sens_box_m<U, 1>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
-    return siddon_ray_sens_box_m<U, 2>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    if (a0 >= a1 && a0 >= a2)
+        return siddon_ray_sens_box_m<U, 0, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    if (a1 >= a2) return siddon_ray_sens_box_m<U, 1, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    return siddon_ray_sens_box_m<U, 2, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
 }
 
 // Backward of one ray restricted to the sub-box [lo, hi) (closed form, see siddon_ray_bwd below for the algebra).

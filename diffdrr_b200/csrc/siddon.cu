@@ -669,6 +669,86 @@ static cudaError_t launch_sens_slab_variant(const float* vol, VolDims dims, cons
     return cudaGetLastError();
 }
 
+// EXPERIMENT: the sensitivities walk (training step) with the same chunk reuse.  Same outputs as siddon_sens_slab_kernel.
+template <int TW, int TH, int U, int CW, int MINB>
+__global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_chunk_kernel(const float* __restrict__ volT, VolDims dims,
+                                                                        int axis, const float* __restrict__ src,
+                                                                        const float* __restrict__ tgt,
+                                                                        const float* __restrict__ raylen,
+                                                                        float* __restrict__ out, float* __restrict__ sens,
+                                                                        int B, int H, int W, int slab, float shift, float eps)
+{
+    constexpr int WX = TW / 8;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    const int tiles = tiles_x * tiles_y;
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B;
+    const int sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * TW + (warp % WX) * 8 + (lane & 7);
+    const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t r = ((int64_t)b * H + py) * W + px;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float L = __ldg(raylen + r);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;
+    const int d0 = dims.d[0], d1 = dims.d[1], d2 = dims.d[2];
+    const int st0 = axis == 0 ? 1 : (axis == 1 ? d1 * d2 : d2 * d1);
+    const int st1 = axis == 1 ? 1 : (axis == 0 ? d0 * d2 : d2);
+    const int st2 = axis == 2 ? 1 : (axis == 0 ? d0 : d1);
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    const float S = siddon_ray_sens_box<U, LoadChunk<CW>>(volT, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    float jt[3], js[3];
+    bool any = S != 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float k = L * ray.inv[a];
+        jt[a] = -k * A[a];
+        js[a] = k * (A[a] - C[a]);
+        any = any || jt[a] != 0.0f || js[a] != 0.0f;
+    }
+    if (any) {
+        red_add4(sens + r * 8, jt[0], jt[1], jt[2], S);
+        red_add4(sens + r * 8 + 4, js[0], js[1], js[2], 0.0f);
+        red_add(out + r, L * S);
+    }
+}
+
+cudaError_t launch_x_siddon_sens_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,
+                                       const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                       float eps, int variant, cudaStream_t stream)
+{
+    if ((int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    const size_t n = (size_t)B * H * W;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 8 * n, stream);
+    if (e != cudaSuccess) return e;
+#define XS(id, TW, TH, U, CW, SLAB, MINB)                                                                                \
+    case id: {                                                                                                           \
+        const int n_slabs = (dims.d[0] + SLAB - 1) / SLAB;                                                               \
+        const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;                         \
+        if (blocks > INT32_MAX) return cudaErrorInvalidValue;                                                            \
+        siddon_sens_slab_chunk_kernel<TW, TH, U, CW, MINB><<<(unsigned)blocks, TW * TH, 0, stream>>>(                    \
+            volT, dims, axis, src, tgt, raylen, out, sens, B, H, W, SLAB, shift, eps);                                   \
+        return cudaGetLastError();                                                                                       \
+    }
+    switch (variant) {
+        XS(0, 8, 16, 4, 4, 48, 8)
+        XS(1, 8, 16, 4, 2, 48, 8)
+        XS(2, 8, 16, 8, 4, 48, 6)
+        XS(3, 8, 16, 8, 2, 48, 8)
+        XS(4, 16, 8, 4, 4, 48, 8)
+        XS(5, 8, 16, 4, 4, 32, 8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef XS
+}
+
 cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                         float eps, int variant, cudaStream_t stream)

@@ -299,6 +299,10 @@ int b200drr_x_transpose_volume(const float *vol, int D0, int D1, int D2, int axi
 int b200drr_x_siddon_fwd_chunk(const float *volT, int D0, int D1, int D2, int axis, const float *src, const float *tgt,
                                const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
                                int variant, void *stream);
+/* the same for the forward-with-sensitivities walk (outputs as b200drr_siddon_fwd_sens_grid) */
+int b200drr_x_siddon_sens_chunk(const float *volT, int D0, int D1, int D2, int axis, const float *src, const float *tgt,
+                                const float *raylen, float *out, float *sens, int B, int H, int W, float voxel_shift,
+                                float eps, int variant, void *stream);
 
 /*
  * Per-ray voxel-visit count of the Siddon walk (number of voxels the line crosses inside the volume),

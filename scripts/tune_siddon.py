@@ -79,6 +79,18 @@ if os.environ.get("XVARIANTS"):
         err = float((out - ref).abs().max() / ref.abs().max())
         print(f"chunk variant {v:2d}      : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff vs plain {err:.1e}")
 
+    for v in [int(x) for x in os.environ.get("XSVARIANTS", "").split(",") if x]:
+        out, sens = torch.empty(B, N, device=dev), torch.empty(B, N, 8, device=dev)
+        def run():
+            _lib.check(lib.b200drr_x_siddon_sens_chunk(_ptr(volT), D, D1, D2, axis, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), _ptr(sens), B, H, H, 0.5, 1e-8, v, _stream()), "sens chunk")
+        try:
+            ms = timeit(run)
+        except Exception as e:
+            print(f"sens chunk variant {v}: {e}")
+            continue
+        err = float((out - ref).abs().max() / ref.abs().max())
+        print(f"sens chunk variant {v:2d} : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {(gbytes + 32e-9 * B * N) / ms * 1e3 / peak * 100:5.1f}% of HBM peak   maxdiff img vs plain {err:.1e}")
+
 # ---- forward + sensitivities (training-step fast path) variants ----------------------------------------------------
 if os.environ.get("SVARIANTS"):
     gout_s = torch.rand(B, N, device=dev)

@@ -196,6 +196,19 @@ def siddon_fwd_chunk(vol, src, tgt, raylen, axis, width=4, voxel_shift=0.5, eps=
     return out, ref
 
 
+def siddon_sens_chunk(vol, src, tgt, raylen, axis, width=4, voxel_shift=0.5, eps=1e-8, slab=0):
+    """EXPERIMENT: (out, sens) of the sensitivities walk through the chunk loader and through the plain loader."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    res = []
+    for chunked, data in ((1, transposed_padded(vol, axis)), (0, np.concatenate([vol.ravel(), np.zeros(4, np.float32)]))):
+        out, sens = np.empty((B, 1, N), np.float32), np.empty((B, N, 8), np.float32)
+        lib().emu_siddon_sens_chunk(_p(data), *map(ctypes.c_int, vol.shape), ctypes.c_int(axis), ctypes.c_int(width), _p(src),
+                                    _p(tgt), _p(raylen), _p(out), _p(sens), ctypes.c_int(B), ctypes.c_long(N),
+                                    ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(slab), ctypes.c_int(chunked))
+        res.append((out, sens))
+    return res
+
+
 def siddon_bilinear(vol, src, tgt, raylen, gout=None, voxel_shift=0.5, eps=1e-8, stop_grad=False, reduce="sum",
                     align_corners=False):
     """Siddon(mode="bilinear"): dict(img, and with gout the gradients)."""

@@ -436,6 +436,48 @@ void emu_siddon_fwd_chunk(const float* volT, int D0, int D1, int D2, int axis, i
         }
 }
 
+// EXPERIMENT: the sensitivities walk through the chunk loader; writes sens [B][N][8] like the kernel
+void emu_siddon_sens_chunk(const float* volT, int D0, int D1, int D2, int axis, int width, const float* src, const float* tgt,
+                           const float* raylen, float* out, float* sens, int B, long N, float shift, float eps, int slab,
+                           int chunked)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const int D[3] = {D0, D1, D2};
+    int st[3] = {D1 * D2, D2, 1};
+    if (chunked) {
+        const int p = axis == 0 ? 1 : 0, q = axis == 2 ? 1 : 2;
+        st[axis] = 1;
+        st[q] = D[axis];
+        st[p] = D[axis] * D[q];
+    }
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    std::memset(sens, 0, sizeof(float) * 8 * (size_t)B * N);
+    for (int b = 0; b < B; ++b)
+        for (long n = 0; n < N; ++n) {
+            const long r = (long)b * N + n;
+            const Ray ray = load_ray(src, tgt, b, r, eps);
+            const float L = raylen[r];
+            float img = 0;
+            for (int sl = 0; sl < n_slabs; ++sl) {
+                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                float A[3] = {0, 0, 0}, C[3] = {0, 0, 0};
+                const float S = !chunked ? siddon_ray_sens_box<4>(volT, dims, lo_v, hi_v, st[0], st[1], st[2], ray, shift, A, C)
+                                : width == 4
+                                    ? siddon_ray_sens_box<4, LoadChunk<4>>(volT, dims, lo_v, hi_v, st[0], st[1], st[2], ray, shift, A, C)
+                                    : siddon_ray_sens_box<4, LoadChunk<2>>(volT, dims, lo_v, hi_v, st[0], st[1], st[2], ray, shift, A, C);
+                for (int a = 0; a < 3; ++a) {
+                    const float k = L * ray.inv[a];
+                    sens[r * 8 + a] += -k * A[a];
+                    sens[r * 8 + 4 + a] += k * (A[a] - C[a]);
+                }
+                sens[r * 8 + 3] += S;
+                img += L * S;
+            }
+            out[r] = img;
+        }
+}
+
 // the reference for it: the plain lean walk on the ORIGINAL layout with the same slab cuts
 void emu_siddon_fwd_lean_slab(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                               const float* raylen, float* out, int B, long N, float shift, float eps, int slab)

@@ -407,3 +407,13 @@ def test_chunk_reuse_walk_is_bitwise_the_lean_walk(axis, width, slab):
     vol, src, tgt, raylen = _random_case(11, (7, 9, 5), B=2, N=101)
     out, ref = emu.siddon_fwd_chunk(vol, src, tgt, raylen, axis, width, slab=slab and 3)
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("axis,width,slab", [(0, 4, 0), (1, 4, 5), (2, 2, 0), (1, 2, 3)])
+def test_chunk_reuse_sensitivities_walk_is_bitwise_the_plain_one(axis, width, slab):
+    """EXPERIMENT (b200drr_x_siddon_sens_chunk): the loader policy only changes HOW a voxel is fetched, so image and all
+    eight sensitivity slots must be bitwise those of the production walk."""
+    for name in ("siddon_nc_b4", "siddon_nc_inside", "siddon_nc_axis"):
+        g = load_golden(name)
+        (out, sens), (out0, sens0) = emu.siddon_sens_chunk(g["volume"], g["source"], g["target"], g["raylen"], axis, width, slab=slab)
+        assert np.array_equal(out, out0) and np.array_equal(sens, sens0), name
