@@ -290,6 +290,8 @@ int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int 
 
 /*
  * EXPERIMENTAL (prefix b200drr_x_: may change or disappear; used by scripts/tune_siddon.py only, never by the module).
+ * Measured on B200 and REJECTED (profiles/r01_tune_chunk_reuse.log: 12-50 % slower than the production kernels); kept, like
+ * the plane-synchronous walk, as a documented negative result.
  * Chunk-reuse Siddon forward: the lean walk over a copy of the volume whose FASTEST axis is the rays' major axis, so a
  * lane serves several consecutive visits from one LDG.64 / LDG.128.  b200drr_x_transpose_volume writes that
  * copy: out [D_p][D_q][D_axis] (p < q the other two axes), D0*D1*D2 + 4 floats (4 floats of padding).  Results are bitwise
