@@ -261,7 +261,8 @@ def test_fused_sensitivities_match_two_walk_backward():
                 res.append((img.detach(), rot.grad, xyz.grad, img2.detach(), s.grad, t_.grad))
             finally:
                 renderers._FUSED_SENSITIVITIES = True
-        for a, b, tol in zip(res[0], res[1], (2e-6, 2e-5, 2e-5, 2e-6, 2e-5, 2e-5)):
+        # partial sums are combined with red.global.add in a run-dependent order: fp32 round-off level, with head-room
+        for a, b, tol in zip(res[0], res[1], (5e-6, 5e-5, 5e-5, 5e-6, 5e-5, 5e-5)):
             assert relerr(a.cpu().numpy(), b.cpu().numpy()) < tol
     # volume gradient requested -> backward walk; pose gradients identical to the fused ones
     sid = Siddon()
@@ -299,6 +300,6 @@ def test_trilinear_fused_sensitivities_match_two_march_backward(B):
             res.append((img.detach(), rot.grad, xyz.grad))
         finally:
             renderers._FUSED_SENSITIVITIES, renderers._PACKED_SLAB_SENS = True, 0
-    for other, tols in ((res[0], (2e-6, 1e-4, 1e-4)), (res[2], (2e-6, 3e-4, 3e-4))):
+    for other, tols in ((res[0], (2e-6, 1e-4, 1e-4)), (res[2], (5e-6, 3e-4, 3e-4))):
         for a, b, tol in zip(other, res[1], tols):
             assert relerr(a.cpu().numpy(), b.cpu().numpy()) < tol
