@@ -445,3 +445,50 @@ def test_sensitivities_walk_at_scale_vs_fp64_oracle():
     assert relerr(out["img"], oracle.siddon_fwd(smooth, src, tgt, raylen, dtype=np.float64)) < 2e-5
     for key in ("g_target", "g_source", "g_raylen"):
         assert relerr(out[key], ref[key]) < 1e-3, key
+
+
+def test_property_random_geometry_trilinear_march():
+    """Property test (hypothesis) of the trilinear device math: random small volumes, sample counts, voxel shifts,
+    align_corners and ray bundles (incl. rays that miss); image vs the fp64 oracle, packed-corner path bitwise vs the gather
+    path, and the closed-form backward vs the fp64 oracle on a smooth field."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.tuples(st.integers(2, 11), st.integers(2, 11), st.integers(2, 11)), st.integers(0, 2**31 - 1),
+           st.sampled_from([0.5, 0.0]), st.integers(3, 60), st.booleans())
+    def check(shape, seed, shift, P, ac):
+        rng = np.random.default_rng(seed)
+        x, y, z = np.meshgrid(*(np.linspace(-1, 1, n) for n in shape), indexing="ij")
+        vol = (np.exp(-(x * x + 0.5 * y * y + 2 * z * z)) + 0.05 * rng.random(shape)).astype(np.float32)
+        B, N = 2, 19
+        c = np.array(shape, dtype=np.float64) / 2
+        src = (c + rng.normal(size=(B, 1, 3)) * np.array(shape) * 2.5).astype(np.float32)
+        tgt = (c + (c - src) * 0.8 + rng.normal(size=(B, N, 3)) * np.array(shape) * 0.6).astype(np.float32)
+        raylen = np.linalg.norm(tgt - src, axis=-1)[:, None, :].astype(np.float32)
+        amin, amax = oracle.alpha_minmax(shape, src, tgt, shift, 1e-8, np.float32)
+        if not amax > amin:
+            return
+        kw = dict(voxel_shift=shift, align_corners=ac)
+        ref = oracle.trilinear_fwd(vol, src, tgt, raylen, n_points=P, alphamin=amin, alphamax=amax, dtype=np.float64, **kw)
+        out = emu.trilinear_fwd(vol, src, tgt, raylen, P, amin, amax, **kw)
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(out - ref).max() / scale < 5e-5
+        w = rng.random((B, 1, N), dtype=np.float32)
+        if ac:  # the ray that defines alphamin/alphamax puts its end sample exactly ON a cell boundary (pix = 0 or D-1): the
+            return  # interpolant's gradient is one-sided there and the side is decided by the last bit -- image only
+        g = emu.trilinear_bwd(vol, src, tgt, raylen, w, P, amin, amax, **kw)
+        gr = oracle.trilinear_bwd(vol, src, tgt, raylen, w, n_points=P, alphamin=amin, alphamax=amax, dtype=np.float64, **kw)
+        g32 = oracle.trilinear_bwd(vol, src, tgt, raylen, w, n_points=P, alphamin=amin, alphamax=amax, dtype=np.float32, **kw)
+        for key in ("g_target", "g_source", "g_raylen", "g_volume"):
+            s_ = np.abs(gr[key]).max()
+            if s_ == 0.0:
+                continue
+            # SURVEY 8c rule: a sample sitting on a cell boundary has a kinked gradient; the op-for-op fp32 restatement of
+            # the reference then differs from fp64 by whole percents, and so may we
+            tol = max(2e-3, 2.0 * np.abs(g32[key] - gr[key]).max() / s_)
+            assert np.abs(g[key] - gr[key]).max() / s_ < tol, key
+        if not ac:
+            po, _ = emu.trilinear_packed(vol, src, tgt, raylen, w, P, amin, amax, voxel_shift=shift)
+            assert np.array_equal(po, out)
+
+    check()
