@@ -72,6 +72,28 @@ int b200drr_siddon_fwd_grid(const float* vol, int D0, int D1, int D2, const floa
                                       (cudaStream_t)stream));
 }
 
+int64_t b200drr_siddon_brick_workspace_bytes(int B, int H, int W)
+{
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return (int64_t)siddon_brick_workspace_bytes(B, H, W);
+}
+
+int b200drr_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                             const float* raylen, const float* G, const float* Wd, const float* rows, const float* cols,
+                             float* out, void* workspace, int64_t workspace_bytes, int B, int H, int W, float voxel_shift,
+                             float eps, int variant, void* stream)
+{
+    const bool pose_in = G != nullptr;
+    if (!vol || !src || !out || !workspace || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if (pose_in ? (!Wd || !rows || !cols) : (!tgt || !raylen)) return B200DRR_EINVAL;
+    if (!siddon_brick_supported(mk(D0, D1, D2), H, W) || ((uintptr_t)vol & 15u) != 0) return B200DRR_EUNSUPPORTED;
+    if (workspace_bytes < (int64_t)siddon_brick_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 255u) != 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd_brick(vol, mk(D0, D1, D2), src, tgt, raylen, G, Wd, rows, cols, out, workspace,
+                                       (size_t)workspace_bytes, B, H, W, voxel_shift, eps, variant, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                        float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int align_corners,

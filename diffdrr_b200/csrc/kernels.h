@@ -91,6 +91,14 @@ cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDi
                                       float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
                                       int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 
+// brick-major Siddon forward (siddon_brick.cu): TMA-staged voxel bricks in shared memory; G == nullptr -> rays from tgt/raylen
+size_t siddon_brick_workspace_bytes(int B, int H, int W);
+bool siddon_brick_supported(VolDims dims, int H, int W);
+cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                    const float* G, const float* Wd, const float* rows, const float* cols, float* out,
+                                    void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
+                                    int variant, cudaStream_t stream);
+
 // experiments (b200drr_x_*): chunk-reuse forward over a major-axis-fastest copy
 cudaError_t launch_x_transpose_volume(const float* vol, VolDims dims, int axis, float* out, cudaStream_t stream);
 cudaError_t launch_x_siddon_fwd_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,

@@ -1,0 +1,488 @@
+// siddon_brick.cu -- brick-major Siddon forward for sm_100a: TMA-staged voxel bricks in shared memory.
+//
+// Persistent CTAs (one per SM).  Each CTA claims bricks from a global counter; a brick (BX x BY x BZ fp32 voxels) is
+// brought into shared memory by ONE cp.async.bulk.tensor.3d box copy (zero fill outside the volume) that completes on
+// an mbarrier, STAGES deep: the copy of the next brick is in flight while the current one is integrated.  For the
+// current brick the CTA
+//   1. projects the brick's 8 corners into every pose's detector -> a pixel rectangle per pose (brick.cuh),
+//   2. tests the rays of those rectangles against the brick (conservative slab test on a 16-byte ray-table entry),
+//   3. counting-sorts the hits by their estimated number of voxel visits (so the 32 lanes of a warp walk chords of
+//      similar length) and
+//   4. lets the warps pull 32-item chunks, longest first: exact walk set-up (start_walk_box), lean walk with the voxel
+//      loads served by ld.shared, one red.global.add of the partial line integral per (ray, brick).
+// The (B, N) ray table {1/d, sum|d| ; d, L} is written once per launch by brick_prep_kernel, which also zero-fills
+// the output and derives the per-pose detector geometry used in step 1.
+//
+// Replaces reference renderers.py:94-113 (alphas + sort) and 156-169 (grid_sample gather) for full detector grids.
+#include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
+#include "brick.cuh"
+#include "kernels.h"
+
+namespace b200drr {
+
+namespace {
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one 3-D box: coordinates are (fastest .. slowest) = (axis 2, axis 1, axis 0) voxel indices of the box origin
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ld.shared with a byte address in the shared window
+struct LdShared {
+    uint32_t base_addr;
+    static constexpr int kScale = 4;
+    __device__ __forceinline__ int base() const { return (int)base_addr; }
+    __device__ __forceinline__ float operator()(int off) const
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(off));
+        return v;
+    }
+};
+
+struct PoseRaysB {
+    const float* G;
+    const float* Wd;
+    const float* rows;
+    const float* cols;
+};
+
+__device__ __forceinline__ Ray make_ray_b(const PoseRaysB& pr, const float* __restrict__ src, const float* __restrict__ tgt,
+                                          const float* __restrict__ raylen, int b, int64_t r, int px, int py, float eps,
+                                          float& L)
+{
+    if (pr.G == nullptr) {
+        L = __ldg(raylen + r);
+        return load_ray(src, tgt, b, r, eps);
+    }
+    const float c = __ldg(pr.cols + px), rr = __ldg(pr.rows + py);
+    const float* g = pr.G + b * 12;
+    const float* wd = pr.Wd + b * 12;
+    Ray ray;
+    float l2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t = fmaf(__ldg(g + a * 4), c, fmaf(__ldg(g + a * 4 + 1), rr, __ldg(g + a * 4 + 2) + __ldg(g + a * 4 + 3)));
+        const float dw = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), rr, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+        l2 = fmaf(dw, dw, l2);
+        ray.s[a] = __ldg(src + b * 3 + a);
+        ray.d[a] = (t - ray.s[a]) + eps;
+        ray.inv[a] = 1.0f / ray.d[a];
+    }
+    L = sqrtf(l2);
+    return ray;
+}
+
+// ---- ray table + per-pose geometry + zero fill ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
+                                                         const float* __restrict__ raylen, PoseRaysB pr,
+                                                         float4* __restrict__ raytab, PoseGeo* __restrict__ geo,
+                                                         float* __restrict__ out, unsigned* __restrict__ counter, int H,
+                                                         int W, float eps)
+{
+    const int64_t N = (int64_t)H * W;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= N) return;
+    const int py = (int)(n / W), px = (int)(n - (int64_t)py * W);
+    const int64_t r = (int64_t)b * N + n;
+    float L;
+    const Ray ray = make_ray_b(pr, src, tgt, raylen, b, r, px, py, eps, L);
+    raytab[2 * r] = make_float4(ray.inv[0], ray.inv[1], ray.inv[2], fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]));
+    raytab[2 * r + 1] = make_float4(ray.d[0], ray.d[1], ray.d[2], L);
+    out[r] = 0.0f;
+    if (n == 0) {
+        float Lx;
+        const Ray r0w = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * N + (W - 1), W - 1, 0, eps, Lx);
+        const Ray rh0 = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * N + (int64_t)(H - 1) * W, 0, H - 1, eps, Lx);
+        float t00[3], t0w[3], th0[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            t00[a] = ray.s[a] + ray.d[a];
+            t0w[a] = ray.s[a] + r0w.d[a];
+            th0[a] = ray.s[a] + rh0.d[a];
+        }
+        geo[b] = make_pose_geo(ray.s, t00, t0w, th0, H, W);
+        if (b == 0) *counter = 0u;
+    }
+}
+
+// ---- the brick kernel -------------------------------------------------------------------------------------------
+struct BrickGrid {
+    int nb0, nb1, nb2;  // bricks per axis
+};
+
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
+struct BrickCfg {
+    static constexpr int kBrickElems = BX * BY * BZ;
+    static constexpr int kBrickBytes = kBrickElems * 4;
+    static constexpr int kWarps = THREADS / 32;
+    static constexpr int kCap = kWarps * K * 32;  // items per round (every candidate of a round may hit)
+    static constexpr int kPB = kBrickPoseChunk;
+    // shared-memory carve-up (bytes)
+    static constexpr int oBricks = 0;
+    static constexpr int oItems = oBricks + STAGES * kBrickBytes;
+    static constexpr int oBar = oItems + kCap * 4;           // STAGES x 8
+    static constexpr int oPoseF = oBar + 64;                  // kPB x 9 floats: S[3], clo[3], chi[3]
+    static constexpr int oRect = oPoseF + kPB * 9 * 4;        // kPB x 4 ints: x0, y0, x1, y1
+    static constexpr int oTw = oRect + kPB * 4 * 4;           // kPB ints: tiles per rectangle row
+    static constexpr int oPrefix = oTw + kPB * 4;             // kPB + 1 ints (+ pad)
+    static constexpr int oHist = oPrefix + (kPB + 4) * 4;     // kBrickBins ints
+    static constexpr int oCursor = oHist + kBrickBins * 4;    // kBrickBins ints
+    static constexpr int oMisc = oCursor + kBrickBins * 4;    // n_items, chunk counter, next brick [2]
+    static constexpr int kSmemBytes = oMisc + 32;
+};
+
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
+__global__ void __launch_bounds__(THREADS, (STAGES == 1 ? 2 : 1))
+    siddon_fwd_brick_kernel(const __grid_constant__ CUtensorMap tmap, VolDims dims, BrickGrid bg,
+                            const float4* __restrict__ raytab, const PoseGeo* __restrict__ geo, float* __restrict__ out,
+                            unsigned* __restrict__ counter, int B, int H, int W, float shift)
+{
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned* s_items = reinterpret_cast<unsigned*>(smem + Cfg::oItems);
+    float* s_posef = reinterpret_cast<float*>(smem + Cfg::oPoseF);
+    int* s_rect = reinterpret_cast<int*>(smem + Cfg::oRect);
+    int* s_tw = reinterpret_cast<int*>(smem + Cfg::oTw);
+    int* s_prefix = reinterpret_cast<int*>(smem + Cfg::oPrefix);
+    int* s_hist = reinterpret_cast<int*>(smem + Cfg::oHist);
+    int* s_cursor = reinterpret_cast<int*>(smem + Cfg::oCursor);
+    int* s_misc = reinterpret_cast<int*>(smem + Cfg::oMisc);  // [0] n_items, [1] chunk counter, [2..3] next brick
+    const uint32_t bar0 = smem_u32(smem + Cfg::oBar);
+    const uint32_t brick0 = smem_u32(smem + Cfg::oBricks);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_bricks = bg.nb0 * bg.nb1 * bg.nb2;
+    const float inv_bin_width = (float)kBrickBins / (float)(BX + BY + BZ + 8);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_barrier_init();
+    }
+    if (tid < kBrickBins) s_hist[tid] = 0;
+    __syncthreads();
+
+    auto issue = [&](int brick, int stage) {  // thread 0 only
+        const int i2 = brick % bg.nb2, i1 = (brick / bg.nb2) % bg.nb1, i0 = brick / (bg.nb2 * bg.nb1);
+        fence_proxy_async();  // earlier generic-proxy reads of this stage are ordered before the async-proxy write
+        mbar_expect_tx(bar0 + 8 * stage, (uint32_t)Cfg::kBrickBytes);
+        tma_load_3d(brick0 + stage * Cfg::kBrickBytes, &tmap, bar0 + 8 * stage, i2 * BZ, i1 * BY, i0 * BX);
+    };
+
+    // prologue: claim the first brick (and start its copy)
+    if (tid == 0) {
+        const int first = (int)atomicAdd(counter, 1u);
+        s_misc[2] = first;
+        if (first < n_bricks) issue(first, 0);
+    }
+    __syncthreads();
+    int cur = s_misc[2];
+
+    for (int it = 0; cur < n_bricks; ++it) {
+        const int stage = STAGES == 1 ? 0 : (it & 1);
+        const uint32_t parity = STAGES == 1 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
+        if (STAGES == 2 && tid == 0) {  // prefetch the next brick into the other stage (free since the last end-of-brick barrier)
+            const int nxt = (int)atomicAdd(counter, 1u);
+            s_misc[2 + ((it + 1) & 1)] = nxt;
+            if (nxt < n_bricks) issue(nxt, stage ^ 1);
+        }
+        const int i2 = cur % bg.nb2, i1 = (cur / bg.nb2) % bg.nb1, i0 = cur / (bg.nb2 * bg.nb1);
+        const int org[3] = {i0 * BX, i1 * BY, i2 * BZ};
+        const int lo_v[3] = {org[0], org[1], org[2]};
+        const int hi_v[3] = {min(org[0] + BX, dims.d[0]), min(org[1] + BY, dims.d[1]), min(org[2] + BZ, dims.d[2])};
+        LdShared ld;
+        ld.base_addr = brick0 + stage * Cfg::kBrickBytes;
+
+        for (int p0 = 0; p0 < B; p0 += Cfg::kPB) {
+            const int npose = min(Cfg::kPB, B - p0);
+            __syncthreads();  // the previous chunk's (or brick's) readers of the pose tables are done
+            // ---- 1. pixel rectangle of the brick per pose: 8 lanes (corners) per pose ----------------------------
+            if (warp < (npose * 8 + 31) / 32) {  // whole warps take part in the shuffles; surplus lanes repeat the last pose
+                const int bl_raw = tid >> 3, c = tid & 7;
+                const int bl = min(bl_raw, npose - 1);
+                const PoseGeo g = geo[p0 + bl];
+                const float X[3] = {(float)((c & 1) ? hi_v[0] : lo_v[0]) - shift, (float)((c & 2) ? hi_v[1] : lo_v[1]) - shift,
+                                    (float)((c & 4) ? hi_v[2] : lo_v[2]) - shift};
+                float u, v, den;
+                project_corner(g, X, u, v, den);
+                const bool bad = (u != u) || (v != v) || (den != den);
+                float umin = u, umax = u, vmin = v, vmax = v, dmin = den, dmax = den;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+                    umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+                    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+                    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+                    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+                }
+                const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+                if (c == 0 && bl_raw < npose) {
+                    const bool anybad = ((badmask >> (lane & 24)) & 0xffu) != 0u;
+                    if (anybad) dmin = NAN;  // -> whole detector
+                    const PixRect rc = rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
+                    int tw = 0, th = 0;
+                    if (rc.x0 <= rc.x1 && rc.y0 <= rc.y1) {
+                        tw = (rc.x1 - rc.x0) / 8 + 1;
+                        th = (rc.y1 - rc.y0) / 4 + 1;
+                    }
+                    s_rect[bl * 4 + 0] = rc.x0;
+                    s_rect[bl * 4 + 1] = rc.y0;
+                    s_rect[bl * 4 + 2] = rc.x1;
+                    s_rect[bl * 4 + 3] = rc.y1;
+                    s_tw[bl] = tw;
+                    s_prefix[bl + 1] = tw * th;  // counts; turned into a prefix sum below
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        s_posef[bl * 9 + a] = g.S[a];
+                        s_posef[bl * 9 + 3 + a] = ((float)lo_v[a] - shift) - g.S[a];
+                        s_posef[bl * 9 + 6 + a] = ((float)hi_v[a] - shift) - g.S[a];
+                    }
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {  // inclusive scan of the tile counts
+                int cnt = lane < npose ? s_prefix[lane + 1] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, cnt, o);
+                    if (lane >= o) cnt += up;
+                }
+                if (lane < npose) s_prefix[lane + 1] = cnt;
+                if (lane == 0) s_prefix[0] = 0;
+            }
+            if (p0 == 0) mbar_wait(bar0 + 8 * stage, parity);  // the brick has landed (first use only)
+            __syncthreads();
+            const int T = s_prefix[npose];
+
+            for (int t0 = 0; t0 < T; t0 += Cfg::kWarps * K) {
+                // ---- 2. candidates -> hits (kept in registers) + histogram of the sort bins --------------------
+                unsigned items[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    items[j] = 0xffffffffu;
+                    const int t = t0 + warp + Cfg::kWarps * j;
+                    if (t < T) {
+                        int bl = 0;
+                        while (s_prefix[bl + 1] <= t) ++bl;  // warp-uniform
+                        const int jl = t - s_prefix[bl], tw = s_tw[bl];
+                        const int ty = jl / tw, tx = jl - ty * tw;
+                        const int px = s_rect[bl * 4 + 0] + tx * 8 + (lane & 7), py = s_rect[bl * 4 + 1] + ty * 4 + (lane >> 3);
+                        if (px <= s_rect[bl * 4 + 2] && py <= s_rect[bl * 4 + 3]) {
+                            const int64_t r = ((int64_t)(p0 + bl) * H + py) * W + px;
+                            const float4 q = __ldg(raytab + 2 * r);
+                            const float inv[3] = {q.x, q.y, q.z};
+                            float a_in, a_out;
+                            if (brick_maybe_hit(inv, s_posef + bl * 9 + 3, s_posef + bl * 9 + 6, a_in, a_out)) {
+                                const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
+                                items[j] = pack_item(bin, bl, py, px);
+                                atomicAdd(&s_hist[bin], 1);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- 3. counting sort, longest bin first ------------------------------------------------------
+                if (warp == 0) {
+                    const int h = s_hist[kBrickBins - 1 - lane];
+                    int incl = h;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += up;
+                    }
+                    s_cursor[kBrickBins - 1 - lane] = incl - h;
+                    s_hist[kBrickBins - 1 - lane] = 0;  // ready for the next round
+                    if (lane == 31) {
+                        s_misc[0] = incl;
+                        s_misc[1] = 0;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < K; ++j)
+                    if (items[j] != 0xffffffffu) s_items[atomicAdd(&s_cursor[item_bin(items[j])], 1)] = items[j];
+                __syncthreads();
+                // ---- 4. the walks: warps pull 32-item chunks ---------------------------------------------------
+                const int n_items = s_misc[0];
+                const int n_chunks = (n_items + 31) >> 5;
+                for (;;) {
+                    int c = 0;
+                    if (lane == 0) c = atomicAdd(&s_misc[1], 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= n_chunks) break;
+                    const int i = c * 32 + lane;
+                    if (i < n_items) {
+                        const unsigned itw = s_items[i];
+                        const int bl = item_pose(itw), py = item_row(itw), px = item_col(itw);
+                        const int64_t r = ((int64_t)(p0 + bl) * H + py) * W + px;
+                        const float4 q0 = __ldg(raytab + 2 * r), q1 = __ldg(raytab + 2 * r + 1);
+                        Ray ray;
+                        ray.s[0] = s_posef[bl * 9 + 0];
+                        ray.s[1] = s_posef[bl * 9 + 1];
+                        ray.s[2] = s_posef[bl * 9 + 2];
+                        ray.d[0] = q1.x; ray.d[1] = q1.y; ray.d[2] = q1.z;
+                        ray.inv[0] = q0.x; ray.inv[1] = q0.y; ray.inv[2] = q0.z;
+                        const float part = brick_pair_fwd<U>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                        if (part != 0.0f) red_add(out + r, q1.w * part);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every reader of this stage (and of s_misc[2 + ...]) is done
+        if (STAGES == 1) {
+            if (tid == 0) {
+                const int nxt = (int)atomicAdd(counter, 1u);
+                s_misc[2 + ((it + 1) & 1)] = nxt;
+                if (nxt < n_bricks) issue(nxt, 0);
+            }
+            __syncthreads();
+        }
+        cur = s_misc[2 + ((it + 1) & 1)];
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, int BY, int BZ)
+{
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)dims.d[2], (cuuint64_t)dims.d[1], (cuuint64_t)dims.d[0]};
+    const cuuint64_t gstride[2] = {(cuuint64_t)dims.d[2] * 4, (cuuint64_t)dims.d[2] * dims.d[1] * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)BZ, (cuuint32_t)BY, (cuuint32_t)BX};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(vol), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
+cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const PoseGeo* geo, float* out,
+                                 unsigned* counter, int B, int H, int W, float shift, cudaStream_t stream)
+{
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U>;
+    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    BrickGrid bg;
+    bg.nb0 = (dims.d[0] + BX - 1) / BX;
+    bg.nb1 = (dims.d[1] + BY - 1) / BY;
+    bg.nb2 = (dims.d[2] + BZ - 1) / BZ;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ctas_per_sm = Cfg::kSmemBytes <= 113 * 1024 ? 2 : 1;
+    const int grid = min(bg.nb0 * bg.nb1 * bg.nb2, sms * ctas_per_sm);
+    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(map, dims, bg, raytab, geo, out, counter, B, H, W, shift);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t siddon_brick_workspace_bytes(int B, int H, int W)
+{
+    return 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256) + sizeof(float4) * 2 * (size_t)B * H * W;
+}
+
+bool siddon_brick_supported(VolDims dims, int H, int W)
+{
+    return dims.d[2] % 4 == 0 && H <= kBrickMaxSide && W <= kBrickMaxSide && H >= 2 && W >= 2 && get_encoder() != nullptr;
+}
+
+cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                    const float* G, const float* Wd, const float* rows, const float* cols, float* out,
+                                    void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
+                                    int variant, cudaStream_t stream)
+{
+    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)vol & 15u) != 0) return cudaErrorNotSupported;
+    if (workspace == nullptr || workspace_bytes < siddon_brick_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 255u) != 0)
+        return cudaErrorInvalidValue;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    unsigned* counter = reinterpret_cast<unsigned*>(ws);
+    PoseGeo* geo = reinterpret_cast<PoseGeo*>(ws + 256);
+    float4* raytab = reinterpret_cast<float4*>(ws + 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256));
+    const int64_t N = (int64_t)H * W;
+    PoseRaysB pr{G, Wd, rows, cols};
+    brick_prep_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, geo, out,
+                                                                                        counter, H, W, eps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    CUtensorMap map;
+#define BV(id, BX, BY, BZ, STAGES, THREADS, K, U)                                                                        \
+    case id:                                                                                                             \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U>(map, dims, raytab, geo, out, counter, B, H, W, shift, \
+                                                                       stream);
+    switch (variant) {
+        BV(0, 24, 32, 32, 2, 1024, 4, 4)
+        BV(1, 24, 32, 32, 2, 1024, 4, 2)
+        BV(2, 24, 32, 32, 2, 512, 8, 4)
+        BV(3, 24, 32, 32, 1, 512, 4, 4)   // two CTAs per SM, one brick each
+        BV(4, 16, 32, 32, 2, 1024, 4, 4)
+        BV(5, 24, 32, 32, 2, 768, 4, 4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef BV
+}
+
+}  // namespace b200drr

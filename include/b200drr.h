@@ -289,6 +289,24 @@ int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int 
                                void *stream);
 
 /*
+ * Brick-major Siddon forward for a FULL detector grid (same result as b200drr_siddon_fwd_grid; replaces
+ * renderers.py:94-113 + 156-169): the volume is cut into 24x32x32-voxel bricks, each staged in shared memory by one TMA
+ * box copy (cp.async.bulk.tensor.3d behind an mbarrier pipeline) and integrated for every ray of every pose of the
+ * batch that crosses it -- L2->SM traffic falls below the algorithmic bytes because a staged voxel serves all poses.
+ * Pays off for batches (B >= ~4); needs D2 % 4 == 0, vol 16-byte aligned, 2 <= H, W <= 2048 (B200DRR_EUNSUPPORTED otherwise).
+ *   rays: either (tgt, raylen) as in b200drr_siddon_fwd_grid with G = Wd = rows = cols = NULL, or generated in-kernel from
+ *   (G, Wd, rows, cols) as in b200drr_siddon_fwd_pose with tgt = raylen = NULL.
+ *   workspace: caller-owned scratch of b200drr_siddon_brick_workspace_bytes(B, H, W) bytes, 256-byte aligned (ray table
+ *   {1/d, sum|d|, d, L} = 32 B per ray, per-pose detector geometry, the brick work counter); contents are don't-care.
+ *   variant: 0 = tuned default.
+ */
+int64_t b200drr_siddon_brick_workspace_bytes(int B, int H, int W);
+int b200drr_siddon_fwd_brick(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                             const float *raylen, const float *G, const float *Wd, const float *rows, const float *cols,
+                             float *out, void *workspace, int64_t workspace_bytes, int B, int H, int W, float voxel_shift,
+                             float eps, int variant, void *stream);
+
+/*
  * EXPERIMENTAL (prefix b200drr_x_: may change or disappear; used by scripts/tune_siddon.py only, never by the module).
  * Measured on B200 and REJECTED (profiles/r01_tune_chunk_reuse.log: 12-50 % slower than the production kernels); kept, like
  * the plane-synchronous walk, as a documented negative result.

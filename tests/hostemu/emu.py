@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         srcs = [os.path.join(_HERE, "hostemu.cpp")] + [
-            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh", "psync.cuh")]
+            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh", "psync.cuh", "brick.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
                                    "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
@@ -265,3 +265,18 @@ def trilinear_packed(vol, src, tgt, raylen, gout, n_points, alphamin, alphamax, 
                                ctypes.c_float(voxel_shift), ctypes.c_float(eps), ctypes.c_int(n_points),
                                ctypes.c_float(alphamin), ctypes.c_float(alphamax), ctypes.c_int(slab))
     return out, dict(g_source=g_src, g_target=g_tgt, g_raylen=g_len, g_alphamin=float(g_ar[0]), g_alphamax=float(g_ar[1]))
+
+
+def siddon_fwd_brick(vol, src, tgt, raylen, H, W, brick=(24, 32, 32), voxel_shift=0.5, eps=1e-8, check=False):
+    """Brick-major forward exactly as siddon_brick.cu decomposes it (full H x W grid).  Returns (image, violations,
+    stats) -- violations counts hits the detector rectangle / conservative test would have dropped (must be 0)."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    assert N == H * W
+    out = np.empty((B, 1, N), np.float32)
+    stats = np.zeros(4, np.int64)
+    fn = lib().emu_siddon_fwd_brick
+    fn.restype = ctypes.c_long
+    viol = fn(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out), ctypes.c_int(B),
+              ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+              *map(ctypes.c_int, brick), ctypes.c_int(int(check)), _p(stats))
+    return out, int(viol), dict(zip(("candidates", "maybe", "exact", "walked"), stats.tolist()))

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../diffdrr_b200/csrc/brick.cuh"
 #include "../../diffdrr_b200/csrc/psync.cuh"
 
 using namespace b200drr;
@@ -547,6 +548,99 @@ void emu_trilinear_bwd_mask(const float* vol, const float* mask, int D0, int D1,
     g_alpha_range[1] = (float)ga1;
 }
 
+
+// Brick-major forward (siddon_brick.cu) as the kernel does it: ray table, per-pose detector geometry from three corner
+// rays, per (brick, pose) pixel rectangle from the projected corners, 8x4 pixel tiles, conservative hit test, exact
+// per-pair walk on a zero-filled copy of the brick.  Returns the number of RECTANGLE VIOLATIONS: pixels outside a
+// brick's rectangle whose exact walk set-up hits the brick (must be 0; counted only when check != 0 -- it is O(all pairs)).
+long emu_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                          float* out, int B, int H, int W, float shift, float eps, int BX, int BY, int BZ, int check,
+                          long* stats /* [4]: candidates, hits (test), hits (exact), pairs walked */)
+{
+    const VolDims dims = mk(D0, D1, D2);
+    const long N = (long)H * W;
+    std::vector<Ray> rays((size_t)B * N);
+    std::vector<PoseGeo> geo(B);
+    for (int b = 0; b < B; ++b) {
+        for (long n = 0; n < N; ++n) rays[(size_t)b * N + n] = load_ray(src, tgt, b, (long)b * N + n, eps);
+        const Ray& r00 = rays[(size_t)b * N];
+        const Ray& r0w = rays[(size_t)b * N + (W - 1)];
+        const Ray& rh0 = rays[(size_t)b * N + (long)(H - 1) * W];
+        float t00[3], t0w[3], th0[3];
+        for (int a = 0; a < 3; ++a) {
+            t00[a] = r00.s[a] + r00.d[a];
+            t0w[a] = r00.s[a] + r0w.d[a];
+            th0[a] = r00.s[a] + rh0.d[a];
+        }
+        geo[b] = make_pose_geo(r00.s, t00, t0w, th0, H, W);
+    }
+    std::fill(out, out + (size_t)B * N, 0.0f);
+    long violations = 0;
+    long st[4] = {0, 0, 0, 0};
+    std::vector<float> brick((size_t)BX * BY * BZ);
+    const int nb0 = (D0 + BX - 1) / BX, nb1 = (D1 + BY - 1) / BY, nb2 = (D2 + BZ - 1) / BZ;
+    for (int i0 = 0; i0 < nb0; ++i0)
+        for (int i1 = 0; i1 < nb1; ++i1)
+            for (int i2 = 0; i2 < nb2; ++i2) {
+                const int org[3] = {i0 * BX, i1 * BY, i2 * BZ};
+                const int lo_v[3] = {org[0], org[1], org[2]};
+                const int hi_v[3] = {std::min(org[0] + BX, D0), std::min(org[1] + BY, D1), std::min(org[2] + BZ, D2)};
+                for (int x = 0; x < BX; ++x)  // what the TMA box copy leaves in shared memory (zero fill past the volume)
+                    for (int y = 0; y < BY; ++y)
+                        for (int z = 0; z < BZ; ++z) {
+                            const int g0 = org[0] + x, g1 = org[1] + y, g2 = org[2] + z;
+                            brick[((size_t)x * BY + y) * BZ + z] =
+                                (g0 < D0 && g1 < D1 && g2 < D2) ? vol[((size_t)g0 * D1 + g1) * D2 + g2] : 0.0f;
+                        }
+                LdHost ld{brick.data()};
+                for (int b = 0; b < B; ++b) {
+                    const PixRect rc = brick_rect(geo[b], lo_v, hi_v, shift, H, W);
+                    float clo[3], chi[3];
+                    for (int a = 0; a < 3; ++a) {
+                        clo[a] = ((float)lo_v[a] - shift) - geo[b].S[a];
+                        chi[a] = ((float)hi_v[a] - shift) - geo[b].S[a];
+                    }
+                    if (check) {
+                        for (int py = 0; py < H; ++py)
+                            for (int px = 0; px < W; ++px) {
+                                const bool inside = rc.x0 <= rc.x1 && px >= rc.x0 && px <= rc.x1 && py >= rc.y0 && py <= rc.y1;
+                                const Ray& ray = rays[(size_t)b * N + (long)py * W + px];
+                                const bool exact = start_walk_box(ray, lo_v, hi_v, shift).hit;
+                                float a_in, a_out;
+                                const bool maybe = brick_maybe_hit(ray.inv, clo, chi, a_in, a_out);
+                                if (exact && (!inside || !maybe)) ++violations;
+                            }
+                    }
+                    if (rc.x0 > rc.x1 || rc.y0 > rc.y1) continue;
+                    const int tw = (rc.x1 - rc.x0) / 8 + 1, th = (rc.y1 - rc.y0) / 4 + 1;
+                    for (int t = 0; t < tw * th; ++t)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int ty = t / tw, tx = t - ty * tw;
+                            const int px = rc.x0 + tx * 8 + (lane & 7), py = rc.y0 + ty * 4 + (lane >> 3);
+                            if (px > rc.x1 || py > rc.y1) continue;
+                            ++st[0];
+                            const long r = (long)b * N + (long)py * W + px;
+                            const Ray& ray = rays[r];
+                            float a_in, a_out;
+                            if (!brick_maybe_hit(ray.inv, clo, chi, a_in, a_out)) continue;
+                            ++st[1];
+                            const unsigned it = pack_item(step_bin(a_in, a_out, fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]),
+                                                                   (float)kBrickBins / (float)(BX + BY + BZ + 8)),
+                                                          b % kBrickPoseChunk, py, px);
+                            if (item_row(it) != py || item_col(it) != px || item_pose(it) != b % kBrickPoseChunk) ++violations;
+                            if (start_walk_box(ray, lo_v, hi_v, shift).hit) ++st[2];
+                            const float part = brick_pair_fwd<4>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                            if (part != 0.0f) {
+                                ++st[3];
+                                out[r] += raylen[r] * part;
+                            }
+                        }
+                }
+            }
+    if (stats)
+        for (int i = 0; i < 4; ++i) stats[i] = st[i];
+    return violations;
+}
 }  // extern "C"
 
 // ---- access-pattern analysis (tuning aid): distinct 32-byte sectors / 128-byte lines per warp-wide gather ----------
