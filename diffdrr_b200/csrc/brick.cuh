@@ -129,6 +129,70 @@ B200_HD PixRect brick_rect(const PoseGeo& g, const int lo_v[3], const int hi_v[3
     return rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
 }
 
+// Column range [umin, umax] of the brick's projected outline inside the pixel-row band [vb0, vb1] (already widened by
+// the caller's margin): the outline is the convex hull of the 8 projected corners and its edges are projections of box
+// edges, so the extent over a band is attained at a corner inside the band or where one of the 12 box edges meets a band
+// boundary.  uv = {u0, v0, u1, v1, ...} in corner order (bit 0/1/2 of the index = high face of axis 0/1/2).
+// Returns false when the band misses the outline.
+B200_HD bool band_extent(const float* uv, float vb0, float vb1, float& umin, float& umax)
+{
+    umin = INFINITY;
+    umax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float u = uv[2 * c], v = uv[2 * c + 1];
+        if (v >= vb0 && v <= vb1) {
+            umin = fminf(umin, u);
+            umax = fmaxf(umax, u);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int bit = 1; bit < 8; bit <<= 1) {
+            if (c & bit) continue;  // each edge once: c has the bit clear, its partner has it set
+            const float u1 = uv[2 * c], v1 = uv[2 * c + 1], u2 = uv[2 * (c | bit)], v2 = uv[2 * (c | bit) + 1];
+            const float dv = v2 - v1;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float vb = k == 0 ? vb0 : vb1;
+                if ((v1 - vb) * (v2 - vb) <= 0.0f && dv != 0.0f) {
+                    const float t = (vb - v1) / dv;
+                    const float u = fmaf(t, u2 - u1, u1);
+                    umin = fminf(umin, u);
+                    umax = fmaxf(umax, u);
+                }
+            }
+        }
+    }
+    return umin <= umax;
+}
+
+// Pixel columns [px_lo, px_hi] of the 4-row tile band starting at row py0 that can hold hits of the brick: the outline's
+// extent over rows [py0 - 1, py0 + 4] (one pixel of margin, as for the rectangle) widened by one pixel and clipped to the
+// rectangle; the whole rectangle width when the projection is not valid (`outline_ok` false).  False = no candidates.
+B200_HD bool row_span(const float* uv, bool outline_ok, const PixRect& rc, int py0, int& px_lo, int& px_hi)
+{
+    px_lo = rc.x0;
+    px_hi = rc.x1;
+    if (!outline_ok) return true;
+    float umin, umax;
+    if (!band_extent(uv, (float)(py0 - 1), (float)(py0 + 4), umin, umax)) return false;
+    const float flo = fmaxf(floorf(umin) - 1.0f, (float)rc.x0), fhi = fminf(ceilf(umax) + 1.0f, (float)rc.x1);
+    if (!(flo <= fhi)) return false;
+    px_lo = (int)flo;
+    px_hi = (int)fhi;
+    return true;
+}
+
+// True when rect_from_extents derived the rectangle from the projected corners (false = whole-detector fallback).
+B200_HD bool outline_valid(float umin, float umax, float vmin, float vmax, float dmin, float dmax)
+{
+    const float lo = fminf(fabsf(dmin), fabsf(dmax)), hi = fmaxf(fabsf(dmin), fabsf(dmax));
+    const bool one_side = (dmin > 0.0f) || (dmax < 0.0f);
+    return one_side && (lo >= 1e-3f * hi) && (umin <= umax) && (vmin <= vmax);
+}
+
 // Conservative (ray, box) test from the ray-table entry: the same expressions as box_surely_missed with the
 // per-(pose, box) constants clo = (lo - shift) - s, chi = (hi - shift) - s hoisted.  Returns false only when the line
 // certainly misses; a_in / a_out feed the step estimate the work list is sorted by.
@@ -201,6 +265,211 @@ B200_HD float brick_pair_fwd(const Ld& ld, const Ray& ray, const int lo_v[3], co
         for (int j = 0; j < U; ++j) acc = fmaf(len[j], v[j], acc);
     }
     return acc;
+}
+
+
+// ---- lean per-pair path (production): set-up without the entry-voxel fix-ups, accumulated crossing alphas ---------------
+// The forward sum does not need start_walk_box's consistency fix-ups (they make the start voxel agree with the ORDER of
+// crossing alphas that sit within round-off of the entry alpha -- required by the backward pass, where a swapped pair
+// moves a crossing coefficient between axes; in the forward sum it only re-attributes a segment of round-off length).
+// Crossing alphas are accumulated with ROUND-UP additions (an = add.rp(an, |1/d|)) from an anchor that is exact per
+// brick, and the stop alpha is the exit plane's alpha ROUNDED DOWN (fma.rm): by induction the accumulated alpha of the
+// exit plane can never fall below it, so the walk never steps out of the staged brick and no tolerance window is needed.
+// The remainder of the chord [acur, a_out] is given to the last voxel, so every brick integrates exactly its
+// [a_in, a_out] whatever the accumulated drift (<= 32 additions deep, ~1e-7 in alpha).
+B200_HD float add_rp(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_ru(a, b);
+#else
+    const double x = (double)a + (double)b;
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+#endif
+}
+B200_HD float fma_rm(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rd(a, b, c);
+#else
+    const double x = (double)a * (double)b + (double)c;
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+#endif
+}
+
+struct AccState {
+    float an0, an1, an2, acur;
+    int off;
+};
+struct AccConst {
+    float da0, da1, da2, a_stop;
+    int so0, so1, so2;
+};
+
+B200_HD float acc_step(AccState& s, const AccConst& k)
+{
+    float len;
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred q, p0, p1, p2;\n\t"
+        ".reg .f32 nx;\n\t"
+        "min.f32 nx, %0, %1, %2;\n\t"
+        "sub.f32 %5, nx, %3;\n\t"
+        "mov.f32 %3, nx;\n\t"
+        "setp.lt.f32 q, nx, %6;\n\t"
+        "setp.eq.and.f32 p0, %0, nx, q;\n\t"
+        "setp.eq.and.f32 p1, %1, nx, q;\n\t"
+        "setp.eq.and.f32 p2, %2, nx, q;\n\t"
+        "@p0 add.rp.f32 %0, %0, %7;\n\t"
+        "@p1 add.rp.f32 %1, %1, %8;\n\t"
+        "@p2 add.rp.f32 %2, %2, %9;\n\t"
+        "@p0 add.s32 %4, %4, %10;\n\t"
+        "@p1 add.s32 %4, %4, %11;\n\t"
+        "@p2 add.s32 %4, %4, %12;\n\t"
+        "}"
+        : "+f"(s.an0), "+f"(s.an1), "+f"(s.an2), "+f"(s.acur), "+r"(s.off), "=f"(len)
+        : "f"(k.a_stop), "f"(k.da0), "f"(k.da1), "f"(k.da2), "r"(k.so0), "r"(k.so1), "r"(k.so2));
+#else
+    const float nx = fminf(fminf(s.an0, s.an1), s.an2);
+    len = nx - s.acur;
+    s.acur = nx;
+    const bool q = nx < k.a_stop;
+    const bool p0 = q && s.an0 == nx, p1 = q && s.an1 == nx, p2 = q && s.an2 == nx;
+    if (p0) { s.an0 = add_rp(s.an0, k.da0); s.off += k.so0; }
+    if (p1) { s.an1 = add_rp(s.an1, k.da1); s.off += k.so1; }
+    if (p2) { s.an2 = add_rp(s.an2, k.da2); s.off += k.so2; }
+#endif
+    return len;
+}
+
+B200_HD float approx_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// s = source, inv = 1/d from the ray table, clo / chi = (box face - shift) - s per axis (the hit test's constants).
+// The direction d is only needed for the entry voxel (a floor that the clamp / entry-face select make robust), so it is
+// re-formed as 1/inv (MUFU.RCP, 1 ulp) instead of being fetched: the ray table is 16 bytes per ray.
+template <int U, class Ld, bool ACC = true, bool PIPE = true>
+B200_HD float brick_pair_fwd_lean(const Ld& ld, const float s[3], const float inv[3], const float clo[3],
+                                  const float chi[3], const int lo_v[3], const int hi_v[3], const int org[3], int st0, int st1,
+                                  int st2, float shift)
+{
+    float lo[3], a_in = -INFINITY, a_hi = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float a0 = clo[a] * inv[a], a1 = chi[a] * inv[a];  // == plane_alpha_acc of the two faces
+        lo[a] = fminf(a0, a1);
+        a_in = fmaxf(a_in, lo[a]);
+        a_hi = fminf(a_hi, fmaxf(a0, a1));
+    }
+    if (!(a_in < a_hi)) return 0.0f;
+    const int st[3] = {st0 * Ld::kScale, st1 * Ld::kScale, st2 * Ld::kScale};
+    AccState w;
+    AccConst k;
+    float an[3], da[3], nxc[3], a_out = INFINITY;
+    int so[3];
+    w.off = ld.base();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = inv[a] > 0.0f;
+        const int lo_i = lo_v[a], hi_i = hi_v[a] - 1;
+        int i = (int)floorf(fmaf(a_in, approx_rcp(inv[a]), s[a] + shift));
+        i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
+        i = (lo[a] >= a_in) ? (fwd ? lo_i : hi_i) : i;  // entering through a face of this axis
+        const float p0 = (float)(fwd ? i + 1 : i);
+        da[a] = fabsf(inv[a]);
+        an[a] = ((p0 - shift) - s[a]) * inv[a];
+        const float nx = fwd ? (float)hi_v[a] - p0 : p0 - (float)lo_v[a];
+        nxc[a] = nx;
+        a_out = fminf(a_out, fmaf(nx, da[a], an[a]));
+        so[a] = fwd ? st[a] : -st[a];
+        w.off += (i - org[a]) * st[a];
+    }
+    if (!ACC) {  // exact crossing alphas (fma from a counter), for A/B comparison with the accumulated form
+        LeanState ls;
+        LeanConst lk;
+        lk.da0 = da[0]; lk.da1 = da[1]; lk.da2 = da[2];
+        lk.a00 = an[0]; lk.a01 = an[1]; lk.a02 = an[2];
+        lk.a_out = a_out;
+        lk.so0 = so[0]; lk.so1 = so[1]; lk.so2 = so[2];
+        ls.an0 = an[0]; ls.an1 = an[1]; ls.an2 = an[2];
+        ls.nf0 = ls.nf1 = ls.nf2 = 0.0f;
+        ls.acur = a_in;
+        ls.off = w.off;
+        float acc = 0.0f;
+        while (ls.acur < lk.a_out) {
+            float len[U], v[U];
+            int offs[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                offs[j] = ls.off;
+                len[j] = lean_step(ls, lk);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) v[j] = ld(offs[j]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) acc = fmaf(len[j], v[j], acc);
+        }
+        return acc;
+    }
+    // accumulate in the pair's own frame beta = alpha - a_in: values of ~0..0.03 instead of ~0.5..1, i.e. additions that
+    // round at ~2e-9 instead of 6e-8 -- 32 of them drift less than ONE rounding of an absolute alpha
+    w.an0 = an[0] - a_in; w.an1 = an[1] - a_in; w.an2 = an[2] - a_in;
+    w.acur = 0.0f;
+    k.da0 = da[0]; k.da1 = da[1]; k.da2 = da[2];
+    k.so0 = so[0]; k.so1 = so[1]; k.so2 = so[2];
+    a_out = fminf(fminf(fma_rm(nxc[0], da[0], w.an0), fma_rm(nxc[1], da[1], w.an1)), fma_rm(nxc[2], da[2], w.an2));
+    k.a_stop = a_out;
+    float acc = 0.0f;
+    if (PIPE) {
+        // software-pipelined: the products of one group of U steps are formed while the NEXT group's loads are in flight
+        float len[U], v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) len[j] = v[j] = 0.0f;
+        while (w.acur < k.a_stop) {
+            float lenn[U];
+            int offs[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                offs[j] = w.off;
+                lenn[j] = acc_step(w, k);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) acc = fmaf(len[j], v[j], acc);
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                v[j] = ld(offs[j]);
+                len[j] = lenn[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) acc = fmaf(len[j], v[j], acc);
+    } else {
+        while (w.acur < k.a_stop) {
+            float len[U], v[U];
+            int offs[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                offs[j] = w.off;
+                len[j] = acc_step(w, k);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) v[j] = ld(offs[j]);
+#pragma unroll
+            for (int j = 0; j < U; ++j) acc = fmaf(len[j], v[j], acc);
+        }
+    }
+    return fmaf(a_out - w.acur, ld(w.off), acc);  // the rest of the chord belongs to the last voxel
 }
 
 }  // namespace b200drr

@@ -10,7 +10,7 @@
 //      similar length) and
 //   4. lets the warps pull 32-item chunks, longest first: exact walk set-up (start_walk_box), lean walk with the voxel
 //      loads served by ld.shared, one red.global.add of the partial line integral per (ray, brick).
-// The (B, N) ray table {1/d, sum|d| ; d, L} is written once per launch by brick_prep_kernel, which also zero-fills
+// The (B, N) ray table {1/d, sum|d|} (+ the ray lengths L) is written once per launch by brick_prep_kernel, which also zero-fills
 // the output and derives the per-pose detector geometry used in step 1.
 //
 // Replaces reference renderers.py:94-113 (alphas + sort) and 156-169 (grid_sample gather) for full detector grids.
@@ -109,9 +109,9 @@ __device__ __forceinline__ Ray make_ray_b(const PoseRaysB& pr, const float* __re
 // ---- ray table + per-pose geometry + zero fill ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                                                          const float* __restrict__ raylen, PoseRaysB pr,
-                                                         float4* __restrict__ raytab, PoseGeo* __restrict__ geo,
-                                                         float* __restrict__ out, unsigned* __restrict__ counter, int H,
-                                                         int W, float eps)
+                                                         float4* __restrict__ raytab, float* __restrict__ ltab,
+                                                         PoseGeo* __restrict__ geo, float* __restrict__ out,
+                                                         unsigned* __restrict__ counter, int H, int W, float eps)
 {
     const int64_t N = (int64_t)H * W;
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict
     const int64_t r = (int64_t)b * N + n;
     float L;
     const Ray ray = make_ray_b(pr, src, tgt, raylen, b, r, px, py, eps, L);
-    raytab[2 * r] = make_float4(ray.inv[0], ray.inv[1], ray.inv[2], fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]));
-    raytab[2 * r + 1] = make_float4(ray.d[0], ray.d[1], ray.d[2], L);
+    raytab[r] = make_float4(ray.inv[0], ray.inv[1], ray.inv[2], fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]));
+    ltab[r] = L;
     out[r] = 0.0f;
     if (n == 0) {
         float Lx;
@@ -145,8 +145,10 @@ struct BrickGrid {
     int nb0, nb1, nb2;  // bricks per axis
 };
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
 struct BrickCfg {
+    // 4-row tile bands per pose chunk (a chunk takes as many poses as fit); the two-CTA-per-SM shape has less room
+    static constexpr int kRowCap = CTAS == 1 ? 512 : 256;
     static constexpr int kBrickElems = BX * BY * BZ;
     static constexpr int kBrickBytes = kBrickElems * 4;
     static constexpr int kWarps = THREADS / 32;
@@ -155,39 +157,51 @@ struct BrickCfg {
     // shared-memory carve-up (bytes)
     static constexpr int oBricks = 0;
     static constexpr int oItems = oBricks + STAGES * kBrickBytes;
-    static constexpr int oBar = oItems + kCap * 4;           // STAGES x 8
-    static constexpr int oPoseF = oBar + 64;                  // kPB x 9 floats: S[3], clo[3], chi[3]
-    static constexpr int oRect = oPoseF + kPB * 9 * 4;        // kPB x 4 ints: x0, y0, x1, y1
-    static constexpr int oTw = oRect + kPB * 4 * 4;           // kPB ints: tiles per rectangle row
-    static constexpr int oPrefix = oTw + kPB * 4;             // kPB + 1 ints (+ pad)
-    static constexpr int oHist = oPrefix + (kPB + 4) * 4;     // kBrickBins ints
-    static constexpr int oCursor = oHist + kBrickBins * 4;    // kBrickBins ints
-    static constexpr int oMisc = oCursor + kBrickBins * 4;    // n_items, chunk counter, next brick [2]
-    static constexpr int kSmemBytes = oMisc + 32;
+    static constexpr int oBar = oItems + kCap * 4;               // STAGES x 8
+    static constexpr int oPoseF = oBar + 64;                      // kPB x 12 floats: S[3],-, clo[3],-, chi[3],-
+    static constexpr int oUV = oPoseF + kPB * 12 * 4;             // kPB x 16 floats: projected corners (u, v)
+    static constexpr int oRect = oUV + kPB * 16 * 4;              // kPB x 4 ints: x0, y0, x1, y1
+    static constexpr int oFlag = oRect + kPB * 4 * 4;             // kPB ints: outline valid
+    static constexpr int oRowBase = oFlag + kPB * 4;              // kPB + 1 ints (+ pad)
+    static constexpr int oRowInfo = oRowBase + (kPB + 4) * 4;     // kRowCap u32: pose | first row | first column
+    static constexpr int oRowEnd = oRowInfo + kRowCap * 4;        // kRowCap ints: last column
+    static constexpr int oRowPrefix = oRowEnd + kRowCap * 4;      // kRowCap + 1 ints (+ pad): tiles before the band
+    static constexpr int oHist = oRowPrefix + (kRowCap + 4) * 4;  // kBrickBins ints
+    static constexpr int oCursor = oHist + kBrickBins * 4;        // kBrickBins ints
+    static constexpr int oMisc = oCursor + kBrickBins * 4;        // see s_misc
+    static constexpr int kSmemBytes = oMisc + 64;
 };
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
-__global__ void __launch_bounds__(THREADS, (STAGES == 1 ? 2 : 1))
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
+__global__ void __launch_bounds__(THREADS, CTAS)
     siddon_fwd_brick_kernel(const __grid_constant__ CUtensorMap tmap, VolDims dims, BrickGrid bg,
-                            const float4* __restrict__ raytab, const PoseGeo* __restrict__ geo, float* __restrict__ out,
-                            unsigned* __restrict__ counter, int B, int H, int W, float shift)
+                            const float4* __restrict__ raytab, const float* __restrict__ ltab,
+                            const PoseGeo* __restrict__ geo, float* __restrict__ out, unsigned* __restrict__ counter, int B,
+                            int H, int W, float shift)
 {
-    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U>;
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
+    constexpr int kRowCap = Cfg::kRowCap;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned* s_items = reinterpret_cast<unsigned*>(smem + Cfg::oItems);
     float* s_posef = reinterpret_cast<float*>(smem + Cfg::oPoseF);
+    float* s_uv = reinterpret_cast<float*>(smem + Cfg::oUV);
     int* s_rect = reinterpret_cast<int*>(smem + Cfg::oRect);
-    int* s_tw = reinterpret_cast<int*>(smem + Cfg::oTw);
-    int* s_prefix = reinterpret_cast<int*>(smem + Cfg::oPrefix);
+    int* s_flag = reinterpret_cast<int*>(smem + Cfg::oFlag);
+    int* s_rowbase = reinterpret_cast<int*>(smem + Cfg::oRowBase);
+    unsigned* s_rowinfo = reinterpret_cast<unsigned*>(smem + Cfg::oRowInfo);
+    int* s_rowend = reinterpret_cast<int*>(smem + Cfg::oRowEnd);
+    int* s_rowprefix = reinterpret_cast<int*>(smem + Cfg::oRowPrefix);
     int* s_hist = reinterpret_cast<int*>(smem + Cfg::oHist);
     int* s_cursor = reinterpret_cast<int*>(smem + Cfg::oCursor);
-    int* s_misc = reinterpret_cast<int*>(smem + Cfg::oMisc);  // [0] n_items, [1] chunk counter, [2..3] next brick
+    // s_misc: [0] n_items, [1] chunk counter, [2..3] next brick, [4] poses in this chunk, [5] bands, [6] tiles
+    int* s_misc = reinterpret_cast<int*>(smem + Cfg::oMisc);
     const uint32_t bar0 = smem_u32(smem + Cfg::oBar);
     const uint32_t brick0 = smem_u32(smem + Cfg::oBricks);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_bricks = bg.nb0 * bg.nb1 * bg.nb2;
     const float inv_bin_width = (float)kBrickBins / (float)(BX + BY + BZ + 8);
+    const int64_t N = (int64_t)H * W;
 
     if (tid == 0) {
 #pragma unroll
@@ -228,13 +242,14 @@ __global__ void __launch_bounds__(THREADS, (STAGES == 1 ? 2 : 1))
         LdShared ld;
         ld.base_addr = brick0 + stage * Cfg::kBrickBytes;
 
-        for (int p0 = 0; p0 < B; p0 += Cfg::kPB) {
-            const int npose = min(Cfg::kPB, B - p0);
-            __syncthreads();  // the previous chunk's (or brick's) readers of the pose tables are done
-            // ---- 1. pixel rectangle of the brick per pose: 8 lanes (corners) per pose ----------------------------
-            if (warp < (npose * 8 + 31) / 32) {  // whole warps take part in the shuffles; surplus lanes repeat the last pose
+        int p0 = 0;
+        while (p0 < B) {
+            const int ntry = min(Cfg::kPB, B - p0);
+            __syncthreads();  // the previous chunk's (or brick's) readers of the pose / band tables are done
+            // ---- 1a. project the brick's corners per pose: 8 lanes (corners) per pose -----------------------------
+            if (warp < (ntry * 8 + 31) / 32) {  // whole warps take part in the shuffles; surplus lanes repeat the last pose
                 const int bl_raw = tid >> 3, c = tid & 7;
-                const int bl = min(bl_raw, npose - 1);
+                const int bl = min(bl_raw, ntry - 1);
                 const PoseGeo g = geo[p0 + bl];
                 const float X[3] = {(float)((c & 1) ? hi_v[0] : lo_v[0]) - shift, (float)((c & 2) ? hi_v[1] : lo_v[1]) - shift,
                                     (float)((c & 4) ? hi_v[2] : lo_v[2]) - shift};
@@ -252,66 +267,132 @@ __global__ void __launch_bounds__(THREADS, (STAGES == 1 ? 2 : 1))
                     dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
                 }
                 const unsigned badmask = __ballot_sync(0xffffffffu, bad);
-                if (c == 0 && bl_raw < npose) {
-                    const bool anybad = ((badmask >> (lane & 24)) & 0xffu) != 0u;
-                    if (anybad) dmin = NAN;  // -> whole detector
-                    const PixRect rc = rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
-                    int tw = 0, th = 0;
-                    if (rc.x0 <= rc.x1 && rc.y0 <= rc.y1) {
-                        tw = (rc.x1 - rc.x0) / 8 + 1;
-                        th = (rc.y1 - rc.y0) / 4 + 1;
-                    }
-                    s_rect[bl * 4 + 0] = rc.x0;
-                    s_rect[bl * 4 + 1] = rc.y0;
-                    s_rect[bl * 4 + 2] = rc.x1;
-                    s_rect[bl * 4 + 3] = rc.y1;
-                    s_tw[bl] = tw;
-                    s_prefix[bl + 1] = tw * th;  // counts; turned into a prefix sum below
+                if (bl_raw < ntry) {
+                    s_uv[bl * 16 + 2 * c] = u;
+                    s_uv[bl * 16 + 2 * c + 1] = v;
+                    if (c == 0) {
+                        const bool anybad = ((badmask >> (lane & 24)) & 0xffu) != 0u;
+                        if (anybad) dmin = NAN;  // -> whole detector
+                        const PixRect rc = rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
+                        s_flag[bl] = outline_valid(umin, umax, vmin, vmax, dmin, dmax) ? 1 : 0;
+                        s_rect[bl * 4 + 0] = rc.x0;
+                        s_rect[bl * 4 + 1] = rc.y0;
+                        s_rect[bl * 4 + 2] = rc.x1;
+                        s_rect[bl * 4 + 3] = rc.y1;
+                        s_rowbase[bl + 1] = (rc.x0 <= rc.x1 && rc.y0 <= rc.y1) ? (rc.y1 - rc.y0) / 4 + 1 : 0;  // band count
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        s_posef[bl * 9 + a] = g.S[a];
-                        s_posef[bl * 9 + 3 + a] = ((float)lo_v[a] - shift) - g.S[a];
-                        s_posef[bl * 9 + 6 + a] = ((float)hi_v[a] - shift) - g.S[a];
+                        for (int a = 0; a < 3; ++a) {
+                            s_posef[bl * 12 + a] = g.S[a];
+                            s_posef[bl * 12 + 4 + a] = ((float)lo_v[a] - shift) - g.S[a];
+                            s_posef[bl * 12 + 8 + a] = ((float)hi_v[a] - shift) - g.S[a];
+                        }
                     }
                 }
             }
             __syncthreads();
-            if (warp == 0) {  // inclusive scan of the tile counts
-                int cnt = lane < npose ? s_prefix[lane + 1] : 0;
+            // ---- 1b. how many poses fit the band table; first band of every pose --------------------------------------
+            if (warp == 0) {
+                const int cnt = lane < ntry ? s_rowbase[lane + 1] : 0;
+                int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, cnt, o);
-                    if (lane >= o) cnt += up;
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
                 }
-                if (lane < npose) s_prefix[lane + 1] = cnt;
-                if (lane == 0) s_prefix[0] = 0;
+                const unsigned fits = __ballot_sync(0xffffffffu, lane < ntry && incl <= kRowCap);
+                const int np = max(1, __popc(fits));  // incl is monotone: the fitting poses are a prefix (one pose always fits)
+                if (lane < np) s_rowbase[lane + 1] = incl;
+                if (lane == 0) s_rowbase[0] = 0;
+                const int R = __shfl_sync(0xffffffffu, incl, np - 1);
+                if (lane == 0) {
+                    s_misc[4] = np;
+                    s_misc[5] = R;
+                }
+            }
+            __syncthreads();
+            const int npose = s_misc[4], R = s_misc[5];
+            // ---- 1c. column span of every 4-row band inside the projected outline --------------------------------------
+            for (int r = tid; r < R; r += THREADS) {
+                int bl = 0;
+                while (s_rowbase[bl + 1] <= r) ++bl;
+                const PixRect rc{s_rect[bl * 4 + 0], s_rect[bl * 4 + 1], s_rect[bl * 4 + 2], s_rect[bl * 4 + 3]};
+                const int py0 = rc.y0 + 4 * (r - s_rowbase[bl]);
+                int px_lo, px_hi, cnt = 0;
+                if (row_span(s_uv + bl * 16, s_flag[bl] != 0, rc, py0, px_lo, px_hi)) cnt = (px_hi - px_lo) / 8 + 1;
+                else px_lo = px_hi = 0;
+                s_rowinfo[r] = pack_item(0, bl, py0, px_lo);
+                s_rowend[r] = px_hi;
+                s_rowprefix[r + 1] = cnt;
+            }
+            __syncthreads();
+            // ---- 1d. tiles before every band (exclusive scan, <= kRowCap entries, 16 per lane) ------------------------
+            if (warp == 0) {
+                constexpr int PER = kRowCap / 32;
+                int c[PER], tot = 0;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int idx = lane * PER + i;
+                    c[i] = idx < R ? s_rowprefix[idx + 1] : 0;
+                    tot += c[i];
+                }
+                int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                int run = incl - tot;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int idx = lane * PER + i;
+                    run += c[i];
+                    if (idx < R) s_rowprefix[idx + 1] = run;
+                }
+                if (lane == 0) s_rowprefix[0] = 0;
+                if (lane == 31) s_misc[6] = incl;
             }
             if (p0 == 0) mbar_wait(bar0 + 8 * stage, parity);  // the brick has landed (first use only)
             __syncthreads();
-            const int T = s_prefix[npose];
+            const int T = s_misc[6];
 
             for (int t0 = 0; t0 < T; t0 += Cfg::kWarps * K) {
                 // ---- 2. candidates -> hits (kept in registers) + histogram of the sort bins --------------------
                 unsigned items[K];
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    items[j] = 0xffffffffu;
-                    const int t = t0 + warp + Cfg::kWarps * j;
-                    if (t < T) {
-                        int bl = 0;
-                        while (s_prefix[bl + 1] <= t) ++bl;  // warp-uniform
-                        const int jl = t - s_prefix[bl], tw = s_tw[bl];
-                        const int ty = jl / tw, tx = jl - ty * tw;
-                        const int px = s_rect[bl * 4 + 0] + tx * 8 + (lane & 7), py = s_rect[bl * 4 + 1] + ty * 4 + (lane >> 3);
-                        if (px <= s_rect[bl * 4 + 2] && py <= s_rect[bl * 4 + 3]) {
-                            const int64_t r = ((int64_t)(p0 + bl) * H + py) * W + px;
-                            const float4 q = __ldg(raytab + 2 * r);
-                            const float inv[3] = {q.x, q.y, q.z};
-                            float a_in, a_out;
-                            if (brick_maybe_hit(inv, s_posef + bl * 9 + 3, s_posef + bl * 9 + 6, a_in, a_out)) {
-                                const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
-                                items[j] = pack_item(bin, bl, py, px);
-                                atomicAdd(&s_hist[bin], 1);
+                for (int j = 0; j < K; ++j) items[j] = 0xffffffffu;
+                const int tw0 = t0 + warp * K;
+                if (tw0 < T) {
+                    int row;
+                    {  // band of the warp's first tile: first index whose prefix exceeds tw0, minus one (two ballots)
+                        constexpr int STEP = kRowCap / 32;
+                        const int probe = min((lane + 1) * STEP, R);
+                        const unsigned le = __ballot_sync(0xffffffffu, s_rowprefix[probe] <= tw0);
+                        const int coarse = __popc(le) * STEP;  // prefix[coarse] <= tw0 (or coarse == 0)
+                        const int p2 = min(coarse + lane + 1, R);
+                        const unsigned le2 = __ballot_sync(0xffffffffu, lane < STEP && s_rowprefix[p2] <= tw0);
+                        row = coarse + __popc(le2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const int t = tw0 + j;
+                        if (t < T) {
+                            while (s_rowprefix[row + 1] <= t) ++row;  // warp-uniform, rarely more than one step
+                            const unsigned info = s_rowinfo[row];
+                            const int bl = item_pose(info);
+                            const int px = item_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
+                            const int py = item_row(info) + (lane >> 3);
+                            if (px <= s_rowend[row] && py <= s_rect[bl * 4 + 3]) {
+                                const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(py * W + px)));
+                                const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
+                                const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
+                                const float inv[3] = {q.x, q.y, q.z};
+                                const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                                float a_in, a_out;
+                                if (brick_maybe_hit(inv, clo3, chi3, a_in, a_out)) {
+                                    const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
+                                    items[j] = pack_item(bin, bl, py, px);
+                                    atomicAdd(&s_hist[bin], 1);
+                                }
                             }
                         }
                     }
@@ -341,28 +422,52 @@ __global__ void __launch_bounds__(THREADS, (STAGES == 1 ? 2 : 1))
                 // ---- 4. the walks: warps pull 32-item chunks ---------------------------------------------------
                 const int n_items = s_misc[0];
                 const int n_chunks = (n_items + 31) >> 5;
-                for (;;) {
+                // (the next chunk's item and ray-table entry are fetched before the current chunk is walked, so the L2
+                // latency of the table hides behind a whole walk instead of stalling every chunk's set-up)
+                auto claim = [&]() {
                     int c = 0;
                     if (lane == 0) c = atomicAdd(&s_misc[1], 1);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    if (c >= n_chunks) break;
+                    return __shfl_sync(0xffffffffu, c, 0);
+                };
+                auto fetch = [&](int c, unsigned& itw, float4& q, float& L) {
                     const int i = c * 32 + lane;
-                    if (i < n_items) {
-                        const unsigned itw = s_items[i];
-                        const int bl = item_pose(itw), py = item_row(itw), px = item_col(itw);
-                        const int64_t r = ((int64_t)(p0 + bl) * H + py) * W + px;
-                        const float4 q0 = __ldg(raytab + 2 * r), q1 = __ldg(raytab + 2 * r + 1);
-                        Ray ray;
-                        ray.s[0] = s_posef[bl * 9 + 0];
-                        ray.s[1] = s_posef[bl * 9 + 1];
-                        ray.s[2] = s_posef[bl * 9 + 2];
-                        ray.d[0] = q1.x; ray.d[1] = q1.y; ray.d[2] = q1.z;
-                        ray.inv[0] = q0.x; ray.inv[1] = q0.y; ray.inv[2] = q0.z;
-                        const float part = brick_pair_fwd<U>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
-                        if (part != 0.0f) red_add(out + r, q1.w * part);
+                    itw = 0xffffffffu;
+                    if (c < n_chunks && i < n_items) {
+                        itw = s_items[i];
+                        const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                        q = __ldg(raytab + r);
+                        L = __ldg(ltab + r);
                     }
+                };
+                int c = claim();
+                unsigned itw;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                float L = 0.0f;
+                fetch(c, itw, q, L);
+                while (c < n_chunks) {
+                    const int cn = claim();
+                    unsigned itn;
+                    float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float Ln = 0.0f;
+                    fetch(cn, itn, qn, Ln);
+                    if (itw != 0xffffffffu) {
+                        const int bl = item_pose(itw);
+                        const float4 S4 = *reinterpret_cast<const float4*>(s_posef + bl * 12);
+                        const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
+                        const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
+                        const float s3[3] = {S4.x, S4.y, S4.z}, inv3[3] = {q.x, q.y, q.z};
+                        const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                        const float part = brick_pair_fwd_lean<U, LdShared, true, PIPE != 0>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                        if (part != 0.0f)
+                            red_add(out + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw))), L * part);
+                    }
+                    c = cn;
+                    itw = itn;
+                    q = qn;
+                    L = Ln;
                 }
             }
+            p0 += npose;
         }
         __syncthreads();  // every reader of this stage (and of s_misc[2 + ...]) is done
         if (STAGES == 1) {
@@ -412,12 +517,13 @@ bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, i
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U>
-cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const PoseGeo* geo, float* out,
-                                 unsigned* counter, int B, int H, int W, float shift, cudaStream_t stream)
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
+cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const float* ltab,
+                                 const PoseGeo* geo, float* out, unsigned* counter, int B, int H, int W, float shift,
+                                 cudaStream_t stream)
 {
-    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U>;
-    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U>;
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
+    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -431,9 +537,10 @@ cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const flo
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ctas_per_sm = Cfg::kSmemBytes <= 113 * 1024 ? 2 : 1;
+    static_assert(Cfg::kSmemBytes <= (233472 - 1024 * CTAS) / CTAS, "shared-memory carve-up exceeds the SM");
+    const int ctas_per_sm = CTAS;
     const int grid = min(bg.nb0 * bg.nb1 * bg.nb2, sms * ctas_per_sm);
-    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(map, dims, bg, raytab, geo, out, counter, B, H, W, shift);
+    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(map, dims, bg, raytab, ltab, geo, out, counter, B, H, W, shift);
     return cudaGetLastError();
 }
 
@@ -441,7 +548,7 @@ cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const flo
 
 size_t siddon_brick_workspace_bytes(int B, int H, int W)
 {
-    return 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256) + sizeof(float4) * 2 * (size_t)B * H * W;
+    return 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256) + (sizeof(float4) + sizeof(float)) * (size_t)B * H * W;
 }
 
 bool siddon_brick_supported(VolDims dims, int H, int W)
@@ -454,7 +561,8 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
                                     void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
                                     int variant, cudaStream_t stream)
 {
-    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)vol & 15u) != 0) return cudaErrorNotSupported;
+    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)vol & 15u) != 0 || (int64_t)B * H * W >= ((int64_t)1 << 31))
+        return cudaErrorNotSupported;
     if (workspace == nullptr || workspace_bytes < siddon_brick_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 255u) != 0)
         return cudaErrorInvalidValue;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -462,24 +570,30 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
     PoseGeo* geo = reinterpret_cast<PoseGeo*>(ws + 256);
     float4* raytab = reinterpret_cast<float4*>(ws + 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256));
     const int64_t N = (int64_t)H * W;
+    float* ltab = reinterpret_cast<float*>(raytab + (size_t)B * N);
     PoseRaysB pr{G, Wd, rows, cols};
-    brick_prep_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, geo, out,
-                                                                                        counter, H, W, eps);
+    brick_prep_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, ltab, geo,
+                                                                                        out, counter, H, W, eps);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap map;
-#define BV(id, BX, BY, BZ, STAGES, THREADS, K, U)                                                                        \
+#define BV(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE)                                                            \
     case id:                                                                                                             \
         if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
-        return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U>(map, dims, raytab, geo, out, counter, B, H, W, shift, \
-                                                                       stream);
+        return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>(map, dims, raytab, ltab, geo, out, counter, \
+                                                                                   B, H, W, shift, stream);
     switch (variant) {
-        BV(0, 24, 32, 32, 2, 1024, 4, 4)
-        BV(1, 24, 32, 32, 2, 1024, 4, 2)
-        BV(2, 24, 32, 32, 2, 512, 8, 4)
-        BV(3, 24, 32, 32, 1, 512, 4, 4)   // two CTAs per SM, one brick each
-        BV(4, 16, 32, 32, 2, 1024, 4, 4)
-        BV(5, 24, 32, 32, 2, 768, 4, 4)
+        BV(0, 24, 32, 32, 1, 512, 4, 2, 2, 1)    // two CTAs per SM, one 96 KB brick each (production shape)
+        BV(1, 24, 32, 32, 1, 512, 4, 2, 2, 0)
+        BV(2, 24, 32, 32, 1, 512, 4, 4, 2, 1)
+        BV(3, 24, 32, 32, 1, 512, 4, 4, 2, 0)
+        BV(4, 22, 32, 32, 1, 512, 8, 2, 2, 1)    // bigger rounds (fewer barriers), slightly smaller brick
+        BV(5, 15, 32, 32, 1, 320, 4, 2, 3, 1)    // three CTAs per SM
+        BV(6, 15, 32, 32, 1, 320, 4, 2, 3, 0)
+        BV(7, 24, 32, 32, 2, 1024, 4, 2, 1, 1)   // one CTA per SM, two-stage TMA pipeline
+        BV(8, 24, 32, 32, 2, 1024, 4, 2, 1, 0)
+        BV(9, 12, 32, 32, 2, 512, 4, 2, 2, 1)    // two CTAs per SM, each with a two-stage pipeline of 48 KB bricks
+        BV(10, 24, 32, 32, 1, 384, 5, 2, 2, 1)
         default: return cudaErrorInvalidValue;
     }
 #undef BV

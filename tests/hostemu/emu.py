@@ -280,3 +280,17 @@ def siddon_fwd_brick(vol, src, tgt, raylen, H, W, brick=(24, 32, 32), voxel_shif
               ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
               *map(ctypes.c_int, brick), ctypes.c_int(int(check)), _p(stats))
     return out, int(viol), dict(zip(("candidates", "maybe", "exact", "walked"), stats.tolist()))
+
+
+def siddon_fwd_brick2(vol, src, tgt, raylen, H, W, brick=(24, 32, 32), voxel_shift=0.5, eps=1e-8, check=False, lean=True):
+    """Production brick decomposition (outline-clipped tile bands; lean=True: set-up without fix-ups + accumulated alphas)."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    assert N == H * W
+    out = np.empty((B, 1, N), np.float32)
+    stats = np.zeros(4, np.int64)
+    fn = lib().emu_siddon_fwd_brick2
+    fn.restype = ctypes.c_long
+    viol = fn(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out), ctypes.c_int(B),
+              ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+              *map(ctypes.c_int, brick), ctypes.c_int(int(check)), ctypes.c_int(int(lean)), _p(stats))
+    return out, int(viol), dict(zip(("candidates", "maybe", "exact", "walked"), stats.tolist()))

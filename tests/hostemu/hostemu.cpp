@@ -641,6 +641,119 @@ long emu_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const float*
         for (int i = 0; i < 4; ++i) stats[i] = st[i];
     return violations;
 }
+
+// Production decomposition of siddon_brick.cu (second generation): per (brick, pose) the 4-row tile bands are clipped to
+// the projected outline (row_span), the per-pair walk is brick_pair_fwd_lean (no entry fix-ups, accumulated alphas).
+// Same return value / stats as emu_siddon_fwd_brick.
+long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                           float* out, int B, int H, int W, float shift, float eps, int BX, int BY, int BZ, int check, int lean,
+                           long* stats)
+{
+    const long N = (long)H * W;
+    std::vector<Ray> rays((size_t)B * N);
+    std::vector<PoseGeo> geo(B);
+    for (int b = 0; b < B; ++b) {
+        for (long n = 0; n < N; ++n) rays[(size_t)b * N + n] = load_ray(src, tgt, b, (long)b * N + n, eps);
+        const Ray& r00 = rays[(size_t)b * N];
+        const Ray& r0w = rays[(size_t)b * N + (W - 1)];
+        const Ray& rh0 = rays[(size_t)b * N + (long)(H - 1) * W];
+        float t00[3], t0w[3], th0[3];
+        for (int a = 0; a < 3; ++a) {
+            t00[a] = r00.s[a] + r00.d[a];
+            t0w[a] = r00.s[a] + r0w.d[a];
+            th0[a] = r00.s[a] + rh0.d[a];
+        }
+        geo[b] = make_pose_geo(r00.s, t00, t0w, th0, H, W);
+    }
+    std::fill(out, out + (size_t)B * N, 0.0f);
+    long violations = 0;
+    long st[4] = {0, 0, 0, 0};
+    std::vector<float> brick((size_t)BX * BY * BZ);
+    std::vector<char> cand((size_t)N);
+    const int nb0 = (D0 + BX - 1) / BX, nb1 = (D1 + BY - 1) / BY, nb2 = (D2 + BZ - 1) / BZ;
+    for (int i0 = 0; i0 < nb0; ++i0)
+        for (int i1 = 0; i1 < nb1; ++i1)
+            for (int i2 = 0; i2 < nb2; ++i2) {
+                const int org[3] = {i0 * BX, i1 * BY, i2 * BZ};
+                const int lo_v[3] = {org[0], org[1], org[2]};
+                const int hi_v[3] = {std::min(org[0] + BX, D0), std::min(org[1] + BY, D1), std::min(org[2] + BZ, D2)};
+                for (int x = 0; x < BX; ++x)
+                    for (int y = 0; y < BY; ++y)
+                        for (int z = 0; z < BZ; ++z) {
+                            const int g0 = org[0] + x, g1 = org[1] + y, g2 = org[2] + z;
+                            brick[((size_t)x * BY + y) * BZ + z] =
+                                (g0 < D0 && g1 < D1 && g2 < D2) ? vol[((size_t)g0 * D1 + g1) * D2 + g2] : 0.0f;
+                        }
+                LdHost ld{brick.data()};
+                for (int b = 0; b < B; ++b) {
+                    float uv[16], umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY, dmin = INFINITY,
+                                  dmax = -INFINITY;
+                    bool bad = false;
+                    for (int c = 0; c < 8; ++c) {
+                        const float X[3] = {(float)((c & 1) ? hi_v[0] : lo_v[0]) - shift, (float)((c & 2) ? hi_v[1] : lo_v[1]) - shift,
+                                            (float)((c & 4) ? hi_v[2] : lo_v[2]) - shift};
+                        float u, v, den;
+                        project_corner(geo[b], X, u, v, den);
+                        bad = bad || u != u || v != v || den != den;
+                        uv[2 * c] = u;
+                        uv[2 * c + 1] = v;
+                        umin = fminf(umin, u); umax = fmaxf(umax, u);
+                        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                        dmin = fminf(dmin, den); dmax = fmaxf(dmax, den);
+                    }
+                    if (bad) dmin = NAN;
+                    const PixRect rc = rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
+                    const bool ok = outline_valid(umin, umax, vmin, vmax, dmin, dmax);
+                    float clo[3], chi[3];
+                    for (int a = 0; a < 3; ++a) {
+                        clo[a] = ((float)lo_v[a] - shift) - geo[b].S[a];
+                        chi[a] = ((float)hi_v[a] - shift) - geo[b].S[a];
+                    }
+                    std::fill(cand.begin(), cand.end(), 0);
+                    if (rc.x0 <= rc.x1 && rc.y0 <= rc.y1) {
+                        const int th = (rc.y1 - rc.y0) / 4 + 1;
+                        for (int ty = 0; ty < th; ++ty) {
+                            const int py0 = rc.y0 + 4 * ty;
+                            int px_lo, px_hi;
+                            if (!row_span(uv, ok, rc, py0, px_lo, px_hi)) continue;
+                            const int cnt = (px_hi - px_lo) / 8 + 1;
+                            for (int t = 0; t < cnt; ++t)
+                                for (int lane = 0; lane < 32; ++lane) {
+                                    const int px = px_lo + 8 * t + (lane & 7), py = py0 + (lane >> 3);
+                                    if (px > px_hi || py > rc.y1) continue;
+                                    ++st[0];
+                                    cand[(size_t)py * W + px] = 1;
+                                    const long r = (long)b * N + (long)py * W + px;
+                                    const Ray& ray = rays[r];
+                                    float a_in, a_out;
+                                    if (!brick_maybe_hit(ray.inv, clo, chi, a_in, a_out)) continue;
+                                    ++st[1];
+                                    if (start_walk_box(ray, lo_v, hi_v, shift).hit) ++st[2];
+                                    const float part =
+                                        lean == 1 ? brick_pair_fwd_lean<4>(ld, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift)
+                                        : lean == 2 ? brick_pair_fwd_lean<4, LdHost, false>(ld, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift)
+                                             : brick_pair_fwd<4>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                                    if (part != 0.0f) {
+                                        ++st[3];
+                                        out[r] += raylen[r] * part;
+                                    }
+                                }
+                        }
+                    }
+                    if (check)
+                        for (int py = 0; py < H; ++py)
+                            for (int px = 0; px < W; ++px) {
+                                const Ray& ray = rays[(size_t)b * N + (long)py * W + px];
+                                float a_in, a_out;
+                                const bool maybe = brick_maybe_hit(ray.inv, clo, chi, a_in, a_out);
+                                if (start_walk_box(ray, lo_v, hi_v, shift).hit && (!cand[(size_t)py * W + px] || !maybe)) ++violations;
+                            }
+                }
+            }
+    if (stats)
+        for (int i = 0; i < 4; ++i) stats[i] = st[i];
+    return violations;
+}
 }  // extern "C"
 
 // ---- access-pattern analysis (tuning aid): distinct 32-byte sectors / 128-byte lines per warp-wide gather ----------
