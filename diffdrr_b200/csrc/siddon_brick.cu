@@ -583,8 +583,8 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>(map, dims, raytab, ltab, geo, out, counter, \
                                                                                    B, H, W, shift, stream);
     switch (variant) {
-        BV(0, 24, 32, 32, 1, 512, 4, 2, 2, 1)    // two CTAs per SM, one 96 KB brick each (production shape)
-        BV(1, 24, 32, 32, 1, 512, 4, 2, 2, 0)
+        BV(0, 24, 32, 32, 1, 512, 4, 2, 2, 0)    // two CTAs per SM, one 96 KB brick each (production shape)
+        BV(1, 24, 32, 32, 1, 512, 4, 2, 2, 1)    // ... with the software-pipelined walk
         BV(2, 24, 32, 32, 1, 512, 4, 4, 2, 1)
         BV(3, 24, 32, 32, 1, 512, 4, 4, 2, 0)
         BV(4, 22, 32, 32, 1, 512, 8, 2, 2, 1)    // bigger rounds (fewer barriers), slightly smaller brick

@@ -92,3 +92,15 @@ for v in variants:
         continue
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"brick variant {v:2d}        : {ms:8.3f} ms  {B / ms * 1e3:9.1f} DRR/s  {gbytes / ms * 1e3:8.1f} GB/s  {gbytes / ms * 1e3 / PEAK * 100:5.1f}% of HBM peak   maxdiff vs slab {err:.1e}", flush=True)
+
+# ---- batch sweep: where does the brick kernel overtake the slab-major one? (BSWEEP=1,2,4,8,32) -------------------------
+if os.environ.get("BSWEEP"):
+    for Bs in [int(x) for x in os.environ["BSWEEP"].split(",")]:
+        src, tgt, raylen = rays(dims, H, H, Bs)
+        ref = torch.empty(Bs, N, device=dev)
+        out = torch.zeros(Bs, N, device=dev)
+        ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(Bs, H, H), dtype=torch.uint8, device=dev)
+        t_slab = timeit(lambda: grid_call(vol, dims, src, tgt, raylen, ref, Bs, H, H))
+        t_brick = timeit(lambda: brick_call(vol, dims, src, tgt, raylen, out, ws, Bs, H, H, 0))
+        err = float((out - ref).abs().max() / ref.abs().max())
+        print(f"B={Bs:3d}: slab-major {t_slab:8.3f} ms ({Bs / t_slab * 1e3:8.1f} DRR/s)   brick {t_brick:8.3f} ms ({Bs / t_brick * 1e3:8.1f} DRR/s)   maxdiff {err:.1e}", flush=True)

@@ -1,0 +1,161 @@
+"""Direct oracle parity for the PRODUCTION kernels at the BASELINE.json configurations.
+
+Every test calls the C ABI entry point the product uses at that size -- the slab-major / brick-major Siddon kernels with
+more than one slab / many bricks, the packed-corner trilinear kernels -- and compares full images (and gradients) with the
+fp64 oracle on the same rays.  The oracle needs ~0.1-0.3 s per 512^3 -> 256^2 DRR on the GPU box's host cores."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from gpu_common import DEV
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4  # north_star: <= 1e-4 relative error
+
+
+def _setup(D, H, B, seed=0, kind="rand"):
+    from diffdrr_b200 import DRR, synthetic
+    from diffdrr_b200.pose import convert
+    vol_np = synthetic.make_volume(D, kind, seed=seed)
+    subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+    subj.volume.affine = synthetic.make_affine(D)
+    drr = DRR(subj, **synthetic.detector_kwargs(H)).to(DEV)
+    rot, xyz = synthetic.make_poses(max(B, 2), seed=seed)
+    rot, xyz = rot[:B], xyz[:B]
+    with torch.no_grad():
+        src, tgt = drr.detector(convert(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).reshape(B, -1).contiguous()
+        src = drr.affine_inverse(src).reshape(B, 3).contiguous()
+        tgt = drr.affine_inverse(tgt).contiguous()
+    vol = torch.as_tensor(vol_np).to(DEV)
+    return vol_np, vol, src, tgt, raylen
+
+
+def _np(*ts):
+    return [x.detach().cpu().numpy() for x in ts]
+
+
+def _p(x):
+    return None if x is None else ctypes.c_void_p(x.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _lib():
+    from diffdrr_b200 import _lib as L
+    return L, L.load()
+
+
+@pytest.mark.parametrize("D,H,B", [(512, 256, 2), (256, 256, 16)])
+def test_siddon_forward_grid_kernels_vs_oracle(D, H, B):
+    """b200drr_siddon_fwd_grid (slab-major: 11 slabs at 512^3) and b200drr_siddon_fwd_brick (TMA bricks: 22x16x16 of them),
+    full images of rotated poses, against the fp64 oracle: the metric's configuration and BASELINE config 2 (256^3, B=16)."""
+    from oracle import oracle
+    L, lib = _lib()
+    vol_np, vol, src, tgt, raylen = _setup(D, H, B)
+    ref = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64).reshape(B, -1)
+    out = torch.full((B, H * H), float("nan"), device=DEV)
+    L.check(lib.b200drr_siddon_fwd_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out), B, H, H, 0.5, 1e-8, 0,
+                                        _stream()), "fwd_grid")
+    assert relerr(out.cpu().numpy(), ref) < IMG_TOL
+    ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, H, H), dtype=torch.uint8, device=DEV)
+    out.fill_(float("nan"))
+    L.check(lib.b200drr_siddon_fwd_brick(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), None, None, None, None, _p(out),
+                                         ctypes.c_void_p(ws.data_ptr()), ws.numel(), B, H, H, 0.5, 1e-8, 0, _stream()),
+            "fwd_brick")
+    assert relerr(out.cpu().numpy(), ref) < IMG_TOL
+
+
+def test_brick_forward_pose_in_and_module_routing():
+    """The brick kernel with rays generated in-kernel from the pose matrices (the DRR module's default inference path for
+    batches) equals the ray-tensor entry; DRR(...) under no_grad at B >= 4 takes it and matches the oracle."""
+    from diffdrr_b200 import DRR, synthetic
+    from diffdrr_b200.pose import convert
+    from oracle import oracle
+    D, H, B = 256, 192, 5
+    vol_np = synthetic.make_volume(D, "rand", seed=2)
+    drr = DRR(synthetic.make_subject(vol_np), **synthetic.detector_kwargs(H)).to(DEV)
+    rot, xyz = synthetic.make_poses(B, seed=4)
+    with torch.no_grad():
+        img = drr(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY")
+        src, tgt = drr.detector(convert(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+        src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+    ref = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64)
+    assert relerr(img.cpu().numpy().reshape(ref.shape), ref) < IMG_TOL
+
+
+def test_siddon_sensitivities_and_volume_gradient_vs_oracle():
+    """b200drr_siddon_fwd_sens_grid + _bwd_sens (the training step's dominant kernel, 48-plane slabs) and b200drr_siddon_bwd_grid
+    WITH g_vol (reconstruction) at 512^3 -> 256^2, two rotated poses, against the fp64 closed form.  Smooth volume for the
+    end-point gradients (on noise the reference's own fp32 is 1e-2 off), noise for image / volume gradient."""
+    from oracle import oracle
+    L, lib = _lib()
+    D, H, B = 512, 256, 2
+    N = H * H
+    vol_np, vol, src, tgt, raylen = _setup(D, H, B, kind="smooth")
+    gout = torch.rand(B, N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    ref = oracle.siddon_bwd(vol_np, *_np(src, tgt, raylen, gout), dtype=np.float64, want_vol=True)
+    ref_img = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64).reshape(B, N)
+    out = torch.empty(B, N, device=DEV)
+    sens = torch.empty(B, N, 8, device=DEV)
+    L.check(lib.b200drr_siddon_fwd_sens_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out), _p(sens), B, H, H, 0.5,
+                                             1e-8, 0, _stream()), "fwd_sens_grid")
+    g_src, g_tgt, g_len = torch.empty(B, 3, device=DEV), torch.empty(B, N, 3, device=DEV), torch.empty(B, N, device=DEV)
+    L.check(lib.b200drr_siddon_bwd_sens(_p(sens), _p(gout), _p(g_src), _p(g_tgt), _p(g_len), B, N, 0, _stream()), "bwd_sens")
+    assert relerr(out.cpu().numpy(), ref_img) < IMG_TOL
+    assert relerr(g_tgt.cpu().numpy(), ref["g_target"]) < 2e-3
+    assert relerr(g_src.cpu().numpy(), ref["g_source"].reshape(B, 3)) < 2e-3
+    assert relerr(g_len.cpu().numpy(), ref["g_raylen"].reshape(B, N)) < IMG_TOL
+    # two-walk backward with the volume gradient
+    g_vol = torch.zeros_like(vol)
+    g_src2, g_tgt2, g_len2 = torch.empty_like(g_src), torch.empty_like(g_tgt), torch.empty_like(g_len)
+    L.check(lib.b200drr_siddon_bwd_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src2), _p(g_tgt2),
+                                        _p(g_len2), _p(g_vol), B, H, H, 0.5, 1e-8, 0, 0, _stream()), "bwd_grid")
+    assert relerr(g_vol.cpu().numpy(), ref["g_volume"]) < IMG_TOL
+    assert relerr(g_tgt2.cpu().numpy(), ref["g_target"]) < 2e-3
+    assert relerr(g_src2.cpu().numpy(), ref["g_source"].reshape(B, 3)) < 2e-3
+    assert relerr(g_len2.cpu().numpy(), ref["g_raylen"].reshape(B, N)) < IMG_TOL
+
+
+def test_trilinear_packed_kernels_vs_oracle_config3_shape():
+    """BASELINE config 3's shape (512^3 -> 512^2, n_points = 500) on 8 poses: the slab-major packed forward and the packed
+    forward-with-sensitivities + elementwise backward, against the fp64 oracle (image) and its closed-form gradients."""
+    from oracle import oracle
+    L, lib = _lib()
+    D, H, B, P = 512, 512, 8, 500
+    N = H * H
+    vol_np, vol, src, tgt, raylen = _setup(D, H, B, kind="smooth")
+    amin, amax = oracle.alpha_minmax(vol_np.shape, *_np(src, tgt), 0.5, 1e-8, np.float32)
+    arange = torch.tensor([amin, amax], dtype=torch.float32, device=DEV)
+    packed = torch.empty(int(lib.b200drr_packed_volume_floats(D, D, D)), device=DEV)
+    L.check(lib.b200drr_pack_corners(_p(vol), D, D, D, _p(packed), _stream()), "pack")
+    sub = slice(0, N, 61)  # oracle on ~4300 rays per pose spread over the detector (500 samples each)
+    args = (vol_np, src.cpu().numpy(), tgt[:, sub].cpu().numpy(), raylen[:, sub].cpu().numpy())
+    ref = oracle.trilinear_fwd(*args, n_points=P, alphamin=amin, alphamax=amax, dtype=np.float64).reshape(B, -1)
+    out = torch.full((B, N), float("nan"), device=DEV)
+    L.check(lib.b200drr_trilinear_fwd_packed(_p(packed), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out), B, H, H, 0.5, 1e-8, P,
+                                             _p(arange), 16, _stream()), "fwd_packed slab")
+    assert relerr(out[:, sub].cpu().numpy(), ref) < IMG_TOL
+    sens = torch.empty(B, N, 12, device=DEV)
+    out2 = torch.full((B, N), float("nan"), device=DEV)
+    L.check(lib.b200drr_trilinear_fwd_sens_packed(_p(packed), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out2), _p(sens), B, H, H,
+                                                  0.5, 1e-8, P, _p(arange), 0, _stream()), "fwd_sens_packed")
+    assert relerr(out2[:, sub].cpu().numpy(), ref) < IMG_TOL
+    gout = torch.zeros(B, N, device=DEV)
+    gout[:, sub] = torch.rand(B, ref.shape[1], device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    g_src, g_tgt, g_len = torch.empty(B, 3, device=DEV), torch.empty(B, N, 3, device=DEV), torch.empty(B, N, device=DEV)
+    g_ar = torch.zeros(2, device=DEV)
+    L.check(lib.b200drr_trilinear_bwd_sens(_p(sens), _p(gout), _p(g_src), _p(g_tgt), _p(g_len), _p(g_ar), B, N, _stream()),
+            "tri bwd_sens")
+    gref = oracle.trilinear_bwd(*args, gout[:, sub].cpu().numpy(), n_points=P, alphamin=amin, alphamax=amax, dtype=np.float64,
+                                want_vol=False)
+    assert relerr(g_tgt[:, sub].cpu().numpy(), gref["g_target"]) < 2e-3
+    assert relerr(g_src.cpu().numpy(), gref["g_source"].reshape(B, 3)) < 2e-3
+    assert relerr(g_len[:, sub].cpu().numpy(), gref["g_raylen"].reshape(B, -1)) < IMG_TOL
