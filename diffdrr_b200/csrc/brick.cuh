@@ -269,9 +269,9 @@ B200_HD float brick_pair_fwd(const Ld& ld, const Ray& ray, const int lo_v[3], co
 
 
 // ---- lean per-pair path (production): set-up without the entry-voxel fix-ups, accumulated crossing alphas ---------------
-// The forward sum does not need start_walk_box's consistency fix-ups (they make the start voxel agree with the ORDER of
-// crossing alphas that sit within round-off of the entry alpha -- required by the backward pass, where a swapped pair
-// moves a crossing coefficient between axes; in the forward sum it only re-attributes a segment of round-off length).
+// A slimmer set-up than start_walk_box: the start voxel is floor(position), corrected by at most one step so that it
+// agrees with the order of the crossing alphas (see below); ties within one ulp of alpha may fall either way -- that only
+// re-attributes a segment of ~1e-7 in alpha in the forward sum (the backward pass needs start_walk_frame's exact order).
 // Crossing alphas are accumulated with ROUND-UP additions (an = add.rp(an, |1/d|)) from an anchor that is exact per
 // brick, and the stop alpha is the exit plane's alpha ROUNDED DOWN (fma.rm): by induction the accumulated alpha of the
 // exit plane can never fall below it, so the walk never steps out of the staged brick and no tolerance window is needed.
@@ -345,6 +345,9 @@ B200_HD float acc_step(AccState& s, const AccConst& k)
     return len;
 }
 
+#if !defined(__CUDACC__)
+static float g_emu_rcp_perturb = 0.0f;  // host emulation only
+#endif
 B200_HD float approx_rcp(float x)
 {
 #if defined(__CUDA_ARCH__)
@@ -352,7 +355,7 @@ B200_HD float approx_rcp(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 #else
-    return 1.0f / x;
+    return (1.0f / x) * (1.0f + g_emu_rcp_perturb);  // tests can model the 1-ulp error of MUFU.RCP
 #endif
 }
 
@@ -386,9 +389,18 @@ B200_HD float brick_pair_fwd_lean(const Ld& ld, const float s[3], const float in
         int i = (int)floorf(fmaf(a_in, approx_rcp(inv[a]), s[a] + shift));
         i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
         i = (lo[a] >= a_in) ? (fwd ? lo_i : hi_i) : i;  // entering through a face of this axis
-        const float p0 = (float)(fwd ? i + 1 : i);
+        float p0 = (float)(fwd ? i + 1 : i);
         da[a] = fabsf(inv[a]);
         an[a] = ((p0 - shift) - s[a]) * inv[a];
+        // Make the start voxel agree with the ORDER of the alphas: the floor() above sees the position to ~1e-4 voxel,
+        // which for a ray nearly parallel to this axis' planes (|d_a| << 1) is a long stretch of alpha (round-off / |d_a|).
+        // One step forward if the plane "ahead" is already behind a_in, one step back if the plane behind is not.
+        const bool ahead = (an[a] < a_in) && (fwd ? i < hi_i : i > lo_i);
+        const bool back = !ahead && (an[a] - da[a] >= a_in) && (fwd ? i > lo_i : i < hi_i);
+        const int dstep = ahead ? 1 : (back ? -1 : 0);  // along the direction of travel
+        i += fwd ? dstep : -dstep;
+        p0 += (float)(fwd ? dstep : -dstep);
+        an[a] = dstep == 0 ? an[a] : ((p0 - shift) - s[a]) * inv[a];
         const float nx = fwd ? (float)hi_v[a] - p0 : p0 - (float)lo_v[a];
         nxc[a] = nx;
         a_out = fminf(a_out, fmaf(nx, da[a], an[a]));

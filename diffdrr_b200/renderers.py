@@ -61,13 +61,19 @@ def _stream():
 # set-up only pays off once a few poses share each staged brick, hence the batch threshold (B200DRR_BRICK_MIN_BATCH).
 import os as _os
 
-_BRICK_MIN_BATCH = int(_os.environ.get("B200DRR_BRICK_MIN_BATCH", "4"))
+_BRICK_MIN_BATCH = int(_os.environ.get("B200DRR_BRICK_MIN_BATCH", "2"))  # measured cross-over at 512^3 -> 256^2: B = 2
 _brick_ws: dict = {}
 
 
+_BRICK_MIN_BRICKS = int(_os.environ.get("B200DRR_BRICK_MIN_BRICKS", "2048"))
+
+
 def _brick_ok(vol, B, H, W) -> bool:
-    return (B >= _BRICK_MIN_BATCH and vol.shape[2] % 4 == 0 and 2 <= H <= 2048 and 2 <= W <= 2048 and B * H * W < 2**31
-            and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
+    # 24 x 32 x 32-voxel bricks over 2 x 148 resident CTAs: below ~7 bricks per CTA the tail of the dynamic brick queue
+    # costs more than the staging returns (256^3 = 704 bricks: 0.66 ms vs 0.48 ms slab-major; 512^3 = 5632 bricks: 1.04 vs 1.13)
+    n_bricks = -(-vol.shape[0] // 24) * -(-vol.shape[1] // 32) * -(-vol.shape[2] // 32)
+    return (B >= _BRICK_MIN_BATCH and n_bricks >= _BRICK_MIN_BRICKS and vol.shape[2] % 4 == 0 and 2 <= H <= 2048
+            and 2 <= W <= 2048 and B * H * W < 2**31 and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
 
 
 def _brick_workspace(device, B, H, W):

@@ -642,6 +642,8 @@ long emu_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const float*
     return violations;
 }
 
+void emu_set_rcp_perturb(float p) { g_emu_rcp_perturb = p; }
+
 // Production decomposition of siddon_brick.cu (second generation): per (brick, pose) the 4-row tile bands are clipped to
 // the projected outline (row_span), the per-pair walk is brick_pair_fwd_lean (no entry fix-ups, accumulated alphas).
 // Same return value / stats as emu_siddon_fwd_brick.
@@ -753,6 +755,50 @@ long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float
     if (stats)
         for (int i = 0; i < 4; ++i) stats[i] = st[i];
     return violations;
+}
+
+// Debug: per-brick partial sums of ONE ray through the exact and the lean pair paths (bricks in linear order).
+long emu_brick_ray_debug(const float* vol, int D0, int D1, int D2, const float* src3, const float* tgt3, float shift, float eps,
+                         int BX, int BY, int BZ, float* part_full, float* part_lean, int* brick_ids, int max_out)
+{
+    Ray ray;
+    for (int a = 0; a < 3; ++a) {
+        ray.s[a] = src3[a];
+        ray.d[a] = (tgt3[a] - src3[a]) + eps;
+        ray.inv[a] = 1.0f / ray.d[a];
+    }
+    std::vector<float> brick((size_t)BX * BY * BZ);
+    const int nb0 = (D0 + BX - 1) / BX, nb1 = (D1 + BY - 1) / BY, nb2 = (D2 + BZ - 1) / BZ;
+    long n = 0;
+    for (int i0 = 0; i0 < nb0; ++i0)
+        for (int i1 = 0; i1 < nb1; ++i1)
+            for (int i2 = 0; i2 < nb2; ++i2) {
+                const int org[3] = {i0 * BX, i1 * BY, i2 * BZ};
+                const int lo_v[3] = {org[0], org[1], org[2]};
+                const int hi_v[3] = {std::min(org[0] + BX, D0), std::min(org[1] + BY, D1), std::min(org[2] + BZ, D2)};
+                float clo[3], chi[3];
+                for (int a = 0; a < 3; ++a) {
+                    clo[a] = ((float)lo_v[a] - shift) - ray.s[a];
+                    chi[a] = ((float)hi_v[a] - shift) - ray.s[a];
+                }
+                float a_in, a_out;
+                if (!brick_maybe_hit(ray.inv, clo, chi, a_in, a_out)) continue;
+                for (int x = 0; x < BX; ++x)
+                    for (int y = 0; y < BY; ++y)
+                        for (int z = 0; z < BZ; ++z) {
+                            const int g0 = org[0] + x, g1 = org[1] + y, g2 = org[2] + z;
+                            brick[((size_t)x * BY + y) * BZ + z] =
+                                (g0 < D0 && g1 < D1 && g2 < D2) ? vol[((size_t)g0 * D1 + g1) * D2 + g2] : 0.0f;
+                        }
+                LdHost ld{brick.data()};
+                if (n < max_out) {
+                    part_full[n] = brick_pair_fwd<4>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                    part_lean[n] = brick_pair_fwd_lean<4, LdHost, false>(ld, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                    brick_ids[n] = (i0 * nb1 + i1) * nb2 + i2;
+                }
+                ++n;
+            }
+    return n;
 }
 }  // extern "C"
 

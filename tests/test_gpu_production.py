@@ -52,7 +52,7 @@ def _lib():
     return L, L.load()
 
 
-@pytest.mark.parametrize("D,H,B", [(512, 256, 2), (256, 256, 16)])
+@pytest.mark.parametrize("D,H,B", [(512, 256, 8), (256, 256, 16)])
 def test_siddon_forward_grid_kernels_vs_oracle(D, H, B):
     """b200drr_siddon_fwd_grid (slab-major: 11 slabs at 512^3) and b200drr_siddon_fwd_brick (TMA bricks: 22x16x16 of them),
     full images of rotated poses, against the fp64 oracle: the metric's configuration and BASELINE config 2 (256^3, B=16)."""
@@ -72,12 +72,13 @@ def test_siddon_forward_grid_kernels_vs_oracle(D, H, B):
     assert relerr(out.cpu().numpy(), ref) < IMG_TOL
 
 
-def test_brick_forward_pose_in_and_module_routing():
+def test_brick_forward_pose_in_and_module_routing(monkeypatch):
     """The brick kernel with rays generated in-kernel from the pose matrices (the DRR module's default inference path for
     batches) equals the ray-tensor entry; DRR(...) under no_grad at B >= 4 takes it and matches the oracle."""
-    from diffdrr_b200 import DRR, synthetic
+    from diffdrr_b200 import DRR, renderers, synthetic
     from diffdrr_b200.pose import convert
     from oracle import oracle
+    monkeypatch.setattr(renderers, "_BRICK_MIN_BRICKS", 1)   # 256^3 is below the production threshold: force the brick path
     D, H, B = 256, 192, 5
     vol_np = synthetic.make_volume(D, "rand", seed=2)
     drr = DRR(synthetic.make_subject(vol_np), **synthetic.detector_kwargs(H)).to(DEV)

@@ -494,7 +494,7 @@ def test_property_random_geometry_trilinear_march():
     check()
 
 
-def _grid_rays(D, H, B, seed, xyz_override=None):
+def _grid_rays(D, H, B, seed, xyz_override=None, rot_zero=False):
     import sys
     sys.path.insert(0, ROOT)
     import torch
@@ -507,6 +507,8 @@ def _grid_rays(D, H, B, seed, xyz_override=None):
     rot, xyz = rot[:B], xyz[:B]
     if xyz_override is not None:
         xyz = torch.tensor([xyz_override] * B, dtype=torch.float32)
+    if rot_zero:
+        rot = torch.zeros_like(rot)
     with torch.no_grad():
         src, tgt = drr.detector(convert(rot, xyz, parameterization="euler_angles", convention="ZXY"), None)
         raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
@@ -520,6 +522,10 @@ def _grid_rays(D, H, B, seed, xyz_override=None):
     ((80, 88, 68), 40, 2, (12, 16, 8), None),
     ((64, 64, 64), 40, 2, (24, 32, 32), (0.0, 60.0, 0.0)),     # source INSIDE the volume (quirk Q1): bricks on both sides
     ((64, 64, 64), 24, 2, (16, 16, 16), (20.0, 140.0, -15.0)),  # source just outside: some bricks straddle its plane
+    # un-rotated view: the central columns / rows run (nearly) parallel to two families of voxel planes, where the
+    # round-off of a POSITION is a long stretch of alpha (found on B200: one pixel off by 1.5e-4 before the
+    # alpha-order correction of the lean set-up)
+    ((64, 64, 64), 48, 1, (8, 16, 16), (0.37, 850.0, -0.21, "rot0")),
 ])
 def test_brick_major_decomposition(dims, H, B, brick, xyz):
     """siddon_brick.cu's decomposition on the CPU: per (brick, pose) pixel rectangle from the projected corners, 4-row tile
@@ -528,7 +534,8 @@ def test_brick_major_decomposition(dims, H, B, brick, xyz):
     exact-alpha and the production (lean set-up, pair-local accumulated alphas) walks must match the fp64 oracle."""
     from diffdrr_b200 import synthetic
     vol = synthetic.make_volume(dims, "rand", seed=1)
-    src, tgt, raylen = _grid_rays(max(dims), H, B, seed=2, xyz_override=xyz)
+    rot_zero = xyz is not None and len(xyz) == 4
+    src, tgt, raylen = _grid_rays(max(dims), H, B, seed=2, xyz_override=None if xyz is None else xyz[:3], rot_zero=rot_zero)
     ref = oracle.siddon_fwd(vol, src, tgt, raylen, dtype=np.float64)
     out, viol, st = emu.siddon_fwd_brick(vol, src, tgt, raylen, H, H, brick=brick, check=True)
     assert viol == 0 and st["walked"] > 0
