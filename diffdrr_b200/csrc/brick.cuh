@@ -354,6 +354,8 @@ B200_HD float approx_rcp(float x)
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#elif defined(__CUDACC__)
+    return 1.0f / x;
 #else
     return (1.0f / x) * (1.0f + g_emu_rcp_perturb);  // tests can model the 1-ulp error of MUFU.RCP
 #endif
