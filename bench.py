@@ -46,6 +46,8 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the default workload
 # (16 poses, 512^3 -> 256^2): profiles/r01_fwd_slab_B16_ncu_summary.txt and gpurun capture of the backward kernel.
 # Only quoted when the run uses that workload; otherwise null.
+NCU_TRAFFIC_SOURCE = ("not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
+                      "the same command (profiles/r01_siddon_ncu_summary.txt, captured 2026-09-24); null off the default workload")
 NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9,
                      "siddon_sens_slab_kernel": 1.38e9 + 0.14e9}
 
@@ -61,6 +63,7 @@ def parse():
     ap.add_argument("--det", type=int, default=DET)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="report the eager end-to-end step only")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configs / reference-on-GPU legs")
     return ap.parse_args()
 
 
@@ -135,6 +138,38 @@ def make_host_rays(vol_n, det_n, batch, seed):
     return src.numpy(), tgt.numpy(), raylen.numpy()
 
 
+def host_threads() -> int:
+    """All host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    return os.cpu_count() or 1
+
+
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def load_reference():
+    """The UNMODIFIED reference renderers (pip-installed into baseline/_ref, git-ignored, travels with the snapshot).
+    diffdrr/renderers.py imports only torch; returns None when the install is absent (the port is timed instead)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "diffdrr")):
+        return None
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_ref_diffdrr_renderers", os.path.join(ref_dir, "diffdrr", "renderers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except Exception:
+        return None
+    return mod
+
+
 def cpu_oracle_time(vol_n, det_n, n_drr, repeats, threads):
     """Seconds per fwd+bwd DRR of the C oracle (reference algorithm: all planes merged/sorted per ray, fp32)."""
     from diffdrr_b200 import synthetic
@@ -154,26 +189,94 @@ def cpu_oracle_time(vol_n, det_n, n_drr, repeats, threads):
     return times
 
 
+class ReferenceRun:
+    """reference renderers.py:34-91 (`Siddon.forward`, unmodified) + autograd w.r.t. the ray end points, on a sample of the
+    workload's rays: one pose of the synthetic batch, `n_rays` detector pixels spread evenly over the detector."""
+
+    def __init__(self, ref_mod, vol_n, det_n, device="cpu"):
+        from diffdrr_b200 import synthetic
+
+        self.device = torch.device(device)
+        self.siddon = ref_mod.Siddon().to(self.device)
+        self.vol = torch.as_tensor(synthetic.make_volume(vol_n, "rand", seed=0)).to(self.device)
+        src, tgt, raylen = make_host_rays(vol_n, det_n, 2, seed=0)
+        self.src, self.tgt, self.raylen = (torch.as_tensor(x[:1]).to(self.device) for x in (src, tgt, raylen))
+        self.n_total = self.tgt.shape[1]
+
+    def step(self, n_rays, img_out=None):
+        sel = torch.linspace(0, self.n_total - 1, n_rays, device=self.device).long()
+        src = self.src.clone().requires_grad_(True)
+        tgt = self.tgt[:, sel].clone().requires_grad_(True)
+        raylen = self.raylen[:, :, sel]
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        img = self.siddon(self.vol, src, tgt, raylen)
+        img.sum().backward()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert torch.isfinite(tgt.grad).all()
+        if img_out is not None:
+            img_out.append((sel.cpu().numpy(), img.detach().cpu().numpy()))
+        return dt
+
+
+def cpu_reference_sample(vol_n, det_n, budget_s, min_runs=5):
+    """Times the unmodified reference on the host cores within ~budget_s seconds.  Returns None without baseline/_ref."""
+    ref_mod = load_reference()
+    if ref_mod is None:
+        return None
+    torch.set_num_threads(host_threads())
+    run = ReferenceRun(ref_mod, vol_n, det_n)
+    n_rays = 2048
+    t = run.step(n_rays)                      # warm-up + calibration
+    per_ray = run.step(n_rays) / n_rays
+    n_rays = int(min(run.n_total, max(2048, budget_s / (min_runs + 1) / per_ray)))
+    times = [run.step(n_rays) for _ in range(min_runs)]
+    return {"n_rays": n_rays, "times": times, "n_total": run.n_total, "warmup_s": t}
+
+
 def run_reference(args, rank, world):
-    """`--impl reference`: the CPU port of the reference's algorithm on the host cores (rank 0 only)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores (rank 0 only): the
+    UNMODIFIED diffdrr.renderers.Siddon from baseline/_ref (forward + autograd to the ray end points) when that install
+    is present, else the C/OpenMP port of the same algorithm (oracle/).  Each step is a bounded sample of the workload."""
     if rank != 0:
         return
-    from oracle import oracle
+    threads = host_threads()
+    ref_mod = load_reference()
+    if ref_mod is not None:
+        torch.set_num_threads(threads)
+        run = ReferenceRun(ref_mod, args.vol, args.det)
+        run.step(1024)
+        per_ray = run.step(2048) / 2048
+        # ~3 s of CPU work per step, at most one full DRR
+        n_rays = int(min(run.n_total, max(1024, 3.0 / per_ray)))
+        for _ in range(args.warmup):
+            run.step(n_rays)
+        times = [run.step(n_rays) for _ in range(args.steps)]
+        frac = n_rays / run.n_total
+        kind, what = "reference", (f"unmodified diffdrr.renderers.Siddon.forward + backward (torch {torch.__version__}, "
+                                   f"{threads} threads, {cpu_model()})")
+        sample = f"{n_rays} of the {run.n_total} rays of one pose ({frac:.3f} DRR) fwd+bwd per step"
+    else:
+        from oracle import oracle  # noqa: F401
 
-    threads = oracle.max_threads()
-    n_drr = 1
-    times = cpu_oracle_time(args.vol, args.det, n_drr, args.warmup + args.steps, threads)[args.warmup:]
+        times = cpu_oracle_time(args.vol, args.det, 1, args.warmup + args.steps, threads)[args.warmup:]
+        frac, kind, what = 1.0, "port", "C/OpenMP port of reference renderers.py (oracle/); baseline/_ref is absent"
+        sample = "1 DRR (pose) fwd+bwd per step"
     sec = float(np.sum(times))
-    value = n_drr * len(times) / sec
+    value = frac * len(times) / sec
+    med = float(np.median(times))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "DRRs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "volume": [args.vol] * 3, "detector": [args.det] * 2,
-                   "sample": f"{n_drr} DRR (pose) fwd+bwd per step", "renderer": "siddon"},
-        "cpu_baseline": {"value": value, "unit": "DRRs/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_drr} DRR fwd+bwd(pose) of the {args.vol}^3->{args.det}^2 workload per step, "
-                                   f"{len(times)} steps, C/OpenMP port of reference renderers.py (oracle/)"},
+        "config": {"workload": WORKLOAD, "volume": [args.vol] * 3, "detector": [args.det] * 2, "sample": sample,
+                   "renderer": "siddon"},
+        "cpu_baseline": {"value": value, "unit": "DRRs/s", "cores": threads, "kind": kind, "cpu": cpu_model(),
+                         "sample": f"{sample}, {len(times)} steps; {what}",
+                         "median_value": frac / med, "min_step_s": float(np.min(times)), "median_step_s": med},
         "e2e": {"value": value, "unit": "DRRs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,6 +286,227 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+def _time_events(fn, steps, warmup=2):
+    """Per-launch CUDA-event times (ms) of fn on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def _stat(ms_list):
+    return {"mean_ms": float(np.mean(ms_list)), "median_ms": float(np.median(ms_list)), "min_ms": float(np.min(ms_list))}
+
+
+def _device_rays(drr, rot, xyz, dev):
+    from diffdrr_b200.pose import convert
+
+    B = rot.shape[0]
+    with torch.no_grad():
+        src, tgt = drr.detector(convert(rot.to(dev), xyz.to(dev), parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).reshape(B, -1).contiguous()
+        src = drr.affine_inverse(src).reshape(B, 3).contiguous()
+        tgt = drr.affine_inverse(tgt).contiguous()
+    return src, tgt, raylen
+
+
+def extra_configs(dev, lib, peak, main):
+    """Secondary, driver-visible numbers: the north star's inference forward (slab-major and brick-major
+    TMA kernels), the reconstruction backward WITH the volume gradient, BASELINE config 2 (256^3 -> 256^2, B = 16, Siddon
+    forward), config 3 (512^3 -> 512^2, B = 64, trilinear fwd+bwd(pose), 500 points) and config 5 (registration loop,
+    1000 steps).  Every entry: CUDA-event times (mean / median / min) and the roofline fraction on ALGORITHMIC bytes."""
+    from diffdrr_b200 import DRR, NormalizedCrossCorrelation2d, Registration, _lib, synthetic
+    from diffdrr_b200.renderers import _get_alpha_minmax, _ptr, _stream, siddon_visits
+
+    res = {}
+    vol, src, tgt, raylen, gout = main["vol"], main["src"], main["tgt"], main["raylen"], main["gout"]
+    B, D, det, N = main["B"], main["D"], main["det"], main["det"] ** 2
+    tot_visits = main["tot_visits"]
+    out = torch.empty(B, N, device=dev)
+
+    def roof(bytes_, ms):
+        gbs = bytes_ / (ms * 1e-3) / 1e9
+        return {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes_per_launch": bytes_}
+
+    # ---- (a) north-star metric: Siddon FORWARD 512^3 -> 256^2, both production kernels ------------------------------
+    fwd_bytes = 4 * tot_visits + 20 * B * N
+    t_slab = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                                         _ptr(out), B, det, det, 0.5, 1e-8, 0, _stream()), "fwd_grid"), 10)
+    ref_img = out.clone()
+    entry = {"workload": f"siddon forward, {D}^3 -> {det}^2, {B} poses", "slab_major": {**_stat(t_slab), "drr_per_s": B / np.median(t_slab) * 1e3,
+                                                                                      "roofline": roof(fwd_bytes, float(np.median(t_slab)))}}
+    try:
+        ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, det, det), dtype=torch.uint8, device=dev)
+        t_brick = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_brick(
+            _ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), None, None, None, None, _ptr(out), _ptr(ws), ws.numel(), B, det,
+            det, 0.5, 1e-8, 0, _stream()), "fwd_brick"), 10)
+        entry["brick_major_tma"] = {**_stat(t_brick), "drr_per_s": B / np.median(t_brick) * 1e3,
+                                    "roofline": roof(fwd_bytes, float(np.median(t_brick))),
+                                    "maxdiff_vs_slab_major": float((out - ref_img).abs().max() / ref_img.abs().max()),
+                                    "note": "ray table + zero fill (brick_prep_kernel) included in the time"}
+        main["brick_img0"] = out[0].clone()
+    except Exception as exc:  # pragma: no cover
+        entry["brick_major_tma"] = {"error": f"{type(exc).__name__}: {exc}"}
+    res["siddon_forward_inference"] = entry
+
+    # ---- (b) reconstruction backward: two-walk backward WITH the volume gradient -----------------------------------
+    g_src, g_tgt, g_len = torch.empty(B, 3, device=dev), torch.empty(B, N, 3, device=dev), torch.empty(B, N, device=dev)
+    g_vol = torch.zeros_like(vol)
+    t_gv = _time_events(lambda: _lib.check(lib.b200drr_siddon_bwd_grid(
+        _ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, det,
+        det, 0.5, 1e-8, 0, 0, _stream()), "bwd_grid"), 5)
+    gv_bytes = 12 * tot_visits + 36 * B * N   # voxel read + 8 B read-modify-write of g_vol per visit + per-ray I/O
+    res["siddon_backward_with_volume_gradient"] = {
+        "workload": f"siddon backward incl. g_vol (reconstruction), {D}^3 -> {det}^2, {B} poses", **_stat(t_gv),
+        "drr_per_s": B / np.median(t_gv) * 1e3, "roofline": roof(gv_bytes, float(np.median(t_gv)))}
+    del g_vol
+
+    # ---- (c) BASELINE config 2: 256^3 -> 256^2, batch 16, Siddon forward ----------------------------------------------
+    D2, B2 = 256, 16
+    vol2 = torch.rand(D2, D2, D2, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+    subj.volume.affine = synthetic.make_affine(D2)
+    drr2 = DRR(subj, **synthetic.detector_kwargs(256)).to(dev)
+    rot, xyz = synthetic.make_poses(B2, seed=0)
+    s2, t2, l2 = _device_rays(drr2, rot, xyz, dev)
+    v2 = int(siddon_visits((D2, D2, D2), s2, t2).sum())
+    o2 = torch.empty(B2, 256 * 256, device=dev)
+    t_c2 = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol2), D2, D2, D2, _ptr(s2), _ptr(t2), _ptr(l2), _ptr(o2),
+                                                                       B2, 256, 256, 0.5, 1e-8, 0, _stream()), "fwd_grid c2"), 10)
+    res["config2_siddon_forward_256"] = {"workload": "BASELINE config 2: 256^3 -> 256^2, 16 poses, Siddon forward (slab-major kernel)",
+                                         **_stat(t_c2), "drr_per_s": B2 / np.median(t_c2) * 1e3,
+                                         "roofline": roof(4 * v2 + 20 * B2 * 256 * 256, float(np.median(t_c2)))}
+    del vol2, o2
+
+    # ---- (d) BASELINE config 3: 512^3 -> 512^2, batch 64, trilinear fwd+bwd(pose), 500 points -------------------------
+    try:
+        H3, B3, P3 = 512, 64, 500
+        N3 = H3 * H3
+        subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+        subj.volume.affine = synthetic.make_affine(D)
+        drr3 = DRR(subj, **synthetic.detector_kwargs(H3)).to(dev)
+        rot, xyz = synthetic.make_poses(B3, seed=0)
+        s3, t3, l3 = _device_rays(drr3, rot, xyz, dev)
+        with torch.no_grad():
+            amin, amax = _get_alpha_minmax(s3.reshape(B3, 1, 3), t3, torch.tensor([D, D, D], device=dev, dtype=torch.float32), 0.5, 1e-8)
+            ar = torch.stack([amin.min(), amax.max()]).contiguous()
+            lin = torch.linspace(0, 1, P3, device=dev) * (ar[1] - ar[0]) + ar[0]
+            cnt = 0
+            for b in range(0, B3, 8):   # in-volume samples of every 8th pose (>= 1 corner in bounds), scaled up
+                for c in range(0, N3, 65536):
+                    pts = s3[b][None, None, :] + lin[None, :, None] * (t3[b, c:c + 65536][:, None, :] - s3[b][None, None, :])
+                    cnt += int(((pts > -1) & (pts < D)).all(-1).sum())
+            cnt *= 8
+        packed = torch.empty(int(lib.b200drr_packed_volume_floats(D, D, D)), device=dev)
+        _lib.check(lib.b200drr_pack_corners(_ptr(vol), D, D, D, _ptr(packed), _stream()), "pack")
+        o3, sens3 = torch.empty(B3, N3, device=dev), torch.empty(B3, N3, 12, device=dev)
+        go3 = torch.rand(B3, N3, device=dev)
+        h_src, h_tgt, h_len, h_ar = torch.empty(B3, 3, device=dev), torch.empty(B3, N3, 3, device=dev), torch.empty(B3, N3, device=dev), torch.zeros(2, device=dev)
+
+        def tri_step():
+            _lib.check(lib.b200drr_trilinear_fwd_sens_packed(_ptr(packed), D, D, D, _ptr(s3), _ptr(t3), _ptr(l3), _ptr(o3), _ptr(sens3), B3,
+                                                             H3, H3, 0.5, 1e-8, P3, _ptr(ar), 0, _stream()), "tri fwd_sens")
+            _lib.check(lib.b200drr_trilinear_bwd_sens(_ptr(sens3), _ptr(go3), _ptr(h_src), _ptr(h_tgt), _ptr(h_len), _ptr(h_ar), B3, N3,
+                                                      _stream()), "tri bwd_sens")
+
+        t_c3 = _time_events(tri_step, 5, warmup=1)
+        t_c3f = _time_events(lambda: _lib.check(lib.b200drr_trilinear_fwd_packed(
+            _ptr(packed), D, D, D, _ptr(s3), _ptr(t3), _ptr(l3), _ptr(o3), B3, H3, H3, 0.5, 1e-8, P3, _ptr(ar), 16, _stream()), "tri fwd"), 3, warmup=1)
+        tri_bytes = 32 * cnt
+        res["config3_trilinear_fwd_bwd_512"] = {
+            "workload": "BASELINE config 3: 512^3 -> 512^2, 64 poses, trilinear (500 points) forward + backward (pose gradients); "
+                        "one march yields image + sensitivities, backward elementwise",
+            **_stat(t_c3), "drr_per_s": B3 / np.median(t_c3) * 1e3, "in_volume_sample_fraction": cnt / (B3 * N3 * P3),
+            "roofline": roof(tri_bytes, float(np.median(t_c3))),
+            "forward_only_slab_major": {**_stat(t_c3f), "drr_per_s": B3 / np.median(t_c3f) * 1e3, "roofline": roof(tri_bytes, float(np.median(t_c3f)))}}
+        del packed, sens3, h_tgt, o3, go3
+    except Exception as exc:  # pragma: no cover
+        res["config3_trilinear_fwd_bwd_512"] = {"error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.empty_cache()
+
+    # ---- (e) BASELINE config 5: 2D/3D registration loop, 1000 gradient steps, 512^3 CT, 256^2 target -------------------
+    try:
+        x = torch.linspace(-1, 1, D, device=dev)
+        X, Y, Z = x[:, None, None], x[None, :, None], x[None, None, :]
+        smooth = torch.exp(-((X - 0.2) ** 2 + (Y + 0.1) ** 2 + (Z - 0.05) ** 2) / 0.18)
+        smooth += 0.6 * torch.exp(-((X + 0.35) ** 2 + (Y - 0.3) ** 2 + (Z + 0.25) ** 2) / 0.05)
+        subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+        subj.volume.affine = synthetic.make_affine(D)
+        drr5 = DRR(subj, **synthetic.detector_kwargs(256), renderer="siddon", stop_gradients_through_grid_sample=True).to(dev)
+        drr5.density = smooth.contiguous()
+        true_rot, true_xyz = torch.tensor([[0.0, 0.0, 0.0]], device=dev), torch.tensor([[0.0, 850.0, 0.0]], device=dev)
+        with torch.no_grad():
+            target = drr5(true_rot, true_xyz, parameterization="euler_angles", convention="ZXY")
+        reg = Registration(drr5, (true_rot + torch.tensor([[0.15, -0.1, 0.08]], device=dev)).clone(),
+                           (true_xyz + torch.tensor([[12.0, -25.0, 9.0]], device=dev)).clone(), "euler_angles", "ZXY").to(dev)
+        ncc = NormalizedCrossCorrelation2d()
+        opt = torch.optim.Adam([{"params": [reg.rotation], "lr": 5e-3}, {"params": [reg.translation], "lr": 5e-1}], capturable=True)
+
+        def reg_step():
+            opt.zero_grad(set_to_none=False)
+            loss = 1.0 - ncc(target, reg()).mean()
+            loss.backward()
+            opt.step()
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(5):
+                reg_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            reg_step()
+        n_it = 1000
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_it):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        with torch.no_grad():
+            final = float(1.0 - ncc(target, reg()).mean())
+        res["config5_registration_loop"] = {
+            "workload": "BASELINE config 5: 1000 gradient steps (Adam, NCC), 512^3 CT, 256^2 target DRR, B = 1, whole step in one CUDA graph",
+            "it_per_s": n_it / (ms * 1e-3), "ms_per_it": ms / n_it, "final_1_minus_ncc": final,
+            "rot_err_rad": float((reg.rotation.detach() - true_rot).abs().max()),
+            "xyz_err_mm": float((reg.translation.detach() - true_xyz).abs().max())}
+        del smooth
+    except Exception as exc:  # pragma: no cover
+        res["config5_registration_loop"] = {"error": f"{type(exc).__name__}: {exc}"}
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_on_gpu(vol_n, det_n):
+    """SURVEY 2b's bar: the reference's own PyTorch path (`Siddon.forward` + autograd) under .to("cuda") on this B200,
+    512^3 -> 256^2, ONE pose, forward + backward (it materialises ~20 (1, 65536, 1539) tensors; B = 16 would not fit the
+    comparison's spirit of a single call).  Wall clock around synchronised calls, 1 warm-up + 5 runs."""
+    ref_mod = load_reference()
+    if ref_mod is None:
+        return {"unavailable": "baseline/_ref is absent"}
+    try:
+        run = ReferenceRun(ref_mod, vol_n, det_n, device="cuda")
+        run.step(run.n_total)
+        times = [run.step(run.n_total) for _ in range(5)]
+        return {"workload": f"reference Siddon.forward + backward on the same B200, {vol_n}^3 -> {det_n}^2, 1 pose per call",
+                "drr_per_s": 1.0 / float(np.median(times)), "median_s": float(np.median(times)), "min_s": float(np.min(times)),
+                "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
 
@@ -294,8 +618,10 @@ def run_ours(args, rank, local_rank, world):
         t_end.record(stream)
         barrier()
     ms_total = t_start.elapsed_time(t_end)
-    sens_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
-    sens_bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    sens_list = [e[0].elapsed_time(e[1]) for e in events]
+    sens_bwd_list = [e[1].elapsed_time(e[2]) for e in events]
+    sens_ms = float(np.mean(sens_list))
+    sens_bwd_ms = float(np.mean(sens_bwd_list))
     # not part of `value`: the plain forward kernel (inference) and the backward walk, timed the same way
     events2 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     for k in range(args.steps):
@@ -435,7 +761,8 @@ def run_ours(args, rank, local_rank, world):
                 "path": "DRR(rot, xyz) -> (img*w).sum().backward(); pinned host pose in; image stack + loss + pose grads out"},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1], "peak": peak, "unit": "GB/s", "frac": dom[1] / peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if (B, D, args.det) == (16, VOL, DET) else None, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
+                     "traffic": NCU_TRAFFIC_BYTES.get(dom[0]) if (B, D, args.det) == (16, VOL, DET) else None,
+                     "traffic_source": NCU_TRAFFIC_SOURCE, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
         "step_breakdown_ms": {"siddon_sens_slab_kernel (image + sensitivities, one walk)": sens_ms,
                               "sens_bwd_kernel (elementwise backward)": sens_bwd_ms},
         "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
@@ -445,14 +772,59 @@ def run_ours(args, rank, local_rank, world):
                          "note": "two-walk backward; used when the volume needs gradients, not part of the timed step"},
         "clocks": clocks.summary(),
     }
+    line["timing"] = {"siddon_sens_slab_kernel": _stat(sens_list), "sens_bwd_kernel": _stat(sens_bwd_list),
+                      "note": "per-launch CUDA-event times over the timed region; roofline.achieved uses the mean"}
+    if world == 1:
+        # ---- parity of the TIMED output: pose 0 of this run against the fp64 oracle on the same rays ------------------
+        try:
+            from oracle import oracle
+
+            oracle.set_threads(host_threads())
+            a = (src[:1].cpu().numpy().reshape(1, 1, 3), tgt[:1].cpu().numpy(), raylen[:1].cpu().numpy().reshape(1, 1, N))
+            ref64 = oracle.siddon_fwd(np.ascontiguousarray(vol.cpu().numpy()), *a, dtype=np.float64).reshape(-1)
+            kernel_step()
+            torch.cuda.synchronize()
+            got = outs[0][0].cpu().numpy().astype(np.float64)
+            err = float(np.abs(got - ref64).max() / np.abs(ref64).max())
+            line["parity_check"] = {"sens_kernel_image_vs_fp64_oracle": err, "tolerance": 1e-4, "pose": 0,
+                                    "what": "max-abs error / max-abs reference over the full 256^2 image of pose 0"}
+            assert err < 1e-4, f"timed kernel output differs from the oracle: {err:.3e}"
+        except ImportError:
+            ref64 = None
+        main_state = dict(vol=vol, src=src, tgt=tgt, raylen=raylen, gout=gout, B=B, D=D, det=args.det, tot_visits=tot_visits)
+        if not args.no_extra:
+            line["configs"] = extra_configs(dev, lib, peak, main_state)
+            if ref64 is not None and "brick_img0" in main_state:
+                e2 = float(np.abs(main_state["brick_img0"].cpu().numpy().astype(np.float64) - ref64).max() / np.abs(ref64).max())
+                line["parity_check"]["brick_forward_image_vs_fp64_oracle"] = e2
+                assert e2 < 1e-4, f"brick forward differs from the oracle: {e2:.3e}"
+            line["reference_on_this_gpu"] = reference_on_gpu(D, args.det)
+            ref_gpu = line["reference_on_this_gpu"].get("drr_per_s")
+            if ref_gpu:
+                line["reference_on_this_gpu"]["ours_over_reference_fwd_bwd"] = value / ref_gpu
     if not args.no_cpu_baseline and world == 1:
+        # the reference's own PyTorch-CPU path on this box's host cores (bounded sample), else the C port of it
+        sample = cpu_reference_sample(D, args.det, budget_s=15.0)
+        if sample is not None:
+            med = float(np.median(sample["times"]))
+            frac = sample["n_rays"] / sample["n_total"]
+            line["cpu_baseline"] = {
+                "value": frac / med, "unit": "DRRs/s", "cores": host_threads(), "kind": "reference", "cpu": cpu_model(),
+                "sample": f"{sample['n_rays']} of {sample['n_total']} rays of one pose ({frac:.3f} DRR) fwd+bwd, median of "
+                          f"{len(sample['times'])} runs after warm-up; unmodified diffdrr.renderers.Siddon (baseline/_ref), torch "
+                          f"{torch.__version__} with {host_threads()} threads",
+                "min_value": frac / float(np.min(sample["times"]))}
         from oracle import oracle
 
-        threads = oracle.max_threads()
-        times = cpu_oracle_time(D, args.det, 1, 3, threads)[1:]
-        line["cpu_baseline"] = {"value": 1.0 / float(np.mean(times)), "unit": "DRRs/s", "cores": threads, "kind": "port",
-                                "sample": f"1 DRR fwd+bwd(pose) of the same {D}^3->{args.det}^2 workload, mean of {len(times)} "
-                                          "runs after 1 warm-up; C/OpenMP port of reference renderers.py (oracle/)"}
+        threads = host_threads()
+        times = cpu_oracle_time(D, args.det, 1, 6, threads)[1:]
+        port = {"value": 1.0 / float(np.median(times)), "unit": "DRRs/s", "cores": threads, "kind": "port",
+                "sample": f"1 DRR fwd+bwd(pose) of the same {D}^3->{args.det}^2 workload, median of {len(times)} runs after 1 warm-up; "
+                          "C/OpenMP port of reference renderers.py (oracle/)"}
+        if "cpu_baseline" in line:
+            line["cpu_port"] = port
+        else:
+            line["cpu_baseline"] = port
     print(json.dumps(line), flush=True)
 
 
