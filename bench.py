@@ -222,19 +222,38 @@ class ReferenceRun:
         return dt
 
 
+def best_reference_threads(run, n_rays=1024):
+    """PyTorch's CPU kernels stop scaling long before 128 threads on this shape (measured on the GPU box: 128 threads are
+    ~20x SLOWER than 8): time a small sample at a few thread counts and keep the fastest, so that the baseline is the
+    reference at its best on these host cores."""
+    best, best_t = host_threads(), float("inf")
+    tried = {}
+    for n in sorted({host_threads(), max(1, host_threads() // 2), max(1, host_threads() // 4), 32, 16, 8}, reverse=True):
+        if n > host_threads():
+            continue
+        torch.set_num_threads(n)
+        run.step(n_rays)
+        t = min(run.step(n_rays), run.step(n_rays))
+        tried[n] = t
+        if t < best_t:
+            best, best_t = n, t
+    torch.set_num_threads(best)
+    return best, tried
+
+
 def cpu_reference_sample(vol_n, det_n, budget_s, min_runs=5):
     """Times the unmodified reference on the host cores within ~budget_s seconds.  Returns None without baseline/_ref."""
     ref_mod = load_reference()
     if ref_mod is None:
         return None
-    torch.set_num_threads(host_threads())
     run = ReferenceRun(ref_mod, vol_n, det_n)
+    threads, tried = best_reference_threads(run)
     n_rays = 2048
     t = run.step(n_rays)                      # warm-up + calibration
     per_ray = run.step(n_rays) / n_rays
     n_rays = int(min(run.n_total, max(2048, budget_s / (min_runs + 1) / per_ray)))
     times = [run.step(n_rays) for _ in range(min_runs)]
-    return {"n_rays": n_rays, "times": times, "n_total": run.n_total, "warmup_s": t}
+    return {"n_rays": n_rays, "times": times, "n_total": run.n_total, "warmup_s": t, "threads": threads, "threads_tried": tried}
 
 
 def run_reference(args, rank, world):
@@ -246,8 +265,8 @@ def run_reference(args, rank, world):
     threads = host_threads()
     ref_mod = load_reference()
     if ref_mod is not None:
-        torch.set_num_threads(threads)
         run = ReferenceRun(ref_mod, args.vol, args.det)
+        threads, _tried = best_reference_threads(run)
         run.step(1024)
         per_ray = run.step(2048) / 2048
         # ~3 s of CPU work per step, at most one full DRR
@@ -257,7 +276,7 @@ def run_reference(args, rank, world):
         times = [run.step(n_rays) for _ in range(args.steps)]
         frac = n_rays / run.n_total
         kind, what = "reference", (f"unmodified diffdrr.renderers.Siddon.forward + backward (torch {torch.__version__}, "
-                                   f"{threads} threads, {cpu_model()})")
+                                   f"{threads} threads = fastest of the counts tried on {host_threads()} cores, {cpu_model()})")
         sample = f"{n_rays} of the {run.n_total} rays of one pose ({frac:.3f} DRR) fwd+bwd per step"
     else:
         from oracle import oracle  # noqa: F401
@@ -557,6 +576,18 @@ def run_ours(args, rank, local_rank, world):
     outs = [out, torch.empty_like(out)] if world > 1 else [out]
     gathered = [torch.empty(B * world, N, device=dev) for _ in range(2)] if world > 1 else None
     pending, state = [None, None], {"k": 0}
+    # the gather of the image stack: peer copies on the copy engines (no SM), NCCL only if symmetric memory is unavailable
+    peer, gather_kind = None, "none (1 GPU)"
+    if world > 1:
+        gather_kind = "nccl all_gather_into_tensor"
+        if os.environ.get("B200DRR_BENCH_GATHER", "peer") == "peer":
+            try:
+                from diffdrr_b200.parallel import PeerGather
+
+                peer = PeerGather((B, N), torch.float32, dev, slots=2)
+                gather_kind = "peer copies over NVLink on the copy engines (symmetric memory), no SM"
+            except Exception as exc:
+                gather_kind += f" (peer gather unavailable: {type(exc).__name__}: {exc})"
 
     def kernel_step(ev=None):
         """One training step at kernel level: image + per-ray sensitivities in ONE walk, then the elementwise backward."""
@@ -576,14 +607,20 @@ def run_ours(args, rank, local_rank, world):
             # double-buffered: the gather of this step's image stack runs on NCCL's stream while the next step walks
             # (the next step writes the other buffer); a buffer is reused only after its gather has been waited for
             slot = state["k"] & 1
-            if pending[slot] is not None:
-                pending[slot].wait()
-            pending[slot] = dist.all_gather_into_tensor(gathered[slot], outs[slot], async_op=True)
+            if peer is not None:
+                peer.wait(slot)           # the previous gather into this slot has been consumed
+                peer.push(outs[slot], slot)
+            else:
+                if pending[slot] is not None:
+                    pending[slot].wait()
+                pending[slot] = dist.all_gather_into_tensor(gathered[slot], outs[slot], async_op=True)
             state["k"] += 1
 
     def drain():
         for slot in (0, 1):
-            if pending[slot] is not None:
+            if peer is not None:
+                peer.wait(slot)
+            elif pending[slot] is not None:
                 pending[slot].wait()
                 pending[slot] = None
 
@@ -642,7 +679,11 @@ def run_ours(args, rank, local_rank, world):
         loss = (img * w).sum()
         loss.backward()
         if world > 1:
-            dist.all_gather_into_tensor(gathered[0], img.detach().reshape(B, N))
+            if peer is not None:
+                peer.push(img.detach().reshape(B, N), 0)
+                peer.wait(0)
+            else:
+                dist.all_gather_into_tensor(gathered[0], img.detach().reshape(B, N))
         img_h.copy_(img.detach(), non_blocking=True)
         grad_h[0].copy_(rot.grad, non_blocking=True)
         grad_h[1].copy_(xyz.grad, non_blocking=True)
@@ -665,9 +706,9 @@ def run_ours(args, rank, local_rank, world):
     # The host buffers are re-read by every replay, so each step can carry new poses.  (Single GPU only: NCCL
     # collectives are kept out of the capture.)
     e2e_ms_total, e2e_mode = e2e_eager_ms_total, "eager"
-    # N > 1: opt-in (B200DRR_BENCH_GRAPH_MULTI=1, not yet measured on a multi-GPU box): the per-rank step is replayed from
-    # its graph and the gather of the image stack is issued after the replay, outside the capture.
-    graph_multi = world > 1 and os.environ.get("B200DRR_BENCH_GRAPH_MULTI") == "1"
+    # N > 1: the per-rank step is replayed from its graph and the gather of the image stack is issued after the replay,
+    # outside the capture (B200DRR_BENCH_GRAPH_MULTI=0 switches back to the eager step).
+    graph_multi = world > 1 and os.environ.get("B200DRR_BENCH_GRAPH_MULTI", "1") == "1"
     if (world == 1 or graph_multi) and not args.no_graph:
         try:
             rot_d = torch.zeros(B, 3, device=dev, requires_grad=True)
@@ -712,7 +753,11 @@ def run_ours(args, rank, local_rank, world):
             def graph_step():
                 graph.replay()
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered[0], img_static.reshape(B, N))
+                    if peer is not None:
+                        peer.push(img_static.reshape(B, N), 0)
+                        peer.wait(0)
+                    else:
+                        dist.all_gather_into_tensor(gathered[0], img_static.reshape(B, N))
                 torch.cuda.current_stream().synchronize()  # the user reads the result every step
 
             for _ in range(args.warmup):
@@ -751,7 +796,7 @@ def run_ours(args, rank, local_rank, world):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "volume": [D] * 3, "detector": [args.det] * 2, "batch_per_gpu": B,
-                   "global_batch": B * world, "renderer": "siddon", "parallelism": f"pose-sharded dp{world}",
+                   "global_batch": B * world, "renderer": "siddon", "parallelism": f"pose-sharded dp{world}", "gather": gather_kind,
                    "l2": f"inputs > L2 ({4 * D ** 3 / 1e6:.0f} MB volume vs 126 MB L2); no explicit flush",
                    "mean_visits_per_ray": tot_visits / (B * N)},
         "e2e": {"value": e2e_value, "unit": "DRRs/s", "ms_per_step": e2e_ms_total / args.steps, "mode": e2e_mode,
@@ -809,10 +854,11 @@ def run_ours(args, rank, local_rank, world):
             med = float(np.median(sample["times"]))
             frac = sample["n_rays"] / sample["n_total"]
             line["cpu_baseline"] = {
-                "value": frac / med, "unit": "DRRs/s", "cores": host_threads(), "kind": "reference", "cpu": cpu_model(),
+                "value": frac / med, "unit": "DRRs/s", "cores": sample["threads"], "host_cores": host_threads(), "kind": "reference",
+                "cpu": cpu_model(), "threads_tried_s": {str(k): v for k, v in sample["threads_tried"].items()},
                 "sample": f"{sample['n_rays']} of {sample['n_total']} rays of one pose ({frac:.3f} DRR) fwd+bwd, median of "
                           f"{len(sample['times'])} runs after warm-up; unmodified diffdrr.renderers.Siddon (baseline/_ref), torch "
-                          f"{torch.__version__} with {host_threads()} threads",
+                          f"{torch.__version__} with {sample['threads']} threads (fastest of the counts tried on {host_threads()} cores)",
                 "min_value": frac / float(np.min(sample["times"]))}
         from oracle import oracle
 
@@ -840,7 +886,13 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        opts = None
+        try:  # the only collectives left are barriers / tiny reductions: keep NCCL's kernels off the walk's SMs
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = 2
+        except Exception:
+            opts = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), **({"pg_options": opts} if opts else {}))
     try:
         run_ours(args, rank, local_rank, world)
     finally:

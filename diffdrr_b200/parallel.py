@@ -16,6 +16,55 @@ import torch
 import torch.distributed as dist
 
 
+class PeerGather:
+    """All-gather of equally sized per-rank shards that uses NO SM: every rank owns a symmetric-memory buffer (CUDA VMM
+    mapped into all peers of the node), a rank PUSHES its shard into every peer's buffer with plain device copies
+    (copy engines over NVLink 5 / NVSwitch) on a side stream, and a symmetric-memory barrier (signal pads) closes the
+    exchange.  The NCCL all-gather it replaces runs as a kernel that shares the SMs with the next step's walk: measured
+    on 8 B200s the walk next to it slows by 10.7 % (1.247 -> 1.381 ms), which was most of the lost scaling efficiency.
+
+    `slots` independent buffers allow the gather of step k to overlap the walk of step k+1 (double buffering).
+    Raises if symmetric memory is unavailable (single node with P2P access is required); callers may then fall back to
+    `dist.all_gather_into_tensor`."""
+
+    def __init__(self, shard_shape, dtype, device, group=None, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.shard_shape, self.slots = tuple(shard_shape), slots
+        self.full_shape = (self.world * self.shard_shape[0],) + self.shard_shape[1:]
+        self.buf = symm_mem.empty((slots,) + self.full_shape, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.peers = [self.hdl.get_buffer(p, (slots,) + self.full_shape, dtype) for p in range(self.world)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.done = [None] * slots
+        self.n = self.shard_shape[0]
+
+    def push(self, local: torch.Tensor, slot: int = 0) -> None:
+        """Start gathering `local` (this rank's shard) into slot `slot` of every rank's buffer; returns immediately."""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        lo, hi = self.rank * self.n, (self.rank + 1) * self.n
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            # start with the right-hand neighbour so the 8 ranks do not all write to the same peer at once
+            for k in range(self.world):
+                p = (self.rank + k) % self.world
+                self.peers[p][slot, lo:hi].copy_(local, non_blocking=True)
+            self.hdl.barrier(channel=slot)   # every rank's pushes into MY buffer are complete once this returns
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.done[slot] = ev
+
+    def wait(self, slot: int = 0) -> torch.Tensor:
+        """Make the current stream wait for the gather of `slot`; returns the gathered (world*B, ...) tensor."""
+        if self.done[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.done[slot])
+            self.done[slot] = None
+        return self.buf[slot]
+
+
 def shard_bounds(n_items: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced [lo, hi) slice of `n_items` for `rank` (first n_items % world ranks get one more)."""
     if world <= 0 or not 0 <= rank < world:

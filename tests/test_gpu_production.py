@@ -126,7 +126,13 @@ def test_siddon_sensitivities_and_volume_gradient_vs_oracle():
     g_src2, g_tgt2, g_len2 = torch.empty_like(g_src), torch.empty_like(g_tgt), torch.empty_like(g_len)
     L.check(lib.b200drr_siddon_bwd_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_src2), _p(g_tgt2),
                                         _p(g_len2), _p(g_vol), B, H, H, 0.5, 1e-8, 0, 0, _stream()), "bwd_grid")
-    assert relerr(g_vol.cpu().numpy(), ref["g_volume"]) < IMG_TOL
+    # per-voxel gradients: which of two neighbouring voxels receives a segment that ends within position round-off of their
+    # common plane is decided differently by ANY fp32 evaluation (the rays start ~1700 voxels away: ~1e-4 voxel of round-off),
+    # so the bar is the reference algorithm's own fp32-vs-fp64 disagreement (SURVEY 8c rule), not a fixed 1e-4
+    ref32 = oracle.siddon_bwd(vol_np, *_np(src, tgt, raylen, gout), dtype=np.float32, want_vol=True)
+    tol = max(IMG_TOL, 2.0 * relerr(ref32["g_volume"], ref["g_volume"]))
+    assert relerr(g_vol.cpu().numpy(), ref["g_volume"]) < tol
+    assert abs(float(g_vol.double().sum()) - float(ref["g_volume"].sum())) < 1e-5 * abs(float(ref["g_volume"].sum()))
     assert relerr(g_tgt2.cpu().numpy(), ref["g_target"]) < 2e-3
     assert relerr(g_src2.cpu().numpy(), ref["g_source"].reshape(B, 3)) < 2e-3
     assert relerr(g_len2.cpu().numpy(), ref["g_raylen"].reshape(B, N)) < IMG_TOL
