@@ -919,8 +919,17 @@ def run_config4(args, rank, local_rank, world):
         _lib.check(lib.b200drr_siddon_fwd_brick(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), None, None, None, None, _ptr(out),
                                                 _ptr(ws), ws.numel(), B, det, det, 0.5, 1e-8, 0, _stream()), "fwd_brick")
 
+    def slab():
+        _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, det, det, 0.5, 1e-8, 0,
+                                               _stream()), "fwd_grid")
+
+    # the module's own choice (renderers._brick_ok): dense ray sets (1024^2 pixels through 512^2-voxel cross-sections, rays half
+    # a voxel apart) take the slab-major kernel, sparse ones the brick-major TMA kernel
+    use_brick = N <= 0.5 * float(D * D)
+    forward = brick if use_brick else slab
+
     def step():
-        brick()
+        forward()
         if world > 1:
             if peer is not None:
                 peer.push(out, 0)
@@ -945,8 +954,7 @@ def run_config4(args, rank, local_rank, world):
         barrier()
     ms_total = e0.elapsed_time(e1)
     t_brick = _time_events(brick, 3, warmup=1)
-    t_slab = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B,
-                                                                         det, det, 0.5, 1e-8, 0, _stream()), "fwd_grid"), 3, warmup=1)
+    t_slab = _time_events(slab, 3, warmup=1)
     stats = torch.tensor([ms_total, float(np.median(t_brick)), float(np.median(t_slab)), float(visits)], device=dev, dtype=torch.float64)
     if world > 1:
         mx = stats.clone()
@@ -968,9 +976,11 @@ def run_config4(args, rank, local_rank, world):
         "config": {"workload": "siddon forward (inference), 512^3 fp32 CT -> 1024^2 detector, 256 poses pose-sharded + one gather of the "
                                "image stack per step", "batch_per_gpu": B, "global_batch": GB, "gather": gather_kind,
                    "mean_visits_per_ray": visits_all / (GB * N), "l2": "inputs > L2; no explicit flush"},
-        "roofline": {"bound": "hbm", "kernel": "siddon_fwd_brick_kernel (slowest rank)", "achieved": bytes_rank / (kb * 1e-3) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": bytes_rank / (kb * 1e-3) / 1e9 / peak, "ms_per_launch": kb,
+        "roofline": {"bound": "hbm", "kernel": ("siddon_fwd_brick_kernel" if use_brick else "siddon_fwd_slab_kernel") + " (slowest rank)",
+                     "achieved": bytes_rank / ((kb if use_brick else ks) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_rank / ((kb if use_brick else ks) * 1e-3) / 1e9 / peak, "ms_per_launch": kb if use_brick else ks,
                      "algorithmic_bytes_per_launch": bytes_rank, "peak_source": peak_src, "traffic": None,
+                     "brick_major_kernel_ms_per_launch": kb, "brick_major_frac": bytes_rank / (kb * 1e-3) / 1e9 / peak,
                      "slab_major_kernel_ms_per_launch": ks, "slab_major_frac": bytes_rank / (ks * 1e-3) / 1e9 / peak,
                      "note": "rays are 0.5 voxel apart at 1024^2: algorithmic bytes exceed the DRAM bytes many times over (every "
                              "staged voxel serves ~4x more rays than at 256^2)"},

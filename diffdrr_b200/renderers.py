@@ -66,13 +66,18 @@ _brick_ws: dict = {}
 
 
 _BRICK_MIN_BRICKS = int(_os.environ.get("B200DRR_BRICK_MIN_BRICKS", "2048"))
+_BRICK_MAX_RAY_DENSITY = float(_os.environ.get("B200DRR_BRICK_MAX_RAY_DENSITY", "0.5"))
 
 
 def _brick_ok(vol, B, H, W) -> bool:
     # 24 x 32 x 32-voxel bricks over 2 x 148 resident CTAs: below ~7 bricks per CTA the tail of the dynamic brick queue
     # costs more than the staging returns (256^3 = 704 bricks: 0.66 ms vs 0.48 ms slab-major; 512^3 = 5632 bricks: 1.04 vs 1.13)
     n_bricks = -(-vol.shape[0] // 24) * -(-vol.shape[1] // 32) * -(-vol.shape[2] // 32)
-    return (B >= _BRICK_MIN_BATCH and n_bricks >= _BRICK_MIN_BRICKS and vol.shape[2] % 4 == 0 and 2 <= H <= 2048
+    # ... and only for SPARSE ray sets (detector pixels fewer than ~half the voxels of a volume cross-section, i.e. rays
+    # >= ~1.4 voxels apart): dense rays share 32-byte sectors in L1 and the slab-major gather wins (measured at 512^3 ->
+    # 1024^2, 32 poses: 24.5 ms slab-major vs 36.5 ms brick-major; at 512^3 -> 256^2 the other way round)
+    sparse = H * W <= _BRICK_MAX_RAY_DENSITY * float(vol.numel()) ** (2.0 / 3.0)
+    return (B >= _BRICK_MIN_BATCH and n_bricks >= _BRICK_MIN_BRICKS and sparse and vol.shape[2] % 4 == 0 and 2 <= H <= 2048
             and 2 <= W <= 2048 and B * H * W < 2**31 and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
 
 
