@@ -133,6 +133,12 @@ _SIGNATURES = {
         _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
         _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
         ctypes.c_float, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_siddon_fwd_sorted": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,
+        ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+    "b200drr_siddon_fwd_sens_sorted": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     "b200drr_siddon_brick_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200drr_siddon_fwd_brick": (ctypes.c_int, [
         _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,

@@ -72,6 +72,24 @@ int b200drr_siddon_fwd_grid(const float* vol, int D0, int D1, int D2, const floa
                                       (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_sorted(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                              float* out, int B, int64_t N, float voxel_shift, float eps, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_sorted(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, (cudaStream_t)stream));
+}
+
+int b200drr_siddon_fwd_sens_sorted(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                                   const float* raylen, float* out, float* sens, int B, int64_t N, float voxel_shift, float eps,
+                                   void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !sens || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_sens_sorted(vol, mk(D0, D1, D2), src, tgt, raylen, out, sens, B, N, voxel_shift, eps,
+                                             (cudaStream_t)stream));
+}
+
 int64_t b200drr_siddon_brick_workspace_bytes(int B, int H, int W)
 {
     if (B <= 0 || H <= 0 || W <= 0) return 0;

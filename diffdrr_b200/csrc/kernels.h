@@ -91,6 +91,12 @@ cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDi
                                       float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
                                       int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 
+// arbitrary ray sets in a caller-provided locality order (slab-major, thread i = ray i)
+cudaError_t launch_siddon_fwd_sorted(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                     float* out, int B, int64_t N, float shift, float eps, cudaStream_t stream);
+cudaError_t launch_siddon_fwd_sens_sorted(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                          float* out, float* sens, int B, int64_t N, float shift, float eps, cudaStream_t stream);
+
 // brick-major Siddon forward (siddon_brick.cu): TMA-staged voxel bricks in shared memory; G == nullptr -> rays from tgt/raylen
 size_t siddon_brick_workspace_bytes(int B, int H, int W);
 bool siddon_brick_supported(VolDims dims, int H, int W);

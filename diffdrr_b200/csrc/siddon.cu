@@ -1200,6 +1200,107 @@ __global__ void __launch_bounds__(kThreads) siddon_sens_kernel(const float* __re
     out[r] = L * S;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Slab-major kernels for ARBITRARY ray sets that the caller has put in a locality order (sub-sampled detectors, patches,
+// user rays: the module sorts them by the Morton code of their target points, renderers._locality_order): ray i of a
+// pose is simply thread i, so the 32 lanes of a warp walk 32 spatial neighbours and share 128-byte lines exactly like
+// the 8 x 4 pixel bundles of the detector-grid kernels.  Same slab decomposition, same per-ray math, same atomics.
+// ---------------------------------------------------------------------------------------------------
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS) siddon_fwd_slab_linear_kernel(const float* __restrict__ vol, VolDims dims,
+                                                                         const float* __restrict__ src,
+                                                                         const float* __restrict__ tgt,
+                                                                         const float* __restrict__ raylen,
+                                                                         float* __restrict__ out, int B, int64_t N, int slab,
+                                                                         float shift, float eps)
+{
+    const int64_t tiles = (N + THREADS - 1) / THREADS;
+    int64_t id = blockIdx.x;
+    const int64_t tile = id % tiles;
+    id /= tiles;
+    const int b = (int)(id % B);
+    const int sl = (int)(id / B);
+    const int64_t n = tile * THREADS + threadIdx.x;
+    if (n >= N) return;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;
+    const float part = siddon_ray_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
+    if (part != 0.0f) red_add(out + r, __ldg(raylen + r) * part);
+}
+
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS / 4) siddon_sens_slab_linear_kernel(
+    const float* __restrict__ vol, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
+    const float* __restrict__ raylen, float* __restrict__ out, float* __restrict__ sens, int B, int64_t N, int slab, float shift,
+    float eps)
+{
+    const int64_t tiles = (N + THREADS - 1) / THREADS;
+    int64_t id = blockIdx.x;
+    const int64_t tile = id % tiles;
+    id /= tiles;
+    const int b = (int)(id % B);
+    const int sl = (int)(id / B);
+    const int64_t n = tile * THREADS + threadIdx.x;
+    if (n >= N) return;
+    const int64_t r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const float L = __ldg(raylen + r);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;
+    float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
+    const float S = siddon_ray_sens_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
+    float jt[3], js[3];
+    bool any = S != 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float k = L * ray.inv[a];
+        jt[a] = -k * A[a];
+        js[a] = k * (A[a] - C[a]);
+        any = any || jt[a] != 0.0f || js[a] != 0.0f;
+    }
+    if (any) {
+        red_add4(sens + r * 8, jt[0], jt[1], jt[2], S);
+        red_add4(sens + r * 8 + 4, js[0], js[1], js[2], 0.0f);
+        red_add(out + r, L * S);
+    }
+}
+
+cudaError_t launch_siddon_fwd_sorted(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                     float* out, int B, int64_t N, float shift, float eps, cudaStream_t stream)
+{
+    constexpr int T = 128, SLAB = 32;
+    if ((int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    const int n_slabs = B >= 3 ? (dims.d[0] + SLAB - 1) / SLAB : 1;  // one or two poses: no batch to share a slab with
+    const int slab = B >= 3 ? SLAB : dims.d[0];
+    const int64_t blocks = ((N + T - 1) / T) * B * n_slabs;
+    if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * N, stream);
+    if (e != cudaSuccess) return e;
+    siddon_fwd_slab_linear_kernel<T, 4><<<(unsigned)blocks, T, 0, stream>>>(vol, dims, src, tgt, raylen, out, B, N, slab, shift, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_siddon_fwd_sens_sorted(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                          float* out, float* sens, int B, int64_t N, float shift, float eps, cudaStream_t stream)
+{
+    constexpr int T = 128, SLAB = 48;
+    if ((int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
+    const int n_slabs = B >= 3 ? (dims.d[0] + SLAB - 1) / SLAB : 1;
+    const int slab = B >= 3 ? SLAB : dims.d[0];
+    const int64_t blocks = ((N + T - 1) / T) * B * n_slabs;
+    if (blocks > INT32_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * N, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 8 * (size_t)B * N, stream);
+    if (e != cudaSuccess) return e;
+    siddon_sens_slab_linear_kernel<T, 8><<<(unsigned)blocks, T, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens, B, N, slab, shift,
+                                                                            eps);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_siddon_fwd_sens(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                    float* out, float* sens, int B, int64_t N, float shift, float eps, cudaStream_t stream)
 {

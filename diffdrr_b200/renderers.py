@@ -95,6 +95,29 @@ def _brick_workspace(device, B, H, W):
     return ws
 
 
+# Arbitrary ray sets (sub-sampled detectors, patches, user rays) reach the tiled, slab-major kernels through a LOCALITY
+# ORDER: rays are sorted by the Morton code of their target points, so consecutive groups of 32 rays are spatial neighbours
+# like the 8x4-pixel bundles of the detector-grid kernels (include/b200drr.h: b200drr_siddon_fwd_sorted / _fwd_sens_sorted).
+_SORT_MIN_RAYS = int(_os.environ.get("B200DRR_SORT_MIN_RAYS", "1024"))
+
+
+def _spread3(x: torch.Tensor) -> torch.Tensor:
+    """10-bit integers -> bits 0, 3, 6, ... (one lane of a 30-bit 3-D Morton code)."""
+    x = (x | (x << 16)) & 0x030000FF
+    x = (x | (x << 8)) & 0x0300F00F
+    x = (x | (x << 4)) & 0x030C30C3
+    return (x | (x << 2)) & 0x09249249
+
+
+def _locality_order(tgt: torch.Tensor) -> torch.Tensor:
+    """(B, N, 3) target points -> (B, N) permutation that sorts every pose's rays along a Z-order curve of their targets."""
+    with torch.no_grad():
+        lo, hi = tgt.amin(dim=1, keepdim=True), tgt.amax(dim=1, keepdim=True)
+        q = ((tgt - lo) / (hi - lo).clamp_min(1e-20) * 1023.0).to(torch.int64).clamp_(0, 1023)
+        key = _spread3(q[..., 0]) | (_spread3(q[..., 1]) << 1) | (_spread3(q[..., 2]) << 2)
+        return key.argsort(dim=1)
+
+
 # Training-step fast path: when only the ray end points need gradients, the forward walk also accumulates the per-ray
 # sensitivities and the backward pass is elementwise (one walk per step instead of two).  Module-level switch for A/B tests.
 _FUSED_SENSITIVITIES = True
@@ -128,7 +151,25 @@ class _SiddonFunction(torch.autograd.Function):
                 and vol.numel() < 2**31 - 1):
             sens = torch.empty(B, N, 8, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
-            if sens is not None and grid is None:   # arbitrary ray set (sub-sampled / patched / user rays)
+            fast = reduce == 0 and not align_corners and vol.numel() < 2**31 - 1
+            if grid is None and fast and N >= _SORT_MIN_RAYS:
+                # arbitrary ray set, big enough to be worth ordering: sort for locality, walk slab-major, un-sort the results
+                perm = _locality_order(tgt)
+                tgt_s = torch.gather(tgt, 1, perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+                len_s = torch.gather(raylen, 1, perm).contiguous()
+                out_s = torch.empty_like(out)
+                if sens is not None:
+                    sens_s = torch.empty_like(sens)
+                    _lib.check(lib.b200drr_siddon_fwd_sens_sorted(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt_s), _ptr(len_s),
+                                                                  _ptr(out_s), _ptr(sens_s), B, N, voxel_shift, eps, _stream()),
+                               "b200drr_siddon_fwd_sens_sorted")
+                    sens.scatter_(1, perm.unsqueeze(-1).expand(-1, -1, 8), sens_s)
+                else:
+                    _lib.check(lib.b200drr_siddon_fwd_sorted(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt_s), _ptr(len_s),
+                                                             _ptr(out_s), B, N, voxel_shift, eps, _stream()),
+                               "b200drr_siddon_fwd_sorted")
+                out.scatter_(1, perm, out_s)
+            elif sens is not None and grid is None:   # small arbitrary ray set (one thread per ray)
                 _lib.check(lib.b200drr_siddon_fwd_sens(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out),
                                                        _ptr(sens), B, N, voxel_shift, eps, _stream()),
                            "b200drr_siddon_fwd_sens")

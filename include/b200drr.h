@@ -289,6 +289,20 @@ int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int 
                                void *stream);
 
 /*
+ * Siddon forward / forward-with-sensitivities for ARBITRARY ray sets that the caller has put in a LOCALITY ORDER
+ * (sub-sampled detectors detector.py:134-137, patches drr.py:217-225, user rays): consecutive groups of 32 rays should be
+ * spatial neighbours (the module sorts by the Morton code of the target points).  Thread i walks ray i, so a warp's
+ * gathers share cache lines like the 8x4-pixel bundles of the *_grid kernels, and the volume is walked slab-major across
+ * the batch.  Same results (fp32 round-off: partial sums are combined with red.global.add) and same argument meaning as
+ * b200drr_siddon_fwd(reduce=0, align_corners=0) / b200drr_siddon_fwd_sens; any order is CORRECT, a poor one is merely slow.
+ */
+int b200drr_siddon_fwd_sorted(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                              const float *raylen, float *out, int B, int64_t N, float voxel_shift, float eps, void *stream);
+int b200drr_siddon_fwd_sens_sorted(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                                   const float *raylen, float *out, float *sens, int B, int64_t N, float voxel_shift,
+                                   float eps, void *stream);
+
+/*
  * Brick-major Siddon forward for a FULL detector grid (same result as b200drr_siddon_fwd_grid; replaces
  * renderers.py:94-113 + 156-169): the volume is cut into 24x32x32-voxel bricks, each staged in shared memory by one TMA
  * box copy (cp.async.bulk.tensor.3d behind an mbarrier pipeline) and integrated for every ray of every pose of the

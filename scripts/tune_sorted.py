@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Per-ray cost of sub-sampled ray sets: locality-ordered slab-major kernels vs one thread per ray vs the full grid."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+os.environ["SMALL"] = "0"
+from diffdrr_b200 import Siddon, renderers  # noqa: E402
+import importlib.util  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("tb", os.path.join(os.path.dirname(__file__), "tune_brick.py"))
+os.environ["BVARIANTS"] = ""
+tb = importlib.util.module_from_spec(spec)
+sys.argv = [sys.argv[0]]
+try:
+    spec.loader.exec_module(tb)
+except ValueError:
+    pass
+dev, B, H, dims = tb.dev, tb.B, tb.H, tb.dims
+vol, src, tgt, raylen = tb.vol, tb.src, tb.tgt, tb.raylen
+N = H * H
+full = tb.timeit(lambda: tb.grid_call(vol, dims, src, tgt, raylen, torch.empty(B, N, device=dev), B, H, H))
+print(f"full grid {H}^2, {B} poses: {full:.3f} ms = {full * 1e6 / (B * N):.2f} ns/ray")
+for frac in (0.5, 0.25, 0.1):
+    sel = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(0))[: int(N * frac)].sort().values
+    tg, ln = tgt[:, sel].contiguous(), raylen[:, sel].contiguous().reshape(B, 1, -1)
+    s3 = src.reshape(B, 1, 3)
+    for name, thr in (("sorted slab-major", 1), ("one thread per ray", 10 ** 9)):
+        renderers._SORT_MIN_RAYS = thr
+        with torch.no_grad():
+            ms = tb.timeit(lambda: Siddon()(vol, s3, tg, ln))
+        print(f"  {frac * 100:4.0f}% sub-sample, {name:20s}: {ms:.3f} ms = {ms * 1e6 / (B * len(sel)):.2f} ns/ray  ({ms * 1e6 / (B * len(sel)) / (full * 1e6 / (B * N)):.2f}x the full-grid per-ray cost)")
+    st, tt = s3.clone().requires_grad_(True), tg.clone().requires_grad_(True)
+    for name, thr in (("sorted slab-major", 1), ("one thread per ray", 10 ** 9)):
+        renderers._SORT_MIN_RAYS = thr
+        def step():
+            o = Siddon()(vol, st, tt, ln)
+            o.sum().backward()
+        ms = tb.timeit(step)
+        print(f"  {frac * 100:4.0f}% sub-sample fwd+bwd(pose), {name:20s}: {ms:.3f} ms")
