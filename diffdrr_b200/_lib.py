@@ -115,14 +115,6 @@ _SIGNATURES = {
         _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
         _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
         ctypes.c_float, ctypes.c_float, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
-    "b200drr_x_transpose_volume": (ctypes.c_int, [
-        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
-    "b200drr_x_siddon_fwd_chunk": (ctypes.c_int, [
-        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
-        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
-    "b200drr_x_siddon_sens_chunk": (ctypes.c_int, [
-        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
-        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
     "b200drr_packed_volume_floats": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200drr_pack_corners": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
     "b200drr_trilinear_fwd_packed": (ctypes.c_int, [
@@ -147,6 +139,18 @@ _SIGNATURES = {
     "b200drr_siddon_visits": (ctypes.c_int, [
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int,
         ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+}
+
+# entry points of rejected experiments (include/b200drr_experimental.h): bound only when the experimental build is loaded
+_EXPERIMENTAL_SIGNATURES = {
+    "b200drr_x_transpose_volume": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, ctypes.c_void_p]),
+    "b200drr_x_siddon_fwd_chunk": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_x_siddon_sens_chunk": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -175,6 +179,11 @@ def load():
             fn = getattr(handle, name)  # AttributeError if the ABI and the header drift apart
             fn.restype = restype
             fn.argtypes = argtypes
+        for name, (restype, argtypes) in _EXPERIMENTAL_SIGNATURES.items():
+            if hasattr(handle, name):
+                fn = getattr(handle, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
         _lib = handle
     return _lib
 

@@ -40,6 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    if os.environ.get("B200DRR_BUILD_EXPERIMENTS") == "1":  # rejected kernel experiments (include/b200drr_experimental.h)
+        cmd.insert(1, "-DB200DRR_EXPERIMENTS")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

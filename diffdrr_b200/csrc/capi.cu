@@ -2,6 +2,9 @@
 #include <cuda_runtime.h>
 
 #include "../../include/b200drr.h"
+#ifdef B200DRR_EXPERIMENTS
+#include "../../include/b200drr_experimental.h"
+#endif
 #include "kernels.h"
 
 using namespace b200drr;
@@ -405,6 +408,7 @@ int b200drr_trilinear_bwd_mask(const float* vol, const float* mask, int D0, int 
                                          (cudaStream_t)stream));
 }
 
+#ifdef B200DRR_EXPERIMENTS
 int b200drr_x_transpose_volume(const float* vol, int D0, int D1, int D2, int axis, float* out, void* stream)
 {
     if (!vol || !out || bad_dims(D0, D1, D2) || axis < 0 || axis > 2) return B200DRR_EINVAL;
@@ -434,6 +438,7 @@ int b200drr_x_siddon_sens_chunk(const float* volT, int D0, int D1, int D2, int a
     return ret(launch_x_siddon_sens_chunk(volT, mk(D0, D1, D2), axis, src, tgt, raylen, out, sens, B, H, W, voxel_shift, eps,
                                           variant, (cudaStream_t)stream));
 }
+#endif  // B200DRR_EXPERIMENTS
 
 int64_t b200drr_packed_volume_floats(int D0, int D1, int D2)
 {

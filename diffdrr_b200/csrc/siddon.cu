@@ -1,7 +1,9 @@
 // siddon.cu -- Siddon exact-path DRR kernels for sm_100a (forward, backward, visit counter).
 // One thread walks one ray (ray_math.cuh); blockIdx.y is the pose, blockIdx.x tiles the rays of that pose.
 #include "kernels.h"
-#include "psync.cuh"
+#ifdef B200DRR_EXPERIMENTS
+#include "psync.cuh"  // rejected experiments live only in the opt-in experimental build (build.py)
+#endif
 #include "ray_math.cuh"
 
 namespace b200drr {
@@ -228,6 +230,7 @@ static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const flo
     return cudaGetLastError();
 }
 
+#ifdef B200DRR_EXPERIMENTS
 // ---------------------------------------------------------------------------------------------------
 // EXPERIMENT (opt-in, b200drr_x_*): slab-major forward over a major-axis-fastest copy with per-lane chunk reuse
 // (ray_math.cuh: siddon_ray_lean_box_chunk).  Not on any default path; kept compiled so the next tuning round can time it.
@@ -390,6 +393,8 @@ static cudaError_t launch_psync_variant(const float* vol, VolDims dims, const fl
                                                                                       H, W, slab, shift, eps);
     return cudaGetLastError();
 }
+
+#endif  // B200DRR_EXPERIMENTS
 
 // ---------------------------------------------------------------------------------------------------
 // Slab-major detector-grid BACKWARD kernel: same decomposition as siddon_fwd_slab_kernel.  Every CTA adds its
@@ -669,6 +674,7 @@ static cudaError_t launch_sens_slab_variant(const float* vol, VolDims dims, cons
     return cudaGetLastError();
 }
 
+#ifdef B200DRR_EXPERIMENTS
 // EXPERIMENT: the sensitivities walk (training step) with the same chunk reuse.  Same outputs as siddon_sens_slab_kernel.
 template <int TW, int TH, int U, int CW, int MINB>
 __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_chunk_kernel(const float* __restrict__ volT, VolDims dims,
@@ -748,6 +754,8 @@ cudaError_t launch_x_siddon_sens_chunk(const float* volT, VolDims dims, int axis
     }
 #undef XS
 }
+
+#endif  // B200DRR_EXPERIMENTS
 
 cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
@@ -969,6 +977,7 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         S(44, 16, 16, 8, 32)
         S(45, 8, 16, 6, 32)
 #undef S
+#ifdef B200DRR_EXPERIMENTS
 #define P(id, TW, TH, U, SLAB, ALIGN) \
     case id: return launch_psync_variant<TW, TH, U, ALIGN>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
         P(20, 16, 8, 2, 32, 1)
@@ -982,6 +991,7 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         P(28, 8, 8, 2, 32, 1)
         P(29, 16, 16, 1, 32, 1)
 #undef P
+#endif
 
         default: return cudaErrorInvalidValue;
     }

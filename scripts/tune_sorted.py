@@ -11,7 +11,7 @@ from diffdrr_b200 import Siddon, renderers  # noqa: E402
 import importlib.util  # noqa: E402
 
 spec = importlib.util.spec_from_file_location("tb", os.path.join(os.path.dirname(__file__), "tune_brick.py"))
-os.environ["BVARIANTS"] = ""
+os.environ["BVARIANTS"] = "0"
 tb = importlib.util.module_from_spec(spec)
 sys.argv = [sys.argv[0]]
 try:

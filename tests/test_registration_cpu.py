@@ -38,3 +38,22 @@ def test_registration_module_holds_pose_parameters():
     assert pose.matrix.shape == (1, 4, 4) and pose.matrix.requires_grad
     # camera centre = R @ t (reference pose.py:149-157): for rot = 0 it is the translation itself
     assert torch.allclose(pose.matrix[0, :3, 3], xyz[0])
+
+
+def test_ncc_matches_the_reference_class_values_and_gradients():
+    """NormalizedCrossCorrelation2d against goldens recorded from the UNMODIFIED reference class (metrics.py:21-44, kornia
+    stubbed in tests/golden/make_golden_ncc.py): scores and d(score)/d(x2), full-image and patch mode (patch_size=5)."""
+    import os
+
+    import numpy as np
+
+    from conftest import GOLDEN, relerr
+    g = dict(np.load(os.path.join(GOLDEN, "ncc_reference.npz")))
+    for tag, patch in (("full", None), ("patch5", 5)):
+        for dt, suf, tol in ((torch.float32, "f32", 1e-5), (torch.float64, "f64", 1e-12)):
+            x1 = torch.as_tensor(g["x1"]).to(dt)
+            x2 = torch.as_tensor(g["x2"]).to(dt).requires_grad_(True)
+            score = NormalizedCrossCorrelation2d(patch_size=patch)(x1, x2)
+            (score * torch.tensor([1.0, -2.0, 0.5], dtype=dt)).sum().backward()
+            assert relerr(score.detach().numpy(), g[f"{tag}_score_{suf}"]) < tol, (tag, suf)
+            assert relerr(x2.grad.numpy(), g[f"{tag}_grad_x2_{suf}"]) < max(tol, 1e-5 if dt == torch.float32 else tol), (tag, suf)
