@@ -47,9 +47,9 @@ HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 # (16 poses, 512^3 -> 256^2): profiles/r01_fwd_slab_B16_ncu_summary.txt and gpurun capture of the backward kernel.
 # Only quoted when the run uses that workload; otherwise null.
 NCU_TRAFFIC_SOURCE = ("not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
-                      "the same command (profiles/r01_siddon_ncu_summary.txt, captured 2026-09-24); null off the default workload")
+                      "the same command (profiles/r02_siddon_sens_slab_ncu_summary.txt, captured 2026-09-24 on a B200 of this pool); null off the default workload")
 NCU_TRAFFIC_BYTES = {"siddon_fwd_slab_kernel": 1.05e9 + 0.02e9, "siddon_bwd_slab_kernel": 2.26e9 + 0.09e9,
-                     "siddon_sens_slab_kernel": 1.38e9 + 0.14e9}
+                     "siddon_sens_slab_kernel": 1.4126e9 + 0.1360e9}
 
 
 def parse():
