@@ -110,7 +110,8 @@ class DRR(nn.Module):
         if (fused and parameterization == "euler_angles" and calibration is None and len(args) == 2
                 and geometry.euler_convention_ok(convention) and all(
                     torch.is_tensor(a) and a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[-1] == 3
-                    for a in args)):
+                    for a in args)
+                and args[0].shape == args[1].shape):  # the kernel takes ONE batch size; broadcasting goes through convert()
             # pose parameters -> pose matrix in one kernel (same algebra as pose.convert)
             pose = RigidTransform(geometry.euler_pose(args[0], args[1], convention, degrees))
         elif parameterization is None:
@@ -164,7 +165,7 @@ class DRR(nn.Module):
         """Q = reorient . calibration, r = reorient[:, 3], Ainv = affine_inverse as contiguous device tensors, rebuilt only
         when the detector / affine buffers change (set_intrinsics_, .to(device))."""
         det = self.detector
-        key = (det._calibration.data_ptr(), det._calibration._version, det._reorient.data_ptr(), det._reorient._version,
+        key = (id(det), det._calibration.data_ptr(), det._calibration._version, det._reorient.data_ptr(), det._reorient._version,
                self._affine_inverse.data_ptr(), self._affine_inverse._version)
         cached = getattr(self, "_pose_consts", None)
         if cached is None or cached[0] != key:
@@ -215,6 +216,14 @@ class DRR(nn.Module):
             pick(x0, -d.x0), pick(y0, -d.y0),  # the x0/y0 properties are negated (quirk Q9): undo it
             self.subject.reorient, pick(n_subsample, d.n_subsample), pick(reverse_x_axis, d.reverse_x_axis),
         ).to(self.density)
+        # the fused path caches Q = reorient . calibration per detector: a NEW detector must never find the old constants
+        # (its buffers can land on the freed addresses of a previous one)
+        object.__setattr__(self, "_pose_consts", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)  # .to(device) / .float() / ... replace the buffers
+        object.__setattr__(self, "_pose_consts", None)
+        return out
 
     def rescale_detector_(self, scale: float):
         """Rescale the detector plane in place (multiscale registration)."""

@@ -32,6 +32,9 @@ class _EulerPoseFunction(torch.autograd.Function):
     def forward(ctx, rot, xyz, axes, scale):
         rot, xyz = rot.contiguous().float(), xyz.contiguous().float()
         B = rot.shape[0]
+        if rot.shape != xyz.shape or rot.dim() != 2 or rot.shape[1] != 3:
+            # the C ABI only receives B: a (1, 3) translation next to (B, 3) rotations would be read out of bounds
+            raise ValueError(f"euler_pose needs rot and xyz of the same (B, 3) shape, got {tuple(rot.shape)} and {tuple(xyz.shape)}")
         P = torch.empty(B, 4, 4, dtype=torch.float32, device=rot.device)
         with torch.cuda.device(rot.device):
             _lib.check(_lib.load().b200drr_euler_pose_fwd(_ptr(rot), _ptr(xyz), *axes, scale, _ptr(P), B, _stream()),

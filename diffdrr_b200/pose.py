@@ -86,7 +86,18 @@ class RigidTransform(torch.nn.Module):
             return R[..., :2, :].reshape(*R.shape[:-2], 6), translation
         if parameterization == "rotation_9d":
             return R.flatten(start_dim=1), translation
-        raise NotImplementedError(f"RigidTransform.convert to {parameterization!r} is not provided by diffdrr_b200")
+        if parameterization == "quaternion_adjugate":   # +q q^T, upper triangle (pose.py:250-253)
+            return quaternion_to_quaternion_adjugate(matrix_to_quaternion(R)), translation
+        if parameterization == "rotation_10d":          # -q q^T, upper triangle (pose.py:229-232)
+            return quaternion_to_rotation_10d(matrix_to_quaternion(R)), translation
+        if parameterization == "se3_log_map":           # pose.py:96-102: the log's own translation part replaces it
+            params = self.get_se3_log()
+            return params[..., 3:], params[..., :3]
+        raise ValueError(f"Must be in {PARAMETERIZATIONS}, not {parameterization}")
+
+    def get_se3_log(self):
+        """(B, 6) = [log translation | log rotation] of this pose (pose.py:104-105)."""
+        return se3_log_map(self.matrix.mT)
 
 
 def make_matrix(R, t):
@@ -276,6 +287,48 @@ def _hat(v: torch.Tensor) -> torch.Tensor:
     x, y, z = v.unbind(-1)
     o = torch.zeros_like(x)
     return torch.stack((o, -z, y, z, o, -x, -y, x, o), dim=-1).reshape(v.shape[:-1] + (3, 3))
+
+
+def _upper_triangle_4x4(A: torch.Tensor) -> torch.Tensor:
+    idx, jdx = torch.triu_indices(4, 4)
+    return A[..., idx, jdx]
+
+
+def quaternion_to_quaternion_adjugate(q: torch.Tensor) -> torch.Tensor:
+    """Unit quaternion -> the 10 upper-triangle entries of q q^T (inverse of quaternion_adjugate_to_quaternion)."""
+    return _upper_triangle_4x4(q.unsqueeze(-1) * q.unsqueeze(-2))
+
+
+def quaternion_to_rotation_10d(q: torch.Tensor) -> torch.Tensor:
+    """Unit quaternion -> the 10 upper-triangle entries of -q q^T (inverse of rotation_10d_to_quaternion)."""
+    return _upper_triangle_4x4(-(q.unsqueeze(-1) * q.unsqueeze(-2)))
+
+
+def so3_log_map(R: torch.Tensor) -> torch.Tensor:
+    """Rotation matrices (B, 3, 3) -> axis-angle logarithms (B, 3)."""
+    return quaternion_to_axis_angle(matrix_to_quaternion(R))
+
+
+def _se3_V(w: torch.Tensor, eps: float):
+    theta2 = (w * w).sum(-1).clamp(min=eps * eps)
+    theta = theta2.sqrt()
+    K = _hat(w)
+    K2 = K @ K
+    b = ((1 - torch.cos(theta)) / theta2)[..., None, None]
+    c = ((theta - torch.sin(theta)) / (theta2 * theta))[..., None, None]
+    eye = torch.eye(3, dtype=w.dtype, device=w.device).expand_as(K)
+    return eye + b * K + c * K2
+
+
+def se3_log_map(transform: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
+    """(B, 4, 4) with rows [R^T 0; T 1] (the transpose convention of se3_exp_map) -> (B, 6) = [V^-1 T | log R]."""
+    if transform.dim() != 3 or transform.shape[-2:] != (4, 4):
+        raise ValueError("Input tensor shape has to be (N, 4, 4).")
+    if not torch.allclose(transform[:, :3, 3], torch.zeros_like(transform[:, :3, 3])):
+        raise ValueError("All elements of `transform[:, :3, 3]` should be 0.")
+    w = so3_log_map(transform[:, :3, :3].mT)
+    v = torch.linalg.solve(_se3_V(w, eps), transform[:, 3, :3].unsqueeze(-1)).squeeze(-1)
+    return torch.cat([v, w], dim=-1)
 
 
 def se3_exp_map(log_transform: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
