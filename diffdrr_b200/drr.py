@@ -67,9 +67,18 @@ class DRR(nn.Module):
             self.renderer = Trilinear(voxel_shift, **renderer_kwargs)
         else:
             raise ValueError(f"renderer must be 'siddon' or 'trilinear', not {renderer}")
-        # compile_renderer: the renderer already is one fused kernel; torch.compile has nothing left to fuse and
-        # is deliberately not applied (no tracing compiler on the hot path).  The flag is accepted for parity.
+        # compile_renderer (reference drr.py:102-103 wraps the renderer in torch.compile): here the renderer already IS one
+        # fused CUDA kernel per direction behind a C ABI, so there is nothing for a tracing compiler to fuse.  The flag is
+        # honoured explicitly instead of being ignored: the renderer is marked opaque to dynamo (an enclosing torch.compile
+        # of the user's model then graph-breaks around it instead of failing on the ctypes calls) and the user is told once.
         self.compile_renderer = compile_renderer
+        if compile_renderer:
+            import warnings
+
+            self.renderer.forward = torch.compiler.disable(self.renderer.forward)
+            warnings.warn("diffdrr_b200: compile_renderer=True has nothing to compile -- the renderer is already a fused sm_100a "
+                          "kernel; it is kept as an opaque call (torch.compiler.disable) so an outer torch.compile can wrap it",
+                          stacklevel=2)
         self.reshape = reshape
         self.patch_size = patch_size
         self.checkpoint_gradients = checkpoint_gradients

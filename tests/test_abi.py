@@ -125,3 +125,14 @@ def test_render_grid_shape_is_validated_on_cpu():
         sub.render(sub.density, src, tgt, grid_shape=(2, 12))      # sub-sampled detector has no row blocks
     from diffdrr_b200.parallel import render_sharded
     assert render_sharded.__kwdefaults__["shard"] == "auto"
+
+
+def test_compile_renderer_flag_is_not_silently_ignored():
+    """compile_renderer=True (reference drr.py:102-103) warns and marks the renderer opaque to dynamo instead of no-op'ing."""
+    import warnings
+
+    vol = synthetic.make_volume(8, "smooth")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(6), compile_renderer=True)
+    assert drr.compile_renderer and any("compile_renderer" in str(x.message) for x in w)
