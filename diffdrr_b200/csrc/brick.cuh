@@ -486,4 +486,93 @@ B200_HD float brick_pair_fwd_lean(const Ld& ld, const float s[3], const float in
     return fmaf(a_out - w.acur, ld(w.off), acc);  // the rest of the chord belongs to the last voxel
 }
 
+
+// ---- two rays per thread (instruction-level parallelism for the issue-bound walk) -------------------------------------------
+// Same set-up and step as brick_pair_fwd_lean<ACC>, split so that one thread can interleave the dependent chains of TWO
+// independent (ray, brick) pairs: the walk is bound by instruction issue with ~1.8 eligible warps per cycle, and a second
+// chain per thread hides the fixed ALU / shared-memory latencies that an extra warp (no registers left) cannot.
+template <class Ld>
+B200_HD bool brick_pair_setup_acc(const Ld& ld, bool valid, const float s[3], const float inv[3], const float clo[3],
+                                  const float chi[3], const int lo_v[3], const int hi_v[3], const int org[3], int st0, int st1,
+                                  int st2, float shift, AccState& w, AccConst& k)
+{
+    float lo[3], a_in = -INFINITY, a_hi = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float a0 = clo[a] * inv[a], a1 = chi[a] * inv[a];
+        lo[a] = fminf(a0, a1);
+        a_in = fmaxf(a_in, lo[a]);
+        a_hi = fminf(a_hi, fmaxf(a0, a1));
+    }
+    const bool hit = valid && (a_in < a_hi);
+    const int st[3] = {st0 * Ld::kScale, st1 * Ld::kScale, st2 * Ld::kScale};
+    float an[3], da[3], nxc[3];
+    int so[3];
+    w.off = ld.base();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool fwd = inv[a] > 0.0f;
+        const int lo_i = lo_v[a], hi_i = hi_v[a] - 1;
+        int i = (int)floorf(fmaf(a_in, approx_rcp(inv[a]), s[a] + shift));
+        i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
+        i = (lo[a] >= a_in) ? (fwd ? lo_i : hi_i) : i;
+        float p0 = (float)(fwd ? i + 1 : i);
+        da[a] = fabsf(inv[a]);
+        an[a] = ((p0 - shift) - s[a]) * inv[a];
+        const bool ahead = (an[a] < a_in) && (fwd ? i < hi_i : i > lo_i);
+        const bool back = !ahead && (an[a] - da[a] >= a_in) && (fwd ? i > lo_i : i < hi_i);
+        const int dstep = ahead ? 1 : (back ? -1 : 0);
+        i += fwd ? dstep : -dstep;
+        p0 += (float)(fwd ? dstep : -dstep);
+        an[a] = dstep == 0 ? an[a] : ((p0 - shift) - s[a]) * inv[a];
+        nxc[a] = fwd ? (float)hi_v[a] - p0 : p0 - (float)lo_v[a];
+        so[a] = fwd ? st[a] : -st[a];
+        w.off += hit ? (i - org[a]) * st[a] : 0;
+    }
+    // a miss / an empty slot is a walk that is already finished: every quantity zero, the offset on the brick's first voxel
+    w.an0 = hit ? an[0] - a_in : 0.0f;
+    w.an1 = hit ? an[1] - a_in : 0.0f;
+    w.an2 = hit ? an[2] - a_in : 0.0f;
+    w.acur = 0.0f;
+    k.da0 = hit ? da[0] : 0.0f;
+    k.da1 = hit ? da[1] : 0.0f;
+    k.da2 = hit ? da[2] : 0.0f;
+    k.so0 = hit ? so[0] : 0;
+    k.so1 = hit ? so[1] : 0;
+    k.so2 = hit ? so[2] : 0;
+    const float a_out = fminf(fminf(fma_rm(nxc[0], da[0], w.an0), fma_rm(nxc[1], da[1], w.an1)), fma_rm(nxc[2], da[2], w.an2));
+    k.a_stop = hit ? a_out : 0.0f;
+    return hit;
+}
+
+template <int U, class Ld>
+B200_HD void brick_pair2_walk(const Ld& ld, AccState& wa, const AccConst& ka, AccState& wb, const AccConst& kb, float& part_a,
+                              float& part_b)
+{
+    float acc_a = 0.0f, acc_b = 0.0f;
+    while (wa.acur < ka.a_stop || wb.acur < kb.a_stop) {
+        float la[U], lb[U], va[U], vb[U];
+        int oa[U], ob[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            oa[j] = wa.off;
+            la[j] = acc_step(wa, ka);
+            ob[j] = wb.off;
+            lb[j] = acc_step(wb, kb);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            va[j] = ld(oa[j]);
+            vb[j] = ld(ob[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            acc_a = fmaf(la[j], va[j], acc_a);
+            acc_b = fmaf(lb[j], vb[j], acc_b);
+        }
+    }
+    part_a = fmaf(ka.a_stop - wa.acur, ld(wa.off), acc_a);
+    part_b = fmaf(kb.a_stop - wb.acur, ld(wb.off), acc_b);
+}
+
 }  // namespace b200drr

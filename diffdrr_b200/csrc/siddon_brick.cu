@@ -145,7 +145,7 @@ struct BrickGrid {
     int nb0, nb1, nb2;  // bricks per axis
 };
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS = 1>
 struct BrickCfg {
     // 4-row tile bands per pose chunk (a chunk takes as many poses as fit); the two-CTA-per-SM shape has less room
     static constexpr int kRowCap = CTAS == 1 ? 512 : 256;
@@ -169,17 +169,17 @@ struct BrickCfg {
     static constexpr int oHist = oRowPrefix + (kRowCap + 4) * 4;  // kBrickBins ints
     static constexpr int oCursor = oHist + kBrickBins * 4;        // kBrickBins ints
     static constexpr int oMisc = oCursor + kBrickBins * 4;        // see s_misc
-    static constexpr int kSmemBytes = oMisc + 64;
+    static constexpr int kSmemBytes = oMisc + 128;
 };
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS>
 __global__ void __launch_bounds__(THREADS, CTAS)
     siddon_fwd_brick_kernel(const __grid_constant__ CUtensorMap tmap, VolDims dims, BrickGrid bg,
                             const float4* __restrict__ raytab, const float* __restrict__ ltab,
                             const PoseGeo* __restrict__ geo, float* __restrict__ out, unsigned* __restrict__ counter, int B,
                             int H, int W, float shift)
 {
-    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
     constexpr int kRowCap = Cfg::kRowCap;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned* s_items = reinterpret_cast<unsigned*>(smem + Cfg::oItems);
@@ -355,6 +355,151 @@ __global__ void __launch_bounds__(THREADS, CTAS)
             __syncthreads();
             const int T = s_misc[6];
 
+            if constexpr (RAYS == 3) {
+                // ---- warp-specialised schedule: NPW producer warps test + sort the candidates of round r+1 into one of two
+                // work lists while the consumer warps walk the chunks of round r -- no CTA-wide barrier inside a pose chunk
+                constexpr int NPW = 4, NCW = Cfg::kWarps - NPW;
+                constexpr int LCAP = Cfg::kCap / 2;          // items per list
+                constexpr int KP = LCAP / (NPW * 32);        // tiles per producer warp per round
+                volatile int* s_ctl = s_misc + 8;            // [0..1] n_items, [2..3] next chunk, [4..5] ready, [6..7] consumers gone
+                const int n_rounds = (T + NPW * KP - 1) / (NPW * KP);
+                if (tid < 8) s_ctl[tid] = 0;
+                __syncthreads();
+                if (warp < NPW) {
+                    for (int r = 0; r < n_rounds; ++r) {
+                        const int slot = r & 1;
+                        unsigned items[KP];
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) items[j] = 0xffffffffu;
+                        const int tw0 = (r * NPW + warp) * KP;
+                        if (tw0 < T) {
+                            int row;
+                            {
+                                constexpr int STEP = kRowCap / 32;
+                                const int probe = min((lane + 1) * STEP, R);
+                                const unsigned le = __ballot_sync(0xffffffffu, s_rowprefix[probe] <= tw0);
+                                const int coarse = __popc(le) * STEP;
+                                const int p2 = min(coarse + lane + 1, R);
+                                const unsigned le2 = __ballot_sync(0xffffffffu, lane < STEP && s_rowprefix[p2] <= tw0);
+                                row = coarse + __popc(le2);
+                            }
+#pragma unroll
+                            for (int j = 0; j < KP; ++j) {
+                                const int t = tw0 + j;
+                                if (t < T) {
+                                    while (s_rowprefix[row + 1] <= t) ++row;
+                                    const unsigned info = s_rowinfo[row];
+                                    const int bl = item_pose(info);
+                                    const int px = item_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
+                                    const int py = item_row(info) + (lane >> 3);
+                                    if (px <= s_rowend[row] && py <= s_rect[bl * 4 + 3]) {
+                                        const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(py * W + px)));
+                                        const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
+                                        const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
+                                        const float inv[3] = {q.x, q.y, q.z};
+                                        const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                                        float a_in, a_out;
+                                        if (brick_maybe_hit(inv, clo3, chi3, a_in, a_out)) {
+                                            const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
+                                            items[j] = pack_item(bin, bl, py, px);
+                                            atomicAdd(&s_hist[bin], 1);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+                        if (warp == 0) {
+                            const int h = s_hist[kBrickBins - 1 - lane];
+                            int incl = h;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += up;
+                            }
+                            s_cursor[kBrickBins - 1 - lane] = incl - h;
+                            s_hist[kBrickBins - 1 - lane] = 0;
+                            if (lane == 31) s_misc[0] = incl;
+                            // the slot is free once every consumer warp has left the round that used it last
+                            if (lane == 0 && r >= 2)
+                                while (s_ctl[6 + slot] < NCW * (r / 2)) __nanosleep(40);
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+#pragma unroll
+                        for (int j = 0; j < KP; ++j)
+                            if (items[j] != 0xffffffffu)
+                                s_items[slot * LCAP + atomicAdd(&s_cursor[item_bin(items[j])], 1)] = items[j];
+                        asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+                        if (tid == 0) {
+                            s_ctl[slot] = s_misc[0];
+                            s_ctl[2 + slot] = 0;
+                            __threadfence_block();
+                            s_ctl[4 + slot] = r + 1;   // publish
+                        }
+                    }
+                } else {
+                    for (int r = 0; r < n_rounds; ++r) {
+                        const int slot = r & 1;
+                        if (lane == 0)
+                            while (s_ctl[4 + slot] < r + 1) __nanosleep(40);
+                        __syncwarp();
+                        __threadfence_block();
+                        const int n_items = s_ctl[slot];
+                        const int n_chunks = (n_items + 31) >> 5;
+                        const unsigned* list = s_items + slot * LCAP;
+                        auto claim = [&]() {
+                            int c = 0;
+                            if (lane == 0) c = atomicAdd(const_cast<int*>(&s_ctl[2 + slot]), 1);
+                            return __shfl_sync(0xffffffffu, c, 0);
+                        };
+                        auto fetch = [&](int c, unsigned& itw, float4& q, float& L) {
+                            const int i = c * 32 + lane;
+                            itw = 0xffffffffu;
+                            if (c < n_chunks && i < n_items) {
+                                itw = list[i];
+                                const unsigned rr = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                                q = __ldg(raytab + rr);
+                                L = __ldg(ltab + rr);
+                            }
+                        };
+                        int c = claim();
+                        unsigned itw;
+                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float L = 0.0f;
+                        fetch(c, itw, q, L);
+                        while (c < n_chunks) {
+                            const int cn = claim();
+                            unsigned itn;
+                            float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float Ln = 0.0f;
+                            fetch(cn, itn, qn, Ln);
+                            if (itw != 0xffffffffu) {
+                                const int bl = item_pose(itw);
+                                const float4 S4 = *reinterpret_cast<const float4*>(s_posef + bl * 12);
+                                const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
+                                const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
+                                const float s3[3] = {S4.x, S4.y, S4.z}, inv3[3] = {q.x, q.y, q.z};
+                                const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                                const float part = brick_pair_fwd_lean<U, LdShared, true, false>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org,
+                                                                                                 BY * BZ, BZ, 1, shift);
+                                if (part != 0.0f)
+                                    red_add(out + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw))), L * part);
+                            }
+                            c = cn;
+                            itw = itn;
+                            q = qn;
+                            L = Ln;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            atomicAdd(const_cast<int*>(&s_ctl[6 + slot]), 1);   // this warp is done with the list
+                        }
+                    }
+                }
+                p0 += npose;
+                continue;   // next pose chunk (its first statement is the CTA-wide barrier)
+            }
             for (int t0 = 0; t0 < T; t0 += Cfg::kWarps * K) {
                 // ---- 2. candidates -> hits (kept in registers) + histogram of the sort bins --------------------
                 unsigned items[K];
@@ -421,6 +566,75 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 __syncthreads();
                 // ---- 4. the walks: warps pull 32-item chunks ---------------------------------------------------
                 const int n_items = s_misc[0];
+                if constexpr (RAYS == 2) {
+                    // two (ray, brick) pairs per thread: lane l of chunk c walks items c*64 + l and c*64 + 32 + l
+                    const int n_chunks2 = (n_items + 63) >> 6;
+                    auto claim2 = [&]() {
+                        int c = 0;
+                        if (lane == 0) c = atomicAdd(&s_misc[1], 1);
+                        return __shfl_sync(0xffffffffu, c, 0);
+                    };
+                    auto fetch1 = [&](int i, unsigned& itw, float4& q, float& L) {
+                        itw = 0xffffffffu;
+                        if (i < n_items) {
+                            itw = s_items[i];
+                            const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                            q = __ldg(raytab + r);
+                            L = __ldg(ltab + r);
+                        }
+                    };
+                    int c = claim2();
+                    unsigned ita, itb;
+                    float4 qa = make_float4(1.f, 1.f, 1.f, 0.f), qb = qa;
+                    float La = 0.0f, Lb = 0.0f;
+                    if (c < n_chunks2) {
+                        fetch1(c * 64 + lane, ita, qa, La);
+                        fetch1(c * 64 + 32 + lane, itb, qb, Lb);
+                    }
+                    while (c < n_chunks2) {
+                        const int cn = claim2();
+                        unsigned itan = 0xffffffffu, itbn = 0xffffffffu;
+                        float4 qan = make_float4(1.f, 1.f, 1.f, 0.f), qbn = qan;
+                        float Lan = 0.0f, Lbn = 0.0f;
+                        if (cn < n_chunks2) {
+                            fetch1(cn * 64 + lane, itan, qan, Lan);
+                            fetch1(cn * 64 + 32 + lane, itbn, qbn, Lbn);
+                        }
+                        if (ita != 0xffffffffu || itb != 0xffffffffu) {
+                            const bool va = ita != 0xffffffffu, vb = itb != 0xffffffffu;
+                            const int bla = va ? item_pose(ita) : 0, blb = vb ? item_pose(itb) : 0;
+                            AccState wa, wb;
+                            AccConst ka, kb;
+                            {
+                                const float4 S4 = *reinterpret_cast<const float4*>(s_posef + bla * 12);
+                                const float4 clo = *reinterpret_cast<const float4*>(s_posef + bla * 12 + 4);
+                                const float4 chi = *reinterpret_cast<const float4*>(s_posef + bla * 12 + 8);
+                                const float s3[3] = {S4.x, S4.y, S4.z}, inv3[3] = {qa.x, qa.y, qa.z};
+                                const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                                brick_pair_setup_acc(ld, va, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wa, ka);
+                            }
+                            {
+                                const float4 S4 = *reinterpret_cast<const float4*>(s_posef + blb * 12);
+                                const float4 clo = *reinterpret_cast<const float4*>(s_posef + blb * 12 + 4);
+                                const float4 chi = *reinterpret_cast<const float4*>(s_posef + blb * 12 + 8);
+                                const float s3[3] = {S4.x, S4.y, S4.z}, inv3[3] = {qb.x, qb.y, qb.z};
+                                const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
+                                brick_pair_setup_acc(ld, vb, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wb, kb);
+                            }
+                            float pa, pb;
+                            brick_pair2_walk<U>(ld, wa, ka, wb, kb, pa, pb);
+                            if (va && pa != 0.0f)
+                                red_add(out + ((unsigned)(p0 + bla) * (unsigned)N + (unsigned)(item_row(ita) * W + item_col(ita))), La * pa);
+                            if (vb && pb != 0.0f)
+                                red_add(out + ((unsigned)(p0 + blb) * (unsigned)N + (unsigned)(item_row(itb) * W + item_col(itb))), Lb * pb);
+                        }
+                        c = cn;
+                        ita = itan; itb = itbn;
+                        qa = qan; qb = qbn;
+                        La = Lan; Lb = Lbn;
+                    }
+                    continue;  // next round
+                }
                 const int n_chunks = (n_items + 31) >> 5;
                 // (the next chunk's item and ray-table entry are fetched before the current chunk is walked, so the L2
                 // latency of the table hides behind a whole walk instead of stalling every chunk's set-up)
@@ -517,13 +731,13 @@ bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, i
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE>
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS = 1>
 cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const float* ltab,
                                  const PoseGeo* geo, float* out, unsigned* counter, int B, int H, int W, float shift,
                                  cudaStream_t stream)
 {
-    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
-    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>;
+    using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
+    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -582,21 +796,42 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
         if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>(map, dims, raytab, ltab, geo, out, counter, \
                                                                                    B, H, W, shift, stream);
+#define BV3(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
+    case id:                                                                                                             \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 3>(map, dims, raytab, ltab, geo, out, counter, \
+                                                                                   B, H, W, shift, stream);
+#define BV2(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
+    case id:                                                                                                             \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 2>(map, dims, raytab, ltab, geo, out, counter, \
+                                                                                   B, H, W, shift, stream);
     switch (variant) {
         BV(0, 24, 32, 32, 1, 512, 4, 2, 2, 0)    // two CTAs per SM, one 96 KB brick each (production shape)
+        BV(7, 24, 32, 32, 2, 1024, 4, 2, 1, 1)   // one CTA per SM with a two-stage TMA + mbarrier pipeline (measured: 1.27 ms vs 1.09)
+#ifdef B200DRR_EXPERIMENTS   // tuning variants, all measured and not chosen (profiles/r02_tune_brick_*.log); not in the shipped library
         BV(1, 24, 32, 32, 1, 512, 4, 2, 2, 1)    // ... with the software-pipelined walk
         BV(2, 24, 32, 32, 1, 512, 4, 4, 2, 1)
         BV(3, 24, 32, 32, 1, 512, 4, 4, 2, 0)
         BV(4, 22, 32, 32, 1, 512, 8, 2, 2, 1)    // bigger rounds (fewer barriers), slightly smaller brick
         BV(5, 15, 32, 32, 1, 320, 4, 2, 3, 1)    // three CTAs per SM
         BV(6, 15, 32, 32, 1, 320, 4, 2, 3, 0)
-        BV(7, 24, 32, 32, 2, 1024, 4, 2, 1, 1)   // one CTA per SM, two-stage TMA pipeline
         BV(8, 24, 32, 32, 2, 1024, 4, 2, 1, 0)
         BV(9, 12, 32, 32, 2, 512, 4, 2, 2, 1)    // two CTAs per SM, each with a two-stage pipeline of 48 KB bricks
         BV(10, 24, 32, 32, 1, 384, 5, 2, 2, 1)
+        BV2(20, 24, 32, 32, 1, 256, 8, 2, 2)     // two rays per thread (ILP), 2 CTAs x 256 threads: 1.28 ms
+        BV2(21, 24, 32, 32, 1, 320, 6, 2, 2)
+        BV2(22, 24, 32, 32, 1, 384, 5, 2, 2)
+        BV2(23, 24, 32, 32, 1, 256, 8, 1, 2)
+        BV2(24, 24, 32, 32, 1, 512, 4, 2, 2)     // 1.22 ms
+        BV3(30, 24, 32, 32, 1, 512, 4, 2, 2)     // warp-specialised: 4 producer warps (test + sort) / 12 consumer warps (walk): 1.25 ms
+        BV3(31, 24, 32, 32, 1, 512, 4, 4, 2)
+#endif
         default: return cudaErrorInvalidValue;
     }
 #undef BV
+#undef BV2
+#undef BV3
 }
 
 }  // namespace b200drr

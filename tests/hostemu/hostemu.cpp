@@ -712,6 +712,7 @@ long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float
                         chi[a] = ((float)hi_v[a] - shift) - geo[b].S[a];
                     }
                     std::fill(cand.begin(), cand.end(), 0);
+                    long pend_r = -1;
                     if (rc.x0 <= rc.x1 && rc.y0 <= rc.y1) {
                         const int th = (rc.y1 - rc.y0) / 4 + 1;
                         for (int ty = 0; ty < th; ++ty) {
@@ -731,6 +732,23 @@ long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float
                                     if (!brick_maybe_hit(ray.inv, clo, chi, a_in, a_out)) continue;
                                     ++st[1];
                                     if (start_walk_box(ray, lo_v, hi_v, shift).hit) ++st[2];
+                                    if (lean == 3) {  // two-rays-per-thread path: pair this hit with the previous pending one
+                                        if (pend_r < 0) {
+                                            pend_r = r;
+                                            continue;
+                                        }
+                                        const Ray& rb = rays[pend_r];
+                                        AccState wa, wb;
+                                        AccConst ka, kb;
+                                        brick_pair_setup_acc(ld, true, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wa, ka);
+                                        brick_pair_setup_acc(ld, true, rb.s, rb.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wb, kb);
+                                        float pa, pb;
+                                        brick_pair2_walk<2>(ld, wa, ka, wb, kb, pa, pb);
+                                        if (pa != 0.0f) { ++st[3]; out[r] += raylen[r] * pa; }
+                                        if (pb != 0.0f) { ++st[3]; out[pend_r] += raylen[pend_r] * pb; }
+                                        pend_r = -1;
+                                        continue;
+                                    }
                                     const float part =
                                         lean == 1 ? brick_pair_fwd_lean<4>(ld, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift)
                                         : lean == 2 ? brick_pair_fwd_lean<4, LdHost, false>(ld, ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift)
@@ -741,6 +759,17 @@ long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float
                                     }
                                 }
                         }
+                    }
+                    if (pend_r >= 0) {  // odd hit left over: paired with an empty slot
+                        const Ray& rb = rays[pend_r];
+                        AccState wa, wb;
+                        AccConst ka, kb;
+                        brick_pair_setup_acc(ld, false, rb.s, rb.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wa, ka);
+                        brick_pair_setup_acc(ld, true, rb.s, rb.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ, 1, shift, wb, kb);
+                        float pa, pb;
+                        brick_pair2_walk<2>(ld, wa, ka, wb, kb, pa, pb);
+                        if (pa != 0.0f) ++violations;  // an empty slot must contribute nothing
+                        if (pb != 0.0f) { ++st[3]; out[pend_r] += raylen[pend_r] * pb; }
                     }
                     if (check)
                         for (int py = 0; py < H; ++py)
