@@ -552,8 +552,23 @@ def run_ours(args, rank, local_rank, world):
 
     # this rank's poses (weak scaling: B per GPU); host copies live in pinned memory for the e2e leg
     rot_all, xyz_all = synthetic.make_poses(B * world, seed=0)
-    rot_h = rot_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
-    xyz_h = xyz_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    mine = list(range(rank * B, (rank + 1) * B))
+    balance = "contiguous slices"
+    if world > 1 and os.environ.get("B200DRR_BENCH_BALANCE", "1") == "1":
+        # every rank still renders exactly B poses (weak scaling), but WHICH poses is decided by their cost (voxels visited,
+        # known from a closed-form count): the step ends when the slowest rank does
+        from diffdrr_b200.parallel import balanced_pose_assignment
+
+        with torch.no_grad():
+            costs = []
+            for b0 in range(0, B * world, 16):
+                p_ = convert(rot_all[b0:b0 + 16].to(dev), xyz_all[b0:b0 + 16].to(dev), parameterization="euler_angles", convention="ZXY")
+                s_, t_ = drr.detector(p_, None)
+                costs += siddon_visits((D, D, D), drr.affine_inverse(s_), drr.affine_inverse(t_)).sum(dim=1).tolist()
+        mine = balanced_pose_assignment(costs, world)[rank]
+        balance = "equal pose counts, groups balanced by visit count (parallel.balanced_pose_assignment)"
+    rot_h = rot_all[mine].contiguous().pin_memory()
+    xyz_h = xyz_all[mine].contiguous().pin_memory()
     with torch.no_grad():
         pose = convert(rot_h.to(dev), xyz_h.to(dev), parameterization="euler_angles", convention="ZXY")
         src, tgt = drr.detector(pose, None)
@@ -798,7 +813,7 @@ def run_ours(args, rank, local_rank, world):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "volume": [D] * 3, "detector": [args.det] * 2, "batch_per_gpu": B,
-                   "global_batch": B * world, "renderer": "siddon", "parallelism": f"pose-sharded dp{world}", "gather": gather_kind,
+                   "global_batch": B * world, "renderer": "siddon", "parallelism": f"pose-sharded dp{world}", "gather": gather_kind, "pose_assignment": balance,
                    "l2": f"inputs > L2 ({4 * D ** 3 / 1e6:.0f} MB volume vs 126 MB L2); no explicit flush",
                    "mean_visits_per_ray": tot_visits / (B * N)},
         "e2e": {"value": e2e_value, "unit": "DRRs/s", "ms_per_step": e2e_ms_total / args.steps, "mode": e2e_mode,

@@ -210,15 +210,18 @@ B200_HD bool brick_maybe_hit(const float inv[3], const float clo[3], const float
     return !(a_in > a_out + margin);
 }
 
-// Work item: bin (5 bits) | pose within the chunk (5 bits) | row (11 bits) | column (11 bits)
+// Work item: bin (5 bits) | pose within the chunk (5 bits) | ray index within the pose (22 bits: up to 2048 x 2048 rays).
+// Band descriptor (same word layout, different fields): pose (5 bits) | first row (11 bits) | first column (11 bits).
 constexpr int kBrickPoseChunk = 32;
 constexpr int kBrickMaxSide = 2048;
 constexpr int kBrickBins = 32;
-B200_HD unsigned pack_item(int bin, int bl, int py, int px) { return ((unsigned)bin << 27) | ((unsigned)bl << 22) | ((unsigned)py << 11) | (unsigned)px; }
+B200_HD unsigned pack_item(int bin, int bl, int n) { return ((unsigned)bin << 27) | ((unsigned)bl << 22) | (unsigned)n; }
 B200_HD int item_bin(unsigned it) { return (int)(it >> 27); }
 B200_HD int item_pose(unsigned it) { return (int)((it >> 22) & 31u); }
-B200_HD int item_row(unsigned it) { return (int)((it >> 11) & 2047u); }
-B200_HD int item_col(unsigned it) { return (int)(it & 2047u); }
+B200_HD int item_ray(unsigned it) { return (int)(it & 0x3fffffu); }
+B200_HD unsigned pack_band(int bl, int py, int px) { return ((unsigned)bl << 22) | ((unsigned)py << 11) | (unsigned)px; }
+B200_HD int band_row(unsigned it) { return (int)((it >> 11) & 2047u); }
+B200_HD int band_col(unsigned it) { return (int)(it & 2047u); }
 
 // Estimated number of voxels a hit visits inside the box -> sort bin (longest first keeps the lanes of a warp alike)
 B200_HD int step_bin(float a_in, float a_out, float sumabs_d, float inv_width)

@@ -115,6 +115,22 @@ int b200drr_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const flo
                                        (size_t)workspace_bytes, B, H, W, voxel_shift, eps, variant, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_brick_subset(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
+                                    const float* raylen, const int32_t* pix_index, const float* corners, float* out,
+                                    void* workspace, int64_t workspace_bytes, int B, int H, int W, int64_t Nsub,
+                                    float voxel_shift, float eps, int variant, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !pix_index || !corners || !out || !workspace || bad_dims(D0, D1, D2) ||
+        bad_rays(B, Nsub) || H <= 0 || W <= 0 || Nsub > (int64_t)H * W)
+        return B200DRR_EINVAL;
+    if (!siddon_brick_supported(mk(D0, D1, D2), H, W) || ((uintptr_t)vol & 15u) != 0) return B200DRR_EUNSUPPORTED;
+    if (workspace_bytes < (int64_t)siddon_brick_workspace_bytes(B, 1, (int)Nsub) || ((uintptr_t)workspace & 255u) != 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd_brick(vol, mk(D0, D1, D2), src, tgt, raylen, nullptr, nullptr, nullptr, nullptr, out, workspace,
+                                       (size_t)workspace_bytes, B, H, W, voxel_shift, eps, variant, (cudaStream_t)stream,
+                                       pix_index, corners, Nsub));
+}
+
 int b200drr_siddon_bwd(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                        const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                        float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int align_corners,

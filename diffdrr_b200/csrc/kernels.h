@@ -103,7 +103,8 @@ bool siddon_brick_supported(VolDims dims, int H, int W);
 cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                     const float* G, const float* Wd, const float* rows, const float* cols, float* out,
                                     void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
-                                    int variant, cudaStream_t stream);
+                                    int variant, cudaStream_t stream, const int* pix_index = nullptr,
+                                    const float* corners = nullptr, int64_t Nsub = 0);
 
 // experiments (b200drr_x_*): chunk-reuse forward over a major-axis-fastest copy
 cudaError_t launch_x_transpose_volume(const float* vol, VolDims dims, int axis, float* out, cudaStream_t stream);

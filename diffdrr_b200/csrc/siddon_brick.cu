@@ -111,29 +111,40 @@ __global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict
                                                          const float* __restrict__ raylen, PoseRaysB pr,
                                                          float4* __restrict__ raytab, float* __restrict__ ltab,
                                                          PoseGeo* __restrict__ geo, float* __restrict__ out,
-                                                         unsigned* __restrict__ counter, int H, int W, float eps)
+                                                         unsigned* __restrict__ counter, int H, int W, float eps,
+                                                         int64_t Nr /* rays per pose */,
+                                                         const float* __restrict__ corners /* [B][3][3] or nullptr */)
 {
-    const int64_t N = (int64_t)H * W;
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (n >= N) return;
-    const int py = (int)(n / W), px = (int)(n - (int64_t)py * W);
-    const int64_t r = (int64_t)b * N + n;
+    if (n >= Nr) return;
+    // full grid: ray n is pixel (n / W, n % W); ray subset (corners != nullptr): n indexes the caller's (B, Nr) ray arrays
+    const int py = corners ? 0 : (int)(n / W), px = corners ? 0 : (int)(n - (int64_t)py * W);
+    const int64_t r = (int64_t)b * Nr + n;
     float L;
     const Ray ray = make_ray_b(pr, src, tgt, raylen, b, r, px, py, eps, L);
     raytab[r] = make_float4(ray.inv[0], ray.inv[1], ray.inv[2], fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]));
     ltab[r] = L;
     out[r] = 0.0f;
     if (n == 0) {
-        float Lx;
-        const Ray r0w = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * N + (W - 1), W - 1, 0, eps, Lx);
-        const Ray rh0 = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * N + (int64_t)(H - 1) * W, 0, H - 1, eps, Lx);
         float t00[3], t0w[3], th0[3];
+        if (corners) {  // targets of the full grid's pixels (0, 0), (0, W-1), (H-1, 0), handed in by the caller
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            t00[a] = ray.s[a] + ray.d[a];
-            t0w[a] = ray.s[a] + r0w.d[a];
-            th0[a] = ray.s[a] + rh0.d[a];
+            for (int a = 0; a < 3; ++a) {
+                t00[a] = corners[b * 9 + a];
+                t0w[a] = corners[b * 9 + 3 + a];
+                th0[a] = corners[b * 9 + 6 + a];
+            }
+        } else {
+            float Lx;
+            const Ray r0w = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * Nr + (W - 1), W - 1, 0, eps, Lx);
+            const Ray rh0 = make_ray_b(pr, src, tgt, raylen, b, (int64_t)b * Nr + (int64_t)(H - 1) * W, 0, H - 1, eps, Lx);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                t00[a] = ray.s[a] + ray.d[a];
+                t0w[a] = ray.s[a] + r0w.d[a];
+                th0[a] = ray.s[a] + rh0.d[a];
+            }
         }
         geo[b] = make_pose_geo(ray.s, t00, t0w, th0, H, W);
         if (b == 0) *counter = 0u;
@@ -176,8 +187,9 @@ template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTA
 __global__ void __launch_bounds__(THREADS, CTAS)
     siddon_fwd_brick_kernel(const __grid_constant__ CUtensorMap tmap, VolDims dims, BrickGrid bg,
                             const float4* __restrict__ raytab, const float* __restrict__ ltab,
-                            const PoseGeo* __restrict__ geo, float* __restrict__ out, unsigned* __restrict__ counter, int B,
-                            int H, int W, float shift)
+                            const PoseGeo* __restrict__ geo, float* __restrict__ out, unsigned* __restrict__ counter,
+                            const int* __restrict__ pix_index /* [H*W] pixel -> ray index, -1 = no ray; nullptr = full grid */,
+                            int Nr /* rays per pose */, int B, int H, int W, float shift)
 {
     using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
     constexpr int kRowCap = Cfg::kRowCap;
@@ -201,7 +213,6 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_bricks = bg.nb0 * bg.nb1 * bg.nb2;
     const float inv_bin_width = (float)kBrickBins / (float)(BX + BY + BZ + 8);
-    const int64_t N = (int64_t)H * W;
 
     if (tid == 0) {
 #pragma unroll
@@ -320,7 +331,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 int px_lo, px_hi, cnt = 0;
                 if (row_span(s_uv + bl * 16, s_flag[bl] != 0, rc, py0, px_lo, px_hi)) cnt = (px_hi - px_lo) / 8 + 1;
                 else px_lo = px_hi = 0;
-                s_rowinfo[r] = pack_item(0, bl, py0, px_lo);
+                s_rowinfo[r] = pack_band(bl, py0, px_lo);
                 s_rowend[r] = px_hi;
                 s_rowprefix[r + 1] = cnt;
             }
@@ -390,10 +401,12 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                                     while (s_rowprefix[row + 1] <= t) ++row;
                                     const unsigned info = s_rowinfo[row];
                                     const int bl = item_pose(info);
-                                    const int px = item_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
-                                    const int py = item_row(info) + (lane >> 3);
+                                    const int px = band_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
+                                    const int py = band_row(info) + (lane >> 3);
                                     if (px <= s_rowend[row] && py <= s_rect[bl * 4 + 3]) {
-                                        const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(py * W + px)));
+                                        const int n = pix_index ? __ldg(pix_index + (py * W + px)) : py * W + px;
+                                        if (n < 0) continue;  // pixel not in the caller's ray subset
+                                        const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)n));
                                         const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
                                         const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
                                         const float inv[3] = {q.x, q.y, q.z};
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                                         float a_in, a_out;
                                         if (brick_maybe_hit(inv, clo3, chi3, a_in, a_out)) {
                                             const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
-                                            items[j] = pack_item(bin, bl, py, px);
+                                            items[j] = pack_item(bin, bl, n);
                                             atomicAdd(&s_hist[bin], 1);
                                         }
                                     }
@@ -457,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                             itw = 0xffffffffu;
                             if (c < n_chunks && i < n_items) {
                                 itw = list[i];
-                                const unsigned rr = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                                const unsigned rr = (unsigned)(p0 + item_pose(itw)) * (unsigned)Nr + (unsigned)item_ray(itw);
                                 q = __ldg(raytab + rr);
                                 L = __ldg(ltab + rr);
                             }
@@ -483,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                                 const float part = brick_pair_fwd_lean<U, LdShared, true, false>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org,
                                                                                                  BY * BZ, BZ, 1, shift);
                                 if (part != 0.0f)
-                                    red_add(out + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw))), L * part);
+                                    red_add(out + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)item_ray(itw)), L * part);
                             }
                             c = cn;
                             itw = itn;
@@ -524,10 +537,12 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                             while (s_rowprefix[row + 1] <= t) ++row;  // warp-uniform, rarely more than one step
                             const unsigned info = s_rowinfo[row];
                             const int bl = item_pose(info);
-                            const int px = item_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
-                            const int py = item_row(info) + (lane >> 3);
+                            const int px = band_col(info) + 8 * (t - s_rowprefix[row]) + (lane & 7);
+                            const int py = band_row(info) + (lane >> 3);
                             if (px <= s_rowend[row] && py <= s_rect[bl * 4 + 3]) {
-                                const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(py * W + px)));
+                                const int n = pix_index ? __ldg(pix_index + (py * W + px)) : py * W + px;
+                                if (n < 0) continue;  // pixel not in the caller's ray subset
+                                const float4 q = __ldg(raytab + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)n));
                                 const float4 clo = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 4);
                                 const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
                                 const float inv[3] = {q.x, q.y, q.z};
@@ -535,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                                 float a_in, a_out;
                                 if (brick_maybe_hit(inv, clo3, chi3, a_in, a_out)) {
                                     const int bin = step_bin(a_in, a_out, q.w, inv_bin_width);
-                                    items[j] = pack_item(bin, bl, py, px);
+                                    items[j] = pack_item(bin, bl, n);
                                     atomicAdd(&s_hist[bin], 1);
                                 }
                             }
@@ -578,7 +593,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                         itw = 0xffffffffu;
                         if (i < n_items) {
                             itw = s_items[i];
-                            const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                            const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)Nr + (unsigned)item_ray(itw);
                             q = __ldg(raytab + r);
                             L = __ldg(ltab + r);
                         }
@@ -624,9 +639,9 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                             float pa, pb;
                             brick_pair2_walk<U>(ld, wa, ka, wb, kb, pa, pb);
                             if (va && pa != 0.0f)
-                                red_add(out + ((unsigned)(p0 + bla) * (unsigned)N + (unsigned)(item_row(ita) * W + item_col(ita))), La * pa);
+                                red_add(out + ((unsigned)(p0 + bla) * (unsigned)Nr + (unsigned)item_ray(ita)), La * pa);
                             if (vb && pb != 0.0f)
-                                red_add(out + ((unsigned)(p0 + blb) * (unsigned)N + (unsigned)(item_row(itb) * W + item_col(itb))), Lb * pb);
+                                red_add(out + ((unsigned)(p0 + blb) * (unsigned)Nr + (unsigned)item_ray(itb)), Lb * pb);
                         }
                         c = cn;
                         ita = itan; itb = itbn;
@@ -648,7 +663,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                     itw = 0xffffffffu;
                     if (c < n_chunks && i < n_items) {
                         itw = s_items[i];
-                        const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw));
+                        const unsigned r = (unsigned)(p0 + item_pose(itw)) * (unsigned)Nr + (unsigned)item_ray(itw);
                         q = __ldg(raytab + r);
                         L = __ldg(ltab + r);
                     }
@@ -673,7 +688,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                         const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
                         const float part = brick_pair_fwd_lean<U, LdShared, true, PIPE != 0>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
                         if (part != 0.0f)
-                            red_add(out + ((unsigned)(p0 + bl) * (unsigned)N + (unsigned)(item_row(itw) * W + item_col(itw))), L * part);
+                            red_add(out + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)item_ray(itw)), L * part);
                     }
                     c = cn;
                     itw = itn;
@@ -733,8 +748,8 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS = 1>
 cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const float* ltab,
-                                 const PoseGeo* geo, float* out, unsigned* counter, int B, int H, int W, float shift,
-                                 cudaStream_t stream)
+                                 const PoseGeo* geo, float* out, unsigned* counter, const int* pix_index, int Nr, int B, int H,
+                                 int W, float shift, cudaStream_t stream)
 {
     using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
     auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
@@ -754,7 +769,7 @@ cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const flo
     static_assert(Cfg::kSmemBytes <= (233472 - 1024 * CTAS) / CTAS, "shared-memory carve-up exceeds the SM");
     const int ctas_per_sm = CTAS;
     const int grid = min(bg.nb0 * bg.nb1 * bg.nb2, sms * ctas_per_sm);
-    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(map, dims, bg, raytab, ltab, geo, out, counter, B, H, W, shift);
+    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(map, dims, bg, raytab, ltab, geo, out, counter, pix_index, Nr, B, H, W, shift);
     return cudaGetLastError();
 }
 
@@ -770,24 +785,30 @@ bool siddon_brick_supported(VolDims dims, int H, int W)
     return dims.d[2] % 4 == 0 && H <= kBrickMaxSide && W <= kBrickMaxSide && H >= 2 && W >= 2 && get_encoder() != nullptr;
 }
 
+// pix_index / corners / Nsub describe a ray SUBSET of the H x W grid (all nullptr / 0 for the full grid): tgt, raylen and out
+// are then (B, Nsub) arrays, pix_index [H*W] maps a pixel to its ray (-1: none), corners [B][3][3] are the voxel-space
+// targets of the full grid's pixels (0,0), (0,W-1), (H-1,0).
 cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                     const float* G, const float* Wd, const float* rows, const float* cols, float* out,
                                     void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
-                                    int variant, cudaStream_t stream)
+                                    int variant, cudaStream_t stream, const int* pix_index, const float* corners, int64_t Nsub)
 {
-    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)vol & 15u) != 0 || (int64_t)B * H * W >= ((int64_t)1 << 31))
+    const bool subset = pix_index != nullptr;
+    const int64_t Nr = subset ? Nsub : (int64_t)H * W;
+    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)vol & 15u) != 0 || (int64_t)B * Nr >= ((int64_t)1 << 31) || Nr <= 0 ||
+        Nr > (int64_t)H * W || (subset && (corners == nullptr || G != nullptr)))
         return cudaErrorNotSupported;
-    if (workspace == nullptr || workspace_bytes < siddon_brick_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 255u) != 0)
-        return cudaErrorInvalidValue;
+    const size_t need = 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256) + (sizeof(float4) + sizeof(float)) * (size_t)B * Nr;
+    if (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 255u) != 0) return cudaErrorInvalidValue;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     unsigned* counter = reinterpret_cast<unsigned*>(ws);
     PoseGeo* geo = reinterpret_cast<PoseGeo*>(ws + 256);
     float4* raytab = reinterpret_cast<float4*>(ws + 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256));
-    const int64_t N = (int64_t)H * W;
-    float* ltab = reinterpret_cast<float*>(raytab + (size_t)B * N);
+    float* ltab = reinterpret_cast<float*>(raytab + (size_t)B * Nr);
     PoseRaysB pr{G, Wd, rows, cols};
-    brick_prep_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, ltab, geo,
-                                                                                        out, counter, H, W, eps);
+    brick_prep_kernel<<<dim3((unsigned)((Nr + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, ltab, geo,
+                                                                                         out, counter, H, W, eps, Nr,
+                                                                                         subset ? corners : nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap map;
@@ -795,17 +816,17 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
     case id:                                                                                                             \
         if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>(map, dims, raytab, ltab, geo, out, counter, \
-                                                                                   B, H, W, shift, stream);
+                                                                                   pix_index, (int)Nr, B, H, W, shift, stream);
 #define BV3(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
     case id:                                                                                                             \
         if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 3>(map, dims, raytab, ltab, geo, out, counter, \
-                                                                                   B, H, W, shift, stream);
+                                                                                   pix_index, (int)Nr, B, H, W, shift, stream);
 #define BV2(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
     case id:                                                                                                             \
         if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 2>(map, dims, raytab, ltab, geo, out, counter, \
-                                                                                   B, H, W, shift, stream);
+                                                                                   pix_index, (int)Nr, B, H, W, shift, stream);
     switch (variant) {
         BV(0, 24, 32, 32, 1, 512, 4, 2, 2, 0)    // two CTAs per SM, one 96 KB brick each (production shape)
         BV(7, 24, 32, 32, 2, 1024, 4, 2, 1, 1)   // one CTA per SM with a two-stage TMA + mbarrier pipeline (measured: 1.27 ms vs 1.09)

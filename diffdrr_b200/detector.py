@@ -78,11 +78,28 @@ class Detector(torch.nn.Module):
         yy, xx = torch.meshgrid(rows, cols, indexing="ij")
         target = torch.stack([xx, yy, torch.ones_like(xx)], dim=-1).reshape(1, -1, 3)
         source = torch.zeros(1, 1, 3)
+        # canonical targets of the FULL grid's pixels (0,0), (0,W-1), (H-1,0): the brick-major kernel derives each pose's
+        # detector plane from them when only a sub-sample of the pixels is rendered
+        self.register_buffer("_corner_points", target[:, [0, self.width - 1, (self.height - 1) * self.width], :].clone(),
+                             persistent=False)
         if self.n_subsample is not None:
             pick = torch.randperm(self.height * self.width)[: int(self.n_subsample)]
             target = target[:, pick, :]
             self.subsamples.append(pick.tolist())
         return source, target
+
+    def corner_targets(self, extrinsic: RigidTransform, calibration: RigidTransform | None):
+        """World-space targets (B, 3, 3) of the full grid's pixels (0,0), (0,W-1), (H-1,0) for the given poses."""
+        calib = self.calibration if calibration is None else calibration
+        pose = self.reorient.compose(extrinsic)
+        return pose(calib(self._corner_points))
+
+    def pixel_index(self):
+        """(H*W,) int32 on the detector's device: position of every pixel in the current sub-sample, -1 if not sampled."""
+        pick = torch.as_tensor(self.subsamples[-1], dtype=torch.int64, device=self.source.device)
+        idx = torch.full((self.height * self.width,), -1, dtype=torch.int32, device=self.source.device)
+        idx[pick] = torch.arange(len(pick), dtype=torch.int32, device=self.source.device)
+        return idx
 
     def forward(self, extrinsic: RigidTransform, calibration: RigidTransform | None):
         """-> source (B,1,3), target (B,N,3) in world coordinates (detector.py:144-154)."""

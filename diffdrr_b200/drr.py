@@ -130,6 +130,16 @@ class DRR(nn.Module):
         if fused:
             return self.reshape_transform(self._render_pose_in(pose, calibration), batch_size=len(pose))
         source, target = self.detector(pose, calibration)
+        if self.detector.n_subsample is not None and hasattr(self.renderer, "ray_subset"):
+            # sub-sampled detector: tell the renderer which pixels the rays are and where the full grid's corners project, so
+            # that inference batches can take the brick-major kernel (its cost per ray does not depend on the ray spacing)
+            det = self.detector
+            cached = getattr(self, "_pix_index", None)
+            if cached is None or cached[0] is not det or cached[1] != len(det.subsamples) or cached[2].device != source.device:
+                cached = (det, len(det.subsamples), det.pixel_index())
+                object.__setattr__(self, "_pix_index", cached)
+            corners = self.affine_inverse(det.corner_targets(pose, calibration))
+            self.renderer.ray_subset = (cached[2], corners, det.height, det.width, len(det.subsamples[-1]))
         if self.checkpoint_gradients:
             # kept for API parity; the fused autograd.Function saves inputs only, so this changes nothing memory-wise
             img = checkpoint(self.render, self.density, source, target, mask_to_channels, **kwargs, use_reentrant=False)
@@ -205,7 +215,11 @@ class DRR(nn.Module):
             self.renderer.detector_shape = (tuple(grid_shape) if grid_shape is not None
                                             else (det.height, det.width) if full_grid else None)
         if self.patch_size is None:
-            return self.renderer(density, source, target, img, **kwargs)
+            try:
+                return self.renderer(density, source, target, img, **kwargs)
+            finally:
+                if hasattr(self.renderer, "ray_subset"):
+                    self.renderer.ray_subset = None   # one-shot hint (set by forward() for sub-sampled detectors)
         # serial patches, as the reference does (drr.py:217-225); note Trilinear is not patch-invariant (quirk Q3)
         parts = [
             self.renderer(density, source, t, i, **kwargs)

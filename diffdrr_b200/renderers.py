@@ -69,14 +69,14 @@ _BRICK_MIN_BRICKS = int(_os.environ.get("B200DRR_BRICK_MIN_BRICKS", "2048"))
 _BRICK_MAX_RAY_DENSITY = float(_os.environ.get("B200DRR_BRICK_MAX_RAY_DENSITY", "0.5"))
 
 
-def _brick_ok(vol, B, H, W) -> bool:
+def _brick_ok(vol, B, H, W, check_density: bool = True) -> bool:
     # 24 x 32 x 32-voxel bricks over 2 x 148 resident CTAs: below ~7 bricks per CTA the tail of the dynamic brick queue
     # costs more than the staging returns (256^3 = 704 bricks: 0.66 ms vs 0.48 ms slab-major; 512^3 = 5632 bricks: 1.04 vs 1.13)
     n_bricks = -(-vol.shape[0] // 24) * -(-vol.shape[1] // 32) * -(-vol.shape[2] // 32)
     # ... and only for SPARSE ray sets (detector pixels fewer than ~half the voxels of a volume cross-section, i.e. rays
     # >= ~1.4 voxels apart): dense rays share 32-byte sectors in L1 and the slab-major gather wins (measured at 512^3 ->
     # 1024^2, 32 poses: 24.5 ms slab-major vs 36.5 ms brick-major; at 512^3 -> 256^2 the other way round)
-    sparse = H * W <= _BRICK_MAX_RAY_DENSITY * float(vol.numel()) ** (2.0 / 3.0)
+    sparse = (not check_density) or H * W <= _BRICK_MAX_RAY_DENSITY * float(vol.numel()) ** (2.0 / 3.0)
     return (B >= _BRICK_MIN_BATCH and n_bricks >= _BRICK_MIN_BRICKS and sparse and vol.shape[2] % 4 == 0 and 2 <= H <= 2048
             and 2 <= W <= 2048 and B * H * W < 2**31 and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
 
@@ -133,7 +133,7 @@ class _SiddonFunction(torch.autograd.Function):
     """out (B,1,N) = Siddon line integrals; backward = closed-form kernel (include/b200drr.h)."""
 
     @staticmethod
-    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad, grid):
+    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad, grid, subset=None):
         B, N = _check_inputs(volume, source, target, img)
         vol = volume.contiguous()
         src = source.reshape(B, 3).contiguous()
@@ -152,7 +152,18 @@ class _SiddonFunction(torch.autograd.Function):
             sens = torch.empty(B, N, 8, dtype=torch.float32, device=vol.device)
         with torch.cuda.device(vol.device):
             fast = reduce == 0 and not align_corners and vol.numel() < 2**31 - 1
-            if grid is None and fast and N >= _SORT_MIN_RAYS:
+            if (grid is None and fast and sens is None and subset is not None and subset[0].numel() == subset[2] * subset[3]
+                    and N == subset[4] and _brick_ok(vol, B, subset[2], subset[3], check_density=False)):
+                # inference on a sub-sampled detector: brick-major kernel with a pixel -> ray map (include/b200drr.h)
+                pix, corners, Hs, Ws, _n = subset
+                need = int(lib.b200drr_siddon_brick_workspace_bytes(B, 1, N))
+                ws = _brick_workspace(vol.device, B, 1, N)
+                assert ws.numel() >= need
+                _lib.check(lib.b200drr_siddon_fwd_brick_subset(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                               ctypes.c_void_p(pix.data_ptr()), _ptr(corners.contiguous().float()),
+                                                               _ptr(out), ctypes.c_void_p(ws.data_ptr()), ws.numel(), B, Hs, Ws, N,
+                                                               voxel_shift, eps, 0, _stream()), "b200drr_siddon_fwd_brick_subset")
+            elif grid is None and fast and N >= _SORT_MIN_RAYS:
                 # arbitrary ray set, big enough to be worth ordering: sort for locality, walk slab-major, un-sort the results
                 perm = _locality_order(tgt)
                 tgt_s = torch.gather(tgt, 1, perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
@@ -215,7 +226,7 @@ class _SiddonFunction(torch.autograd.Function):
                 _lib.check(_lib.load().b200drr_siddon_bwd_sens(_ptr(sens), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len),
                                                                B, N, int(stop_grad), _stream()), "b200drr_siddon_bwd_sens")
             return (None, None if g_src is None else g_src.view(src_shape), g_tgt,
-                    None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
+                    None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None, None)
         vol, src, tgt, raylen = ctx.saved_tensors
         B, N = tgt.shape[0], tgt.shape[1]
         need_vol, need_src, need_tgt, need_len = ctx.needs_input_grad[:4]
@@ -242,7 +253,7 @@ class _SiddonFunction(torch.autograd.Function):
                                                   int(stop_grad), int(align_corners), _stream()),
                            "b200drr_siddon_bwd")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
-                None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None)
+                None if g_len is None else g_len.view(img_shape), None, None, None, None, None, None, None)
 
 
 class _SiddonBilinearFunction(torch.autograd.Function):
@@ -586,6 +597,9 @@ class Siddon(torch.nn.Module):
         # (H, W) when the rays handed to forward() are the full row-major detector grid (set by DRR.render);
         # enables the tiled slab-major kernels.  None = arbitrary ray set (sub-sampled / patched / user rays).
         self.detector_shape = None
+        # (pix_index (H*W,) int32, corners (B,3,3) voxel space, H, W, n_rays) when the rays are a SUB-SAMPLE of the detector grid
+        # (one-shot hint set by DRR.forward): inference batches then take the brick-major kernel
+        self.ray_subset = None
 
     def dims(self, volume):
         return _dims_tensor(volume.shape, volume.device, volume.dtype)
@@ -610,7 +624,7 @@ class Siddon(torch.nn.Module):
                                                  bool(self.stop_gradients_through_grid_sample))
         return _SiddonFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                      _reduce_code(self.reducefn), bool(align_corners),
-                                     bool(self.stop_gradients_through_grid_sample), self.detector_shape)
+                                     bool(self.stop_gradients_through_grid_sample), self.detector_shape, self.ray_subset)
 
 
 def siddon_pose_render(renderer, volume, src, G, Wd, rows, cols):

@@ -321,6 +321,19 @@ int b200drr_siddon_fwd_brick(const float *vol, int D0, int D1, int D2, const flo
                              float eps, int variant, void *stream);
 
 /*
+ * The same brick-major kernel for a ray SUBSET of the H x W detector grid (p_subsample, detector.py:134-137): tgt, raylen and
+ * out are (B, Nsub) arrays in the caller's order; pix_index [H*W] int32 maps a detector pixel (h*W + w) to its position in that
+ * order (-1 = pixel not rendered); corners [B][3][3] are the voxel-space targets of the FULL grid's pixels (0,0), (0,W-1),
+ * (H-1,0) of every pose (the kernel derives each pose's detector plane from them).  Shared-memory gathers do not care how far
+ * apart the rays are, so the per-ray cost stays close to the full grid's, where the slab-major gather loses its sector sharing.
+ * workspace: b200drr_siddon_brick_workspace_bytes(B, 1, Nsub) bytes.
+ */
+int b200drr_siddon_fwd_brick_subset(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
+                                    const float *raylen, const int32_t *pix_index, const float *corners, float *out,
+                                    void *workspace, int64_t workspace_bytes, int B, int H, int W, int64_t Nsub,
+                                    float voxel_shift, float eps, int variant, void *stream);
+
+/*
  * Per-ray voxel-visit count of the Siddon walk (number of voxels the line crosses inside the volume),
  * the unit of the ALGORITHMIC byte count used for roofline accounting: visits [B][N]
  * int32.  Measurement helper; not part of the reference surface.

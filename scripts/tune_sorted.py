@@ -40,3 +40,21 @@ for frac in (0.5, 0.25, 0.1):
             o.sum().backward()
         ms = tb.timeit(step)
         print(f"  {frac * 100:4.0f}% sub-sample fwd+bwd(pose), {name:20s}: {ms:.3f} ms")
+
+# ---- sub-sampled detector through the module (inference): brick-major kernel with a pixel -> ray map vs the sorted path
+from diffdrr_b200 import DRR, synthetic  # noqa: E402
+for frac in (0.5, 0.25, 0.1):
+    subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+    subj.volume.affine = synthetic.make_affine(dims)
+    torch.manual_seed(0)
+    drr = DRR(subj, **synthetic.detector_kwargs(H), p_subsample=frac).to(dev)
+    drr.density = vol
+    rot, xyz = synthetic.make_poses(B, seed=0)
+    rot, xyz = rot.to(dev), xyz.to(dev)
+    for name, mb in (("brick-major + pixel map", 2), ("sorted slab-major", 10 ** 9)):
+        renderers._BRICK_MIN_BATCH = mb
+        renderers._SORT_MIN_RAYS = 1
+        with torch.no_grad():
+            ms = tb.timeit(lambda: drr(rot, xyz, parameterization="euler_angles", convention="ZXY"))
+        n_sub = int(N * frac)
+        print(f"  DRR(p_subsample={frac}) inference, {name:24s}: {ms:.3f} ms (module call incl. pose algebra) = {ms * 1e6 / (B * n_sub):.2f} ns/ray")

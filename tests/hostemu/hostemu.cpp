@@ -626,8 +626,8 @@ long emu_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const float*
                             ++st[1];
                             const unsigned it = pack_item(step_bin(a_in, a_out, fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]),
                                                                    (float)kBrickBins / (float)(BX + BY + BZ + 8)),
-                                                          b % kBrickPoseChunk, py, px);
-                            if (item_row(it) != py || item_col(it) != px || item_pose(it) != b % kBrickPoseChunk) ++violations;
+                                                          b % kBrickPoseChunk, py * W + px);
+                            if (item_ray(it) != py * W + px || item_pose(it) != b % kBrickPoseChunk) ++violations;
                             if (start_walk_box(ray, lo_v, hi_v, shift).hit) ++st[2];
                             const float part = brick_pair_fwd<4>(ld, ray, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
                             if (part != 0.0f) {

@@ -212,3 +212,32 @@ def test_sorted_arbitrary_ray_sets_match_plain_kernels_and_goldens(monkeypatch):
         res[name] = (img_, o.detach(), t_.grad, s_.grad)
     for a, b in zip(res["sorted"], res["plain"]):
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+def test_subsampled_detector_inference_takes_the_brick_kernel(monkeypatch):
+    """DRR(p_subsample=0.25) under no_grad on a batch: the brick-major kernel with a pixel -> ray map (b200drr_siddon_fwd_brick_subset)
+    gives the same sub-sampled image as the ray-by-ray kernels and the fp64 oracle on the same rays."""
+    from diffdrr_b200 import DRR, renderers, synthetic
+    from diffdrr_b200.pose import convert
+    from oracle import oracle
+    D, H, B = 256, 128, 4
+    monkeypatch.setattr(renderers, "_BRICK_MIN_BRICKS", 1)
+    vol_np = synthetic.make_volume(D, "rand", seed=7)
+    torch.manual_seed(0)
+    drr = DRR(synthetic.make_subject(vol_np), **synthetic.detector_kwargs(H), p_subsample=0.25).to(DEV)
+    rot, xyz = synthetic.make_poses(B, seed=9)
+    calls = []
+    orig = renderers._lib.load().b200drr_siddon_fwd_brick_subset
+    with torch.no_grad():
+        img = drr(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY")       # scattered to (B,1,H,W)
+        monkeypatch.setattr(renderers, "_BRICK_MIN_BATCH", 10 ** 9)
+        img_ref = drr(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY")
+        src, tgt = drr.detector(convert(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+        src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+    assert img.shape == (B, 1, H, H) and int((img != 0).sum()) > 0.2 * B * H * H * 0.5
+    assert relerr(img.cpu().numpy(), img_ref.cpu().numpy()) < 3e-5
+    ref = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64)            # (B, 1, n_sub) in sub-sample order
+    pick = torch.as_tensor(drr.detector.subsamples[-1])
+    got = img.reshape(B, -1)[:, pick].cpu().numpy()
+    assert relerr(got, ref.reshape(B, -1)) < IMG_TOL

@@ -111,3 +111,18 @@ def test_ray_sharding_world2(batch, height):
     """Detector rows split over 2 gloo ranks (ragged when H is odd): gathered image == unsharded, pose gradients summed."""
     port = 31500 + (os.getpid() % 2000) + batch
     mp.spawn(_ray_worker, args=(2, port, batch, height), nprocs=2, join=True)
+
+
+def test_balanced_pose_assignment():
+    from diffdrr_b200.parallel import balanced_pose_assignment
+    import random
+    rnd = random.Random(0)
+    costs = [rnd.uniform(0.8, 1.2) for _ in range(128)]
+    groups = balanced_pose_assignment(costs, 8)
+    assert sorted(i for g in groups for i in g) == list(range(128)) and all(len(g) == 16 for g in groups)
+    loads = [sum(costs[i] for i in g) for g in groups]
+    contiguous = [sum(costs[r * 16:(r + 1) * 16]) for r in range(8)]
+    assert max(loads) / (sum(loads) / 8) < 1.005 < max(contiguous) / (sum(contiguous) / 8)
+    import pytest
+    with pytest.raises(ValueError):
+        balanced_pose_assignment(costs[:10], 8)
