@@ -275,7 +275,9 @@ class DRR(nn.Module):
 
 
 def reshape_subsampled_drr(img: torch.Tensor, detector: Detector, batch_size: int):
-    """Scatter sub-sampled rays back onto the (H, W) grid, zeros elsewhere (drr.py:142-147)."""
-    drr = torch.zeros(batch_size, detector.height * detector.width).to(img)
-    drr[:, detector.subsamples[-1]] = img
-    return drr.view(batch_size, 1, detector.height, detector.width)
+    """Scatter sub-sampled rays back onto the (H, W) grid, zeros elsewhere (drr.py:142-147).  The reference's own version only
+    broadcasts for batch_size == 1 (it assigns a (B, 1, n) image into a (B, n) slice); here any batch / channel count works."""
+    img = img.reshape(batch_size, -1, img.shape[-1])
+    drr = torch.zeros(batch_size, img.shape[1], detector.height * detector.width, dtype=img.dtype, device=img.device)
+    drr[:, :, detector.subsamples[-1]] = img
+    return drr.view(batch_size, img.shape[1], detector.height, detector.width)
