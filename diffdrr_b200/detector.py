@@ -94,9 +94,18 @@ class Detector(torch.nn.Module):
         pose = self.reorient.compose(extrinsic)
         return pose(calib(self._corner_points))
 
+    def pick_tensor(self):
+        """The current sub-sample's pixel indices as a cached int64 tensor on the detector's device (indexing with the Python
+        list re-uploads it on every call: milliseconds per render)."""
+        cached = getattr(self, "_pick_cache", None)
+        if cached is None or cached[0] != len(self.subsamples) or cached[1].device != self.source.device:
+            cached = (len(self.subsamples), torch.as_tensor(self.subsamples[-1], dtype=torch.int64, device=self.source.device))
+            object.__setattr__(self, "_pick_cache", cached)
+        return cached[1]
+
     def pixel_index(self):
         """(H*W,) int32 on the detector's device: position of every pixel in the current sub-sample, -1 if not sampled."""
-        pick = torch.as_tensor(self.subsamples[-1], dtype=torch.int64, device=self.source.device)
+        pick = self.pick_tensor()
         idx = torch.full((self.height * self.width,), -1, dtype=torch.int32, device=self.source.device)
         idx[pick] = torch.arange(len(pick), dtype=torch.int32, device=self.source.device)
         return idx

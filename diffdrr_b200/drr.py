@@ -279,5 +279,5 @@ def reshape_subsampled_drr(img: torch.Tensor, detector: Detector, batch_size: in
     broadcasts for batch_size == 1 (it assigns a (B, 1, n) image into a (B, n) slice); here any batch / channel count works."""
     img = img.reshape(batch_size, -1, img.shape[-1])
     drr = torch.zeros(batch_size, img.shape[1], detector.height * detector.width, dtype=img.dtype, device=img.device)
-    drr[:, :, detector.subsamples[-1]] = img
+    drr[:, :, detector.pick_tensor().to(img.device)] = img
     return drr.view(batch_size, img.shape[1], detector.height, detector.width)
