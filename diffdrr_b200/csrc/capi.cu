@@ -75,6 +75,46 @@ int b200drr_siddon_fwd_grid(const float* vol, int D0, int D1, int D2, const floa
                                       (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_f64(const double* vol, int D0, int D1, int D2, const double* src, const double* tgt, const double* raylen,
+                           double* out, int B, int64_t N, double voxel_shift, double eps, int reduce, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_fwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, reduce, align_corners != 0,
+                                     (cudaStream_t)stream));
+}
+
+int b200drr_siddon_bwd_f64(const double* vol, int D0, int D1, int D2, const double* src, const double* tgt, const double* raylen,
+                           const double* gout, double* g_src, double* g_tgt, double* g_raylen, double* g_vol, int B, int64_t N,
+                           double voxel_shift, double eps, int stop_grad, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, N, voxel_shift,
+                                     eps, stop_grad != 0, align_corners != 0, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_fwd_f64(const double* vol, int D0, int D1, int D2, const double* src, const double* tgt,
+                              const double* raylen, double* out, int B, int64_t N, double voxel_shift, double eps, int n_points,
+                              const double* alpha_range, int reduce, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) || n_points < 2 ||
+        reduce < 0 || reduce > 1)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, n_points, alpha_range,
+                                        reduce, align_corners != 0, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_bwd_f64(const double* vol, int D0, int D1, int D2, const double* src, const double* tgt,
+                              const double* raylen, const double* gout, double* g_src, double* g_tgt, double* g_raylen,
+                              double* g_vol, double* g_alpha_range, int B, int64_t N, double voxel_shift, double eps,
+                              int n_points, const double* alpha_range, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, g_alpha_range, B,
+                                        N, voxel_shift, eps, n_points, alpha_range, align_corners != 0, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_sorted(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
                               float* out, int B, int64_t N, float voxel_shift, float eps, void* stream)
 {

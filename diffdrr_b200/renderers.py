@@ -30,13 +30,14 @@ _PACKED_SLAB_SENS = 0   # forward+sensitivities march: unslabbed is faster (meas
 _PACKED_SLAB_MIN_BATCH = 8
 
 
-def _check_inputs(volume, source, target, img):
+def _check_inputs(volume, source, target, img, dtype=torch.float32):
     for name, t in (("volume", volume), ("source", source), ("target", target), ("img", img)):
         if not t.is_cuda:
             raise _lib.B200DRRError(
                 f"diffdrr_b200 renderers run on CUDA devices only ({name} is on {t.device}); there is no CPU fallback")
-        if t.dtype != torch.float32:
-            raise NotImplementedError(f"diffdrr_b200 kernels are fp32 ({name} is {t.dtype})")
+        if t.dtype != dtype:
+            raise NotImplementedError(
+                f"diffdrr_b200 kernels take fp32 tensors, or fp64 tensors throughout ({name} is {t.dtype}, volume is {volume.dtype})")
     if volume.dim() != 3:
         raise ValueError(f"volume must be (D0, D1, D2), got {tuple(volume.shape)}")
     B, N = target.shape[0], target.shape[1]
@@ -481,6 +482,90 @@ class _TrilinearFunction(torch.autograd.Function):
                 None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None)
 
 
+class _SiddonFunction64(torch.autograd.Function):
+    """fp64 Siddon (include/b200drr.h: b200drr_siddon_fwd_f64 / _bwd_f64): what `drr.to(torch.float64)` reaches in the
+    reference (drr.py:75).  mode="nearest"; reduce "max" is forward-only."""
+
+    @staticmethod
+    def forward(ctx, volume, source, target, img, voxel_shift, eps, reduce, align_corners, stop_grad):
+        B, N = _check_inputs(volume, source, target, img, torch.float64)
+        vol, src = volume.contiguous(), source.reshape(B, 3).contiguous()
+        tgt, raylen = target.contiguous(), img.reshape(B, N).contiguous()
+        out = torch.empty(B, N, dtype=torch.float64, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(_lib.load().b200drr_siddon_fwd_f64(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B, N,
+                                                          voxel_shift, eps, reduce, int(align_corners), _stream()),
+                       "b200drr_siddon_fwd_f64")
+        ctx.save_for_backward(vol, src, tgt, raylen)
+        ctx.cfg = (voxel_shift, eps, reduce, align_corners, stop_grad, tuple(source.shape), tuple(img.shape))
+        return out.view(B, 1, N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        voxel_shift, eps, reduce, align_corners, stop_grad, src_shape, img_shape = ctx.cfg
+        if reduce != 0:
+            raise NotImplementedError("fp64 Siddon: backward is implemented for reducefn='sum'")
+        vol, src, tgt, raylen = ctx.saved_tensors
+        B, N = tgt.shape[0], tgt.shape[1]
+        need_vol, need_src, need_tgt, need_len = ctx.needs_input_grad[:4]
+        gout = gout.reshape(B, N).contiguous().double()
+        dev = vol.device
+        g_src = torch.empty(B, 3, dtype=torch.float64, device=dev) if need_src else None
+        g_tgt = torch.empty(B, N, 3, dtype=torch.float64, device=dev) if need_tgt else None
+        g_len = torch.empty(B, N, dtype=torch.float64, device=dev) if (need_len and not stop_grad) else None
+        g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_siddon_bwd_f64(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                          _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift, eps,
+                                                          int(stop_grad), int(align_corners), _stream()), "b200drr_siddon_bwd_f64")
+        return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
+                None if g_len is None else g_len.view(img_shape), None, None, None, None, None)
+
+
+class _TrilinearFunction64(torch.autograd.Function):
+    """fp64 trilinear (b200drr_trilinear_fwd_f64 / _bwd_f64); alpha_range (2,) fp64 carries the batch-global range."""
+
+    @staticmethod
+    def forward(ctx, volume, source, target, img, alpha_range, voxel_shift, eps, n_points, reduce, align_corners):
+        B, N = _check_inputs(volume, source, target, img, torch.float64)
+        vol, src = volume.contiguous(), source.reshape(B, 3).contiguous()
+        tgt, raylen = target.contiguous(), img.reshape(B, N).contiguous()
+        arange = alpha_range.detach().to(device=vol.device, dtype=torch.float64).contiguous()
+        out = torch.empty(B, N, dtype=torch.float64, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(_lib.load().b200drr_trilinear_fwd_f64(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(out), B,
+                                                             N, voxel_shift, eps, n_points, _ptr(arange), reduce,
+                                                             int(align_corners), _stream()), "b200drr_trilinear_fwd_f64")
+        ctx.save_for_backward(vol, src, tgt, raylen, arange)
+        ctx.cfg = (voxel_shift, eps, n_points, reduce, align_corners, tuple(source.shape), tuple(img.shape))
+        return out.view(B, 1, N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        voxel_shift, eps, n_points, reduce, align_corners, src_shape, img_shape = ctx.cfg
+        if reduce != 0:
+            raise NotImplementedError("fp64 trilinear: backward is implemented for reducefn='sum'")
+        vol, src, tgt, raylen, arange = ctx.saved_tensors
+        B, N = tgt.shape[0], tgt.shape[1]
+        need_vol, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
+        gout = gout.reshape(B, N).contiguous().double()
+        dev = vol.device
+        g_src = torch.empty(B, 3, dtype=torch.float64, device=dev) if need_src else None
+        g_tgt = torch.empty(B, N, 3, dtype=torch.float64, device=dev) if need_tgt else None
+        g_len = torch.empty(B, N, dtype=torch.float64, device=dev) if need_len else None
+        g_vol = torch.zeros_like(vol) if need_vol else None
+        g_ar = torch.zeros(2, dtype=torch.float64, device=dev) if need_ar else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_trilinear_bwd_f64(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                             _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), _ptr(g_ar), B, N,
+                                                             voxel_shift, eps, n_points, _ptr(arange), int(align_corners),
+                                                             _stream()), "b200drr_trilinear_bwd_f64")
+        return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None)
+
+
 def _mask_channels(mask: torch.Tensor) -> int:
     """Number of label channels, as the reference computes it (renderers.py:81; one host sync per call)."""
     return int(mask.max().item() + 1)
@@ -611,6 +696,12 @@ class Siddon(torch.nn.Module):
             # the reference crashes on this flag (renderers.py:118 calls _get_alpha_minmax with too few arguments)
             raise NotImplementedError("filter_intersections_outside_volume=True is broken in the reference and "
                                       "unnecessary here: the fused walk already clips to the volume")
+        if volume.dtype == torch.float64:  # `drr.to(torch.float64)` (reference drr.py:75): the reference-literal fp64 kernels
+            if mask is not None or self.mode != "nearest":
+                raise NotImplementedError("fp64 Siddon is implemented for mode='nearest' without mask_to_channels")
+            return _SiddonFunction64.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
+                                           _reduce_code(self.reducefn), bool(align_corners),
+                                           bool(self.stop_gradients_through_grid_sample))
         if mask is not None:
             if align_corners or _reduce_code(self.reducefn) != 0:
                 raise NotImplementedError("mask_to_channels is implemented for reducefn='sum', align_corners=False")
@@ -707,6 +798,13 @@ class Trilinear(torch.nn.Module):
             dims = _dims_tensor(volume.shape, source.device, source.dtype)
             amin, amax = _get_alpha_minmax(source, target, dims, self.voxel_shift, self.eps)
             alphamin, alphamax = amin.min(), amax.max()
+        if volume.dtype == torch.float64:  # `drr.to(torch.float64)`: reference-literal fp64 kernels
+            if mask is not None:
+                raise NotImplementedError("fp64 trilinear is implemented without mask_to_channels")
+            alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=torch.float64, device=volume.device),
+                                       torch.as_tensor(alphamax, dtype=torch.float64, device=volume.device)])
+            return _TrilinearFunction64.apply(volume, source, target, img, alpha_range, float(self.voxel_shift), float(self.eps),
+                                              int(n_points), _reduce_code(self.reducefn), bool(align_corners))
         alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=torch.float32, device=volume.device),
                                    torch.as_tensor(alphamax, dtype=torch.float32, device=volume.device)])
         if mask is not None:

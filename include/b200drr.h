@@ -289,6 +289,28 @@ int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int 
                                void *stream);
 
 /*
+ * Double precision.  The reference reaches fp64 through `drr.to(torch.float64)` (drr.py:75): these entry points take fp64
+ * device pointers with the same meaning as their fp32 namesakes (b200drr_siddon_fwd / _bwd, b200drr_trilinear_fwd / _bwd)
+ * and restate renderers.py:34-76 / 205-240 literally, one thread per ray (accuracy path: no tiling, no packed copy).
+ * reduce = 1 ("max") is forward-only; Siddon is mode="nearest"; g_src is overwritten, g_vol / g_alpha_range are
+ * ACCUMULATED into (caller zero-fills), NULL outputs are skipped.
+ */
+int b200drr_siddon_fwd_f64(const double *vol, int D0, int D1, int D2, const double *src, const double *tgt,
+                           const double *raylen, double *out, int B, int64_t N, double voxel_shift, double eps, int reduce,
+                           int align_corners, void *stream);
+int b200drr_siddon_bwd_f64(const double *vol, int D0, int D1, int D2, const double *src, const double *tgt,
+                           const double *raylen, const double *gout, double *g_src, double *g_tgt, double *g_raylen,
+                           double *g_vol, int B, int64_t N, double voxel_shift, double eps, int stop_grad, int align_corners,
+                           void *stream);
+int b200drr_trilinear_fwd_f64(const double *vol, int D0, int D1, int D2, const double *src, const double *tgt,
+                              const double *raylen, double *out, int B, int64_t N, double voxel_shift, double eps,
+                              int n_points, const double *alpha_range, int reduce, int align_corners, void *stream);
+int b200drr_trilinear_bwd_f64(const double *vol, int D0, int D1, int D2, const double *src, const double *tgt,
+                              const double *raylen, const double *gout, double *g_src, double *g_tgt, double *g_raylen,
+                              double *g_vol, double *g_alpha_range, int B, int64_t N, double voxel_shift, double eps,
+                              int n_points, const double *alpha_range, int align_corners, void *stream);
+
+/*
  * Siddon forward / forward-with-sensitivities for ARBITRARY ray sets that the caller has put in a LOCALITY ORDER
  * (sub-sampled detectors detector.py:134-137, patches drr.py:217-225, user rays): consecutive groups of 32 rays should be
  * spatial neighbours (the module sorts by the Morton code of the target points).  Thread i walks ray i, so a warp's
