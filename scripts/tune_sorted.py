@@ -58,3 +58,27 @@ for frac in (0.5, 0.25, 0.1):
             ms = tb.timeit(lambda: drr(rot, xyz, parameterization="euler_angles", convention="ZXY"))
         n_sub = int(N * frac)
         print(f"  DRR(p_subsample={frac}) inference, {name:24s}: {ms:.3f} ms (module call incl. pose algebra) = {ms * 1e6 / (B * n_sub):.2f} ns/ray")
+
+# ---- the subset kernel alone (C ABI, rays resident): per-ray cost vs the full grid
+from diffdrr_b200 import _lib  # noqa: E402
+from diffdrr_b200.renderers import _ptr, _stream  # noqa: E402
+lib = _lib.load()
+ws_full = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, H, H), dtype=torch.uint8, device=dev)
+out_full = torch.empty(B, N, device=dev)
+t_full = tb.timeit(lambda: tb.brick_call(vol, dims, src, tgt, raylen, out_full, ws_full, B, H, H, 0))
+print(f"brick-major full grid: {t_full:.3f} ms = {t_full * 1e6 / (B * N):.2f} ns/ray")
+corners = tgt[:, [0, H - 1, (H - 1) * H], :].contiguous()
+for frac in (0.5, 0.25, 0.1):
+    sel = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(0))[: int(N * frac)]
+    ns = len(sel)
+    pix = torch.full((N,), -1, dtype=torch.int32, device=dev)
+    pix[sel] = torch.arange(ns, dtype=torch.int32, device=dev)
+    tg, ln = tgt[:, sel].contiguous(), raylen[:, sel].contiguous()
+    o = torch.empty(B, ns, device=dev)
+    ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, 1, ns), dtype=torch.uint8, device=dev)
+    def call():
+        _lib.check(lib.b200drr_siddon_fwd_brick_subset(_ptr(vol), *dims, _ptr(src), _ptr(tg), _ptr(ln), pix.data_ptr(), _ptr(corners), _ptr(o),
+                                                       ws.data_ptr(), ws.numel(), B, H, H, ns, 0.5, 1e-8, 0, _stream()), "subset")
+    ms = tb.timeit(call)
+    err = float((o - out_full[:, sel]).abs().max() / out_full.abs().max())
+    print(f"  brick-major {frac * 100:4.0f}% sub-sample (kernel only): {ms:.3f} ms = {ms * 1e6 / (B * ns):.2f} ns/ray ({ms * 1e6 / (B * ns) / (t_full * 1e6 / (B * N)):.2f}x the brick full-grid per-ray cost, {ms * 1e6 / (B * ns) / (full * 1e6 / (B * N)):.2f}x the slab-major full grid's)  maxdiff {err:.1e}")
