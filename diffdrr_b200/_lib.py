@@ -138,7 +138,7 @@ _SIGNATURES = {
         ctypes.c_void_p]),
     "b200drr_trilinear_bwd_f64": (ctypes.c_int, [
         _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
-        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
         ctypes.c_double, ctypes.c_int, _c_float_p, ctypes.c_int, ctypes.c_void_p]),
     "b200drr_siddon_fwd_sorted": (ctypes.c_int, [
         _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int,

@@ -136,3 +136,15 @@ def test_compile_renderer_flag_is_not_silently_ignored():
         warnings.simplefilter("always")
         drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(6), compile_renderer=True)
     assert drr.compile_renderer and any("compile_renderer" in str(x.message) for x in w)
+
+
+def test_ctypes_signatures_have_the_arity_of_the_header_prototypes():
+    """Every ctypes argtypes list has exactly as many entries as the C prototype in include/b200drr.h has parameters (a
+    mismatch only shows up as a TypeError on the GPU box otherwise)."""
+    header = open(os.path.join(ROOT, "include", "b200drr.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char \*)\s*(b200drr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 40
+    for name, args in protos:
+        n = 0 if args.strip() in ("void", "") else len(args.split(","))
+        assert len(_lib._SIGNATURES[name][1]) == n, f"{name}: header has {n} parameters, ctypes binding {len(_lib._SIGNATURES[name][1])}"
