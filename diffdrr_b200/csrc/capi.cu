@@ -23,6 +23,31 @@ inline VolDims mk(int D0, int D1, int D2)
 }
 inline int ret(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
+template <typename R>
+int segments_fwd(int kind, const void* vol, int D0, int D1, int D2, const void* src, const void* tgt, const void* raylen, void* out,
+                 int B, int64_t N, double shift, double eps, int n_points, const void* alpha_range, int align_corners, void* stream)
+{
+    const VolDims d = mk(D0, D1, D2);
+    if (kind == 0)
+        return ret(launch_siddon_fwd_literal<R>((const R*)vol, d, (const R*)src, (const R*)tgt, (const R*)raylen, (R*)out, B, N, (R)shift,
+                                                (R)eps, 2, align_corners, (cudaStream_t)stream));
+    return ret(launch_trilinear_fwd_literal<R>((const R*)vol, d, (const R*)src, (const R*)tgt, (const R*)raylen, (R*)out, B, N, (R)shift,
+                                               (R)eps, n_points, (const R*)alpha_range, 2, align_corners, (cudaStream_t)stream));
+}
+template <typename R>
+int segments_bwd(int kind, const void* vol, int D0, int D1, int D2, const void* src, const void* tgt, const void* raylen,
+                 const void* gseg, void* g_src, void* g_tgt, void* g_raylen, void* g_vol, void* g_alpha_range, int B, int64_t N,
+                 double shift, double eps, int n_points, const void* alpha_range, int stop_grad, int align_corners, void* stream)
+{
+    const VolDims d = mk(D0, D1, D2);
+    if (kind == 0)
+        return ret(launch_siddon_bwd_literal<R>((const R*)vol, d, (const R*)src, (const R*)tgt, (const R*)raylen, nullptr, (const R*)gseg,
+                                                (R*)g_src, (R*)g_tgt, (R*)g_raylen, (R*)g_vol, B, N, (R)shift, (R)eps, stop_grad,
+                                                align_corners, (cudaStream_t)stream));
+    return ret(launch_trilinear_bwd_literal<R>((const R*)vol, d, (const R*)src, (const R*)tgt, (const R*)raylen, nullptr,
+                                               (const R*)gseg, (R*)g_src, (R*)g_tgt, (R*)g_raylen, (R*)g_vol, (R*)g_alpha_range, B, N,
+                                               (R)shift, (R)eps, n_points, (const R*)alpha_range, align_corners, (cudaStream_t)stream));
+}
 }  // namespace
 
 extern "C" {
@@ -80,7 +105,7 @@ int b200drr_siddon_fwd_f64(const double* vol, int D0, int D1, int D2, const doub
 {
     if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || reduce < 0 || reduce > 1)
         return B200DRR_EINVAL;
-    return ret(launch_siddon_fwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, reduce, align_corners != 0,
+    return ret(launch_siddon_fwd_literal<double>(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, reduce, align_corners != 0,
                                      (cudaStream_t)stream));
 }
 
@@ -89,7 +114,7 @@ int b200drr_siddon_bwd_f64(const double* vol, int D0, int D1, int D2, const doub
                            double voxel_shift, double eps, int stop_grad, int align_corners, void* stream)
 {
     if (!vol || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || bad_rays(B, N)) return B200DRR_EINVAL;
-    return ret(launch_siddon_bwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B, N, voxel_shift,
+    return ret(launch_siddon_bwd_literal<double>(vol, mk(D0, D1, D2), src, tgt, raylen, gout, nullptr, g_src, g_tgt, g_raylen, g_vol, B, N, voxel_shift,
                                      eps, stop_grad != 0, align_corners != 0, (cudaStream_t)stream));
 }
 
@@ -100,7 +125,7 @@ int b200drr_trilinear_fwd_f64(const double* vol, int D0, int D1, int D2, const d
     if (!vol || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) || n_points < 2 ||
         reduce < 0 || reduce > 1)
         return B200DRR_EINVAL;
-    return ret(launch_trilinear_fwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, n_points, alpha_range,
+    return ret(launch_trilinear_fwd_literal<double>(vol, mk(D0, D1, D2), src, tgt, raylen, out, B, N, voxel_shift, eps, n_points, alpha_range,
                                         reduce, align_corners != 0, (cudaStream_t)stream));
 }
 
@@ -111,8 +136,35 @@ int b200drr_trilinear_bwd_f64(const double* vol, int D0, int D1, int D2, const d
 {
     if (!vol || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) || bad_rays(B, N) || n_points < 2)
         return B200DRR_EINVAL;
-    return ret(launch_trilinear_bwd_f64(vol, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, g_alpha_range, B,
+    return ret(launch_trilinear_bwd_literal<double>(vol, mk(D0, D1, D2), src, tgt, raylen, gout, nullptr, g_src, g_tgt, g_raylen, g_vol, g_alpha_range, B,
                                         N, voxel_shift, eps, n_points, alpha_range, align_corners != 0, (cudaStream_t)stream));
+}
+
+int b200drr_segments_fwd(int kind, int is_f64, const void* vol, int D0, int D1, int D2, const void* src, const void* tgt,
+                         const void* raylen, void* out, int B, int64_t N, double voxel_shift, double eps, int n_points,
+                         const void* alpha_range, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || bad_rays(B, N) || kind < 0 || kind > 1 ||
+        (kind == 1 && (!alpha_range || n_points < 2)))
+        return B200DRR_EINVAL;
+    return is_f64 ? segments_fwd<double>(kind, vol, D0, D1, D2, src, tgt, raylen, out, B, N, voxel_shift, eps, n_points, alpha_range,
+                                         align_corners != 0, stream)
+                  : segments_fwd<float>(kind, vol, D0, D1, D2, src, tgt, raylen, out, B, N, voxel_shift, eps, n_points, alpha_range,
+                                        align_corners != 0, stream);
+}
+
+int b200drr_segments_bwd(int kind, int is_f64, const void* vol, int D0, int D1, int D2, const void* src, const void* tgt,
+                         const void* raylen, const void* gseg, void* g_src, void* g_tgt, void* g_raylen, void* g_vol,
+                         void* g_alpha_range, int B, int64_t N, double voxel_shift, double eps, int n_points,
+                         const void* alpha_range, int stop_grad, int align_corners, void* stream)
+{
+    if (!vol || !src || !tgt || !raylen || !gseg || bad_dims(D0, D1, D2) || bad_rays(B, N) || kind < 0 || kind > 1 ||
+        (kind == 1 && (!alpha_range || n_points < 2)))
+        return B200DRR_EINVAL;
+    return is_f64 ? segments_bwd<double>(kind, vol, D0, D1, D2, src, tgt, raylen, gseg, g_src, g_tgt, g_raylen, g_vol, g_alpha_range,
+                                         B, N, voxel_shift, eps, n_points, alpha_range, stop_grad != 0, align_corners != 0, stream)
+                  : segments_bwd<float>(kind, vol, D0, D1, D2, src, tgt, raylen, gseg, g_src, g_tgt, g_raylen, g_vol, g_alpha_range,
+                                        B, N, voxel_shift, eps, n_points, alpha_range, stop_grad != 0, align_corners != 0, stream);
 }
 
 int b200drr_siddon_fwd_sorted(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,

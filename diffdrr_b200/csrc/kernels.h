@@ -91,20 +91,23 @@ cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDi
                                       float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
                                       int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
 
-// double precision (fp64.cu): reference-literal, one thread per ray
-cudaError_t launch_siddon_fwd_f64(const double* vol, VolDims dims, const double* src, const double* tgt, const double* raylen,
-                                  double* out, int B, int64_t N, double shift, double eps, int reduce, int align_corners,
-                                  cudaStream_t stream);
-cudaError_t launch_siddon_bwd_f64(const double* vol, VolDims dims, const double* src, const double* tgt, const double* raylen,
-                                  const double* gout, double* g_src, double* g_tgt, double* g_raylen, double* g_vol, int B,
-                                  int64_t N, double shift, double eps, int stop_grad, int align_corners, cudaStream_t stream);
-cudaError_t launch_trilinear_fwd_f64(const double* vol, VolDims dims, const double* src, const double* tgt, const double* raylen,
-                                     double* out, int B, int64_t N, double shift, double eps, int n_points,
-                                     const double* alpha_range, int reduce, int align_corners, cudaStream_t stream);
-cudaError_t launch_trilinear_bwd_f64(const double* vol, VolDims dims, const double* src, const double* tgt, const double* raylen,
-                                     const double* gout, double* g_src, double* g_tgt, double* g_raylen, double* g_vol,
-                                     double* g_alpha_range, int B, int64_t N, double shift, double eps, int n_points,
-                                     const double* alpha_range, int align_corners, cudaStream_t stream);
+// reference-literal kernels (literal.cu), R = float | double: fp64 path and per-segment / per-sample outputs (reduce == 2)
+template <typename R>
+cudaError_t launch_siddon_fwd_literal(const R* vol, VolDims dims, const R* src, const R* tgt, const R* raylen, R* out, int B,
+                                      int64_t N, R shift, R eps, int reduce, int align_corners, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_siddon_bwd_literal(const R* vol, VolDims dims, const R* src, const R* tgt, const R* raylen, const R* gout,
+                                      const R* gseg, R* g_src, R* g_tgt, R* g_raylen, R* g_vol, int B, int64_t N, R shift, R eps,
+                                      int stop_grad, int align_corners, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_trilinear_fwd_literal(const R* vol, VolDims dims, const R* src, const R* tgt, const R* raylen, R* out, int B,
+                                         int64_t N, R shift, R eps, int n_points, const R* alpha_range, int reduce,
+                                         int align_corners, cudaStream_t stream);
+template <typename R>
+cudaError_t launch_trilinear_bwd_literal(const R* vol, VolDims dims, const R* src, const R* tgt, const R* raylen, const R* gout,
+                                         const R* gsmp, R* g_src, R* g_tgt, R* g_raylen, R* g_vol, R* g_alpha_range, int B,
+                                         int64_t N, R shift, R eps, int n_points, const R* alpha_range, int align_corners,
+                                         cudaStream_t stream);
 
 // arbitrary ray sets in a caller-provided locality order (slab-major, thread i = ray i)
 cudaError_t launch_siddon_fwd_sorted(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,

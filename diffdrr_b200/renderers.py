@@ -566,6 +566,51 @@ class _TrilinearFunction64(torch.autograd.Function):
                 None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None)
 
 
+class _SegmentsFunction(torch.autograd.Function):
+    """Un-reduced render for a CALLABLE `reducefn` (reference renderers.py:175-183 hands it the per-segment tensor):
+    kind 0 = Siddon -> (B, N, D0+D1+D2+2) segments in the reference's sorted order, kind 1 = trilinear -> (B, N, n_points).
+    include/b200drr.h: b200drr_segments_fwd / _bwd (reference-literal kernels, fp32 or fp64 after the volume's dtype)."""
+
+    @staticmethod
+    def forward(ctx, volume, source, target, img, alpha_range, kind, voxel_shift, eps, n_points, align_corners, stop_grad):
+        dtype = volume.dtype
+        B, N = _check_inputs(volume, source, target, img, dtype)
+        vol, src = volume.contiguous(), source.reshape(B, 3).contiguous()
+        tgt, raylen = target.contiguous(), img.reshape(B, N).contiguous()
+        arange = None if alpha_range is None else alpha_range.detach().to(device=vol.device, dtype=dtype).contiguous()
+        M = sum(vol.shape) + 2 if kind == 0 else int(n_points)
+        out = torch.empty(B, N, M, dtype=dtype, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(_lib.load().b200drr_segments_fwd(kind, int(dtype == torch.float64), _ptr(vol), *vol.shape, _ptr(src), _ptr(tgt),
+                                                        _ptr(raylen), _ptr(out), B, N, voxel_shift, eps, int(n_points),
+                                                        _ptr(arange), int(align_corners), _stream()), "b200drr_segments_fwd")
+        ctx.save_for_backward(vol, src, tgt, raylen, arange)
+        ctx.cfg = (kind, voxel_shift, eps, int(n_points), align_corners, stop_grad, tuple(source.shape), tuple(img.shape))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gseg):
+        kind, voxel_shift, eps, n_points, align_corners, stop_grad, src_shape, img_shape = ctx.cfg
+        vol, src, tgt, raylen, arange = ctx.saved_tensors
+        B, N = tgt.shape[0], tgt.shape[1]
+        need_vol, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
+        dev, dtype = vol.device, vol.dtype
+        gseg = gseg.to(dtype).contiguous()
+        g_src = torch.empty(B, 3, dtype=dtype, device=dev) if need_src else None
+        g_tgt = torch.empty(B, N, 3, dtype=dtype, device=dev) if need_tgt else None
+        g_len = torch.empty(B, N, dtype=dtype, device=dev) if (need_len and not stop_grad) else None
+        g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
+        g_ar = torch.zeros(2, dtype=dtype, device=dev) if (need_ar and kind == 1) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_segments_bwd(kind, int(dtype == torch.float64), _ptr(vol), *vol.shape, _ptr(src), _ptr(tgt),
+                                                        _ptr(raylen), _ptr(gseg), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol),
+                                                        _ptr(g_ar), B, N, voxel_shift, eps, n_points, _ptr(arange), int(stop_grad),
+                                                        int(align_corners), _stream()), "b200drr_segments_bwd")
+        return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None)
+
+
 def _mask_channels(mask: torch.Tensor) -> int:
     """Number of label channels, as the reference computes it (renderers.py:81; one host sync per call)."""
     return int(mask.max().item() + 1)
@@ -661,9 +706,7 @@ def _reduce_code(reducefn):
     if isinstance(reducefn, str) and reducefn in _REDUCE:
         return _REDUCE[reducefn]
     if isinstance(reducefn, Callable):
-        raise NotImplementedError(
-            "a callable reducefn needs the (B, N, M) per-segment tensor that the fused kernels never materialise; "
-            "diffdrr_b200 supports reducefn='sum' and 'max'")
+        return 2  # un-reduced render (_SegmentsFunction), then reducefn(img) as in reference renderers.py:175-183
     raise ValueError(f"Only supports reducefn 'sum' or 'max', not {reducefn}")
 
 
@@ -696,6 +739,12 @@ class Siddon(torch.nn.Module):
             # the reference crashes on this flag (renderers.py:118 calls _get_alpha_minmax with too few arguments)
             raise NotImplementedError("filter_intersections_outside_volume=True is broken in the reference and "
                                       "unnecessary here: the fused walk already clips to the volume")
+        if _reduce_code(self.reducefn) == 2:  # callable: it receives the (B, N, M-1) segment tensor (renderers.py:175-183)
+            if mask is not None or self.mode != "nearest":
+                raise NotImplementedError("a callable reducefn is implemented for mode='nearest' without mask_to_channels")
+            seg = _SegmentsFunction.apply(volume, source, target, img, None, 0, float(self.voxel_shift), float(self.eps), 0,
+                                          bool(align_corners), bool(self.stop_gradients_through_grid_sample))
+            return self.reducefn(seg).unsqueeze(1)
         if volume.dtype == torch.float64:  # `drr.to(torch.float64)` (reference drr.py:75): the reference-literal fp64 kernels
             if mask is not None or self.mode != "nearest":
                 raise NotImplementedError("fp64 Siddon is implemented for mode='nearest' without mask_to_channels")
@@ -798,6 +847,14 @@ class Trilinear(torch.nn.Module):
             dims = _dims_tensor(volume.shape, source.device, source.dtype)
             amin, amax = _get_alpha_minmax(source, target, dims, self.voxel_shift, self.eps)
             alphamin, alphamax = amin.min(), amax.max()
+        if _reduce_code(self.reducefn) == 2:  # callable: it receives the (B, N, n_points) sample tensor
+            if mask is not None:
+                raise NotImplementedError("a callable reducefn is implemented without mask_to_channels")
+            alpha_range = torch.stack([torch.as_tensor(alphamin, dtype=volume.dtype, device=volume.device),
+                                       torch.as_tensor(alphamax, dtype=volume.dtype, device=volume.device)])
+            smp = _SegmentsFunction.apply(volume, source, target, img, alpha_range, 1, float(self.voxel_shift), float(self.eps),
+                                          int(n_points), bool(align_corners), False)
+            return self.reducefn(smp).unsqueeze(1)
         if volume.dtype == torch.float64:  # `drr.to(torch.float64)`: reference-literal fp64 kernels
             if mask is not None:
                 raise NotImplementedError("fp64 trilinear is implemented without mask_to_channels")

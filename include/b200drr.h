@@ -311,6 +311,23 @@ int b200drr_trilinear_bwd_f64(const double *vol, int D0, int D1, int D2, const d
                               int n_points, const double *alpha_range, int align_corners, void *stream);
 
 /*
+ * Un-reduced renders for a CALLABLE `reducefn` (renderers.py:175-183 calls `reducefn(img)` on the per-segment tensor):
+ *   kind = 0 (Siddon):    out [B][N][D0+D1+D2+2] = raylen * v_j * (alpha_{j+1} - alpha_j) for every pair of consecutive plane
+ *                         alphas in the reference's sorted order (renderers.py:70-74 before `reduce`);
+ *   kind = 1 (trilinear): out [B][N][n_points]   = raylen * sample_m * step (renderers.py:231-236 before `reduce`).
+ * b200drr_segments_bwd takes the upstream gradient of that tensor (gseg, same shape) and returns the same gradients as
+ * b200drr_siddon_bwd / b200drr_trilinear_bwd (g_src overwritten; g_vol, g_alpha_range ACCUMULATED into; NULL = skipped).
+ * is_f64 selects double pointers (and the fp64 kernels) instead of float.  Reference-literal, one thread per ray.
+ */
+int b200drr_segments_fwd(int kind, int is_f64, const void *vol, int D0, int D1, int D2, const void *src, const void *tgt,
+                         const void *raylen, void *out, int B, int64_t N, double voxel_shift, double eps, int n_points,
+                         const void *alpha_range, int align_corners, void *stream);
+int b200drr_segments_bwd(int kind, int is_f64, const void *vol, int D0, int D1, int D2, const void *src, const void *tgt,
+                         const void *raylen, const void *gseg, void *g_src, void *g_tgt, void *g_raylen, void *g_vol,
+                         void *g_alpha_range, int B, int64_t N, double voxel_shift, double eps, int n_points,
+                         const void *alpha_range, int stop_grad, int align_corners, void *stream);
+
+/*
  * Siddon forward / forward-with-sensitivities for ARBITRARY ray sets that the caller has put in a LOCALITY ORDER
  * (sub-sampled detectors detector.py:134-137, patches drr.py:217-225, user rays): consecutive groups of 32 rays should be
  * spatial neighbours (the module sorts by the Morton code of the target points).  Thread i walks ray i, so a warp's
