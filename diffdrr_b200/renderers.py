@@ -7,7 +7,8 @@ sum) is ONE kernel launch per direction through the C ABI of include/b200drr.h; 
 kernel (no saved activations: `checkpoint_gradients` is a no-op by construction).  When only ray / pose gradients are
 needed the forward kernel also writes each ray's end-point sensitivities (32-48 B per ray) and the backward is elementwise.
 
-There is no CPU / PyTorch fallback: tensors must be CUDA fp32, otherwise the call raises.
+There is no CPU / PyTorch fallback: tensors must be CUDA fp32 (tuned kernels) or CUDA fp64 (reference-literal kernels of
+csrc/literal.cu, which also serve a callable `reducefn`), otherwise the call raises.
 """
 from __future__ import annotations
 
@@ -483,7 +484,7 @@ class _TrilinearFunction(torch.autograd.Function):
 
 
 class _SiddonFunction64(torch.autograd.Function):
-    """fp64 Siddon (include/b200drr.h: b200drr_siddon_fwd_f64 / _bwd_f64): what `drr.to(torch.float64)` reaches in the
+    """fp64 Siddon (csrc/literal.cu; include/b200drr.h: b200drr_siddon_fwd_f64 / _bwd_f64): what `drr.to(torch.float64)` reaches in the
     reference (drr.py:75).  mode="nearest"; reduce "max" is forward-only."""
 
     @staticmethod

@@ -1,4 +1,4 @@
-"""fp64 kernels (csrc/fp64.cu; what `drr.to(torch.float64)` reaches in the reference, drr.py:75) against the reference's own
+"""fp64 kernels (csrc/literal.cu; what `drr.to(torch.float64)` reaches in the reference, drr.py:75) against the reference's own
 fp64 outputs and autograd gradients recorded in the goldens -- every Siddon / trilinear option the goldens cover."""
 import numpy as np
 import pytest
