@@ -446,9 +446,32 @@ def extra_configs(dev, lib, peak, main):
             **_stat(t_c3), "drr_per_s": B3 / np.median(t_c3) * 1e3, "in_volume_sample_fraction": cnt / (B3 * N3 * P3),
             "roofline": roof(tri_bytes, float(np.median(t_c3))),
             "forward_only_slab_major": {**_stat(t_c3f), "drr_per_s": B3 / np.median(t_c3f) * 1e3, "roofline": roof(tri_bytes, float(np.median(t_c3f)))}}
-        del packed, sens3, h_tgt, o3, go3
+        del packed, sens3, h_tgt, o3
+        # the same step through the module API, `DRR(rot, xyz)` + backward(): pose-in entry (rays generated in-kernel,
+        # b200drr_trilinear_fwd_sens_pose) against detector.forward + the ray-tensor kernels
+        import diffdrr_b200.drr as drr_mod
+
+        drr3m = DRR(subj, **synthetic.detector_kwargs(H3), renderer="trilinear").to(dev)
+        drr3m.density = vol
+        rot_d, xyz_d = rot.to(dev).requires_grad_(True), xyz.to(dev).requires_grad_(True)
+        w3 = go3.view(B3, 1, H3, H3)
+
+        def mod_step():
+            rot_d.grad, xyz_d.grad = None, None
+            img = drr3m(rot_d, xyz_d, parameterization="euler_angles", convention="ZXY", n_points=P3)
+            (img * w3).sum().backward()
+
+        module = {}
+        keep = drr_mod._TRILINEAR_POSE_IN
+        for tag, flag in (("pose_in", True), ("ray_tensors", False)):
+            drr_mod._TRILINEAR_POSE_IN = flag
+            t_m = _time_events(mod_step, 5, warmup=2)
+            module[tag] = {**_stat(t_m), "drr_per_s": B3 / np.median(t_m) * 1e3}
+        drr_mod._TRILINEAR_POSE_IN = keep
+        res["config3_trilinear_fwd_bwd_512"]["module_drr_rot_xyz_backward"] = module
+        del drr3m, go3, w3
     except Exception as exc:  # pragma: no cover
-        res["config3_trilinear_fwd_bwd_512"] = {"error": f"{type(exc).__name__}: {exc}"}
+        res.setdefault("config3_trilinear_fwd_bwd_512", {})["error"] = f"{type(exc).__name__}: {exc}"
     torch.cuda.empty_cache()
 
     # ---- (e) BASELINE config 5: 2D/3D registration loop, 1000 gradient steps, 512^3 CT, 256^2 target -------------------

@@ -79,6 +79,16 @@ _SIGNATURES = {
     "b200drr_trilinear_bwd_sens": (ctypes.c_int, [
         _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int64,
         ctypes.c_void_p]),
+    "b200drr_trilinear_alpha_range_pose": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+    "b200drr_trilinear_fwd_sens_pose": (ctypes.c_int, [
+        _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+        _c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "b200drr_trilinear_bwd_sens_pose": (ctypes.c_int, [
+        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200drr_euler_pose_fwd": (ctypes.c_int, [
         _c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, _c_float_p, ctypes.c_int,
         ctypes.c_void_p]),

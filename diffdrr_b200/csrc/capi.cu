@@ -399,6 +399,37 @@ int b200drr_trilinear_bwd_sens(const float* sens, const float* gout, float* g_sr
     return ret(launch_trilinear_bwd_sens(sens, gout, g_src, g_tgt, g_raylen, g_alpha_range, B, N, (cudaStream_t)stream));
 }
 
+int b200drr_trilinear_alpha_range_pose(int D0, int D1, int D2, const float* src, const float* G, const float* Wd, const float* rows,
+                                       const float* cols, float* range, int64_t* arg, void* scratch16, int B, int H, int W,
+                                       float voxel_shift, float eps, void* stream)
+{
+    if (!src || !G || !Wd || !rows || !cols || !range || !arg || !scratch16 || bad_dims(D0, D1, D2) ||
+        bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_alpha_range_pose(mk(D0, D1, D2), src, G, Wd, rows, cols, range, arg, scratch16, B, H, W, voxel_shift,
+                                                 eps, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_fwd_sens_pose(const float* packed, int D0, int D1, int D2, const float* src, const float* G, const float* Wd,
+                                    const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                    float voxel_shift, float eps, int n_points, const float* alpha_range, int slab, void* stream)
+{
+    if (!packed || !src || !G || !Wd || !rows || !cols || !out || !sens || !alpha_range || bad_dims(D0, D1, D2) ||
+        bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0 || n_points < 2 || slab < 0)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_sens_pose(packed, mk(D0, D1, D2), src, G, Wd, rows, cols, out, sens, B, H, W, voxel_shift, eps,
+                                              n_points, alpha_range, slab, (cudaStream_t)stream));
+}
+
+int b200drr_trilinear_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows, const float* cols,
+                                    float* g_src, float* g_G, float* g_Wd, float* g_alpha_range, int B, int H, int W, void* stream)
+{
+    if (!sens || !gout || !Wd || !rows || !cols || !g_src || !g_G || !g_Wd || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd_sens_pose(sens, gout, Wd, rows, cols, g_src, g_G, g_Wd, g_alpha_range, B, H, W,
+                                              (cudaStream_t)stream));
+}
+
 static bool bad_axes(int c0, int c1, int c2)
 {
     return c0 < 0 || c0 > 2 || c1 < 0 || c1 > 2 || c2 < 0 || c2 > 2 || c1 == c0 || c1 == c2;

@@ -108,6 +108,44 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats 
     if (warp == 0) v = warp_sum(v);
     return v;
 }
+
+// Optional in-kernel ray generation ("pose-in" entry points): when G != nullptr the rays of pose b are made from
+//   target_voxel(h, w) = G[b] . (cols[w], rows[h], 1, 1),   raylen(h, w) = | Wd[b] . (cols[w], rows[h], 1, 1) |
+// (G = affine_inverse . extrinsic . reorient . calibration, Wd = the same without affine_inverse and with the source
+// subtracted; reference detector.py:144-154 + drr.py:201-205 collapsed into two 3x4 matrices per pose), so the
+// (B, N, 3) target tensor and the ray-length image never exist in HBM.
+struct PoseRays {
+    const float* G;     // [B][3][4]
+    const float* Wd;    // [B][3][4]
+    const float* rows;  // [H]  canonical detector y of image row h   (detector.py:114-126)
+    const float* cols;  // [W]  canonical detector x of image column w
+};
+
+__device__ __forceinline__ Ray make_ray(const PoseRays& pr, const float* __restrict__ src, const float* __restrict__ tgt,
+                                        const float* __restrict__ raylen, int b, int64_t r, int px, int py, float eps,
+                                        float& L)
+{
+    if (pr.G == nullptr) {
+        L = __ldg(raylen + r);
+        return load_ray(src, tgt, b, r, eps);
+    }
+    const float c = __ldg(pr.cols + px), rr = __ldg(pr.rows + py);
+    const float* g = pr.G + b * 12;
+    const float* wd = pr.Wd + b * 12;
+    Ray ray;
+    float l2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t = fmaf(__ldg(g + a * 4), c, fmaf(__ldg(g + a * 4 + 1), rr, __ldg(g + a * 4 + 2) + __ldg(g + a * 4 + 3)));
+        const float dw = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), rr, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+        l2 = fmaf(dw, dw, l2);
+        ray.s[a] = __ldg(src + b * 3 + a);
+        ray.d[a] = (t - ray.s[a]) + eps;
+        ray.inv[a] = 1.0f / ray.d[a];
+    }
+    L = sqrtf(l2);
+    return ray;
+}
 #endif
 
 }  // namespace b200drr

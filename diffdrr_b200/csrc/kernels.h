@@ -74,6 +74,17 @@ cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, 
                                              cudaStream_t stream);
 cudaError_t launch_trilinear_bwd_sens(const float* sens, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                       float* g_alpha_range, int B, int64_t N, cudaStream_t stream);
+// pose-in forms of the trilinear training path (rays generated in-kernel from per-pose 3x4 matrices)
+cudaError_t launch_trilinear_alpha_range_pose(VolDims dims, const float* src, const float* G, const float* Wd, const float* rows,
+                                              const float* cols, float* range, int64_t* arg, void* keys, int B, int H, int W,
+                                              float shift, float eps, cudaStream_t stream);
+cudaError_t launch_trilinear_fwd_sens_pose(const float* packed, VolDims dims, const float* src, const float* G, const float* Wd,
+                                           const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                           float shift, float eps, int n_points, const float* alpha_range, int slab,
+                                           cudaStream_t stream);
+cudaError_t launch_trilinear_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows,
+                                           const float* cols, float* g_src, float* g_G, float* g_Wd, float* g_alpha_range, int B,
+                                           int H, int W, cudaStream_t stream);
 
 cudaError_t launch_siddon_bwd_general(const float* vol, VolDims dims, const float* src, const float* tgt, const float* raylen,
                                       const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol, int B,

@@ -393,7 +393,7 @@ template <int TW, int TH, bool SLAB>
 __global__ void __launch_bounds__(TW* TH) trilinear_sens_packed_kernel(
     const float4* __restrict__ packed, VolDims dims, const float* __restrict__ src, const float* __restrict__ tgt,
     const float* __restrict__ raylen, float* __restrict__ out, float* __restrict__ sens, int B, int H, int W, int slab,
-    float shift, float eps, int P, const float* __restrict__ alpha_range)
+    float shift, float eps, int P, const float* __restrict__ alpha_range, PoseRays pr)
 {
     constexpr int WX = TW / 8;
     const int tiles_x = (W + TW - 1) / TW, tiles = tiles_x * ((H + TH - 1) / TH);
@@ -407,10 +407,10 @@ __global__ void __launch_bounds__(TW* TH) trilinear_sens_packed_kernel(
     const int py = tile_y * TH + (warp / WX) * 4 + (lane >> 3);
     if (px >= W || py >= H) return;
     const int64_t r = ((int64_t)b * H + py) * W + px;
-    const Ray ray = load_ray(src, tgt, b, r, eps);
+    float L;
+    const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);  // pr.G != nullptr: rays generated here (pose-in)
     const float amin = __ldg(alpha_range), amax = __ldg(alpha_range + 1);
     const float step = (amax - amin) / (float)(P - 1);
-    const float L = __ldg(raylen + r);
     const float s_lo = SLAB ? (float)(sl * slab - 1) : -INFINITY, s_hi = SLAB ? (float)((sl + 1) * slab - 1) : INFINITY;
     const TriGrad tg = trilinear_ray_bwd_packed(packed, dims, ray, shift, P, amin, amax, 1.0f, L, s_lo, s_hi);
     const float sv = step * tg.sumV;
@@ -541,10 +541,10 @@ cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDi
     return cudaGetLastError();
 }
 
-cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
-                                             const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
-                                             float eps, int n_points, const float* alpha_range, int slab,
-                                             cudaStream_t stream)
+static cudaError_t launch_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
+                                      const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                      float eps, int n_points, const float* alpha_range, int slab, cudaStream_t stream,
+                                      PoseRays pr)
 {
     const int64_t tiles = (int64_t)((W + 15) / 16) * ((H + 15) / 16);
     if (slab > 0) {
@@ -556,12 +556,186 @@ cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, 
         if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 12 * n, stream);
         if (e != cudaSuccess) return e;
         trilinear_sens_packed_kernel<16, 16, true><<<(unsigned)blocks, 256, 0, stream>>>(
-            (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, slab, shift, eps, n_points, alpha_range);
+            (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, slab, shift, eps, n_points, alpha_range, pr);
         return cudaGetLastError();
     }
     if (tiles * B > INT32_MAX) return cudaErrorInvalidValue;
     trilinear_sens_packed_kernel<16, 16, false><<<(unsigned)(tiles * B), 256, 0, stream>>>(
-        (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, 0, shift, eps, n_points, alpha_range);
+        (const float4*)packed, dims, src, tgt, raylen, out, sens, B, H, W, 0, shift, eps, n_points, alpha_range, pr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trilinear_fwd_sens_packed(const float* packed, VolDims dims, const float* src, const float* tgt,
+                                             const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
+                                             float eps, int n_points, const float* alpha_range, int slab,
+                                             cudaStream_t stream)
+{
+    return launch_sens_packed(packed, dims, src, tgt, raylen, out, sens, B, H, W, shift, eps, n_points, alpha_range, slab, stream,
+                              PoseRays{nullptr, nullptr, nullptr, nullptr});
+}
+
+// ---- pose-in entry (SURVEY 8f-2 for the trilinear renderer) -----------------------------------------------------------------
+// The batch-global sampling range of renderers.py:217-222 (min over ALL rays of the slab-entry alpha, max of the slab-exit
+// alpha, `_get_alpha_minmax` renderers.py:124-140 incl. its dims + 1 far plane) from in-kernel rays: values AND the ray that
+// attains each, so that the host can rebuild the two scalars differentiably from the pose of those two rays alone.
+__device__ __forceinline__ unsigned int ordered_bits(float f)
+{
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(unsigned int k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) alpha_range_pose_kernel(VolDims dims, const float* __restrict__ src, PoseRays pr,
+                                                               unsigned long long* __restrict__ keys, int H, int W, float shift,
+                                                               float eps)
+{
+    const int b = blockIdx.y;
+    const int64_t N = (int64_t)H * W;
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int py = (int)(n / W), px = (int)(n % W);
+        float L;
+        const Ray ray = make_ray(pr, src, nullptr, nullptr, b, 0, px, py, eps, L);
+        float lo = -INFINITY, hi = INFINITY;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float a0 = ((-shift) - ray.s[a]) / ray.d[a];
+            const float a1 = (((float)dims.d[a] + (1.0f - shift)) - ray.s[a]) / ray.d[a];
+            lo = fmaxf(lo, fminf(a0, a1));
+            hi = fminf(hi, fmaxf(a0, a1));
+        }
+        lo = fmaxf(lo, 0.0f);
+        hi = fminf(hi, 1.0f);
+        const unsigned long long idx = (unsigned long long)((int64_t)b * N + n) & 0xffffffffull;
+        const unsigned long long k0 = ((unsigned long long)ordered_bits(lo) << 32) | idx;
+        const unsigned long long k1 = ((unsigned long long)ordered_bits(hi) << 32) | idx;
+        kmin = k0 < kmin ? k0 : kmin;
+        kmax = k1 > kmax ? k1 : kmax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long m0 = __shfl_xor_sync(0xffffffffu, kmin, o), m1 = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = m0 < kmin ? m0 : kmin;
+        kmax = m1 > kmax ? m1 : kmax;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys, kmin);
+        atomicMax(keys + 1, kmax);
+    }
+}
+
+__global__ void alpha_range_decode_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ range,
+                                          int64_t* __restrict__ arg)
+{
+    if (threadIdx.x < 2) {
+        const unsigned long long k = keys[threadIdx.x];
+        range[threadIdx.x] = from_ordered_bits((unsigned int)(k >> 32));
+        arg[threadIdx.x] = (int64_t)(k & 0xffffffffull);
+    }
+}
+
+cudaError_t launch_trilinear_alpha_range_pose(VolDims dims, const float* src, const float* G, const float* Wd, const float* rows,
+                                              const float* cols, float* range, int64_t* arg, void* keys, int B, int H, int W,
+                                              float shift, float eps, cudaStream_t stream)
+{
+    if ((int64_t)B * H * W > 0xffffffffll) return cudaErrorInvalidValue;
+    unsigned long long* k = (unsigned long long*)keys;
+    cudaError_t e = cudaMemsetAsync(k, 0xff, sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(k + 1, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    const int chunks = (int)min((int64_t)64, ((int64_t)H * W + 255) / 256);
+    alpha_range_pose_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>(dims, src, PoseRays{G, Wd, rows, cols}, k, H, W,
+                                                                                   shift, eps);
+    alpha_range_decode_kernel<<<1, 32, 0, stream>>>(k, range, arg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trilinear_fwd_sens_pose(const float* packed, VolDims dims, const float* src, const float* G, const float* Wd,
+                                           const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
+                                           float shift, float eps, int n_points, const float* alpha_range, int slab,
+                                           cudaStream_t stream)
+{
+    return launch_sens_packed(packed, dims, src, nullptr, nullptr, out, sens, B, H, W, shift, eps, n_points, alpha_range, slab,
+                              stream, PoseRays{G, Wd, rows, cols});
+}
+
+// gradients of the pose-in form reduced to the per-pose matrices (the trilinear twin of sens_bwd_pose_kernel, siddon.cu):
+// target(h,w) = G.p and raylen = |Wd.p| with p = (cols[w], rows[h], 1, 1)  =>  g_G = sum g dI/dtgt p^T, g_Wd = sum g (dI/dL) (Wd.p / L) p^T
+__global__ void __launch_bounds__(256) trilinear_sens_bwd_pose_kernel(const float4* __restrict__ sens, const float* __restrict__ gout,
+                                                                      const float* __restrict__ Wd, const float* __restrict__ rows,
+                                                                      const float* __restrict__ cols, float* __restrict__ g_src,
+                                                                      float* __restrict__ g_G, float* __restrict__ g_Wd,
+                                                                      float* __restrict__ g_alpha_range, int H, int W)
+{
+    __shared__ float red[32];
+    const int b = blockIdx.y;
+    const int64_t N = (int64_t)H * W;
+    float acc[23];
+#pragma unroll
+    for (int i = 0; i < 23; ++i) acc[i] = 0.0f;
+    const float* wd = Wd + b * 12;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(n / W), w = (int)(n % W);
+        const float c = __ldg(cols + w), r = __ldg(rows + h);
+        const int64_t ray = (int64_t)b * N + n;
+        const float g = __ldg(gout + ray);
+        const float4 t = __ldg(sens + ray * 3), s = __ldg(sens + ray * 3 + 1), u = __ldg(sens + ray * 3 + 2);
+        float dl[3], l2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dl[a] = fmaf(__ldg(wd + a * 4), c, fmaf(__ldg(wd + a * 4 + 1), r, __ldg(wd + a * 4 + 2) + __ldg(wd + a * 4 + 3)));
+            l2 = fmaf(dl[a], dl[a], l2);
+        }
+        const float gl = g * t.w * rsqrtf(fmaxf(l2, 1e-30f));
+        const float gt[3] = {g * t.x, g * t.y, g * t.z};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = gl * dl[a];
+            acc[a * 3 + 0] = fmaf(gt[a], c, acc[a * 3 + 0]);
+            acc[a * 3 + 1] = fmaf(gt[a], r, acc[a * 3 + 1]);
+            acc[a * 3 + 2] += gt[a];
+            acc[9 + a * 3 + 0] = fmaf(v, c, acc[9 + a * 3 + 0]);
+            acc[9 + a * 3 + 1] = fmaf(v, r, acc[9 + a * 3 + 1]);
+            acc[9 + a * 3 + 2] += v;
+        }
+        acc[18] = fmaf(g, s.x, acc[18]);
+        acc[19] = fmaf(g, s.y, acc[19]);
+        acc[20] = fmaf(g, s.z, acc[20]);
+        acc[21] = fmaf(g, s.w, acc[21]);
+        acc[22] = fmaf(g, u.x, acc[22]);
+    }
+#pragma unroll
+    for (int i = 0; i < 23; ++i) {
+        const float tot = block_sum(acc[i], red);
+        if (threadIdx.x == 0) {
+            if (i >= 21) {
+                if (g_alpha_range) atomicAdd(g_alpha_range + (i - 21), tot);
+            } else if (i >= 18) {
+                atomicAdd(g_src + b * 3 + (i - 18), tot);
+            } else {
+                float* dst = (i < 9 ? g_G : g_Wd) + b * 12;
+                const int a = (i % 9) / 3, k = i % 3;
+                atomicAdd(dst + a * 4 + k, tot);
+                if (k == 2) atomicAdd(dst + a * 4 + 3, tot);  // the homogeneous 1 multiplies column 3 as well
+            }
+        }
+    }
+}
+
+cudaError_t launch_trilinear_bwd_sens_pose(const float* sens, const float* gout, const float* Wd, const float* rows,
+                                           const float* cols, float* g_src, float* g_G, float* g_Wd, float* g_alpha_range, int B,
+                                           int H, int W, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_G, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_Wd, 0, sizeof(float) * 12 * (size_t)B, stream);
+    if (e != cudaSuccess) return e;
+    const int chunks = (int)min((int64_t)64, ((int64_t)H * W + 255) / 256);
+    trilinear_sens_bwd_pose_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, stream>>>((const float4*)sens, gout, Wd, rows, cols,
+                                                                                          g_src, g_G, g_Wd, g_alpha_range, H, W);
     return cudaGetLastError();
 }
 

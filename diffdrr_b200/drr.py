@@ -12,6 +12,8 @@ so registration / reconstruction code written against DiffDRR runs unchanged:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 from torch.utils.checkpoint import checkpoint
@@ -19,7 +21,10 @@ from torch.utils.checkpoint import checkpoint
 from . import geometry
 from .detector import Detector
 from .pose import RigidTransform, convert
-from .renderers import Siddon, Trilinear, siddon_pose_render
+from .renderers import Siddon, Trilinear, siddon_pose_render, trilinear_pose_render
+
+# B200DRR_TRILINEAR_POSE_IN=0 sends Trilinear training steps through detector.forward + the ray-tensor kernels (A/B runs)
+_TRILINEAR_POSE_IN = os.environ.get("B200DRR_TRILINEAR_POSE_IN", "1") != "0"
 
 
 class DRR(nn.Module):
@@ -115,7 +120,7 @@ class DRR(nn.Module):
     def forward(self, *args, parameterization: str = None, convention: str = None, calibration: RigidTransform = None,
                 mask_to_channels: bool = False, degrees: bool = False, **kwargs):
         """SE(3) pose (a RigidTransform, or rotation/translation parameters) -> DRR of shape (B, C, H, W)."""
-        fused = self._pose_in_ok(mask_to_channels, kwargs)
+        fused = self._pose_in_ok(mask_to_channels, kwargs) or self._pose_in_trilinear_ok(mask_to_channels, kwargs, args)
         if (fused and parameterization == "euler_angles" and calibration is None and len(args) == 2
                 and geometry.euler_convention_ok(convention) and all(
                     torch.is_tensor(a) and a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[-1] == 3
@@ -128,7 +133,8 @@ class DRR(nn.Module):
         else:
             pose = convert(*args, parameterization=parameterization, convention=convention, degrees=degrees)
         if fused:
-            return self.reshape_transform(self._render_pose_in(pose, calibration), batch_size=len(pose))
+            return self.reshape_transform(self._render_pose_in(pose, calibration, n_points=kwargs.get("n_points", 500)),
+                                          batch_size=len(pose))
         source, target = self.detector(pose, calibration)
         if self.detector.n_subsample is not None and hasattr(self.renderer, "ray_subset"):
             # sub-sampled detector: tell the renderer which pixels the rays are and where the full grid's corners project, so
@@ -158,7 +164,22 @@ class DRR(nn.Module):
                 and self.density.is_cuda and self.density.dtype == torch.float32 and self.density.dim() == 3
                 and self.density.numel() < 2**31 - 1)
 
-    def _render_pose_in(self, pose: RigidTransform, calibration: RigidTransform | None, rows: tuple | None = None):
+    def _pose_in_trilinear_ok(self, mask_to_channels, kwargs, args) -> bool:
+        """True when pose -> rays -> trilinear march can run with in-kernel ray generation: the TRAINING step (pose gradients
+        wanted) of a static volume whose packed-corner copy exists; everything else takes the general path."""
+        r = self.renderer
+        if not (isinstance(r, Trilinear) and r.mode == "bilinear" and r.reducefn == "sum" and _TRILINEAR_POSE_IN
+                and not mask_to_channels and set(kwargs) <= {"n_points"}
+                and self.detector.n_subsample is None and self.patch_size is None and torch.is_grad_enabled()
+                and self.density.is_cuda and self.density.dtype == torch.float32 and self.density.dim() == 3
+                and not self.density.requires_grad):
+            return False
+        wants_grad = any((a.matrix if isinstance(a, RigidTransform) else a).requires_grad
+                         for a in args if isinstance(a, RigidTransform) or torch.is_tensor(a))
+        return wants_grad and r._packed_volume(self.density) is not None
+
+    def _render_pose_in(self, pose: RigidTransform, calibration: RigidTransform | None, rows: tuple | None = None,
+                        n_points: int = 500):
         """detector.forward (detector.py:144-154) + ray lengths / affine_inverse (drr.py:201-205) collapsed into two
         3x4 matrices per pose; the rays themselves are generated inside the CUDA kernel.  `rows=(h0, h1)` renders only
         that block of detector rows (ray sharding across GPUs, parallel.py) -> (B, 1, (h1-h0)*W)."""
@@ -170,7 +191,7 @@ class DRR(nn.Module):
             # the whole composition below as one kernel per direction (include/b200drr.h: b200drr_pose_rays_fwd/_bwd)
             Q, r, Ainv = self._pose_constants()
             src, G, Wd = geometry.pose_rays(pose.matrix, Q, r, Ainv)
-            return siddon_pose_render(self.renderer, self.density, src, G, Wd, grid[:, 0, 1], grid[0, :, 0])
+            return self._pose_render(src, G, Wd, grid[:, 0, 1], grid[0, :, 0], n_points)
         calib = det._calibration if calibration is None else calibration.matrix
         M = pose.matrix @ det._reorient            # canonical C-arm frame -> world   (reorient.compose(extrinsic))
         T = M @ calib                              # ... including the intrinsic scaling of the detector plane
@@ -178,7 +199,13 @@ class DRR(nn.Module):
         G = (A_inv @ T)[:, :3, :]
         src = (A_inv @ M)[:, :3, 3]                # the canonical source is the origin
         Wd = torch.cat([T[:, :3, :3], (T[:, :3, 3] - M[:, :3, 3]).unsqueeze(-1)], dim=-1)  # target - source, world
-        return siddon_pose_render(self.renderer, self.density, src, G, Wd, grid[:, 0, 1], grid[0, :, 0])
+        return self._pose_render(src, G, Wd, grid[:, 0, 1], grid[0, :, 0], n_points)
+
+    def _pose_render(self, src, G, Wd, rows, cols, n_points):
+        if isinstance(self.renderer, Trilinear):
+            return trilinear_pose_render(self.renderer, self.density, self.renderer._packed_volume(self.density), src, G, Wd,
+                                         rows, cols, n_points)
+        return siddon_pose_render(self.renderer, self.density, src, G, Wd, rows, cols)
 
     def _pose_constants(self):
         """Q = reorient . calibration, r = reorient[:, 3], Ainv = affine_inverse as contiguous device tensors, rebuilt only

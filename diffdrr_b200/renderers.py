@@ -483,6 +483,75 @@ class _TrilinearFunction(torch.autograd.Function):
                 None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None)
 
 
+class _TrilinearPoseFunction(torch.autograd.Function):
+    """Trilinear line integrals of the full detector grid with the rays generated IN the kernel from per-pose 3x4 matrices
+    (include/b200drr.h: b200drr_trilinear_fwd_sens_pose / _bwd_sens_pose): the training-step path of a STATIC (packed) volume;
+    gradients come back as matrices + the two range partials, no (B,N,3) tensors exist."""
+
+    @staticmethod
+    def forward(ctx, packed, dims, src, G, Wd, rows, cols, alpha_range, voxel_shift, eps, n_points):
+        B, H, W = G.shape[0], rows.numel(), cols.numel()
+        src, G, Wd = src.contiguous().float(), G.contiguous().float(), Wd.contiguous().float()
+        rows, cols = rows.contiguous().float(), cols.contiguous().float()
+        arange = alpha_range.detach().to(device=packed.device, dtype=torch.float32).contiguous()
+        out = torch.empty(B, H * W, dtype=torch.float32, device=packed.device)
+        sens = torch.empty(B, H * W, 12, dtype=torch.float32, device=packed.device)
+        with torch.cuda.device(packed.device):
+            _lib.check(_lib.load().b200drr_trilinear_fwd_sens_pose(_ptr(packed), *dims, _ptr(src), _ptr(G), _ptr(Wd), _ptr(rows),
+                                                                   _ptr(cols), _ptr(out), _ptr(sens), B, H, W, voxel_shift, eps,
+                                                                   n_points, _ptr(arange),
+                                                                   _PACKED_SLAB_SENS if B >= _PACKED_SLAB_MIN_BATCH else 0,
+                                                                   _stream()), "b200drr_trilinear_fwd_sens_pose")
+        ctx.save_for_backward(sens, Wd, rows, cols)
+        return out.view(B, 1, H * W)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        sens, Wd, rows, cols = ctx.saved_tensors
+        B, H, W = Wd.shape[0], rows.numel(), cols.numel()
+        dev = sens.device
+        gout = gout.reshape(B, H * W).contiguous().float()
+        g_src = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        g_G = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+        g_Wd = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
+        g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if ctx.needs_input_grad[7] else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200drr_trilinear_bwd_sens_pose(_ptr(sens), _ptr(gout), _ptr(Wd), _ptr(rows), _ptr(cols),
+                                                                   _ptr(g_src), _ptr(g_G), _ptr(g_Wd), _ptr(g_ar), B, H, W,
+                                                                   _stream()), "b200drr_trilinear_bwd_sens_pose")
+        return None, None, g_src, g_G, g_Wd, None, None, g_ar, None, None, None
+
+
+def trilinear_pose_render(renderer, volume, packed, src, G, Wd, rows, cols, n_points):
+    """Fused pose-in rendering for a `Trilinear` module with default options and a packed static volume (used by DRR.forward
+    when pose gradients are wanted); -> (B, 1, H*W).  The batch-global sampling range (reference renderers.py:217-222) is found
+    by a reduction kernel over the in-kernel rays, then rebuilt differentiably in torch from the TWO rays that attain it."""
+    B, H, W = G.shape[0], rows.numel(), cols.numel()
+    dev = volume.device
+    src_c, G_c, Wd_c = src.detach().contiguous().float(), G.detach().contiguous().float(), Wd.detach().contiguous().float()
+    rows_c, cols_c = rows.contiguous().float(), cols.contiguous().float()
+    rng = torch.empty(2, dtype=torch.float32, device=dev)
+    arg = torch.empty(2, dtype=torch.int64, device=dev)
+    scratch = torch.empty(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b200drr_trilinear_alpha_range_pose(*volume.shape, _ptr(src_c), _ptr(G_c), _ptr(Wd_c), _ptr(rows_c),
+                                                                  _ptr(cols_c), _ptr(rng), _ptr(arg), _ptr(scratch), B, H, W,
+                                                                  float(renderer.voxel_shift), float(renderer.eps), _stream()),
+                   "b200drr_trilinear_alpha_range_pose")
+    # the two extremal rays, rebuilt with torch ops so that autograd reaches the pose through the range as the reference's
+    # `.min()` / `.max()` do (the gradient goes to the arg-min / arg-max ray); no host sync: indices stay on the device
+    b, n = arg // (H * W), arg % (H * W)
+    p = torch.stack([cols_c[n % W], rows_c[n // W], torch.ones(2, device=dev), torch.ones(2, device=dev)], dim=-1)  # (2, 4)
+    tgt2 = torch.einsum("kij,kj->ki", G[b].float(), p).unsqueeze(1)            # (2, 1, 3)
+    src2 = src[b].float().unsqueeze(1)                                           # (2, 1, 3)
+    dims = _dims_tensor(volume.shape, dev, torch.float32)
+    amin, amax = _get_alpha_minmax(src2, tgt2, dims, renderer.voxel_shift, renderer.eps)
+    alpha_range = torch.stack([amin[0, 0, 0], amax[1, 0, 0]])
+    return _TrilinearPoseFunction.apply(packed, tuple(volume.shape), src, G, Wd, rows, cols, alpha_range,
+                                        float(renderer.voxel_shift), float(renderer.eps), int(n_points))
+
+
 class _SiddonFunction64(torch.autograd.Function):
     """fp64 Siddon (csrc/literal.cu; include/b200drr.h: b200drr_siddon_fwd_f64 / _bwd_f64): what `drr.to(torch.float64)` reaches in the
     reference (drr.py:75).  mode="nearest"; reduce "max" is forward-only."""

@@ -238,6 +238,29 @@ int b200drr_trilinear_bwd_sens(const float *sens, const float *gout, float *g_sr
                                float *g_alpha_range, int B, int64_t N, void *stream);
 
 /*
+ * Pose-in forms of the trilinear training path (the twin of b200drr_siddon_fwd_sens_pose): the rays of the
+ * full detector grid are generated in-kernel from src [B][3], G, Wd [B][3][4], rows [H], cols [W]
+ * (detector.py:144-154 + drr.py:201-205 collapsed), so neither the (B,N,3) target tensor nor the ray-length image exists.
+ *   b200drr_trilinear_alpha_range_pose: the batch-global sampling range of renderers.py:217-222 (`_get_alpha_minmax`,
+ *     renderers.py:124-140, min / max over ALL rays): range [2] = {alphamin, alphamax}, arg [2] = the linear ray index
+ *     b*H*W + h*W + w attaining each (the host rebuilds the two scalars differentiably from those two rays' pose);
+ *     scratch16 = 16 bytes of device scratch.
+ *   b200drr_trilinear_fwd_sens_pose: out / sens exactly as b200drr_trilinear_fwd_sens_packed.
+ *   b200drr_trilinear_bwd_sens_pose: g_src [B][3], g_G, g_Wd [B][3][4] overwritten; g_alpha_range [2] ACCUMULATED INTO (NULL =
+ *     not wanted).
+ */
+int b200drr_trilinear_alpha_range_pose(int D0, int D1, int D2, const float *src, const float *G, const float *Wd,
+                                       const float *rows, const float *cols, float *range, int64_t *arg, void *scratch16,
+                                       int B, int H, int W, float voxel_shift, float eps, void *stream);
+int b200drr_trilinear_fwd_sens_pose(const float *packed, int D0, int D1, int D2, const float *src, const float *G,
+                                    const float *Wd, const float *rows, const float *cols, float *out, float *sens, int B,
+                                    int H, int W, float voxel_shift, float eps, int n_points, const float *alpha_range,
+                                    int slab, void *stream);
+int b200drr_trilinear_bwd_sens_pose(const float *sens, const float *gout, const float *Wd, const float *rows,
+                                    const float *cols, float *g_src, float *g_G, float *g_Wd, float *g_alpha_range, int B,
+                                    int H, int W, void *stream);
+
+/*
  * mask_to_channels forward (reference renderers.py:77-89 and 242-252): `mask` is the label volume [D0][D1][D2] stored
  * as fp32 (as DRR registers it, drr.py:86-91); every segment / sample contributes to channel label(voxel), sampled
  * nearest with zero padding.  out [B][C][N] is overwritten.  Siddon: reduce="sum", align_corners=0.

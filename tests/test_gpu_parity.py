@@ -256,8 +256,8 @@ def test_unsupported_options_raise():
         Siddon(filter_intersections_outside_volume=True)(*args)   # quirk Q5: the reference crashes too
     with pytest.raises(ValueError):
         Siddon(mode="bicubic")(*args)
-    with pytest.raises(NotImplementedError):
-        Siddon(reducefn=lambda x: x.mean(-1))(*args)
+    with pytest.raises(NotImplementedError):  # a callable reducefn (tests/test_gpu_callable.py) is not combined with a mask
+        Siddon(reducefn=lambda x: x.mean(-1))(*args, mask=torch.zeros_like(args[0]))
     with pytest.raises(NotImplementedError):  # mask rendering: reducefn="sum", align_corners=False only
         Siddon()(*args, align_corners=True, mask=torch.zeros_like(args[0]))
     with pytest.raises(NotImplementedError):
