@@ -486,6 +486,30 @@ int b200drr_trilinear_fwd_mask(const float* vol, const float* mask, int D0, int 
                                          n_points, alpha_range, align_corners != 0, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_fwd_mask_grid(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                                 const float* raylen, float* out, int B, int H, int W, int C, float voxel_shift, float eps,
+                                 void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !out || bad_dims(D0, D1, D2) || H <= 0 || W <= 0 ||
+        bad_rays(B, (int64_t)H * W) || C <= 0)
+        return B200DRR_EINVAL;
+    if ((int64_t)D0 * D1 * D2 >= (int64_t)INT32_MAX) return B200DRR_EUNSUPPORTED;
+    return ret(launch_siddon_fwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, out, B, (int64_t)H * W, C, voxel_shift, eps,
+                                      (cudaStream_t)stream, W));
+}
+
+int b200drr_trilinear_fwd_mask_grid(const float* vol, const float* mask, int D0, int D1, int D2, const float* src,
+                                    const float* tgt, const float* raylen, float* out, int B, int H, int W, int C,
+                                    float voxel_shift, float eps, int n_points, const float* alpha_range, int align_corners,
+                                    void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !out || !alpha_range || bad_dims(D0, D1, D2) || H <= 0 || W <= 0 ||
+        bad_rays(B, (int64_t)H * W) || C <= 0 || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_fwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, out, B, (int64_t)H * W, C, voxel_shift, eps,
+                                         n_points, alpha_range, align_corners != 0, (cudaStream_t)stream, W));
+}
+
 int b200drr_siddon_bwd_general(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                                const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                float* g_vol, int B, int64_t N, float voxel_shift, float eps, int stop_grad, int reduce,

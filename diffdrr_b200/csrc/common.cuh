@@ -109,6 +109,27 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats 
     return v;
 }
 
+// Ray handled by this thread of a 128-thread CTA: row order (W == 0, any ray set) or, for a full detector grid of width W,
+// a 16 x 8 pixel tile made of four 8 x 4 warp bundles (neighbouring rays gather neighbouring voxels).  -1 = no ray.
+__device__ __forceinline__ int64_t tiled_ray_index(int64_t N, int W)
+{
+    if (W <= 0) {
+        const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        return n < N ? n : -1;
+    }
+    const int H = (int)(N / W), tiles_x = (W + 15) / 16;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * 16 + (warp & 1) * 8 + (lane & 7), py = tile_y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    return (px < W && py < H) ? (int64_t)py * W + px : -1;
+}
+inline dim3 tiled_ray_grid(int B, int64_t N, int W)
+{
+    if (W <= 0) return dim3((unsigned)((N + 127) / 128), (unsigned)B, 1);
+    const int64_t H = N / W;
+    return dim3((unsigned)(((W + 15) / 16) * ((H + 7) / 8)), (unsigned)B, 1);
+}
+
 // Optional in-kernel ray generation ("pose-in" entry points): when G != nullptr the rays of pose b are made from
 //   target_voxel(h, w) = G[b] . (cols[w], rows[h], 1, 1),   raylen(h, w) = | Wd[b] . (cols[w], rows[h], 1, 1) |
 // (G = affine_inverse . extrinsic . reorient . calibration, Wd = the same without affine_inverse and with the source

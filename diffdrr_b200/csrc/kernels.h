@@ -157,11 +157,11 @@ cudaError_t launch_pose_rays_bwd(const float* Q, const float* r, const float* Ai
 
 cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, int W = 0);  // W > 0: the rays are a full row-major grid of width W
 cudaError_t launch_trilinear_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src,
                                       const float* tgt, const float* raylen, float* out, int B, int64_t N, int C,
                                       float shift, float eps, int n_points, const float* alpha_range, int align_corners,
-                                      cudaStream_t stream);
+                                      cudaStream_t stream, int W = 0);
 
 cudaError_t launch_pack_corners(const float* vol, VolDims dims, float* packed, cudaStream_t stream);
 cudaError_t launch_trilinear_fwd_packed(const float* packed, VolDims dims, const float* src, const float* tgt,

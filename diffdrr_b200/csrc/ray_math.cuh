@@ -721,18 +721,26 @@ B200_HD float lean_step_ax(LeanState& s, const LeanConst& k, int& ax)
 // sum per label RUN and flushes it to out[label] when the label changes (few flushes per ray; each (pose, ray) column of
 // `out` belongs to exactly one thread, so a plain += suffices).  `out_n` points at out[b][0][n]; channels are `cstride`
 // floats apart.  Labels outside [0, C) are dropped (the reference's scatter_add_ would raise).
-template <int U>
-B200_HD void siddon_ray_lean_mask(const float* vol, const float* mask, const VolDims& dims, const Ray& ray, float shift,
-                                  float L, float* out_n, int64_t cstride, int C)
+template <int U, bool ATOMIC>
+B200_HD void siddon_ray_lean_mask_box(const float* vol, const float* mask, const int lo_v[3], const int hi_v[3], int st0, int st1,
+                                      int st2, const Ray& ray, float shift, float L, float* out_n, int64_t cstride, int C)
 {
-    const int lo_v[3] = {0, 0, 0};
-    const Walk w = start_walk_box(ray, lo_v, dims.d, shift);
+    const Walk w = start_walk_box(ray, lo_v, hi_v, shift);
     if (!w.hit) return;
     LeanConst k;
     LeanState s;
-    lean_init(w, dims.d[1] * dims.d[2], dims.d[2], 1, s, k);
+    lean_init(w, st0, st1, st2, s, k);
     int cur = -1;
     float run = 0.0f;
+    // ATOMIC: several CTAs (one per slab of the volume) own pieces of the same ray -> red.global.add instead of +=
+    auto flush = [&](int c, float v) {
+        if (v != 0.0f && (unsigned)c < (unsigned)C) {
+            if (ATOMIC)
+                red_add(out_n + (int64_t)c * cstride, L * v);
+            else
+                out_n[(int64_t)c * cstride] += L * v;
+        }
+    };
     while (s.acur < k.a_out) {
         float len[U], v[U], lab[U];
         int offs[U];
@@ -750,14 +758,23 @@ B200_HD void siddon_ray_lean_mask(const float* vol, const float* mask, const Vol
         for (int j = 0; j < U; ++j) {
             const int c = (int)lab[j];
             if (c != cur) {
-                if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += L * run;
+                flush(cur, run);
                 cur = c;
                 run = 0.0f;
             }
             run = fmaf(len[j], v[j], run);
         }
     }
-    if (run != 0.0f && (unsigned)cur < (unsigned)C) out_n[(int64_t)cur * cstride] += L * run;
+    flush(cur, run);
+}
+
+template <int U>
+B200_HD void siddon_ray_lean_mask(const float* vol, const float* mask, const VolDims& dims, const Ray& ray, float shift,
+                                  float L, float* out_n, int64_t cstride, int C)
+{
+    const int lo_v[3] = {0, 0, 0};
+    siddon_ray_lean_mask_box<U, false>(vol, mask, lo_v, dims.d, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, L, out_n, cstride,
+                                       C);
 }
 
 // Trilinear with a label mask (reference renderers.py:242-252): density sampled trilinearly, label sampled NEAREST at

@@ -966,24 +966,60 @@ __global__ void __launch_bounds__(kThreads) siddon_fwd_mask_kernel(const float* 
                                                                    const float* __restrict__ src,
                                                                    const float* __restrict__ tgt,
                                                                    const float* __restrict__ raylen, float* out, int64_t N,
-                                                                   int C, float shift, float eps)
+                                                                   int C, float shift, float eps, int W)
 {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int64_t n = tiled_ray_index(N, W);
+    if (n < 0) return;
     const int b = blockIdx.y;
     const int64_t r = (int64_t)b * N + n;
     const Ray ray = load_ray(src, tgt, b, r, eps);
     siddon_ray_lean_mask<4>(vol, mask, dims, ray, shift, __ldg(raylen + r), out + (int64_t)b * C * N + n, N, C);
 }
 
+// Full detector grid: the slab-major decomposition of siddon_fwd_slab_kernel (the poses of a batch share each 32-plane slab of
+// BOTH the density and the label volume through L2), label runs flushed per (ray, slab) with red.global.add.
+__global__ void __launch_bounds__(256) siddon_fwd_mask_slab_kernel(const float* __restrict__ vol, const float* __restrict__ mask,
+                                                                   VolDims dims, const float* __restrict__ src,
+                                                                   const float* __restrict__ tgt, const float* __restrict__ raylen,
+                                                                   float* __restrict__ out, int B, int H, int W, int C, int slab,
+                                                                   float shift, float eps)
+{
+    const int tiles_x = (W + 15) / 16, tiles = tiles_x * ((H + 15) / 16);
+    int id = blockIdx.x;
+    const int tile = id % tiles;
+    id /= tiles;
+    const int b = id % B, sl = id / B;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tile_x * 16 + (warp % 2) * 8 + (lane & 7), py = tile_y * 16 + (warp / 2) * 4 + (lane >> 3);
+    if (px >= W || py >= H) return;
+    const int64_t N = (int64_t)H * W, n = (int64_t)py * W + px, r = (int64_t)b * N + n;
+    const Ray ray = load_ray(src, tgt, b, r, eps);
+    const int lo_v[3] = {sl * slab, 0, 0};
+    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (box_surely_missed(ray, lo_v, hi_v, shift)) return;
+    siddon_ray_lean_mask_box<4, true>(vol, mask, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, __ldg(raylen + r),
+                                      out + (int64_t)b * C * N + n, N, C);
+}
+
 cudaError_t launch_siddon_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, float* out, int B, int64_t N, int C, float shift, float eps,
-                                   cudaStream_t stream)
+                                   cudaStream_t stream, int W)
 {
+    static_assert(kThreads == 128, "tiled_ray_index assumes 128-thread CTAs");
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * N, stream);
     if (e != cudaSuccess) return e;
-    siddon_fwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
-        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps);
+    if (W > 0) {
+        const int H = (int)(N / W), slab = 32, n_slabs = (dims.d[0] + slab - 1) / slab;
+        const int64_t blocks = (int64_t)((W + 15) / 16) * ((H + 15) / 16) * B * n_slabs;
+        if (blocks <= INT32_MAX) {
+            siddon_fwd_mask_slab_kernel<<<(unsigned)blocks, 256, 0, stream>>>(vol, mask, dims, src, tgt, raylen, out, B, H, W, C, slab,
+                                                                            shift, eps);
+            return cudaGetLastError();
+        }
+    }
+    siddon_fwd_mask_kernel<<<tiled_ray_grid(B, N, W), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps, W);
     return cudaGetLastError();
 }
 

@@ -853,10 +853,10 @@ __global__ void __launch_bounds__(kThreads) trilinear_fwd_mask_kernel(const floa
                                                                       const float* __restrict__ raylen, float* out,
                                                                       int64_t N, int C, float shift, float eps, int P,
                                                                       const float* __restrict__ alpha_range,
-                                                                      int align_corners)
+                                                                      int align_corners, int W)
 {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const int64_t n = tiled_ray_index(N, W);
+    if (n < 0) return;
     const int b = blockIdx.y;
     const int64_t r = (int64_t)b * N + n;
     const Ray ray = load_ray(src, tgt, b, r, eps);
@@ -869,12 +869,13 @@ __global__ void __launch_bounds__(kThreads) trilinear_fwd_mask_kernel(const floa
 cudaError_t launch_trilinear_fwd_mask(const float* vol, const float* mask, VolDims dims, const float* src,
                                       const float* tgt, const float* raylen, float* out, int B, int64_t N, int C,
                                       float shift, float eps, int n_points, const float* alpha_range, int align_corners,
-                                      cudaStream_t stream)
+                                      cudaStream_t stream, int W)
 {
+    static_assert(kThreads == 128, "tiled_ray_index assumes 128-thread CTAs");
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * N, stream);
     if (e != cudaSuccess) return e;
-    trilinear_fwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
-        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps, n_points, alpha_range, align_corners);
+    trilinear_fwd_mask_kernel<<<tiled_ray_grid(B, N, W), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, out, N, C, shift, eps, n_points, alpha_range, align_corners, W);
     return cudaGetLastError();
 }
 

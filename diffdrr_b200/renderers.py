@@ -692,18 +692,30 @@ class _MaskFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, volume, source, target, img, alpha_range, mask, kind, voxel_shift, eps, n_points, align_corners,
-                stop_grad, C):
+                stop_grad, C, grid=None):
         B, N = _check_inputs(volume, source, target, img)
+        if grid is not None and grid[0] * grid[1] != N:
+            grid = None
         vol, msk = volume.contiguous(), mask
         src, tgt, raylen = source.reshape(B, 3).contiguous(), target.contiguous(), img.reshape(B, N).contiguous()
         out = torch.empty(B, C, N, dtype=torch.float32, device=vol.device)
         lib = _lib.load()
         ar = None
         with torch.cuda.device(vol.device):
-            if kind == "siddon":
+            if kind == "siddon" and grid is not None:   # full detector grid: tile-ordered threads (same per-ray results)
+                _lib.check(lib.b200drr_siddon_fwd_mask_grid(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                            _ptr(out), B, grid[0], grid[1], C, voxel_shift, eps, _stream()),
+                           "b200drr_siddon_fwd_mask_grid")
+            elif kind == "siddon":
                 _lib.check(lib.b200drr_siddon_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                        _ptr(out), B, N, C, voxel_shift, eps, _stream()),
                            "b200drr_siddon_fwd_mask")
+            elif grid is not None:
+                ar = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
+                _lib.check(lib.b200drr_trilinear_fwd_mask_grid(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),
+                                                               _ptr(raylen), _ptr(out), B, grid[0], grid[1], C, voxel_shift, eps,
+                                                               int(n_points), _ptr(ar), int(align_corners), _stream()),
+                           "b200drr_trilinear_fwd_mask_grid")
             else:
                 ar = alpha_range.detach().to(device=vol.device, dtype=torch.float32).contiguous()
                 _lib.check(lib.b200drr_trilinear_fwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),
@@ -742,11 +754,11 @@ class _MaskFunction(torch.autograd.Function):
                                                           _ptr(ar), int(align_corners), _stream()),
                            "b200drr_trilinear_bwd_mask")
         return (g_vol, None if g_src is None else g_src.view(src_shape), g_tgt,
-                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None, None)
+                None if g_len is None else g_len.view(img_shape), g_ar, None, None, None, None, None, None, None, None, None)
 
 
 def _render_mask(kind, volume, mask, source, target, img, voxel_shift, eps, n_points=None, alpha_range=None,
-                 align_corners=False, stop_grad=False):
+                 align_corners=False, stop_grad=False, grid=None):
     """mask_to_channels rendering -> (B, C, N), differentiable w.r.t. volume, rays, ray lengths (and the trilinear
     sampling range)."""
     if not mask.is_cuda or mask.shape != volume.shape:
@@ -756,7 +768,7 @@ def _render_mask(kind, volume, mask, source, target, img, voxel_shift, eps, n_po
         alpha_range = torch.zeros(2, dtype=torch.float32, device=volume.device)
     return _MaskFunction.apply(volume, source, target, img, alpha_range, msk, kind, float(voxel_shift), float(eps),
                                0 if n_points is None else int(n_points), bool(align_corners), bool(stop_grad),
-                               _mask_channels(msk))
+                               _mask_channels(msk), grid)
 
 
 _DIMS_CACHE: dict = {}
@@ -827,7 +839,7 @@ class Siddon(torch.nn.Module):
             if self.mode != "nearest":
                 raise NotImplementedError("mask_to_channels is implemented for mode='nearest'")
             return _render_mask("siddon", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps),
-                                stop_grad=self.stop_gradients_through_grid_sample)
+                                stop_grad=self.stop_gradients_through_grid_sample, grid=self.detector_shape)
         if self.mode == "bilinear":  # trilinear sampling at the segment midpoints: general walk (slow path)
             return _SiddonBilinearFunction.apply(volume, source, target, img, float(self.voxel_shift), float(self.eps),
                                                  _reduce_code(self.reducefn), bool(align_corners),
@@ -936,7 +948,8 @@ class Trilinear(torch.nn.Module):
                                    torch.as_tensor(alphamax, dtype=torch.float32, device=volume.device)])
         if mask is not None:
             return _render_mask("trilinear", volume, mask, source, target, img, float(self.voxel_shift), float(self.eps),
-                                n_points=n_points, alpha_range=alpha_range, align_corners=align_corners)
+                                n_points=n_points, alpha_range=alpha_range, align_corners=align_corners,
+                                grid=self.detector_shape)
         return _TrilinearFunction.apply(volume, source, target, img, alpha_range, float(self.voxel_shift), float(self.eps),
                                         int(n_points), _reduce_code(self.reducefn), bool(align_corners),
                                         self.detector_shape,

@@ -272,6 +272,16 @@ int b200drr_trilinear_fwd_mask(const float *vol, const float *mask, int D0, int 
                                const float *tgt, const float *raylen, float *out, int B, int64_t N, int C,
                                float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
                                void *stream);
+/* The same for the FULL row-major detector grid (N = H*W): threads are mapped to pixel tiles of 8 x 4 warp bundles so that
+ * neighbouring rays gather neighbouring voxels and labels; Siddon additionally runs slab-major over 32-plane slabs of the
+ * density AND label volumes (label runs flushed per (ray, slab) with red.global.add: results agree to fp32 round-off). */
+int b200drr_siddon_fwd_mask_grid(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                                 const float *tgt, const float *raylen, float *out, int B, int H, int W, int C,
+                                 float voxel_shift, float eps, void *stream);
+int b200drr_trilinear_fwd_mask_grid(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                                    const float *tgt, const float *raylen, float *out, int B, int H, int W, int C,
+                                    float voxel_shift, float eps, int n_points, const float *alpha_range,
+                                    int align_corners, void *stream);
 
 /*
  * Backward for the renderer options outside the fast kernels (reference renderers.py:175-183 `reduce`, :40/:161
