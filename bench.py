@@ -386,6 +386,29 @@ def extra_configs(dev, lib, peak, main):
     res["siddon_backward_with_volume_gradient"] = {
         "workload": f"siddon backward incl. g_vol (reconstruction), {D}^3 -> {det}^2, {B} poses", **_stat(t_gv),
         "drr_per_s": B / np.median(t_gv) * 1e3, "roofline": roof(gv_bytes, float(np.median(t_gv)))}
+    try:
+        # the volume gradient alone (fixed poses: what a reconstruction step needs) by the brick kernel run as a scatter
+        # (shared-memory accumulation, one TMA store per brick, no global atomics) vs the slab-major walk with global atomics
+        g_ref = g_vol.clone()   # (accumulated over the timed launches above: compare shapes of one launch below)
+        g_vol.zero_()
+        one_slab = lambda: _lib.check(lib.b200drr_siddon_bwd_grid(  # noqa: E731
+            _ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), None, None, None, _ptr(g_vol), B, det, det, 0.5, 1e-8, 0,
+            0, _stream()), "bwd_grid")
+        one_slab()
+        g_ref.copy_(g_vol)
+        t_gs = _time_events(one_slab, 5)
+        ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, det, det), dtype=torch.uint8, device=dev)
+        t_gb = _time_events(lambda: _lib.check(lib.b200drr_siddon_bwd_vol_brick(
+            _ptr(gout), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen), None, None, None, None, _ptr(g_vol), _ptr(ws), ws.numel(), B, det,
+            det, 0.5, 1e-8, _stream()), "bwd_vol_brick"), 5)
+        sc_bytes = 8 * tot_visits + 4 * D ** 3 + 20 * B * N   # read-modify-write per visit + the volume store + per-ray inputs
+        res["siddon_backward_with_volume_gradient"]["volume_gradient_only"] = {
+            "slab_major_global_atomics": {**_stat(t_gs), "drr_per_s": B / np.median(t_gs) * 1e3, "roofline": roof(sc_bytes, float(np.median(t_gs)))},
+            "brick_scatter_tma_store": {**_stat(t_gb), "drr_per_s": B / np.median(t_gb) * 1e3, "roofline": roof(sc_bytes, float(np.median(t_gb))),
+                                        "maxdiff_vs_slab_major": float((g_vol - g_ref).abs().max() / g_ref.abs().max())}}
+        del g_ref
+    except Exception as exc:  # pragma: no cover
+        res["siddon_backward_with_volume_gradient"]["volume_gradient_only"] = {"error": f"{type(exc).__name__}: {exc}"}
     del g_vol
 
     # ---- (c) BASELINE config 2: 256^3 -> 256^2, batch 16, Siddon forward ----------------------------------------------

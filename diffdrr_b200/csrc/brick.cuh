@@ -578,4 +578,39 @@ B200_HD void brick_pair2_walk(const Ld& ld, AccState& wa, const AccConst& ka, Ac
     part_b = fmaf(kb.a_stop - wb.acur, ld(wb.off), acc_b);
 }
 
+// ---- volume gradient (transpose of the walk): the same chord lengths scattered into a brick of accumulators -------------------
+// d(out[ray]) / d(vol[voxel]) = L * len(ray, voxel), so g_vol[voxel] += sum over rays of (gout * L) * len: the pair's walk with
+// the load replaced by an add of len * wgt into the staged brick (`st.add`: shared-memory atomic on the device, += in the host
+// emulation).  Same set-up (brick_pair_setup_acc), same steps, same tail term as brick_pair_fwd_lean<ACC = true>.
+struct StHost {
+    float* brick;
+    static constexpr int kScale = 1;
+    B200_HD int base() const { return 0; }
+    B200_HD void add(int off, float v) const { brick[off] += v; }
+};
+
+template <int U, class St>
+B200_HD void brick_pair_bwd_lean(const St& st, float wgt, const float s[3], const float inv[3], const float clo[3],
+                                 const float chi[3], const int lo_v[3], const int hi_v[3], const int org[3], int st0, int st1,
+                                 int st2, float shift)
+{
+    AccState w;
+    AccConst k;
+    if (!brick_pair_setup_acc(st, true, s, inv, clo, chi, lo_v, hi_v, org, st0, st1, st2, shift, w, k)) return;
+    while (w.acur < k.a_stop) {
+        float len[U];
+        int offs[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            offs[j] = w.off;
+            len[j] = acc_step(w, k);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if (len[j] != 0.0f) st.add(offs[j], len[j] * wgt);
+    }
+    const float rest = k.a_stop - w.acur;  // the rest of the chord belongs to the last voxel (<= 0 when the last step overshot)
+    if (rest != 0.0f) st.add(w.off, rest * wgt);
+}
+
 }  // namespace b200drr

@@ -207,6 +207,22 @@ int b200drr_siddon_fwd_brick(const float* vol, int D0, int D1, int D2, const flo
                                        (size_t)workspace_bytes, B, H, W, voxel_shift, eps, variant, (cudaStream_t)stream));
 }
 
+int b200drr_siddon_bwd_vol_brick(const float* gout, int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen,
+                                 const float* G, const float* Wd, const float* rows, const float* cols, float* g_vol,
+                                 void* workspace, int64_t workspace_bytes, int B, int H, int W, float voxel_shift, float eps,
+                                 void* stream)
+{
+    const bool pose_in = G != nullptr;
+    if (!gout || !src || !g_vol || !workspace || bad_dims(D0, D1, D2) || bad_rays(B, (int64_t)H * W) || H <= 0 || W <= 0)
+        return B200DRR_EINVAL;
+    if (pose_in ? (!Wd || !rows || !cols) : (!tgt || !raylen)) return B200DRR_EINVAL;
+    if (!siddon_brick_supported(mk(D0, D1, D2), H, W) || ((uintptr_t)g_vol & 15u) != 0) return B200DRR_EUNSUPPORTED;
+    if (workspace_bytes < (int64_t)siddon_brick_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 255u) != 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_vol_brick(gout, mk(D0, D1, D2), src, tgt, raylen, G, Wd, rows, cols, g_vol, workspace,
+                                           (size_t)workspace_bytes, B, H, W, voxel_shift, eps, (cudaStream_t)stream));
+}
+
 int b200drr_siddon_fwd_brick_subset(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                                     const float* raylen, const int32_t* pix_index, const float* corners, float* out,
                                     void* workspace, int64_t workspace_bytes, int B, int H, int W, int64_t Nsub,

@@ -135,6 +135,11 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
                                     int variant, cudaStream_t stream, const int* pix_index = nullptr,
                                     const float* corners = nullptr, int64_t Nsub = 0);
 
+cudaError_t launch_siddon_bwd_vol_brick(const float* gout, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                        const float* G, const float* Wd, const float* rows, const float* cols, float* g_vol,
+                                        void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
+                                        cudaStream_t stream);
+
 // experiments (b200drr_x_*): chunk-reuse forward over a major-axis-fastest copy
 cudaError_t launch_x_transpose_volume(const float* vol, VolDims dims, int axis, float* out, cudaStream_t stream);
 cudaError_t launch_x_siddon_fwd_chunk(const float* volT, VolDims dims, int axis, const float* src, const float* tgt,

@@ -60,6 +60,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// one 3-D box shared -> global (clipped to the tensor), bulk async-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// volume-gradient mode: the staged brick is an ACCUMULATOR; fp32 add on a byte address in the shared window
+// (red.shared.add.f32 = an ATOMS.CAST.SPIN loop on sm_100a: there is no native fp32 shared-memory add)
+struct StShared {
+    uint32_t base_addr;
+    static constexpr int kScale = 4;
+    __device__ __forceinline__ int base() const { return (int)base_addr; }
+    __device__ __forceinline__ void add(int off, float v) const
+    {
+        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(off), "f"(v) : "memory");
+    }
+};
+
 // ld.shared with a byte address in the shared window
 struct LdShared {
     uint32_t base_addr;
@@ -113,7 +136,8 @@ __global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict
                                                          PoseGeo* __restrict__ geo, float* __restrict__ out,
                                                          unsigned* __restrict__ counter, int H, int W, float eps,
                                                          int64_t Nr /* rays per pose */,
-                                                         const float* __restrict__ corners /* [B][3][3] or nullptr */)
+                                                         const float* __restrict__ corners /* [B][3][3] or nullptr */,
+                                                         const float* __restrict__ gout /* volume-gradient mode, else nullptr */)
 {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -124,8 +148,8 @@ __global__ void __launch_bounds__(256) brick_prep_kernel(const float* __restrict
     float L;
     const Ray ray = make_ray_b(pr, src, tgt, raylen, b, r, px, py, eps, L);
     raytab[r] = make_float4(ray.inv[0], ray.inv[1], ray.inv[2], fabsf(ray.d[0]) + fabsf(ray.d[1]) + fabsf(ray.d[2]));
-    ltab[r] = L;
-    out[r] = 0.0f;
+    ltab[r] = gout ? L * __ldg(gout + r) : L;  // volume-gradient mode: the weight every chord length is scattered with
+    if (out) out[r] = 0.0f;
     if (n == 0) {
         float t00[3], t0w[3], th0[3];
         if (corners) {  // targets of the full grid's pixels (0, 0), (0, W-1), (H-1, 0), handed in by the caller
@@ -183,7 +207,10 @@ struct BrickCfg {
     static constexpr int kSmemBytes = oMisc + 128;
 };
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS>
+// BWD = 1: volume-gradient mode.  `tmap` then describes g_vol, the staged brick starts as zeros instead of a TMA load, every
+// pair's walk scatters (gout * L) * chord length into it (brick_pair_bwd_lean; ltab holds gout * L), and the finished brick is
+// written with ONE TMA store -- every voxel belongs to exactly one brick, so there is no global atomic and g_vol is overwritten.
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS, int BWD = 0>
 __global__ void __launch_bounds__(THREADS, CTAS)
     siddon_fwd_brick_kernel(const __grid_constant__ CUtensorMap tmap, VolDims dims, BrickGrid bg,
                             const float4* __restrict__ raytab, const float* __restrict__ ltab,
@@ -192,6 +219,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                             int Nr /* rays per pose */, int B, int H, int W, float shift)
 {
     using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
+    static_assert(BWD == 0 || (STAGES == 1 && RAYS == 1), "volume-gradient mode: single stage, one pair per thread");
     constexpr int kRowCap = Cfg::kRowCap;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned* s_items = reinterpret_cast<unsigned*>(smem + Cfg::oItems);
@@ -233,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
     if (tid == 0) {
         const int first = (int)atomicAdd(counter, 1u);
         s_misc[2] = first;
-        if (first < n_bricks) issue(first, 0);
+        if (BWD == 0 && first < n_bricks) issue(first, 0);
     }
     __syncthreads();
     int cur = s_misc[2];
@@ -252,6 +280,10 @@ __global__ void __launch_bounds__(THREADS, CTAS)
         const int hi_v[3] = {min(org[0] + BX, dims.d[0]), min(org[1] + BY, dims.d[1]), min(org[2] + BZ, dims.d[2])};
         LdShared ld;
         ld.base_addr = brick0 + stage * Cfg::kBrickBytes;
+        if constexpr (BWD != 0) {  // the accumulator brick starts at zero (ordered before the walks by the barriers below)
+            float4* z = reinterpret_cast<float4*>(smem + Cfg::oBricks);
+            for (int i = tid; i < Cfg::kBrickElems / 4; i += THREADS) z[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
 
         int p0 = 0;
         while (p0 < B) {
@@ -362,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                 if (lane == 0) s_rowprefix[0] = 0;
                 if (lane == 31) s_misc[6] = incl;
             }
-            if (p0 == 0) mbar_wait(bar0 + 8 * stage, parity);  // the brick has landed (first use only)
+            if (BWD == 0 && p0 == 0) mbar_wait(bar0 + 8 * stage, parity);  // the brick has landed (first use only)
             __syncthreads();
             const int T = s_misc[6];
 
@@ -686,9 +718,15 @@ __global__ void __launch_bounds__(THREADS, CTAS)
                         const float4 chi = *reinterpret_cast<const float4*>(s_posef + bl * 12 + 8);
                         const float s3[3] = {S4.x, S4.y, S4.z}, inv3[3] = {q.x, q.y, q.z};
                         const float clo3[3] = {clo.x, clo.y, clo.z}, chi3[3] = {chi.x, chi.y, chi.z};
-                        const float part = brick_pair_fwd_lean<U, LdShared, true, PIPE != 0>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
-                        if (part != 0.0f)
-                            red_add(out + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)item_ray(itw)), L * part);
+                        if constexpr (BWD != 0) {
+                            if (L != 0.0f)  // L = gout * raylen here (brick_prep_kernel)
+                                brick_pair_bwd_lean<U>(StShared{ld.base_addr}, L, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1,
+                                                       shift);
+                        } else {
+                            const float part = brick_pair_fwd_lean<U, LdShared, true, PIPE != 0>(ld, s3, inv3, clo3, chi3, lo_v, hi_v, org, BY * BZ, BZ, 1, shift);
+                            if (part != 0.0f)
+                                red_add(out + ((unsigned)(p0 + bl) * (unsigned)Nr + (unsigned)item_ray(itw)), L * part);
+                        }
                     }
                     c = cn;
                     itw = itn;
@@ -698,16 +736,24 @@ __global__ void __launch_bounds__(THREADS, CTAS)
             }
             p0 += npose;
         }
+        if constexpr (BWD != 0) fence_proxy_async();  // this thread's scatter adds become visible to the async proxy (TMA store)
         __syncthreads();  // every reader of this stage (and of s_misc[2 + ...]) is done
         if (STAGES == 1) {
             if (tid == 0) {
+                if constexpr (BWD != 0) {
+                    tma_store_3d(&tmap, brick0, i2 * BZ, i1 * BY, i0 * BX);
+                    tma_store_wait_read();  // the brick has been read out: the next zero fill may overwrite it
+                }
                 const int nxt = (int)atomicAdd(counter, 1u);
                 s_misc[2 + ((it + 1) & 1)] = nxt;
-                if (nxt < n_bricks) issue(nxt, 0);
+                if (BWD == 0 && nxt < n_bricks) issue(nxt, 0);
             }
             __syncthreads();
         }
         cur = s_misc[2 + ((it + 1) & 1)];
+    }
+    if constexpr (BWD != 0) {
+        if (tid == 0) tma_store_wait_all();
     }
 }
 
@@ -746,13 +792,13 @@ bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, i
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS = 1>
+template <int BX, int BY, int BZ, int STAGES, int THREADS, int K, int U, int CTAS, int PIPE, int RAYS = 1, int BWD = 0>
 cudaError_t launch_brick_variant(const CUtensorMap& map, VolDims dims, const float4* raytab, const float* ltab,
                                  const PoseGeo* geo, float* out, unsigned* counter, const int* pix_index, int Nr, int B, int H,
                                  int W, float shift, cudaStream_t stream)
 {
     using Cfg = BrickCfg<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
-    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS>;
+    auto kern = siddon_fwd_brick_kernel<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE, RAYS, BWD>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -808,7 +854,7 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
     PoseRaysB pr{G, Wd, rows, cols};
     brick_prep_kernel<<<dim3((unsigned)((Nr + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, ltab, geo,
                                                                                          out, counter, H, W, eps, Nr,
-                                                                                         subset ? corners : nullptr);
+                                                                                         subset ? corners : nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap map;
@@ -853,6 +899,35 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
 #undef BV
 #undef BV2
 #undef BV3
+}
+
+// Volume gradient of the full-grid Siddon render through the brick kernel's BWD mode: g_vol [D0][D1][D2] is OVERWRITTEN with
+// sum over poses and rays of gout * raylen * chord length (what autograd gives for renderers.py:40-76 w.r.t. the volume).
+cudaError_t launch_siddon_bwd_vol_brick(const float* gout, VolDims dims, const float* src, const float* tgt, const float* raylen,
+                                        const float* G, const float* Wd, const float* rows, const float* cols, float* g_vol,
+                                        void* workspace, size_t workspace_bytes, int B, int H, int W, float shift, float eps,
+                                        cudaStream_t stream)
+{
+    const int64_t Nr = (int64_t)H * W;
+    if (!siddon_brick_supported(dims, H, W) || ((uintptr_t)g_vol & 15u) != 0 || (int64_t)B * Nr >= ((int64_t)1 << 31))
+        return cudaErrorNotSupported;
+    const size_t need = siddon_brick_workspace_bytes(B, H, W);
+    if (workspace == nullptr || workspace_bytes < need || ((uintptr_t)workspace & 255u) != 0) return cudaErrorInvalidValue;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    unsigned* counter = reinterpret_cast<unsigned*>(ws);
+    PoseGeo* geo = reinterpret_cast<PoseGeo*>(ws + 256);
+    float4* raytab = reinterpret_cast<float4*>(ws + 256 + align_up(sizeof(PoseGeo) * (size_t)B, 256));
+    float* ltab = reinterpret_cast<float*>(raytab + (size_t)B * Nr);
+    PoseRaysB pr{G, Wd, rows, cols};
+    brick_prep_kernel<<<dim3((unsigned)((Nr + 255) / 256), (unsigned)B), 256, 0, stream>>>(src, tgt, raylen, pr, raytab, ltab, geo,
+                                                                                         nullptr, counter, H, W, eps, Nr, nullptr,
+                                                                                         gout);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    CUtensorMap map;
+    if (!make_volume_map(&map, g_vol, dims, 24, 32, 32)) return cudaErrorNotSupported;
+    return launch_brick_variant<24, 32, 32, 1, 512, 4, 2, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter, nullptr, (int)Nr,
+                                                                     B, H, W, shift, stream);
 }
 
 }  // namespace b200drr

@@ -83,6 +83,17 @@ def _brick_ok(vol, B, H, W, check_density: bool = True) -> bool:
             and 2 <= W <= 2048 and B * H * W < 2**31 and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
 
 
+_BRICK_BWD = _os.environ.get("B200DRR_BRICK_BWD", "1") != "0"
+_BRICK_BWD_MIN_BATCH = int(_os.environ.get("B200DRR_BRICK_BWD_MIN_BATCH", "1"))
+
+
+def _brick_bwd_ok(vol, B, H, W) -> bool:
+    """Volume gradient through the brick kernel's scatter mode (b200drr_siddon_bwd_vol_brick): shared-memory accumulation and one
+    TMA store per brick instead of one global atomic per voxel visit."""
+    return (_BRICK_BWD and B >= _BRICK_BWD_MIN_BATCH
+            and _brick_ok(vol, max(B, _BRICK_MIN_BATCH), H, W))  # sparse rays only: at 512^3 -> 512^2 the CAS loops collide (1.08x)
+
+
 def _brick_workspace(device, B, H, W):
     """Cached scratch for the brick kernel (ray table + per-pose geometry), grown on demand; one buffer per device and
     stream so concurrent streams never share it (the pointer is stable, so captured CUDA graphs stay valid)."""
@@ -236,7 +247,9 @@ class _SiddonFunction(torch.autograd.Function):
         g_src = torch.empty(B, 3, dtype=torch.float32, device=vol.device) if need_src else None
         g_tgt = torch.empty(B, N, 3, dtype=torch.float32, device=vol.device) if need_tgt else None
         g_len = torch.empty(B, N, dtype=torch.float32, device=vol.device) if (need_len and not stop_grad) else None
-        g_vol = torch.zeros_like(vol) if (need_vol and not stop_grad) else None
+        vol_by_brick = (need_vol and not stop_grad and grid is not None and reduce == 0 and not align_corners
+                        and _brick_bwd_ok(vol, B, grid[0], grid[1]))
+        g_vol = (torch.empty_like(vol) if vol_by_brick else torch.zeros_like(vol)) if (need_vol and not stop_grad) else None
         lib = _lib.load()
         with torch.cuda.device(vol.device):
             if reduce != 0 or align_corners:  # options outside the fast kernels: plane-by-plane general walk
@@ -244,6 +257,19 @@ class _SiddonFunction(torch.autograd.Function):
                                                           _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, voxel_shift,
                                                           eps, int(stop_grad), reduce, int(align_corners), 0, _stream()),
                            "b200drr_siddon_bwd_general")
+            elif vol_by_brick:
+                # volume gradient by the brick kernel's scatter mode (no global atomics; g_vol overwritten), ray gradients --
+                # when wanted at all -- by the slab-major walk without a volume gradient
+                ws = _brick_workspace(vol.device, B, grid[0], grid[1])
+                _lib.check(lib.b200drr_siddon_bwd_vol_brick(_ptr(gout), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), None, None,
+                                                            None, None, _ptr(g_vol), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                                            B, grid[0], grid[1], voxel_shift, eps, _stream()),
+                           "b200drr_siddon_bwd_vol_brick")
+                if g_src is not None or g_tgt is not None or g_len is not None:
+                    _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
+                                                           _ptr(g_src), _ptr(g_tgt), _ptr(g_len), None, B, grid[0], grid[1],
+                                                           voxel_shift, eps, int(stop_grad), 0, _stream()),
+                               "b200drr_siddon_bwd_grid")
             elif grid is not None:
                 _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout),
                                                        _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, grid[0], grid[1],
@@ -356,16 +382,33 @@ class _SiddonPoseFunction(torch.autograd.Function):
         B, H, W = G.shape[0], rows.numel(), cols.numel()
         dev = vol.device
         gout = gout.reshape(B, H * W).contiguous().float()
+        want_vol = ctx.needs_input_grad[0] and not stop_grad
+        want_pose = any(ctx.needs_input_grad[1:4])
+        g_vol = None
+        if want_vol and _brick_bwd_ok(vol, B, H, W):
+            # volume gradient by the brick kernel's scatter mode (rays generated in-kernel, no global atomics, g_vol overwritten)
+            g_vol = torch.empty_like(vol)
+            ws = _brick_workspace(dev, B, H, W)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().b200drr_siddon_bwd_vol_brick(_ptr(gout), *vol.shape, _ptr(src), None, None, _ptr(G), _ptr(Wd),
+                                                                    _ptr(rows), _ptr(cols), _ptr(g_vol),
+                                                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), B, H, W,
+                                                                    voxel_shift, eps, _stream()), "b200drr_siddon_bwd_vol_brick")
+            if not want_pose:  # reconstruction: fixed poses, only the volume is optimised
+                return g_vol, None, None, None, None, None, None, None, None
+            want_vol = False
         g_src = torch.empty(B, 3, dtype=torch.float32, device=dev)
         g_G = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
         g_Wd = torch.empty(B, 3, 4, dtype=torch.float32, device=dev)
         ws_tgt = torch.empty(B, H * W, 3, dtype=torch.float32, device=dev)
         ws_len = torch.empty(B, H * W, dtype=torch.float32, device=dev)
-        g_vol = torch.zeros_like(vol) if (ctx.needs_input_grad[0] and not stop_grad) else None
+        if want_vol:
+            g_vol = torch.zeros_like(vol)
+        g_vol_walk = g_vol if want_vol else None
         with torch.cuda.device(dev):
             _lib.check(_lib.load().b200drr_siddon_bwd_pose(_ptr(vol), *vol.shape, _ptr(src), _ptr(G), _ptr(Wd), _ptr(rows),
                                                            _ptr(cols), _ptr(gout), _ptr(g_src), _ptr(g_G), _ptr(g_Wd),
-                                                           _ptr(g_vol), _ptr(ws_tgt), _ptr(ws_len), B, H, W, voxel_shift,
+                                                           _ptr(g_vol_walk), _ptr(ws_tgt), _ptr(ws_len), B, H, W, voxel_shift,
                                                            eps, int(stop_grad), _stream()), "b200drr_siddon_bwd_pose")
         return g_vol, g_src, g_G, g_Wd, None, None, None, None, None
 

@@ -393,6 +393,20 @@ int b200drr_siddon_fwd_brick(const float *vol, int D0, int D1, int D2, const flo
                              float eps, int variant, void *stream);
 
 /*
+ * Volume gradient of the full-grid Siddon render (what autograd gives for reference renderers.py:40-76 w.r.t. `volume`; the
+ * reconstruction path) through the SAME brick-major kernel run as a scatter: the staged brick starts as zeros, every (ray,
+ * brick) walk adds gout * raylen * chord length into it in shared memory, and the finished brick leaves with one TMA store --
+ * every voxel belongs to exactly one brick, so there are no global atomics.  g_vol [D0][D1][D2] (16-byte aligned) is
+ * OVERWRITTEN (unlike the g_vol of b200drr_siddon_bwd[_grid], which is accumulated into).  gout [B][H*W]; rays and workspace as
+ * in b200drr_siddon_fwd_brick.  Pose gradients are not produced here (b200drr_siddon_bwd_grid with g_vol = NULL, or the
+ * sensitivities of b200drr_siddon_fwd_sens_grid).
+ */
+int b200drr_siddon_bwd_vol_brick(const float *gout, int D0, int D1, int D2, const float *src, const float *tgt,
+                                 const float *raylen, const float *G, const float *Wd, const float *rows, const float *cols,
+                                 float *g_vol, void *workspace, int64_t workspace_bytes, int B, int H, int W,
+                                 float voxel_shift, float eps, void *stream);
+
+/*
  * The same brick-major kernel for a ray SUBSET of the H x W detector grid (p_subsample, detector.py:134-137): tgt, raylen and
  * out are (B, Nsub) arrays in the caller's order; pix_index [H*W] int32 maps a detector pixel (h*W + w) to its position in that
  * order (-1 = pixel not rendered); corners [B][3][3] are the voxel-space targets of the FULL grid's pixels (0,0), (0,W-1),

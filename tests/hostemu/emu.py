@@ -294,3 +294,15 @@ def siddon_fwd_brick2(vol, src, tgt, raylen, H, W, brick=(24, 32, 32), voxel_shi
               ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
               *map(ctypes.c_int, brick), ctypes.c_int(int(check)), ctypes.c_int(int(lean)), _p(stats))
     return out, int(viol), dict(zip(("candidates", "maybe", "exact", "walked"), stats.tolist()))
+
+
+def siddon_bwd_vol_brick(vol_shape, src, tgt, raylen, gout, H, W, brick=(24, 32, 32), voxel_shift=0.5, eps=1e-8):
+    """Volume gradient through the brick decomposition (siddon_brick.cu, BWD mode); g_vol (D0, D1, D2) overwritten."""
+    src, tgt, raylen, gout = _f(src), _f(tgt), _f(raylen), _f(gout)
+    B, N = tgt.shape[0], tgt.shape[1]
+    assert N == H * W
+    g_vol = np.full(tuple(vol_shape), np.nan, np.float32)
+    lib().emu_siddon_bwd_vol_brick(*map(ctypes.c_int, vol_shape), _p(src), _p(tgt), _p(raylen), _p(gout), _p(g_vol), ctypes.c_int(B),
+                                   ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                                   *map(ctypes.c_int, brick))
+    return g_vol

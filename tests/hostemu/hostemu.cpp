@@ -786,6 +786,89 @@ long emu_siddon_fwd_brick2(const float* vol, int D0, int D1, int D2, const float
     return violations;
 }
 
+// Volume gradient through the brick decomposition (siddon_brick.cu, BWD mode): per brick a zeroed accumulator brick, every
+// candidate pair of every pose scatters (gout * raylen) * chord length into it (brick_pair_bwd_lean), then the brick is stored
+// (clipped to the volume) -- each voxel belongs to exactly one brick, so g_vol is OVERWRITTEN.
+void emu_siddon_bwd_vol_brick(int D0, int D1, int D2, const float* src, const float* tgt, const float* raylen, const float* gout,
+                              float* g_vol, int B, int H, int W, float shift, float eps, int BX, int BY, int BZ)
+{
+    const long N = (long)H * W;
+    std::vector<Ray> rays((size_t)B * N);
+    std::vector<PoseGeo> geo(B);
+    for (int b = 0; b < B; ++b) {
+        for (long n = 0; n < N; ++n) rays[(size_t)b * N + n] = load_ray(src, tgt, b, (long)b * N + n, eps);
+        const Ray& r00 = rays[(size_t)b * N];
+        const Ray& r0w = rays[(size_t)b * N + (W - 1)];
+        const Ray& rh0 = rays[(size_t)b * N + (long)(H - 1) * W];
+        float t00[3], t0w[3], th0[3];
+        for (int a = 0; a < 3; ++a) {
+            t00[a] = r00.s[a] + r00.d[a];
+            t0w[a] = r00.s[a] + r0w.d[a];
+            th0[a] = r00.s[a] + rh0.d[a];
+        }
+        geo[b] = make_pose_geo(r00.s, t00, t0w, th0, H, W);
+    }
+    std::vector<float> brick((size_t)BX * BY * BZ);
+    const int nb0 = (D0 + BX - 1) / BX, nb1 = (D1 + BY - 1) / BY, nb2 = (D2 + BZ - 1) / BZ;
+    for (int i0 = 0; i0 < nb0; ++i0)
+        for (int i1 = 0; i1 < nb1; ++i1)
+            for (int i2 = 0; i2 < nb2; ++i2) {
+                const int org[3] = {i0 * BX, i1 * BY, i2 * BZ};
+                const int lo_v[3] = {org[0], org[1], org[2]};
+                const int hi_v[3] = {std::min(org[0] + BX, D0), std::min(org[1] + BY, D1), std::min(org[2] + BZ, D2)};
+                std::fill(brick.begin(), brick.end(), 0.0f);
+                StHost st{brick.data()};
+                for (int b = 0; b < B; ++b) {
+                    float uv[16], umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY, dmin = INFINITY,
+                                  dmax = -INFINITY;
+                    bool bad = false;
+                    for (int c = 0; c < 8; ++c) {
+                        const float X[3] = {(float)((c & 1) ? hi_v[0] : lo_v[0]) - shift, (float)((c & 2) ? hi_v[1] : lo_v[1]) - shift,
+                                            (float)((c & 4) ? hi_v[2] : lo_v[2]) - shift};
+                        float u, v, den;
+                        project_corner(geo[b], X, u, v, den);
+                        bad = bad || u != u || v != v || den != den;
+                        uv[2 * c] = u;
+                        uv[2 * c + 1] = v;
+                        umin = fminf(umin, u); umax = fmaxf(umax, u);
+                        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                        dmin = fminf(dmin, den); dmax = fmaxf(dmax, den);
+                    }
+                    if (bad) dmin = NAN;
+                    const PixRect rc = rect_from_extents(umin, umax, vmin, vmax, dmin, dmax, H, W);
+                    const bool ok = outline_valid(umin, umax, vmin, vmax, dmin, dmax);
+                    float clo[3], chi[3];
+                    for (int a = 0; a < 3; ++a) {
+                        clo[a] = ((float)lo_v[a] - shift) - geo[b].S[a];
+                        chi[a] = ((float)hi_v[a] - shift) - geo[b].S[a];
+                    }
+                    if (!(rc.x0 <= rc.x1 && rc.y0 <= rc.y1)) continue;
+                    const int th = (rc.y1 - rc.y0) / 4 + 1;
+                    for (int ty = 0; ty < th; ++ty) {
+                        const int py0 = rc.y0 + 4 * ty;
+                        int px_lo, px_hi;
+                        if (!row_span(uv, ok, rc, py0, px_lo, px_hi)) continue;
+                        const int cnt = (px_hi - px_lo) / 8 + 1;
+                        for (int t = 0; t < cnt; ++t)
+                            for (int lane = 0; lane < 32; ++lane) {
+                                const int px = px_lo + 8 * t + (lane & 7), py = py0 + (lane >> 3);
+                                if (px > px_hi || py > rc.y1) continue;
+                                const long r = (long)b * N + (long)py * W + px;
+                                const Ray& ray = rays[r];
+                                float a_in, a_out;
+                                if (!brick_maybe_hit(ray.inv, clo, chi, a_in, a_out)) continue;
+                                brick_pair_bwd_lean<2>(st, gout[r] * raylen[r], ray.s, ray.inv, clo, chi, lo_v, hi_v, org, BY * BZ, BZ,
+                                                       1, shift);
+                            }
+                    }
+                }
+                for (int x = 0; x < hi_v[0] - org[0]; ++x)
+                    for (int y = 0; y < hi_v[1] - org[1]; ++y)
+                        for (int z = 0; z < hi_v[2] - org[2]; ++z)
+                            g_vol[((size_t)(org[0] + x) * D1 + (org[1] + y)) * D2 + (org[2] + z)] = brick[((size_t)x * BY + y) * BZ + z];
+            }
+}
+
 // Debug: per-brick partial sums of ONE ray through the exact and the lean pair paths (bricks in linear order).
 long emu_brick_ray_debug(const float* vol, int D0, int D1, int D2, const float* src3, const float* tgt3, float shift, float eps,
                          int BX, int BY, int BZ, float* part_full, float* part_lean, int* brick_ids, int max_out)
