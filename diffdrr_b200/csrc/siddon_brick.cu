@@ -73,12 +73,23 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 
 // volume-gradient mode: the staged brick is an ACCUMULATOR; fp32 add on a byte address in the shared window
 // (red.shared.add.f32 = an ATOMS.CAST.SPIN loop on sm_100a: there is no native fp32 shared-memory add)
+// SWZ: the brick rows (BZ = 32 floats = 128 B) are stored in TMA's 128-byte swizzle (16-byte chunk index ^= row index & 7, i.e.
+// address bits 4-6 ^= bits 7-9; the brick base is 1024-byte aligned), so lanes that share z but differ in y hit different banks
+// -- the un-swizzled bank is z mod 32 alone, whatever x and y are.  The TMA store of the finished brick undoes it.
+// Measured (profiles/r02_tune_brick_bwd.log): 2.19 -> 1.91 ms at 512^3 -> 256^2 x 16 poses.  -DB200DRR_BWD_SWIZZLE=0 builds the
+// linear layout for A/B runs.
+#ifndef B200DRR_BWD_SWIZZLE
+#define B200DRR_BWD_SWIZZLE 1
+#endif
 struct StShared {
     uint32_t base_addr;
     static constexpr int kScale = 4;
     __device__ __forceinline__ int base() const { return (int)base_addr; }
     __device__ __forceinline__ void add(int off, float v) const
     {
+#if B200DRR_BWD_SWIZZLE
+        off ^= (off >> 3) & 0x70;
+#endif
         asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(off), "f"(v) : "memory");
     }
 };
@@ -777,7 +788,7 @@ EncodeTiledFn get_encoder()
     return fn;
 }
 
-bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, int BY, int BZ)
+bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, int BY, int BZ, bool swizzle128 = false)
 {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
@@ -786,7 +797,8 @@ bool make_volume_map(CUtensorMap* map, const float* vol, VolDims dims, int BX, i
     const cuuint32_t box[3] = {(cuuint32_t)BZ, (cuuint32_t)BY, (cuuint32_t)BX};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(vol), gdim, gstride, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -925,7 +937,7 @@ cudaError_t launch_siddon_bwd_vol_brick(const float* gout, VolDims dims, const f
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap map;
-    if (!make_volume_map(&map, g_vol, dims, 24, 32, 32)) return cudaErrorNotSupported;
+    if (!make_volume_map(&map, g_vol, dims, 24, 32, 32, B200DRR_BWD_SWIZZLE != 0)) return cudaErrorNotSupported;
     return launch_brick_variant<24, 32, 32, 1, 512, 4, 2, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter, nullptr, (int)Nr,
                                                                      B, H, W, shift, stream);
 }

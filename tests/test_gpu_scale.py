@@ -87,7 +87,8 @@ def test_full_size_properties(big):
     del vol2, ones
     # (3) batch / patch invariance of Siddon (every ray is independent)
     one = sid(vol, src[1:2], tgt[1:2, 1000:3000].contiguous(), raylen[1:2, :, 1000:3000].contiguous())
-    assert torch.equal(one[0, 0], out[1, 0, 1000:3000])
+    # (both calls take the locality-sorted slab kernels, whose partial sums meet in red.global.add: run-dependent order)
+    assert relerr(one[0, 0].cpu().numpy(), out[1, 0, 1000:3000].cpu().numpy()) < 2e-6
     # (4) the general (plane-by-plane, reference-literal) kernel: max over segments is in [0, sum] for a density >= 0
     mx = Siddon(reducefn="max")(vol, src[:1], tgt[:1, :4096].contiguous(), raylen[:1, :, :4096].contiguous())
     assert (mx >= 0).all() and (mx <= out[:1, :, :4096] + 1e-6).all()
@@ -200,14 +201,20 @@ def test_trilinear_packed_corner_path():
     drr = DRR(synthetic.make_subject(vol), sdd=1020.0, height=64, width=72, delx=3.0, renderer="trilinear").to(DEV)
     rot0, xyz0 = synthetic.make_poses(3, seed=8)
     w = torch.rand(3, 1, 64, 72, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    import diffdrr_b200.drr as drr_mod
     res = []
-    for packed in (True, False):
-        drr.renderer.pack_corners = packed
-        rot, xyz = rot0.to(DEV).requires_grad_(True), xyz0.to(DEV).requires_grad_(True)
-        img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY", n_points=180)
-        (img * w).sum().backward()
-        res.append((img.detach(), rot.grad, xyz.grad))
-        assert (drr.renderer._packed is not None) == packed or not packed
+    keep = drr_mod._TRILINEAR_POSE_IN
+    drr_mod._TRILINEAR_POSE_IN = False   # this test compares KERNELS on identical ray tensors (pose-in: test_gpu_trilinear_pose.py)
+    try:
+        for packed in (True, False):
+            drr.renderer.pack_corners = packed
+            rot, xyz = rot0.to(DEV).requires_grad_(True), xyz0.to(DEV).requires_grad_(True)
+            img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY", n_points=180)
+            (img * w).sum().backward()
+            res.append((img.detach(), rot.grad, xyz.grad))
+            assert (drr.renderer._packed is not None) == packed or not packed
+    finally:
+        drr_mod._TRILINEAR_POSE_IN = keep
     assert torch.equal(res[0][0], res[1][0])
     assert relerr(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 1e-5
     assert relerr(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-5
