@@ -94,7 +94,11 @@ struct StShared {
     }
 };
 
-// ld.shared with a byte address in the shared window
+// ld.shared with a byte address in the shared window.  B200DRR_FWD_SWIZZLE=1 (A/B builds): bricks loaded through a 128-byte
+// swizzled tensor map, the address un-swizzled per load (see StShared).
+#ifndef B200DRR_FWD_SWIZZLE
+#define B200DRR_FWD_SWIZZLE 0
+#endif
 struct LdShared {
     uint32_t base_addr;
     static constexpr int kScale = 4;
@@ -102,6 +106,9 @@ struct LdShared {
     __device__ __forceinline__ float operator()(int off) const
     {
         float v;
+#if B200DRR_FWD_SWIZZLE
+        off ^= (off >> 3) & 0x70;
+#endif
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(off));
         return v;
     }
@@ -872,17 +879,17 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
     CUtensorMap map;
 #define BV(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE)                                                            \
     case id:                                                                                                             \
-        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ, B200DRR_FWD_SWIZZLE != 0 && BZ == 32)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, PIPE>(map, dims, raytab, ltab, geo, out, counter, \
                                                                                    pix_index, (int)Nr, B, H, W, shift, stream);
 #define BV3(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
     case id:                                                                                                             \
-        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ, B200DRR_FWD_SWIZZLE != 0 && BZ == 32)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 3>(map, dims, raytab, ltab, geo, out, counter, \
                                                                                    pix_index, (int)Nr, B, H, W, shift, stream);
 #define BV2(id, BX, BY, BZ, STAGES, THREADS, K, U, CTAS)                                                                 \
     case id:                                                                                                             \
-        if (!make_volume_map(&map, vol, dims, BX, BY, BZ)) return cudaErrorNotSupported;                                 \
+        if (!make_volume_map(&map, vol, dims, BX, BY, BZ, B200DRR_FWD_SWIZZLE != 0 && BZ == 32)) return cudaErrorNotSupported;                                 \
         return launch_brick_variant<BX, BY, BZ, STAGES, THREADS, K, U, CTAS, 0, 2>(map, dims, raytab, ltab, geo, out, counter, \
                                                                                    pix_index, (int)Nr, B, H, W, shift, stream);
     switch (variant) {

@@ -87,8 +87,10 @@ def test_full_size_properties(big):
     del vol2, ones
     # (3) batch / patch invariance of Siddon (every ray is independent)
     one = sid(vol, src[1:2], tgt[1:2, 1000:3000].contiguous(), raylen[1:2, :, 1000:3000].contiguous())
-    # (both calls take the locality-sorted slab kernels, whose partial sums meet in red.global.add: run-dependent order)
-    assert relerr(one[0, 0].cpu().numpy(), out[1, 0, 1000:3000].cpu().numpy()) < 2e-6
+    # (not bitwise: the 4-pose call takes the locality-sorted SLAB-major kernels -- per-slab partial sums combined by
+    # red.global.add in run-dependent order -- while a 2000-ray call of one pose may take another decomposition; kernels agree
+    # to fp32 round-off of the partial sums)
+    assert relerr(one[0, 0].cpu().numpy(), out[1, 0, 1000:3000].cpu().numpy()) < 1e-5
     # (4) the general (plane-by-plane, reference-literal) kernel: max over segments is in [0, sum] for a density >= 0
     mx = Siddon(reducefn="max")(vol, src[:1], tgt[:1, :4096].contiguous(), raylen[:1, :, :4096].contiguous())
     assert (mx >= 0).all() and (mx <= out[:1, :, :4096] + 1e-6).all()
