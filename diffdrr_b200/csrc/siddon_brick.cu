@@ -945,7 +945,10 @@ cudaError_t launch_siddon_bwd_vol_brick(const float* gout, VolDims dims, const f
     if (e != cudaSuccess) return e;
     CUtensorMap map;
     if (!make_volume_map(&map, g_vol, dims, 24, 32, 32, B200DRR_BWD_SWIZZLE != 0)) return cudaErrorNotSupported;
-    return launch_brick_variant<24, 32, 32, 1, 512, 4, 2, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter, nullptr, (int)Nr,
+#ifndef B200DRR_BWD_U
+#define B200DRR_BWD_U 4  // steps per group of the scatter walk: 2.08 ms (U = 1), 1.91 (2), 1.84 (4) at 512^3 -> 256^2 x 16
+#endif
+    return launch_brick_variant<24, 32, 32, 1, 512, 4, B200DRR_BWD_U, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter, nullptr, (int)Nr,
                                                                      B, H, W, shift, stream);
 }
 
