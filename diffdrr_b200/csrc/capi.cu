@@ -563,6 +563,30 @@ int b200drr_trilinear_bwd_max(const float* vol, int D0, int D1, int D2, const fl
                                     1));
 }
 
+int b200drr_siddon_bwd_mask_grid(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                                 const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen, float* g_vol,
+                                 int B, int H, int W, int C, float voxel_shift, float eps, int stop_grad, void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !gout || bad_dims(D0, D1, D2) || H <= 0 || W <= 0 ||
+        bad_rays(B, (int64_t)H * W) || C <= 0)
+        return B200DRR_EINVAL;
+    return ret(launch_siddon_bwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, B,
+                                      (int64_t)H * W, C, voxel_shift, eps, stop_grad != 0, (cudaStream_t)stream, W));
+}
+
+int b200drr_trilinear_bwd_mask_grid(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
+                                    const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
+                                    float* g_vol, float* g_alpha_range, int B, int H, int W, int C, float voxel_shift, float eps,
+                                    int n_points, const float* alpha_range, int align_corners, void* stream)
+{
+    if (!vol || !mask || !src || !tgt || !raylen || !gout || !alpha_range || bad_dims(D0, D1, D2) || H <= 0 || W <= 0 ||
+        bad_rays(B, (int64_t)H * W) || C <= 0 || n_points < 2)
+        return B200DRR_EINVAL;
+    return ret(launch_trilinear_bwd_mask(vol, mask, mk(D0, D1, D2), src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol,
+                                         g_alpha_range, B, (int64_t)H * W, C, voxel_shift, eps, n_points, alpha_range,
+                                         align_corners != 0, (cudaStream_t)stream, W));
+}
+
 int b200drr_siddon_bwd_mask(const float* vol, const float* mask, int D0, int D1, int D2, const float* src, const float* tgt,
                             const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                             float* g_vol, int B, int64_t N, int C, float voxel_shift, float eps, int stop_grad, void* stream)

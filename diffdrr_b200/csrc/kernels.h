@@ -96,11 +96,12 @@ cudaError_t launch_siddon_fwd_general(const float* vol, VolDims dims, const floa
 cudaError_t launch_siddon_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                    float* g_vol, int B, int64_t N, int C, float shift, float eps, int stop_grad,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, int W = 0);  // W > 0: full row-major grid of width W (tile-ordered threads)
 cudaError_t launch_trilinear_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                       const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                       float* g_vol, float* g_alpha_range, int B, int64_t N, int C, float shift, float eps,
-                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream);
+                                      int n_points, const float* alpha_range, int align_corners, cudaStream_t stream,
+                                      int W = 0);
 
 // reference-literal kernels (literal.cu), R = float | double: fp64 path and per-segment / per-sample outputs (reduce == 2)
 template <typename R>

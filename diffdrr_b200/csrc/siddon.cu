@@ -1115,13 +1115,13 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_mask_kernel(
     const float* __restrict__ vol, const float* __restrict__ mask, VolDims dims, const float* __restrict__ src,
     const float* __restrict__ tgt, const float* __restrict__ raylen, const float* __restrict__ gout,
     float* __restrict__ g_src, float* __restrict__ g_tgt, float* __restrict__ g_raylen, float* __restrict__ g_vol, int64_t N,
-    int C, float shift, float eps, int stop_grad)
+    int C, float shift, float eps, int stop_grad, int W)
 {
     __shared__ float red[32];
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = tiled_ray_index(N, W);  // W > 0: full detector grid, threads in pixel tiles
     const int b = blockIdx.y;
     float gs[3] = {0.0f, 0.0f, 0.0f};
-    if (n < N) {
+    if (n >= 0) {
         const int64_t r = (int64_t)b * N + n;
         const Ray ray = load_ray(src, tgt, b, r, eps);
         const float L = __ldg(raylen + r);
@@ -1146,14 +1146,14 @@ __global__ void __launch_bounds__(kThreads) siddon_bwd_mask_kernel(
 cudaError_t launch_siddon_bwd_mask(const float* vol, const float* mask, VolDims dims, const float* src, const float* tgt,
                                    const float* raylen, const float* gout, float* g_src, float* g_tgt, float* g_raylen,
                                    float* g_vol, int B, int64_t N, int C, float shift, float eps, int stop_grad,
-                                   cudaStream_t stream)
+                                   cudaStream_t stream, int W)
 {
     if (g_src) {
         const cudaError_t e = cudaMemsetAsync(g_src, 0, sizeof(float) * 3 * (size_t)B, stream);
         if (e != cudaSuccess) return e;
     }
-    siddon_bwd_mask_kernel<<<dim3((unsigned)((N + kThreads - 1) / kThreads), (unsigned)B, 1), kThreads, 0, stream>>>(
-        vol, mask, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, N, C, shift, eps, stop_grad);
+    siddon_bwd_mask_kernel<<<tiled_ray_grid(B, N, W), kThreads, 0, stream>>>(
+        vol, mask, dims, src, tgt, raylen, gout, g_src, g_tgt, g_raylen, g_vol, N, C, shift, eps, stop_grad, W);
     return cudaGetLastError();
 }
 

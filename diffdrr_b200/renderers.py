@@ -766,14 +766,14 @@ class _MaskFunction(torch.autograd.Function):
                                                           _ptr(ar), int(align_corners), _stream()),
                            "b200drr_trilinear_fwd_mask")
         ctx.save_for_backward(vol, msk, src, tgt, raylen, ar)
-        ctx.cfg = (kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, tuple(source.shape), tuple(img.shape))
+        ctx.cfg = (kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, tuple(source.shape), tuple(img.shape), grid)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout):
         vol, msk, src, tgt, raylen, ar = ctx.saved_tensors
-        kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, src_shape, img_shape = ctx.cfg
+        kind, voxel_shift, eps, n_points, align_corners, stop_grad, C, src_shape, img_shape, grid = ctx.cfg
         B, N = tgt.shape[0], tgt.shape[1]
         need_vol, need_src, need_tgt, need_len, need_ar = ctx.needs_input_grad[:5]
         dev = vol.device
@@ -785,10 +785,22 @@ class _MaskFunction(torch.autograd.Function):
         g_ar = None
         lib = _lib.load()
         with torch.cuda.device(dev):
-            if kind == "siddon":
+            if kind == "siddon" and grid is not None:
+                _lib.check(lib.b200drr_siddon_bwd_mask_grid(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                            _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B,
+                                                            grid[0], grid[1], C, voxel_shift, eps, int(stop_grad), _stream()),
+                           "b200drr_siddon_bwd_mask_grid")
+            elif kind == "siddon":
                 _lib.check(lib.b200drr_siddon_bwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                        _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len), _ptr(g_vol), B, N, C,
                                                        voxel_shift, eps, int(stop_grad), _stream()), "b200drr_siddon_bwd_mask")
+            elif grid is not None:
+                g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
+                _lib.check(lib.b200drr_trilinear_bwd_mask_grid(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),
+                                                               _ptr(raylen), _ptr(gout), _ptr(g_src), _ptr(g_tgt), _ptr(g_len),
+                                                               _ptr(g_vol), _ptr(g_ar), B, grid[0], grid[1], C, voxel_shift, eps,
+                                                               int(n_points), _ptr(ar), int(align_corners), _stream()),
+                           "b200drr_trilinear_bwd_mask_grid")
             else:
                 g_ar = torch.zeros(2, dtype=torch.float32, device=dev) if need_ar else None
                 _lib.check(lib.b200drr_trilinear_bwd_mask(_ptr(vol), _ptr(msk), *vol.shape, _ptr(src), _ptr(tgt),

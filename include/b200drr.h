@@ -320,6 +320,16 @@ int b200drr_trilinear_bwd_mask(const float *vol, const float *mask, int D0, int 
                                float *g_raylen, float *g_vol, float *g_alpha_range, int B, int64_t N, int C,
                                float voxel_shift, float eps, int n_points, const float *alpha_range, int align_corners,
                                void *stream);
+/* Full row-major detector grid (N = H*W): tile-ordered threads, otherwise identical to the two entries above. */
+int b200drr_siddon_bwd_mask_grid(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                                 const float *tgt, const float *raylen, const float *gout, float *g_src, float *g_tgt,
+                                 float *g_raylen, float *g_vol, int B, int H, int W, int C, float voxel_shift, float eps,
+                                 int stop_grad, void *stream);
+int b200drr_trilinear_bwd_mask_grid(const float *vol, const float *mask, int D0, int D1, int D2, const float *src,
+                                    const float *tgt, const float *raylen, const float *gout, float *g_src, float *g_tgt,
+                                    float *g_raylen, float *g_vol, float *g_alpha_range, int B, int H, int W, int C,
+                                    float voxel_shift, float eps, int n_points, const float *alpha_range,
+                                    int align_corners, void *stream);
 
 /*
  * Double precision.  The reference reaches fp64 through `drr.to(torch.float64)` (drr.py:75): these entry points take fp64

@@ -37,6 +37,19 @@ with torch.no_grad():
             mod.detector_shape = grid
             res["plain " + tag] = timed(lambda: mod(vol, s, t, l, **kw))
             res["mask " + tag] = timed(lambda: mod(vol, s, t, l, mask=lab, **kw))
+        # backward of the masked render (ray gradients; label routing of the upstream gradient), rows vs tiles
+        g = torch.rand(B, 8, H * H, device=dev)
+        for tag, grid in (("rows", None), ("tiles", (H, H))):
+            mod.detector_shape = grid
+            with torch.enable_grad():
+                tt = t.detach().clone().requires_grad_(True)
+                out = mod(vol, s, tt, l, mask=lab, **kw)
+
+                def bwd():
+                    tt.grad = None
+                    out.backward(g, retain_graph=True)
+
+                res["mask bwd " + tag] = timed(bwd, 3)
         mod.detector_shape = None
         a = mod(vol, s, t, l, mask=lab, **kw)
         mod.detector_shape = (H, H)

@@ -277,11 +277,19 @@ def test_mask_to_channels_tile_ordered_grid_kernels_equal_the_row_ordered_ones()
     src, tgt = drr.detector(convert(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
     img = (tgt - src).norm(dim=-1).unsqueeze(1)
     s, tg = drr.affine_inverse(src), drr.affine_inverse(tgt)
+    wimg = torch.rand(3, 6, 21 * 30, device=DEV, generator=torch.Generator(DEV).manual_seed(5))
     for mod, kw in ((Siddon(), {}), (Trilinear(), dict(n_points=90))):
-        mod.detector_shape = None
-        rows = mod(drr.density, s, tg, img, mask=lab, **kw)
-        mod.detector_shape = (21, 30)
-        tiles = mod(drr.density, s, tg, img, mask=lab, **kw)
-        assert rows.shape == tiles.shape == (3, 6, 21 * 30)
+        res = []
+        for grid in (None, (21, 30)):
+            mod.detector_shape = grid
+            v, ss, tt = drr.density.detach().clone().requires_grad_(True), s.detach().clone().requires_grad_(True), \
+                tg.detach().clone().requires_grad_(True)
+            out = mod(v, ss, tt, img, mask=lab, **kw)
+            (out * wimg).sum().backward()     # b200drr_*_bwd_mask vs b200drr_*_bwd_mask_grid
+            res.append((out.detach(), v.grad, ss.grad, tt.grad))
+        rows, tiles = res
+        assert rows[0].shape == tiles[0].shape == (3, 6, 21 * 30)
         # trilinear: same per-ray code, threads re-ordered -> bitwise; Siddon: slab-major partial sums -> fp32 round-off
-        assert relerr(tiles.cpu().numpy(), rows.cpu().numpy()) < (1e-5 if isinstance(mod, Siddon) else 1e-12)
+        assert relerr(tiles[0].cpu().numpy(), rows[0].cpu().numpy()) < (1e-5 if isinstance(mod, Siddon) else 1e-12)
+        for a, b in zip(tiles[1:], rows[1:]):   # gradients: identical per-ray math, atomics / block sums in another order
+            assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
