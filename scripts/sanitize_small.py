@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small invocations of the round-2 kernels for compute-sanitizer (memcheck / racecheck / synccheck): brick-major TMA forward
-(several bricks per CTA, partial bricks, two pose chunks), the locality-ordered slab kernels, PeerGather is multi-GPU only."""
+(several bricks per CTA, partial bricks, two pose chunks), the locality-ordered slab kernels, the brick scatter (volume gradient),
+the mask grid kernels, the un-reduced segment kernels, fp64 and the trilinear pose-in step; PeerGather is multi-GPU only."""
 import os
 import sys
 
@@ -39,4 +40,37 @@ for dims, H, B in (((50, 72, 64), 40, 3), ((30, 40, 36), 24, 35)):
     o.sum().backward()
     torch.cuda.synchronize()
     print(dims, "sorted sens maxdiff", float((o.detach().reshape(B, N) - ref).abs().max() / ref.abs().max()))
+    # volume gradient: the brick kernel as a scatter (swizzled accumulator brick, TMA store) vs the slab-major walk with atomics
+    gout = torch.rand(B, N, device=dev)
+    g_b, g_s = torch.full_like(vol, float("nan")), torch.zeros_like(vol)
+    _lib.check(lib.b200drr_siddon_bwd_vol_brick(_ptr(gout), *dims, _ptr(src), _ptr(tgt), _ptr(raylen), None, None, None, None, _ptr(g_b),
+                                                _ptr(ws), ws.numel(), B, H, H, 0.5, 1e-8, _stream()), "bwd_vol_brick")
+    _lib.check(lib.b200drr_siddon_bwd_grid(_ptr(vol), *dims, _ptr(src), _ptr(tgt), _ptr(raylen), _ptr(gout), None, None, None, _ptr(g_s),
+                                           B, H, H, 0.5, 1e-8, 0, 0, _stream()), "bwd_grid")
+    torch.cuda.synchronize()
+    print(dims, "brick scatter g_vol maxdiff", float((g_b - g_s).abs().max() / g_s.abs().max()))
+    # mask_to_channels grid kernels (slab-major forward, tile-ordered backward), un-reduced segments + their backward, fp64
+    lab = (torch.arange(dims[0], device=dev)[:, None, None] // 17 + 2 * (torch.arange(dims[2], device=dev)[None, None, :] // 20)).float()
+    lab = lab.expand(*dims).contiguous()
+    sid = Siddon()
+    sid.detector_shape = (H, H)
+    t4 = tgt.clone().requires_grad_(True)
+    m = sid(vol, src.reshape(B, 1, 3), t4, l3, mask=lab)
+    m.sum().backward()
+    seg_mod = Siddon(reducefn=lambda x: x.square().sum(-1))
+    t5 = tgt[:, :256].clone().requires_grad_(True)
+    seg_mod(vol, src.reshape(B, 1, 3), t5, l3[:, :, :256].contiguous()).sum().backward()
+    t6 = tgt[:, :256].double().clone().requires_grad_(True)
+    Siddon()(vol.double(), src.reshape(B, 1, 3).double(), t6, l3[:, :, :256].double().contiguous()).sum().backward()
+    torch.cuda.synchronize()
+    print(dims, "mask / segments / fp64 ok", float(m.detach().sum()), float(t5.grad.abs().max()), float(t6.grad.abs().max()))
+# trilinear pose-in training step (alpha-range reduction kernel, in-kernel rays, matrix gradients)
+vol = synthetic.make_volume((40, 48, 56), "phantom", seed=5)
+drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(24), renderer="trilinear").to(dev)
+rot, xyz = synthetic.make_poses(3, seed=2)
+rot, xyz = rot.to(dev).requires_grad_(True), xyz.to(dev).requires_grad_(True)
+img = drr(rot, xyz, parameterization="euler_angles", convention="ZXY", n_points=64)
+img.sum().backward()
+torch.cuda.synchronize()
+print("trilinear pose-in ok", float(img.sum()), float(rot.grad.abs().max()))
 print("done")
