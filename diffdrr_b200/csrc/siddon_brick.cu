@@ -905,6 +905,9 @@ cudaError_t launch_siddon_fwd_brick(const float* vol, VolDims dims, const float*
         BV(8, 24, 32, 32, 2, 1024, 4, 2, 1, 0)
         BV(9, 12, 32, 32, 2, 512, 4, 2, 2, 1)    // two CTAs per SM, each with a two-stage pipeline of 48 KB bricks
         BV(10, 24, 32, 32, 1, 384, 5, 2, 2, 1)
+        BV(11, 48, 32, 32, 1, 1024, 4, 2, 1, 0)  // one CTA per SM, one 192 KB brick: fewer (ray, brick) pairs, no second CTA to hide barriers
+        BV(12, 32, 32, 32, 1, 1024, 4, 2, 1, 0)
+        BV(13, 48, 32, 32, 1, 768, 4, 2, 1, 0)
         BV2(20, 24, 32, 32, 1, 256, 8, 2, 2)     // two rays per thread (ILP), 2 CTAs x 256 threads: 1.28 ms
         BV2(21, 24, 32, 32, 1, 320, 6, 2, 2)
         BV2(22, 24, 32, 32, 1, 384, 5, 2, 2)
