@@ -947,12 +947,20 @@ cudaError_t launch_siddon_bwd_vol_brick(const float* gout, VolDims dims, const f
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap map;
-    if (!make_volume_map(&map, g_vol, dims, 24, 32, 32, B200DRR_BWD_SWIZZLE != 0)) return cudaErrorNotSupported;
 #ifndef B200DRR_BWD_U
 #define B200DRR_BWD_U 4  // steps per group of the scatter walk: 2.08 ms (U = 1), 1.91 (2), 1.84 (4) at 512^3 -> 256^2 x 16
 #endif
-    return launch_brick_variant<24, 32, 32, 1, 512, 4, B200DRR_BWD_U, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter, nullptr, (int)Nr,
-                                                                     B, H, W, shift, stream);
+    // Candidate tiles per warp and round (K): bigger rounds = fewer CTA-wide barriers (27 % of the stall samples), at the price of
+    // a smaller brick to keep two CTAs per SM.  Measured (profiles/r02_tune_brick_bwd.log): 16 poses 2.14 ms (K = 2), 1.84 (K = 4,
+    // 24-plane bricks), 1.73 (K = 8, 22-plane bricks); 4 poses 0.61 / 0.55 / 0.57 -- so big batches take K = 8.
+    if (B >= 8) {
+        if (!make_volume_map(&map, g_vol, dims, 22, 32, 32, B200DRR_BWD_SWIZZLE != 0)) return cudaErrorNotSupported;
+        return launch_brick_variant<22, 32, 32, 1, 512, 8, B200DRR_BWD_U, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter,
+                                                                                     nullptr, (int)Nr, B, H, W, shift, stream);
+    }
+    if (!make_volume_map(&map, g_vol, dims, 24, 32, 32, B200DRR_BWD_SWIZZLE != 0)) return cudaErrorNotSupported;
+    return launch_brick_variant<24, 32, 32, 1, 512, 4, B200DRR_BWD_U, 2, 0, 1, 1>(map, dims, raytab, ltab, geo, nullptr, counter,
+                                                                                 nullptr, (int)Nr, B, H, W, shift, stream);
 }
 
 }  // namespace b200drr

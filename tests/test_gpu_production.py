@@ -243,7 +243,8 @@ def test_subsampled_detector_inference_takes_the_brick_kernel(monkeypatch):
     assert relerr(got, ref.reshape(B, -1)) < IMG_TOL
 
 
-@pytest.mark.parametrize("dims,H,W,B", [((56, 72, 44), 40, 36, 3), ((96, 96, 96), 64, 64, 2), ((256, 256, 256), 128, 128, 4)])
+@pytest.mark.parametrize("dims,H,W,B", [((56, 72, 44), 40, 36, 3), ((96, 96, 96), 64, 64, 2), ((256, 256, 256), 128, 128, 4),
+                                        ((100, 96, 64), 48, 40, 9)])   # B >= 8: the 22-plane-brick / 8-tile-round instantiation
 def test_brick_volume_gradient_vs_oracle_and_slab_kernel(dims, H, W, B):
     """b200drr_siddon_bwd_vol_brick (the brick kernel as a scatter: shared-memory accumulation, one TMA store per brick) against
     the fp64 oracle's g_volume and the slab-major kernel with global atomics; partial bricks on every axis in the first case."""

@@ -551,6 +551,7 @@ def test_brick_major_decomposition(dims, H, B, brick, xyz):
     ((64, 72, 52), 32, 3, (8, 16, 16)),
     ((56, 40, 44), 40, 2, (24, 32, 32)),     # partial bricks on every axis
     ((48, 48, 48), 36, 2, (12, 16, 8)),
+    ((70, 64, 64), 32, 2, (22, 32, 32)),     # the big-batch instantiation's brick shape
 ])
 def test_brick_major_volume_gradient(dims, H, B, brick):
     """The transpose of the brick walk (brick_pair_bwd_lean: chord lengths scattered into a zeroed accumulator brick, one store
