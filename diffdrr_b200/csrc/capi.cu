@@ -686,4 +686,25 @@ int b200drr_siddon_visits(int D0, int D1, int D2, const float* src, const float*
     return ret(launch_siddon_visits(mk(D0, D1, D2), src, tgt, visits, B, N, voxel_shift, eps, (cudaStream_t)stream));
 }
 
+int64_t b200drr_ncc_workspace_bytes(int B, int C, int64_t N)
+{
+    if (B <= 0 || C <= 0 || N <= 0) return 0;
+    return ncc_workspace_bytes(B, C, N);
+}
+
+int b200drr_ncc_fwd(const float* x1, const float* x2, int B, int C, int64_t N, float eps, void* workspace, float* stats,
+                    float* score, void* stream)
+{
+    if (!x1 || !x2 || !workspace || !stats || !score || B <= 0 || C <= 0 || N <= 0 || (int64_t)B * C > 65535) return B200DRR_EINVAL;
+    return ret(launch_ncc_fwd(x1, x2, B, C, N, eps, workspace, stats, score, (cudaStream_t)stream));
+}
+
+int b200drr_ncc_bwd(const float* x1, const float* x2, const float* stats, const float* gscore, float* g_x1, float* g_x2, int B,
+                    int C, int64_t N, void* stream)
+{
+    if (!x1 || !x2 || !stats || !gscore || (!g_x1 && !g_x2) || B <= 0 || C <= 0 || N <= 0 || (int64_t)B * C > 65535)
+        return B200DRR_EINVAL;
+    return ret(launch_ncc_bwd(x1, x2, stats, gscore, g_x1, g_x2, B, C, N, (cudaStream_t)stream));
+}
+
 }  // extern "C"

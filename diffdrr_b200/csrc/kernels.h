@@ -178,4 +178,11 @@ cudaError_t launch_trilinear_bwd_packed(const float* packed, VolDims dims, const
                                         float* g_raylen, float* g_alpha_range, int B, int H, int W, float shift, float eps,
                                         int n_points, const float* alpha_range, int slab, cudaStream_t stream);
 
+// image similarity of the registration loop (ncc.cu)
+int64_t ncc_workspace_bytes(int B, int C, int64_t N);
+cudaError_t launch_ncc_fwd(const float* x1, const float* x2, int B, int C, int64_t N, float eps, void* workspace, float* stats,
+                           float* score, cudaStream_t stream);
+cudaError_t launch_ncc_bwd(const float* x1, const float* x2, const float* stats, const float* gscore, float* g_x1, float* g_x2,
+                           int B, int C, int64_t N, cudaStream_t stream);
+
 }  // namespace b200drr

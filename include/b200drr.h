@@ -437,6 +437,24 @@ int b200drr_siddon_fwd_brick_subset(const float *vol, int D0, int D1, int D2, co
 int b200drr_siddon_visits(int D0, int D1, int D2, const float *src, const float *tgt, int32_t *visits, int B,
                           int64_t N, float voxel_shift, float eps, void *stream);
 
+/*
+ * Image similarity of the 2D/3D registration loop: zero-normalised cross correlation of two image stacks and its gradient
+ * (reference diffdrr/metrics.py:21-44, NormalizedCrossCorrelation2d.forward / .norm with patch_size = None; eps as in the
+ * reference's constructor).  x1, x2 [B][C][N] (N = H*W pixels, row-major, device):
+ *   norm(x) = (x - mean_N x) / sqrt(var_N x + eps) (population variance),  score[b] = mean_{c,n} norm(x1) norm(x2).
+ * b200drr_ncc_fwd: one pass over both stacks (five moments per image pair, accumulated in double, fixed summation order:
+ *   deterministic), then score [B] and stats [B*C][8] = {mean1, 1/std1, mean2, 1/std2, ncc of the pair, 0, 0, 0}, the only thing
+ *   the backward pass keeps besides the images.  workspace: b200drr_ncc_workspace_bytes(B, C, N) bytes, 8-byte aligned.
+ * b200drr_ncc_bwd: gscore [B] -> g_x1, g_x2 [B][C][N] (either may be NULL) by the closed form
+ *   d score[b] / d x2[b,c,n] = (n1 - n2 * ncc_bc) / (C N std2)   (and symmetrically for x1) -- one elementwise pass instead of the
+ *   ~25 launches of the reference's autograd graph.  B*C <= 65535.
+ */
+int64_t b200drr_ncc_workspace_bytes(int B, int C, int64_t N);
+int b200drr_ncc_fwd(const float *x1, const float *x2, int B, int C, int64_t N, float eps, void *workspace, float *stats,
+                    float *score, void *stream);
+int b200drr_ncc_bwd(const float *x1, const float *x2, const float *stats, const float *gscore, float *g_x1, float *g_x2, int B,
+                    int C, int64_t N, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

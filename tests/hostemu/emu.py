@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         srcs = [os.path.join(_HERE, "hostemu.cpp")] + [
-            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh", "psync.cuh", "brick.cuh")]
+            os.path.join(_ROOT, "diffdrr_b200", "csrc", f) for f in ("ray_math.cuh", "common.cuh", "psync.cuh", "brick.cuh", "ncc_math.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
                                    "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
@@ -306,3 +306,18 @@ def siddon_bwd_vol_brick(vol_shape, src, tgt, raylen, gout, H, W, brick=(24, 32,
                                    ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
                                    *map(ctypes.c_int, brick))
     return g_vol
+
+
+def ncc(x1, x2, gscore=None, eps=1e-5):
+    """ncc.cu's math (chunked double moments, closed-form gradient) on the CPU: (score [B], g_x1, g_x2) for x [B, C, H, W]."""
+    x1, x2 = _f(x1), _f(x2)
+    B, C = x1.shape[:2]
+    N = int(np.prod(x1.shape[2:]))
+    stats = np.empty((B * C, 8), np.float32)
+    score = np.empty(B, np.float32)
+    lib().emu_ncc_fwd(_p(x1), _p(x2), ctypes.c_int(B), ctypes.c_int(C), ctypes.c_long(N), ctypes.c_float(eps), _p(stats), _p(score))
+    if gscore is None:
+        return score
+    g1, g2 = np.empty_like(x1), np.empty_like(x2)
+    lib().emu_ncc_bwd(_p(x1), _p(x2), _p(stats), _p(_f(gscore)), _p(g1), _p(g2), ctypes.c_int(B), ctypes.c_int(C), ctypes.c_long(N))
+    return score, g1, g2

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../diffdrr_b200/csrc/brick.cuh"
+#include "../../diffdrr_b200/csrc/ncc_math.cuh"
 #include "../../diffdrr_b200/csrc/psync.cuh"
 
 using namespace b200drr;
@@ -1127,4 +1128,38 @@ extern "C" void emu_chunk_reuse(int D0, int D1, int D2, const float* src, const 
                 }
             }
     out[0] = steps; out[1] = visits; out[2] = loads; out[3] = lines;
+}
+
+extern "C" {
+// ncc.cu on the CPU: the same chunked moments (ncc_partial_kernel -> ncc_finalize_kernel) and closed-form gradient (ncc_bwd_kernel).
+void emu_ncc_fwd(const float* x1, const float* x2, int B, int C, long N, float eps, float* stats, float* score)
+{
+    for (int b = 0; b < B; ++b) {
+        double total = 0.0;
+        for (int c = 0; c < C; ++c) {
+            const long img = (long)b * C + c;
+            NccSums acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+            for (long lo = 0; lo < N; lo += kNccChunk) {
+                NccSums part = {0.0, 0.0, 0.0, 0.0, 0.0};
+                for (long i = lo; i < std::min<long>(N, lo + kNccChunk); ++i) ncc_accumulate(part, x1[img * N + i], x2[img * N + i]);
+                ncc_merge(acc, part);
+            }
+            const NccStats s = ncc_finalize(acc, N, eps);
+            std::memcpy(stats + img * 8, &s, sizeof(s));
+            total += (double)s.score;
+        }
+        score[b] = (float)(total / (double)C);
+    }
+}
+
+void emu_ncc_bwd(const float* x1, const float* x2, const float* stats, const float* gscore, float* g_x1, float* g_x2, int B, int C,
+                 long N)
+{
+    for (long img = 0; img < (long)B * C; ++img) {
+        NccStats s;
+        std::memcpy(&s, stats + img * 8, sizeof(s));
+        const float k = gscore[img / C] / ((float)C * (float)N);
+        for (long i = 0; i < N; ++i) ncc_grad(s, k, x1[img * N + i], x2[img * N + i], g_x1[img * N + i], g_x2[img * N + i]);
+    }
+}
 }

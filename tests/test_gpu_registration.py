@@ -70,3 +70,59 @@ def test_ncc_gradient_flows_to_the_pose_through_the_kernels():
     from diffdrr_b200 import NormalizedCrossCorrelation2d
     s = NormalizedCrossCorrelation2d(patch_size=9)(target, reg().detach())
     assert s.shape == (1,) and -1.0 <= float(s) <= 1.0
+
+
+def _ncc_torch(x1, x2, eps=1e-5):
+    """The reference formula (metrics.py:29-44, patch_size None) in plain torch ops, for comparison with the CUDA kernels."""
+    def norm(x):
+        mu = x.mean(dim=(-1, -2), keepdim=True)
+        return (x - mu) / (x.var(dim=(-1, -2), keepdim=True, correction=0) + eps).sqrt()
+    return (norm(x1) * norm(x2)).flatten(1).sum(dim=1) / x1[0].numel()
+
+
+def test_ncc_kernels_match_the_reference_goldens():
+    """b200drr_ncc_fwd / _bwd (csrc/ncc.cu) against scores + d(score)/d(x2) recorded from the UNMODIFIED reference class
+    (tests/golden/make_golden_ncc.py; N = 480 pixels: a single ragged chunk, vector path)."""
+    import os
+
+    import numpy as np
+
+    from conftest import GOLDEN, relerr
+    from diffdrr_b200 import NormalizedCrossCorrelation2d
+    g = dict(np.load(os.path.join(GOLDEN, "ncc_reference.npz")))
+    x1 = torch.as_tensor(g["x1"]).to(DEV)
+    x2 = torch.as_tensor(g["x2"]).to(DEV).requires_grad_(True)
+    ncc = NormalizedCrossCorrelation2d()
+    assert ncc.fused_ok(x1, x2)
+    score = ncc(x1, x2)
+    (score * torch.tensor([1.0, -2.0, 0.5], device=DEV)).sum().backward()
+    assert relerr(score.detach().cpu().numpy(), g["full_score_f64"]) < 2e-6
+    assert relerr(x2.grad.cpu().numpy(), g["full_grad_x2_f64"]) < max(1e-5, 2 * relerr(g["full_grad_x2_f32"], g["full_grad_x2_f64"]))
+
+
+@pytest.mark.parametrize("shape,offset", [((2, 3, 50, 47), 0.0), ((1, 1, 256, 256), 0.0), ((3, 1, 33, 3), 500.0),
+                                          ((1, 2, 1, 5), 0.0), ((2, 1, 300, 300), 40.0)])
+def test_ncc_kernels_match_autograd_of_the_reference_formula(shape, offset):
+    """Scores and the gradients with respect to BOTH images against fp64 autograd of the reference formula: several channels,
+    sizes that are not a multiple of four (scalar path) or of the 2048-pixel chunk, a large intensity offset."""
+    from conftest import relerr
+    from diffdrr_b200 import NormalizedCrossCorrelation2d
+    gen = torch.Generator().manual_seed(5)
+    x1 = (torch.rand(*shape, generator=gen) * 3.0 + offset).to(DEV)
+    x2 = (0.5 * x1.cpu() + torch.rand(*shape, generator=gen)).to(DEV)
+    wb = (torch.rand(shape[0], generator=gen) - 0.3).to(DEV)
+    a, b = x1.double().requires_grad_(True), x2.double().requires_grad_(True)
+    ref = _ncc_torch(a, b)
+    (ref * wb.double()).sum().backward()
+    p, q = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    score = NormalizedCrossCorrelation2d()(p, q)
+    (score * wb).sum().backward()
+    assert relerr(score.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 5e-6
+    assert relerr(p.grad.cpu().numpy(), a.grad.cpu().numpy()) < 2e-4
+    assert relerr(q.grad.cpu().numpy(), b.grad.cpu().numpy()) < 2e-4
+    # only one input needs a gradient (the registration loop: the target is fixed); unaligned views take the scalar path
+    q2 = x2.clone().requires_grad_(True)
+    NormalizedCrossCorrelation2d()(x1, q2).sum().backward()
+    s1 = NormalizedCrossCorrelation2d()(x1, x2)
+    assert torch.equal(s1, NormalizedCrossCorrelation2d()(x1, x2))  # fixed summation order: run-to-run identical
+    assert q2.grad is not None and torch.isfinite(q2.grad).all()

@@ -57,3 +57,37 @@ def test_ncc_matches_the_reference_class_values_and_gradients():
             (score * torch.tensor([1.0, -2.0, 0.5], dtype=dt)).sum().backward()
             assert relerr(score.detach().numpy(), g[f"{tag}_score_{suf}"]) < tol, (tag, suf)
             assert relerr(x2.grad.numpy(), g[f"{tag}_grad_x2_{suf}"]) < max(tol, 1e-5 if dt == torch.float32 else tol), (tag, suf)
+
+
+def test_ncc_kernel_math_matches_the_reference_class_and_autograd():
+    """ncc.cu's math (ncc_math.cuh compiled for the CPU by tests/hostemu: one-pass double moments + closed-form gradient) against
+    (a) the goldens of the UNMODIFIED reference class and (b) torch autograd of the reference formula in fp64, for several
+    channels, image sizes with a ragged last chunk, a large intensity offset (the one-pass variance must not cancel) and
+    gradients with respect to BOTH images."""
+    import os
+
+    import numpy as np
+
+    from conftest import GOLDEN, relerr
+    from hostemu import emu
+    g = dict(np.load(os.path.join(GOLDEN, "ncc_reference.npz")))
+    w = np.array([1.0, -2.0, 0.5], np.float32)
+    score, _, g2 = emu.ncc(g["x1"], g["x2"], w)
+    assert relerr(score, g["full_score_f64"]) < 2e-6
+    assert relerr(g2, g["full_grad_x2_f64"]) < max(1e-5, 2 * relerr(g["full_grad_x2_f32"], g["full_grad_x2_f64"]))
+    gen = torch.Generator().manual_seed(3)
+    for (B, C, H, W), offset in (((2, 3, 50, 47), 0.0), ((1, 1, 64, 64), 0.0), ((2, 1, 33, 3), 500.0), ((1, 2, 1, 5), 0.0)):
+        x1 = torch.rand(B, C, H, W, generator=gen) * 3.0 + offset
+        x2 = (0.5 * x1 + torch.rand(B, C, H, W, generator=gen)).contiguous()
+        wb = torch.rand(B, generator=gen) - 0.3
+        a = x1.double().requires_grad_(True)
+        b = x2.double().requires_grad_(True)
+        ref = _ncc_reference(a, b)
+        (ref * wb.double()).sum().backward()
+        score, g1, g2 = emu.ncc(x1.numpy(), x2.numpy(), wb.numpy())
+        assert relerr(score, ref.detach().numpy()) < 5e-6, (B, C, H, W)
+        assert relerr(g1, a.grad.numpy()) < 2e-4 and relerr(g2, b.grad.numpy()) < 2e-4, (B, C, H, W, relerr(g2, b.grad.numpy()))
+    # a constant image: variance 0, the score is 0 and nothing is NaN (eps keeps the normalisation finite, as in the reference)
+    score, g1, g2 = emu.ncc(np.full((1, 1, 8, 8), 2.0, np.float32), np.random.default_rng(0).random((1, 1, 8, 8), np.float32),
+                            np.ones(1, np.float32))
+    assert np.isfinite(score).all() and np.isfinite(g1).all() and np.isfinite(g2).all() and abs(float(score[0])) < 1e-3
