@@ -231,6 +231,28 @@ B200_HD bool box_surely_missed(const Ray& ray, const int lo_v[3], const int hi_v
     return a_in > a_out + margin;
 }
 
+// Piece `piece` of `pieces` of the volume along the ray's OWN major axis (largest |d|): the ray crosses that axis' planes at the
+// highest rate, so the pieces carry about equal shares of its voxel visits whatever the pose is (slabs along a FIXED axis give a
+// ray that runs across them one to three pieces only).  Splitting at voxel planes is exact, and each ray may pick its own axis.
+// Returns false for an empty piece (pieces does not divide the axis).  Used for batches of one or two poses, where a thread per
+// (ray, piece) is what fills the machine: 65 536 rays are 21 % of a B200's thread slots.
+B200_HD bool major_axis_piece(const Ray& ray, const VolDims& dims, int piece, int pieces, int lo_v[3], int hi_v[3])
+{
+    const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
+    const int M = (a0 >= a1 && a0 >= a2) ? 0 : (a1 >= a2 ? 1 : 2);
+    bool any = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int len = (dims.d[a] + pieces - 1) / pieces;
+        const bool m = a == M;
+        lo_v[a] = m ? piece * len : 0;
+        const int top = (piece + 1) * len;
+        hi_v[a] = (m && top < dims.d[a]) ? top : dims.d[a];
+        any = any && lo_v[a] < hi_v[a];
+    }
+    return any;
+}
+
 // Walk restricted to the sub-box of voxels [lo_a, hi_a) per axis (planes lo_a .. hi_a); the whole volume is
 // lo = 0, hi = dims.  Splitting a ray at voxel planes is exact: every Siddon segment ends on a plane anyway.
 // Crossing alphas are generated as fma(n, |1/d|, alpha_first) from an integer crossing count n (never

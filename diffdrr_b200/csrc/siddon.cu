@@ -1,5 +1,7 @@
 // siddon.cu -- Siddon exact-path DRR kernels for sm_100a (forward, backward, visit counter).
 // One thread walks one ray (ray_math.cuh); blockIdx.y is the pose, blockIdx.x tiles the rays of that pose.
+#include <stdlib.h>
+
 #include "kernels.h"
 #ifdef B200DRR_EXPERIMENTS
 #include "psync.cuh"  // rejected experiments live only in the opt-in experimental build (build.py)
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_grid_kernel(const float* __
 // ray at voxel planes is exact) and adds the partial line integral to out with red.global.add.f32
 // (out is zero-filled by the launcher).
 // ---------------------------------------------------------------------------------------------------
-template <int TW, int TH, int U>
+// MAJ = true: `slab` is a piece COUNT along each ray's own major axis (major_axis_piece; batches of one or two poses).
+template <int TW, int TH, int U, bool MAJ = false>
 __global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __restrict__ vol, VolDims dims,
                                                                  const float* __restrict__ src,
                                                                  const float* __restrict__ tgt,
@@ -170,25 +173,26 @@ __global__ void __launch_bounds__(TW* TH) siddon_fwd_slab_kernel(const float* __
     const int64_t r = ((int64_t)b * H + py) * W + px;
     float L;
     const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
-    const int lo_v[3] = {sl * slab, 0, 0};
-    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    int lo_v[3] = {sl * slab, 0, 0};
+    int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (MAJ && !major_axis_piece(ray, dims, sl, slab, lo_v, hi_v)) return;
     if (box_surely_missed(ray, lo_v, hi_v, shift)) return;  // most (ray, slab) pairs: skip the walk set-up
     const float part = siddon_ray_lean_box<U>(vol, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift);
     if (part != 0.0f) red_add(out + r, L * part);
 }
 
-template <int TW, int TH, int U>
+template <int TW, int TH, int U, bool MAJ = false>
 static cudaError_t launch_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                        const float* raylen, float* out, int B, int H, int W, int slab, float shift,
                                        float eps, cudaStream_t stream, PoseRays pr = PoseRays{nullptr, nullptr, nullptr, nullptr})
 {
-    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int n_slabs = MAJ ? slab : (dims.d[0] + slab - 1) / slab;
     const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
     if (blocks > INT32_MAX) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * H * W, stream);
     if (e != cudaSuccess) return e;
-    siddon_fwd_slab_kernel<TW, TH, U><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, B, H, W,
-                                                                              slab, shift, eps, pr);
+    siddon_fwd_slab_kernel<TW, TH, U, MAJ><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, B, H, W,
+                                                                                   slab, shift, eps, pr);
     return cudaGetLastError();
 }
 
@@ -484,10 +488,16 @@ static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const flo
 // ---------------------------------------------------------------------------------------------------
 // Pose-in entry points: rays generated in-kernel (PoseRays), gradients reduced to the 3x4 matrices.
 // ---------------------------------------------------------------------------------------------------
+int small_batch_pieces(int B, int H, int W);  // defined next to the sensitivities launchers below
+
 cudaError_t launch_siddon_fwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
                                    const float* rows, const float* cols, float* out, int B, int H, int W, float shift,
                                    float eps, cudaStream_t stream)
 {
+    const int pieces = small_batch_pieces(B, H, W);
+    if (pieces > 0 && (int64_t)dims.d[0] * dims.d[1] * dims.d[2] < (int64_t)INT32_MAX)
+        return launch_slab_variant<16, 16, 4, true>(vol, dims, src, nullptr, nullptr, out, B, H, W, pieces, shift, eps, stream,
+                                                    PoseRays{G, Wd, rows, cols});
     return launch_slab_variant<16, 16, 4>(vol, dims, src, nullptr, nullptr, out, B, H, W, 32, shift, eps, stream,
                                           PoseRays{G, Wd, rows, cols});
 }
@@ -573,7 +583,8 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int TW, int TH, int U, int MINB>
+// MAJ = true: `slab` is a piece COUNT and the volume is cut along each ray's own major axis (major_axis_piece; small batches).
+template <int TW, int TH, int U, int MINB, bool MAJ = false>
 __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const float* __restrict__ vol, VolDims dims,
                                                                   const float* __restrict__ src,
                                                                   const float* __restrict__ tgt,
@@ -597,8 +608,9 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const fl
     const int64_t r = ((int64_t)b * H + py) * W + px;
     float L;
     const Ray ray = make_ray(pr, src, tgt, raylen, b, r, px, py, eps, L);
-    const int lo_v[3] = {sl * slab, 0, 0};
-    const int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    int lo_v[3] = {sl * slab, 0, 0};
+    int hi_v[3] = {min(dims.d[0], (sl + 1) * slab), dims.d[1], dims.d[2]};
+    if (MAJ && !major_axis_piece(ray, dims, sl, slab, lo_v, hi_v)) return;
     if (box_surely_missed(ray, lo_v, hi_v, shift)) return;  // most (ray, slab) pairs: skip the walk set-up
     float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
     const float S = siddon_ray_sens_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
@@ -618,21 +630,21 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const fl
     }
 }
 
-template <int TW, int TH, int U, int MINB>
+template <int TW, int TH, int U, int MINB, bool MAJ = false>
 static cudaError_t launch_sens_slab_variant(const float* vol, VolDims dims, const float* src, const float* tgt,
                                             const float* raylen, float* out, float* sens, int B, int H, int W, int slab,
                                             float shift, float eps, cudaStream_t stream,
                                             PoseRays pr = PoseRays{nullptr, nullptr, nullptr, nullptr})
 {
-    const int n_slabs = (dims.d[0] + slab - 1) / slab;
+    const int n_slabs = MAJ ? slab : (dims.d[0] + slab - 1) / slab;
     const int64_t blocks = (int64_t)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * n_slabs;
     if (blocks > INT32_MAX || (int64_t)dims.d[0] * dims.d[1] * dims.d[2] >= (int64_t)INT32_MAX) return cudaErrorInvalidValue;
     const size_t n = (size_t)B * H * W;
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(sens, 0, sizeof(float) * 8 * n, stream);
     if (e != cudaSuccess) return e;
-    siddon_sens_slab_kernel<TW, TH, U, MINB><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens, B,
-                                                                                    H, W, slab, shift, eps, pr);
+    siddon_sens_slab_kernel<TW, TH, U, MINB, MAJ><<<(unsigned)blocks, TW * TH, 0, stream>>>(vol, dims, src, tgt, raylen, out, sens,
+                                                                                         B, H, W, slab, shift, eps, pr);
     return cudaGetLastError();
 }
 
@@ -719,6 +731,22 @@ cudaError_t launch_x_siddon_sens_chunk(const float* volT, VolDims dims, int axis
 
 #endif  // B200DRR_EXPERIMENTS
 
+// Batches of one or two poses (the registration loop renders ONE pose per step): slabs have no other pose to share the volume
+// with, and a thread per ray leaves most of the machine idle (256^2 rays = 21 % of the thread slots, each walking ~670 voxels in
+// series).  The rays are cut into pieces along their own major axis instead (major_axis_piece), a thread per (ray, piece).
+// Returns the piece count, 0 = one thread per ray.  B200DRR_MAJOR_PIECES / B200DRR_MAJOR_MAXB override it (kernel A/B runs).
+int small_batch_pieces(int B, int H, int W)
+{
+    static const int env_k = [] { const char* e = getenv("B200DRR_MAJOR_PIECES"); return e ? atoi(e) : -1; }();
+    static const int env_b = [] { const char* e = getenv("B200DRR_MAJOR_MAXB"); return e ? atoi(e) : 2; }();
+    if (B > env_b) return 0;
+    if (env_k >= 0) return env_k > 64 ? 64 : env_k;
+    const int64_t rays = (int64_t)B * H * W;
+    int k = (int)((524288 + rays / 2) / rays);  // ~0.5 M threads: 3.5 waves of 1024 threads on 148 SMs
+    k = k > 16 ? 16 : k;
+    return k < 2 ? 0 : k;
+}
+
 cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const float* src, const float* tgt,
                                         const float* raylen, float* out, float* sens, int B, int H, int W, float shift,
                                         float eps, int variant, cudaStream_t stream)
@@ -727,6 +755,15 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
     case id:                                                                                                             \
         return launch_sens_slab_variant<TW, TH, U, MINB>(vol, dims, src, tgt, raylen, out, sens, B, H, W, SLAB, shift, eps, \
                                                          stream);
+    if (variant > 100 && variant <= 164)  // tuning: 101..164 = that many major-axis pieces, whatever the batch size
+        return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, variant - 100, shift, eps,
+                                                           stream);
+    if (variant == 0) {
+        const int pieces = small_batch_pieces(B, H, W);
+        if (pieces > 0)
+            return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, pieces, shift, eps,
+                                                               stream);
+    }
     if (variant == 0 && B <= 2)  // few poses: no cross-pose L2 sharing to win, skip the slab decomposition
         return launch_sens_slab_variant<8, 16, 8, 8>(vol, dims, src, tgt, raylen, out, sens, B, H, W, dims.d[0], shift, eps,
                                                      stream);
@@ -776,6 +813,10 @@ cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const fl
                                         const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
                                         float shift, float eps, cudaStream_t stream)
 {
+    const int pieces = small_batch_pieces(B, H, W);
+    if (pieces > 0)
+        return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, pieces, shift, eps,
+                                                           stream, PoseRays{G, Wd, rows, cols});
     // slabs exist to share the volume through L2 across the poses of a batch; with one or two poses they only repeat the
     // per-ray set-up (measured at B = 1: 0.147 ms with 48-plane slabs, 0.136 ms unslabbed)
     return launch_sens_slab_variant<8, 16, 8, 8>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W,
@@ -908,6 +949,14 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
     case id: return launch_grid_variant<TW, TH, U, LEAN>(vol, dims, src, tgt, raylen, out, B, H, W, shift, eps, stream);
 #define S0(id, TW, TH, U, SLAB) \
     case id: return launch_slab_variant<TW, TH, U>(vol, dims, src, tgt, raylen, out, B, H, W, SLAB, shift, eps, stream);
+    if (variant > 100 && variant <= 164)  // tuning: 101..164 = that many major-axis pieces, whatever the batch size
+        return launch_slab_variant<16, 16, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 100, shift, eps, stream);
+    if (variant > 200 && variant <= 264)
+        return launch_slab_variant<8, 16, 8, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 200, shift, eps, stream);
+    if (variant == 0) {
+        const int pieces = small_batch_pieces(B, H, W);
+        if (pieces > 0) return launch_slab_variant<16, 16, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, pieces, shift, eps, stream);
+    }
     switch (variant) {
         S0(0, 16, 16, 4, 32)
         V(30, 16, 8, 4, 1)

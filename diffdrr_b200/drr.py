@@ -184,14 +184,14 @@ class DRR(nn.Module):
         3x4 matrices per pose; the rays themselves are generated inside the CUDA kernel.  `rows=(h0, h1)` renders only
         that block of detector rows (ray sharding across GPUs, parallel.py) -> (B, 1, (h1-h0)*W)."""
         det = self.detector
-        grid = det.target.view(det.height, det.width, 3)
-        if rows is not None:
-            grid = grid[rows[0]:rows[1]]
         if calibration is None and pose.matrix.dtype == torch.float32:
             # the whole composition below as one kernel per direction (include/b200drr.h: b200drr_pose_rays_fwd/_bwd)
             Q, r, Ainv = self._pose_constants()
             src, G, Wd = geometry.pose_rays(pose.matrix, Q, r, Ainv)
-            return self._pose_render(src, G, Wd, grid[:, 0, 1], grid[0, :, 0], n_points)
+            return self._pose_render(src, G, Wd, *self._grid_axes(rows), n_points)
+        grid = det.target.view(det.height, det.width, 3)
+        if rows is not None:
+            grid = grid[rows[0]:rows[1]]
         calib = det._calibration if calibration is None else calibration.matrix
         M = pose.matrix @ det._reorient            # canonical C-arm frame -> world   (reorient.compose(extrinsic))
         T = M @ calib                              # ... including the intrinsic scaling of the detector plane
@@ -206,6 +206,21 @@ class DRR(nn.Module):
             return trilinear_pose_render(self.renderer, self.density, self.renderer._packed_volume(self.density), src, G, Wd,
                                          rows, cols, n_points)
         return siddon_pose_render(self.renderer, self.density, src, G, Wd, rows, cols)
+
+    def _grid_axes(self, rows: tuple | None):
+        """Detector-plane coordinates of the pixel rows / columns (grid[:, 0, 1], grid[0, :, 0]) as contiguous fp32 tensors, cached:
+        the strided slices cost two copy kernels per call, and one-pose registration steps are launch-bound."""
+        det = self.detector
+        key = (id(det), det.target.data_ptr(), det.target._version, det.height, det.width, rows)
+        cached = getattr(self, "_grid_axes_cache", None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                grid = det.target.view(det.height, det.width, 3)
+                if rows is not None:
+                    grid = grid[rows[0]:rows[1]]
+                cached = (key, (grid[:, 0, 1].float().contiguous().clone(), grid[0, :, 0].float().contiguous().clone()))
+            object.__setattr__(self, "_grid_axes_cache", cached)
+        return cached[1]
 
     def _pose_constants(self):
         """Q = reorient . calibration, r = reorient[:, 3], Ainv = affine_inverse as contiguous device tensors, rebuilt only
@@ -269,10 +284,12 @@ class DRR(nn.Module):
         # the fused path caches Q = reorient . calibration per detector: a NEW detector must never find the old constants
         # (its buffers can land on the freed addresses of a previous one)
         object.__setattr__(self, "_pose_consts", None)
+        object.__setattr__(self, "_grid_axes_cache", None)
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)  # .to(device) / .float() / ... replace the buffers
         object.__setattr__(self, "_pose_consts", None)
+        object.__setattr__(self, "_grid_axes_cache", None)
         return out
 
     def rescale_detector_(self, scale: float):

@@ -321,3 +321,13 @@ def ncc(x1, x2, gscore=None, eps=1e-5):
     g1, g2 = np.empty_like(x1), np.empty_like(x2)
     lib().emu_ncc_bwd(_p(x1), _p(x2), _p(stats), _p(_f(gscore)), _p(g1), _p(g2), ctypes.c_int(B), ctypes.c_int(C), ctypes.c_long(N))
     return score, g1, g2
+
+
+def siddon_fwd_lean_pieces(vol, src, tgt, raylen, pieces, voxel_shift=0.5, eps=1e-8):
+    """Lean forward walk cut into `pieces` along each ray's own major axis (the MAJ small-batch kernels); pieces=0: uncut."""
+    vol, src, tgt, raylen, B, N = _common(vol, src, tgt, raylen)
+    out = np.empty((B, 1, N), np.float32)
+    lib().emu_siddon_fwd_lean_slab(_p(vol), *map(ctypes.c_int, vol.shape), _p(src), _p(tgt), _p(raylen), _p(out),
+                                   ctypes.c_int(B), ctypes.c_long(N), ctypes.c_float(voxel_shift), ctypes.c_float(eps),
+                                   ctypes.c_int(-int(pieces)))
+    return out

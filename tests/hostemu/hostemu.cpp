@@ -152,7 +152,8 @@ void emu_siddon_sens(const float* vol, int D0, int D1, int D2, const float* src,
                      float eps, int stop_grad, int slab)
 {
     const VolDims dims = mk(D0, D1, D2);
-    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    // slab > 0: slabs of that many planes along axis 0; slab < 0: -slab pieces along each ray's own major axis (MAJ kernels)
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : slab < 0 ? -slab : 1;
     std::memset(g_src, 0, sizeof(float) * 3 * B);
     for (int b = 0; b < B; ++b)
         for (long n = 0; n < N; ++n) {
@@ -161,9 +162,10 @@ void emu_siddon_sens(const float* vol, int D0, int D1, int D2, const float* src,
             const float L = raylen[r];
             float sens[8] = {0, 0, 0, 0, 0, 0, 0, 0}, img = 0;
             for (int sl = 0; sl < n_slabs; ++sl) {
-                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
-                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
-                if (slab > 0 && box_surely_missed(ray, lo_v, hi_v, shift)) continue;  // as the slab kernels do
+                int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                if (slab < 0 && !major_axis_piece(ray, dims, sl, -slab, lo_v, hi_v)) continue;
+                if (slab != 0 && box_surely_missed(ray, lo_v, hi_v, shift)) continue;  // as the slab kernels do
                 float A[3] = {0, 0, 0}, C[3] = {0, 0, 0};
                 const float S = siddon_ray_sens_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C);
                 for (int a = 0; a < 3; ++a) {
@@ -484,15 +486,18 @@ void emu_siddon_sens_chunk(const float* volT, int D0, int D1, int D2, int axis, 
 void emu_siddon_fwd_lean_slab(const float* vol, int D0, int D1, int D2, const float* src, const float* tgt,
                               const float* raylen, float* out, int B, long N, float shift, float eps, int slab)
 {
-    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : 1;
+    const VolDims dims = mk(D0, D1, D2);
+    const int n_slabs = slab > 0 ? (D0 + slab - 1) / slab : slab < 0 ? -slab : 1;  // slab < 0: major-axis pieces (MAJ kernels)
     for (int b = 0; b < B; ++b)
         for (long n = 0; n < N; ++n) {
             const long r = (long)b * N + n;
             const Ray ray = load_ray(src, tgt, b, r, eps);
             float acc = 0.0f;
             for (int sl = 0; sl < n_slabs; ++sl) {
-                const int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
-                const int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                int lo_v[3] = {slab > 0 ? sl * slab : 0, 0, 0};
+                int hi_v[3] = {slab > 0 ? std::min(D0, (sl + 1) * slab) : D0, D1, D2};
+                if (slab < 0 && (!major_axis_piece(ray, dims, sl, -slab, lo_v, hi_v) || box_surely_missed(ray, lo_v, hi_v, shift)))
+                    continue;
                 acc += siddon_ray_lean_box<4>(vol, lo_v, hi_v, D1 * D2, D2, 1, ray, shift);
             }
             out[r] = raylen[r] * acc;

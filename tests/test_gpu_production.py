@@ -99,13 +99,14 @@ def test_brick_forward_pose_in_and_module_routing(monkeypatch):
     assert (err > IMG_TOL).sum() <= 5 and err.max() < 1e-3 and float(np.sqrt((err ** 2).mean())) < 1e-5
 
 
-def test_siddon_sensitivities_and_volume_gradient_vs_oracle():
-    """b200drr_siddon_fwd_sens_grid + _bwd_sens (the training step's dominant kernel, 48-plane slabs) and b200drr_siddon_bwd_grid
-    WITH g_vol (reconstruction) at 512^3 -> 256^2, two rotated poses, against the fp64 closed form.  Smooth volume for the
+@pytest.mark.parametrize("B", [2, 3])  # 2: rays cut into pieces along their own major axis (small batches); 3: 48-plane slabs
+def test_siddon_sensitivities_and_volume_gradient_vs_oracle(B):
+    """b200drr_siddon_fwd_sens_grid + _bwd_sens (the training step's dominant kernel) and b200drr_siddon_bwd_grid
+    WITH g_vol (reconstruction) at 512^3 -> 256^2, rotated poses, against the fp64 closed form.  Smooth volume for the
     end-point gradients (on noise the reference's own fp32 is 1e-2 off), noise for image / volume gradient."""
     from oracle import oracle
     L, lib = _lib()
-    D, H, B = 512, 256, 2
+    D, H = 512, 256
     N = H * H
     vol_np, vol, src, tgt, raylen = _setup(D, H, B, kind="smooth")
     gout = torch.rand(B, N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
@@ -304,3 +305,71 @@ def test_module_volume_gradient_takes_the_brick_scatter_and_matches_the_slab_pat
     finally:
         R._BRICK_BWD, R._BRICK_MIN_BRICKS = keep
     assert relerr(grads[0].cpu().numpy(), grads[1].cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("D,H,B", [(512, 256, 1), (256, 200, 1), (256, 200, 2), (96, 40, 1)])
+def test_small_batch_major_axis_pieces_vs_oracle(D, H, B):
+    """Batches of one or two poses (the registration loop; single-DRR inference): b200drr_siddon_fwd_grid,
+    b200drr_siddon_fwd_sens_grid + _bwd_sens and the pose-in module path cut every ray into pieces along its OWN major axis
+    (siddon.cu small_batch_pieces: 8 pieces at 256^2 x 1, 13 at 200^2 x 1, 16 at 40^2).  Full images and end-point gradients
+    against the fp64 oracle; detector sizes that are not a multiple of the 16 x 16 / 8 x 16 tiles."""
+    from oracle import oracle
+    L, lib = _lib()
+    N = H * H
+    vol_np, vol, src, tgt, raylen = _setup(D, H, B, seed=3, kind="smooth")
+    ref_img = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64).reshape(B, N)
+    out = torch.full((B, N), float("nan"), device=DEV)
+    L.check(lib.b200drr_siddon_fwd_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out), B, H, H, 0.5, 1e-8, 0,
+                                        _stream()), "fwd_grid")
+    assert relerr(out.cpu().numpy(), ref_img) < IMG_TOL
+    gout = torch.rand(B, N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    ref = oracle.siddon_bwd(vol_np, *_np(src, tgt, raylen, gout), dtype=np.float64, want_vol=False)
+    out2 = torch.full((B, N), float("nan"), device=DEV)
+    sens = torch.full((B, N, 8), float("nan"), device=DEV)
+    L.check(lib.b200drr_siddon_fwd_sens_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out2), _p(sens), B, H, H, 0.5,
+                                             1e-8, 0, _stream()), "fwd_sens_grid")
+    g_src, g_tgt, g_len = torch.empty(B, 3, device=DEV), torch.empty(B, N, 3, device=DEV), torch.empty(B, N, device=DEV)
+    L.check(lib.b200drr_siddon_bwd_sens(_p(sens), _p(gout), _p(g_src), _p(g_tgt), _p(g_len), B, N, 0, _stream()), "bwd_sens")
+    assert relerr(out2.cpu().numpy(), ref_img) < IMG_TOL
+    assert relerr(g_tgt.cpu().numpy(), ref["g_target"]) < 2e-3
+    assert relerr(g_src.cpu().numpy(), ref["g_source"].reshape(B, 3)) < 2e-3
+    assert relerr(g_len.cpu().numpy(), ref["g_raylen"].reshape(B, N)) < IMG_TOL
+    # the un-cut kernel (one thread per ray: variant 34 = a single 512-plane slab) agrees to fp32 summation order
+    if D <= 512:
+        out3, sens3 = torch.empty(B, N, device=DEV), torch.empty(B, N, 8, device=DEV)
+        L.check(lib.b200drr_siddon_fwd_sens_grid(_p(vol), D, D, D, _p(src), _p(tgt), _p(raylen), _p(out3), _p(sens3), B, H, H,
+                                                 0.5, 1e-8, 34, _stream()), "fwd_sens_grid uncut")
+        assert relerr(out2.cpu().numpy(), out3.cpu().numpy()) < 1e-5
+        assert relerr(sens.cpu().numpy(), sens3.cpu().numpy()) < 1e-3  # crossing coefficients cancel: compare loosely
+
+
+def test_small_batch_module_path_matches_the_oracle_image_and_two_walk_gradients():
+    """DRR(rot, xyz) for ONE pose (pose-in kernels with major-axis pieces, forward-only AND forward-with-sensitivities): image
+    against the fp64 oracle on the module's own rays, pose gradients against the same module run with four copies of the pose
+    (batch of 4: the slab-major kernels)."""
+    from diffdrr_b200 import DRR, synthetic
+    from diffdrr_b200.pose import convert
+    from oracle import oracle
+    D, H = 128, 72
+    vol_np = synthetic.make_volume(D, "smooth", seed=5)
+    drr = DRR(synthetic.make_subject(vol_np), **synthetic.detector_kwargs(H), stop_gradients_through_grid_sample=True).to(DEV)
+    rot, xyz = synthetic.make_poses(2, seed=6)
+    rot, xyz = rot[:1].to(DEV), xyz[:1].to(DEV)
+    w = torch.rand(1, 1, H, H, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    with torch.no_grad():
+        img_inf = drr(rot, xyz, parameterization="euler_angles", convention="ZXY")
+        src, tgt = drr.detector(convert(rot, xyz, parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+        src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+    ref = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64).reshape(1, 1, H, H)
+    assert relerr(img_inf.cpu().numpy(), ref) < IMG_TOL
+    r1, t1 = rot.clone().requires_grad_(True), xyz.clone().requires_grad_(True)
+    img = drr(r1, t1, parameterization="euler_angles", convention="ZXY")
+    (img * w).sum().backward()
+    assert relerr(img.detach().cpu().numpy(), ref) < IMG_TOL
+    r4, t4 = rot.repeat(4, 1).requires_grad_(True), xyz.repeat(4, 1).requires_grad_(True)
+    img4 = drr(r4, t4, parameterization="euler_angles", convention="ZXY")
+    (img4 * w).sum().backward()
+    assert relerr(img4[:1].detach().cpu().numpy(), img.detach().cpu().numpy()) < 1e-5
+    assert relerr(r1.grad.cpu().numpy(), r4.grad[:1].cpu().numpy()) < 1e-3
+    assert relerr(t1.grad.cpu().numpy(), t4.grad[:1].cpu().numpy()) < 1e-3

@@ -107,7 +107,7 @@ def test_siddon_backward(name, kw, lean_slab):
     ("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)), ("siddon_nc_b4_ragged", {}),
     ("siddon_nc_b4_stopgrad", dict(stop_grad=True)), ("siddon_nc_inside", {}), ("siddon_nc_axis", {}),
 ])
-@pytest.mark.parametrize("slab", [0, 5])
+@pytest.mark.parametrize("slab", [0, 5, -3, -7])  # < 0: that many pieces along each ray's own major axis (small batches)
 def test_siddon_sensitivities_walk(name, kw, slab):
     """Training-step fast path: one walk -> image + per-ray end-point sensitivities (two accumulated axes, the major axis
     from the telescoping identities), backward = sensitivities x upstream gradient.  Same bar as the backward walk."""
@@ -122,7 +122,7 @@ def test_siddon_sensitivities_walk(name, kw, slab):
     else:
         assert relerr(out["g_raylen"], g["g_raylen_f64"]) < _grad_tol(g, "g_raylen")
     # and against the three-axis backward walk it replaces
-    ref = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], lean_slab=slab, **kw)
+    ref = emu.siddon_bwd(g["volume"], g["source"], g["target"], g["raylen"], g["w"], lean_slab=max(slab, 0), **kw)
     assert relerr(out["g_target"], ref["g_target"]) < 2e-5
     assert relerr(out["g_source"], ref["g_source"]) < 2e-5
 
@@ -564,3 +564,17 @@ def test_brick_major_volume_gradient(dims, H, B, brick):
     # a voxel's gradient is a handful of chord lengths, each the difference of two fp32 alphas (no averaging as in a line
     # integral): measured 2e-5; the fp32 oracle itself sits at the same level
     assert relerr(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("name,kw", [("siddon_nc_b4", {}), ("siddon_nc_b4_shift0", dict(voxel_shift=0.0)),
+                                     ("siddon_nc_inside", {}), ("siddon_nc_axis", {}), ("siddon_nc_b4_ragged", {})])
+def test_major_axis_pieces_forward(name, kw):
+    """Small-batch kernels (MAJ): every ray cut into K pieces along its OWN major axis; the pieces add up to the reference's
+    line integral (fp64 golden) and to the uncut lean walk, for K that does and does not divide the volume, incl. K > planes."""
+    g = load_golden(name)
+    whole = emu.siddon_fwd_lean_pieces(g["volume"], g["source"], g["target"], g["raylen"], 0, **kw)
+    assert relerr(whole, g["img_f64"]) < IMG_TOL
+    for pieces in (1, 2, 3, 8, 16, 100):
+        out = emu.siddon_fwd_lean_pieces(g["volume"], g["source"], g["target"], g["raylen"], pieces, **kw)
+        assert relerr(out, g["img_f64"]) < IMG_TOL, pieces
+        assert relerr(out, whole) < 1e-5, pieces  # fp32 summation order only
