@@ -357,11 +357,20 @@ def extra_configs(dev, lib, peak, main):
 
     # ---- (a) north-star metric: Siddon FORWARD 512^3 -> 256^2, both production kernels ------------------------------
     fwd_bytes = 4 * tot_visits + 20 * B * N
+    # variant 15 = the slab-major kernel (16 x 16 tiles, 32-plane slabs) by its explicit id; variant 0 = the library's choice for
+    # this batch (up to 16 poses of 256^2 rays at >= 384^3: every ray cut into pieces along its own major axis)
     t_slab = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen),
-                                                                         _ptr(out), B, det, det, 0.5, 1e-8, 0, _stream()), "fwd_grid"), 10)
+                                                                         _ptr(out), B, det, det, 0.5, 1e-8, 15, _stream()), "fwd_grid"), 10)
     ref_img = out.clone()
     entry = {"workload": f"siddon forward, {D}^3 -> {det}^2, {B} poses", "slab_major": {**_stat(t_slab), "drr_per_s": B / np.median(t_slab) * 1e3,
                                                                                       "roofline": roof(fwd_bytes, float(np.median(t_slab)))}}
+    t_def = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(src), _ptr(tgt), _ptr(raylen),
+                                                                        _ptr(out), B, det, det, 0.5, 1e-8, 0, _stream()), "fwd_grid"), 10)
+    entry["library_default_major_axis_pieces"] = {**_stat(t_def), "drr_per_s": B / np.median(t_def) * 1e3,
+                                                  "roofline": roof(fwd_bytes, float(np.median(t_def))),
+                                                  "maxdiff_vs_slab_major": float((out - ref_img).abs().max() / ref_img.abs().max()),
+                                                  "note": "b200drr_siddon_fwd_grid variant 0: siddon_fwd_slab_kernel<16,16,4,MAJ> with 16 pieces "
+                                                          "per ray at this size (csrc/siddon.cu small_batch_pieces); the zero fill is in the time"}
     try:
         ws = torch.empty(lib.b200drr_siddon_brick_workspace_bytes(B, det, det), dtype=torch.uint8, device=dev)
         t_brick = _time_events(lambda: _lib.check(lib.b200drr_siddon_fwd_brick(
@@ -513,7 +522,9 @@ def extra_configs(dev, lib, peak, main):
         reg = Registration(drr5, (true_rot + torch.tensor([[0.15, -0.1, 0.08]], device=dev)).clone(),
                            (true_xyz + torch.tensor([[12.0, -25.0, 9.0]], device=dev)).clone(), "euler_angles", "ZXY").to(dev)
         ncc = NormalizedCrossCorrelation2d()
-        opt = torch.optim.Adam([{"params": [reg.rotation], "lr": 5e-3}, {"params": [reg.translation], "lr": 5e-1}], capturable=True)
+        # torch's own fused (multi-tensor) Adam: 4 launches per step instead of ~25; the loss is the fused NCC (csrc/ncc.cu)
+        opt = torch.optim.Adam([{"params": [reg.rotation], "lr": 5e-3}, {"params": [reg.translation], "lr": 5e-1}], capturable=True,
+                               fused=True)
 
         def reg_step():
             opt.zero_grad(set_to_none=False)
@@ -543,7 +554,9 @@ def extra_configs(dev, lib, peak, main):
         with torch.no_grad():
             final = float(1.0 - ncc(target, reg()).mean())
         res["config5_registration_loop"] = {
-            "workload": "BASELINE config 5: 1000 gradient steps (Adam, NCC), 512^3 CT, 256^2 target DRR, B = 1, whole step in one CUDA graph",
+            "workload": "BASELINE config 5: 1000 gradient steps (Adam, NCC), 512^3 CT, 256^2 target DRR, B = 1, whole step in one CUDA graph; "
+                        "renderer: forward-with-sensitivities kernel with 12 major-axis pieces per ray, loss: b200drr_ncc_fwd/_bwd, optimiser: "
+                        "torch.optim.Adam(fused=True, capturable=True)",
             "it_per_s": n_it / (ms * 1e-3), "ms_per_it": ms / n_it, "final_1_minus_ncc": final,
             "rot_err_rad": float((reg.rotation.detach() - true_rot).abs().max()),
             "xyz_err_mm": float((reg.translation.detach() - true_xyz).abs().max())}
@@ -873,7 +886,8 @@ def run_ours(args, rank, local_rank, world):
                      "traffic_source": NCU_TRAFFIC_SOURCE, "algorithmic_bytes_per_launch": dom[2], "ms_per_launch": dom[3], "peak_source": peak_src},
         "step_breakdown_ms": {"siddon_sens_slab_kernel (image + sensitivities, one walk)": sens_ms,
                               "sens_bwd_kernel (elementwise backward)": sens_bwd_ms},
-        "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
+        "roofline_fwd": {"kernel": "siddon_fwd_slab_kernel (b200drr_siddon_fwd_grid's choice for this batch: rays cut into major-axis "
+                                   "pieces up to 16 poses of 256^2 rays, slab-major beyond)", "achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms_per_launch": fwd_ms,
                          "algorithmic_bytes_per_launch": fwd_bytes, "drr_per_s_fwd_only": B / (fwd_ms * 1e-3)},
         "roofline_bwd": {"kernel": "siddon_bwd_slab_kernel", "achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms_per_launch": bwd_ms,
                          "algorithmic_bytes_per_launch": bwd_bytes,

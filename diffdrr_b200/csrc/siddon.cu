@@ -488,13 +488,13 @@ static cudaError_t launch_grid_variant(const float* vol, VolDims dims, const flo
 // ---------------------------------------------------------------------------------------------------
 // Pose-in entry points: rays generated in-kernel (PoseRays), gradients reduced to the 3x4 matrices.
 // ---------------------------------------------------------------------------------------------------
-int small_batch_pieces(int B, int H, int W);  // defined next to the sensitivities launchers below
+int small_batch_pieces(const VolDims& dims, int B, int H, int W, bool sens);  // defined next to the sensitivities launchers below
 
 cudaError_t launch_siddon_fwd_pose(const float* vol, VolDims dims, const float* src, const float* G, const float* Wd,
                                    const float* rows, const float* cols, float* out, int B, int H, int W, float shift,
                                    float eps, cudaStream_t stream)
 {
-    const int pieces = small_batch_pieces(B, H, W);
+    const int pieces = small_batch_pieces(dims, B, H, W, false);
     if (pieces > 0 && (int64_t)dims.d[0] * dims.d[1] * dims.d[2] < (int64_t)INT32_MAX)
         return launch_slab_variant<16, 16, 4, true>(vol, dims, src, nullptr, nullptr, out, B, H, W, pieces, shift, eps, stream,
                                                     PoseRays{G, Wd, rows, cols});
@@ -731,19 +731,34 @@ cudaError_t launch_x_siddon_sens_chunk(const float* volT, VolDims dims, int axis
 
 #endif  // B200DRR_EXPERIMENTS
 
-// Batches of one or two poses (the registration loop renders ONE pose per step): slabs have no other pose to share the volume
-// with, and a thread per ray leaves most of the machine idle (256^2 rays = 21 % of the thread slots, each walking ~670 voxels in
-// series).  The rays are cut into pieces along their own major axis instead (major_axis_piece), a thread per (ray, piece).
-// Returns the piece count, 0 = one thread per ray.  B200DRR_MAJOR_PIECES / B200DRR_MAJOR_MAXB override it (kernel A/B runs).
-int small_batch_pieces(int B, int H, int W)
+// Major-axis pieces (MAJ kernels): every ray is cut into K pieces along its OWN major axis, a thread per (ray, piece).
+// Why: (1) the registration loop renders ONE pose per step -- 256^2 rays are 21 % of a B200's thread slots, each walking ~670
+// voxels in series; (2) slabs along a FIXED axis give a ray that runs across them one to three pieces of very different length,
+// so the lanes of a warp finish at different times, while the major-axis pieces of a warp's rays carry equal shares of the visits.
+// Measured on B200, 512^3 -> 256^2 (profiles/r02_tune_small_batch.log; us per launch):
+//   forward   B = 1: 187 (32-plane slabs) -> 95 (K = 12);  2: 250 -> 152;  4: 365 -> 248;  8: 601 (brick 591) -> 504;
+//             16: 1142 (brick 1099) -> 1032 (K = 16)  -- the fastest forward kernel at every batch size measured (41 % of HBM roofline)
+//   sens      B = 1: 193 (thread per ray) -> 115 (K = 8..16);  2: 281 -> 192;  4: 394 (96-plane slabs) -> 312;  8: 637 (48-plane
+//             slabs) -> 639;  16: 1243 -> 1273  -- the slab-major kernel keeps batches >= 8 (its volume re-use through L2 pays there)
+// `load` = B * H * W in units of 256^2 rays.  Pieces thinner than ~24 planes only add set-up; volumes below 384^3 were not measured
+// at batch sizes > 4 (the slab-major tuning of BASELINE config 2 stands there), volumes below 96 voxels keep one thread per ray.
+// Returns K, 0 = not used.
+// B200DRR_MAJOR_PIECES / B200DRR_MAJOR_MAXB override it for kernel A/B runs (K for every batch up to MAXB poses).
+int small_batch_pieces(const VolDims& dims, int B, int H, int W, bool sens)
 {
     static const int env_k = [] { const char* e = getenv("B200DRR_MAJOR_PIECES"); return e ? atoi(e) : -1; }();
-    static const int env_b = [] { const char* e = getenv("B200DRR_MAJOR_MAXB"); return e ? atoi(e) : 2; }();
-    if (B > env_b) return 0;
-    if (env_k >= 0) return env_k > 64 ? 64 : env_k;
-    const int64_t rays = (int64_t)B * H * W;
-    int k = (int)((524288 + rays / 2) / rays);  // ~0.5 M threads: 3.5 waves of 1024 threads on 148 SMs
-    k = k > 16 ? 16 : k;
+    static const int env_b = [] { const char* e = getenv("B200DRR_MAJOR_MAXB"); return e ? atoi(e) : -1; }();
+    if (env_k >= 0 || env_b >= 0) {
+        if (B > (env_b >= 0 ? env_b : 2)) return 0;
+        if (env_k >= 0) return env_k > 64 ? 64 : env_k;
+    }
+    const int dmax = dims.d[0] > dims.d[1] ? (dims.d[0] > dims.d[2] ? dims.d[0] : dims.d[2]) : (dims.d[1] > dims.d[2] ? dims.d[1] : dims.d[2]);
+    if (dmax < 96) return 0;  // tiny volumes: a launch is latency-bound whatever the decomposition
+    const double load = (double)B * H * W / 65536.0;
+    const double max_load = dmax < 384 ? 4.0 : (sens ? 6.0 : 16.0);
+    if (load > max_load) return 0;
+    int k = (!sens && load > 4.0) ? 16 : 12;
+    if (k > dmax / 24) k = dmax / 24;
     return k < 2 ? 0 : k;
 }
 
@@ -758,8 +773,14 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
     if (variant > 100 && variant <= 164)  // tuning: 101..164 = that many major-axis pieces, whatever the batch size
         return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, variant - 100, shift, eps,
                                                            stream);
+    if (variant > 300 && variant <= 364)
+        return launch_sens_slab_variant<16, 8, 8, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, variant - 300, shift, eps,
+                                                           stream);
+    if (variant > 400 && variant <= 464)
+        return launch_sens_slab_variant<8, 16, 4, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, variant - 400, shift, eps,
+                                                           stream);
     if (variant == 0) {
-        const int pieces = small_batch_pieces(B, H, W);
+        const int pieces = small_batch_pieces(dims, B, H, W, true);
         if (pieces > 0)
             return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, tgt, raylen, out, sens, B, H, W, pieces, shift, eps,
                                                                stream);
@@ -769,6 +790,7 @@ cudaError_t launch_siddon_fwd_sens_grid(const float* vol, VolDims dims, const fl
                                                      stream);
     switch (variant) {
         SV(0, 8, 16, 8, 48, 8)  // tuned default (profiles/r01_tune_sens.log)
+        SV(38, 8, 16, 8, 48, 8)  // the same kernel by an explicit id, for batches whose default is the major-axis-pieces kernel
         SV(32, 16, 8, 8, 48, 8)
         SV(33, 8, 16, 8, 128, 8)
         SV(34, 8, 16, 8, 512, 8)
@@ -813,7 +835,7 @@ cudaError_t launch_siddon_fwd_sens_pose(const float* vol, VolDims dims, const fl
                                         const float* rows, const float* cols, float* out, float* sens, int B, int H, int W,
                                         float shift, float eps, cudaStream_t stream)
 {
-    const int pieces = small_batch_pieces(B, H, W);
+    const int pieces = small_batch_pieces(dims, B, H, W, true);
     if (pieces > 0)
         return launch_sens_slab_variant<8, 16, 8, 8, true>(vol, dims, src, nullptr, nullptr, out, sens, B, H, W, pieces, shift, eps,
                                                            stream, PoseRays{G, Wd, rows, cols});
@@ -953,8 +975,12 @@ cudaError_t launch_siddon_fwd_grid(const float* vol, VolDims dims, const float* 
         return launch_slab_variant<16, 16, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 100, shift, eps, stream);
     if (variant > 200 && variant <= 264)
         return launch_slab_variant<8, 16, 8, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 200, shift, eps, stream);
+    if (variant > 300 && variant <= 364)
+        return launch_slab_variant<16, 8, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 300, shift, eps, stream);
+    if (variant > 400 && variant <= 464)
+        return launch_slab_variant<8, 16, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, variant - 400, shift, eps, stream);
     if (variant == 0) {
-        const int pieces = small_batch_pieces(B, H, W);
+        const int pieces = small_batch_pieces(dims, B, H, W, false);
         if (pieces > 0) return launch_slab_variant<16, 16, 4, true>(vol, dims, src, tgt, raylen, out, B, H, W, pieces, shift, eps, stream);
     }
     switch (variant) {

@@ -83,6 +83,16 @@ def _brick_ok(vol, B, H, W, check_density: bool = True) -> bool:
             and 2 <= W <= 2048 and B * H * W < 2**31 and vol.data_ptr() % 16 == 0 and vol.numel() < 2**31 - 1)
 
 
+# Full detector grids: up to a load of 16 (B * H * W in units of 256^2 rays) the library's own forward kernel cuts every ray into
+# pieces along its major axis (csrc/siddon.cu small_batch_pieces) and beats the brick kernel (512^3 -> 256^2, us per launch:
+# B = 2: 152 vs 229, 8: 504 vs 591, 16: 1032 vs 1099); the brick kernel keeps the bigger batches (62 us per pose at B = 32 / 64).
+_BRICK_FULL_GRID_MIN_LOAD = float(_os.environ.get("B200DRR_BRICK_MIN_LOAD", "16"))
+
+
+def _brick_full_grid_ok(vol, B, H, W) -> bool:
+    return B * H * W > _BRICK_FULL_GRID_MIN_LOAD * 65536.0 and _brick_ok(vol, B, H, W)
+
+
 _BRICK_BWD = _os.environ.get("B200DRR_BRICK_BWD", "1") != "0"
 _BRICK_BWD_MIN_BATCH = int(_os.environ.get("B200DRR_BRICK_BWD_MIN_BATCH", "1"))
 
@@ -201,7 +211,7 @@ class _SiddonFunction(torch.autograd.Function):
                 _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen),
                                                             _ptr(out), _ptr(sens), B, grid[0], grid[1], voxel_shift, eps, 0,
                                                             _stream()), "b200drr_siddon_fwd_sens_grid")
-            elif grid is not None and _brick_ok(vol, B, grid[0], grid[1]):
+            elif grid is not None and _brick_full_grid_ok(vol, B, grid[0], grid[1]):
                 ws = _brick_workspace(vol.device, B, grid[0], grid[1])
                 _lib.check(lib.b200drr_siddon_fwd_brick(_ptr(vol), *vol.shape, _ptr(src), _ptr(tgt), _ptr(raylen), None, None,
                                                         None, None, _ptr(out), ctypes.c_void_p(ws.data_ptr()), ws.numel(), B,
@@ -348,7 +358,7 @@ class _SiddonPoseFunction(torch.autograd.Function):
                            "b200drr_siddon_fwd_sens_pose")
                 ctx.save_for_backward(sens, Wd, rows, cols)
                 return out.view(B, 1, H * W)
-            if _brick_ok(vol, B, H, W):
+            if _brick_full_grid_ok(vol, B, H, W):
                 ws = _brick_workspace(vol.device, B, H, W)
                 _lib.check(_lib.load().b200drr_siddon_fwd_brick(_ptr(vol), *vol.shape, _ptr(src), None, None, _ptr(G), _ptr(Wd),
                                                                 _ptr(rows), _ptr(cols), _ptr(out),

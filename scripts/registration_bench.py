@@ -28,7 +28,7 @@ reg = Registration(drr, rot0.clone(), xyz0.clone(), "euler_angles", "ZXY").to(de
 ncc = NormalizedCrossCorrelation2d()
 opt = torch.optim.SGD([{"params": [reg.rotation], "lr": 5e-2}, {"params": [reg.translation], "lr": 3e2}], momentum=0.9,
                       capturable=False) if False else torch.optim.Adam(
-    [{"params": [reg.rotation], "lr": 5e-3}, {"params": [reg.translation], "lr": 5e-1}], capturable=args.graph)
+    [{"params": [reg.rotation], "lr": 5e-3}, {"params": [reg.translation], "lr": 5e-1}], capturable=args.graph, fused=True)
 
 
 def step():

@@ -18,6 +18,7 @@ from diffdrr_b200.renderers import _ptr, _stream, siddon_visits  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--loop", action="store_true")
+ap.add_argument("--big", action="store_true", help="batches of 8 / 16 poses: major-axis pieces against the slab-major and brick kernels")
 ap.add_argument("--trace", action="store_true", help="with --loop: kernel names x counts of one eager step (torch.profiler)")
 ap.add_argument("--pieces", default="1,2,3,4,6,8,12,16,24,32")
 ap.add_argument("--batches", default="1,2,3,4")
@@ -143,7 +144,60 @@ def loop():
                   f"xyz err {float((reg.translation.detach() - true_xyz).abs().max()):.3f}", flush=True)
 
 
+def big():
+    import ctypes
+    vol = torch.as_tensor(synthetic.make_volume(D, "rand", seed=0)).to(dev)
+    subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+    subj.volume.affine = synthetic.make_affine(D)
+    drr = DRR(subj, **synthetic.detector_kwargs(H)).to(dev)
+    N = H * H
+    for B in [int(b) for b in args.batches.split(",")]:
+        rot, xyz = synthetic.make_poses(max(B, 2), seed=0)
+        s, t, l = bench._device_rays(drr, rot[:B], xyz[:B], dev)
+        visits = int(siddon_visits((D, D, D), s, t).sum().item())
+        out, sens = torch.empty(B, N, device=dev), torch.empty(B, N, 8, device=dev)
+        ref_out = torch.empty(B, N, device=dev)
+        ws = torch.empty(int(lib.b200drr_siddon_brick_workspace_bytes(B, H, H)), dtype=torch.uint8, device=dev)
+
+        def fwd(variant, o=out):
+            _lib.check(lib.b200drr_siddon_fwd_grid(_ptr(vol), D, D, D, _ptr(s), _ptr(t), _ptr(l), _ptr(o), B, H, H, 0.5, 1e-8,
+                                                   variant, _stream()), "fwd_grid")
+
+        def brick():
+            _lib.check(lib.b200drr_siddon_fwd_brick(_ptr(vol), D, D, D, _ptr(s), _ptr(t), _ptr(l), None, None, None, None, _ptr(out),
+                                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), B, H, H, 0.5, 1e-8, 0, _stream()), "brick")
+
+        def sns(variant, o=out, q=sens):
+            _lib.check(lib.b200drr_siddon_fwd_sens_grid(_ptr(vol), D, D, D, _ptr(s), _ptr(t), _ptr(l), _ptr(o), _ptr(q), B, H, H,
+                                                        0.5, 1e-8, variant, _stream()), "fwd_sens_grid")
+
+        def ms(fn):
+            return float(np.median(bench._time_events(fn, 9, warmup=3)))
+
+        fwd(15, ref_out)
+        pct = lambda tt: 4 * visits / tt * 1e-6 / peak * 100  # noqa: E731
+        t_slab, t_brick, t_sens = ms(lambda: fwd(15)), ms(brick), ms(lambda: sns(32 if False else 0))
+        print(f"{D}^3 -> {H}^2 x {B} poses ({visits / (B * N):.0f} visits/ray): forward slab-major {t_slab * 1e3:7.1f} us ({pct(t_slab):4.1f} %) | "
+              f"brick {t_brick * 1e3:7.1f} us ({pct(t_brick):4.1f} %) | sens 48-plane slabs {t_sens * 1e3:7.1f} us ({pct(t_sens):4.1f} %)", flush=True)
+        for K in [int(k) for k in args.pieces.split(",")]:
+            row = f"  K = {K:2d}: forward"
+            for base, name in ((100, "16x16/U4"), (200, "8x16/U8"), (300, "16x8/U4"), (400, "8x16/U4")):
+                fwd(base + K)
+                e = float((out - ref_out).abs().max() / ref_out.abs().max())
+                tt = ms(lambda: fwd(base + K))
+                row += f" {name} {tt * 1e3:7.1f} ({pct(tt):4.1f} %, {e:.0e})"
+            row += " | sens"
+            for base, name in ((100, "8x16/U8"), (300, "16x8/U8"), (400, "8x16/U4")):
+                sns(base + K)
+                e = float((out - ref_out).abs().max() / ref_out.abs().max())
+                tt = ms(lambda: sns(base + K))
+                row += f" {name} {tt * 1e3:7.1f} ({pct(tt):4.1f} %, {e:.0e})"
+            print(row, flush=True)
+
+
 if args.loop:
     loop()
+elif args.big:
+    big()
 else:
     kernels()

@@ -45,7 +45,7 @@ def test_subsample_and_patches_match_full_render(setup):
         mask[pick] = False
         assert float(flat_sub[mask].abs().max()) == 0.0
         raw = _drr(vol, reshape=False)(rot, xyz, **kw)
-        assert raw.shape == (3, 1, 40 * 36) and torch.equal(raw.view(3, 1, 40, 36), full)
+        assert raw.shape == (3, 1, 40 * 36) and relerr(raw.view(3, 1, 40, 36).cpu().numpy(), full.cpu().numpy()) < 1e-6
 
 
 def test_calibration_override_and_intrinsics_editing(setup):
