@@ -97,7 +97,7 @@ def test_brick_forward_pose_in_and_module_routing(monkeypatch):
         src, tgt = drr.detector(convert(rot.to(DEV), xyz.to(DEV), parameterization="euler_angles", convention="ZXY"), None)
         raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
         src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
-    assert relerr(img.cpu().numpy(), img_slab.cpu().numpy()) < 3e-5
+    assert relerr(img.cpu().numpy(), img_slab.cpu().numpy()) < 5e-5   # two decompositions of the same fp32 sums
     ref = oracle.siddon_fwd(vol_np, *_np(src, tgt, raylen), dtype=np.float64)
     got = img.cpu().numpy().reshape(ref.shape)
     err = np.abs(got - ref) / np.abs(ref).max()

@@ -107,8 +107,8 @@ def test_full_size_properties(big):
 
 
 def test_full_size_grid_kernels_match_plain_kernels(big):
-    """The tiled slab-major kernels (used when the rays are a full detector grid) against the one-thread-per-ray
-    kernels on the metric's configuration; gradients too.  Partial sums are combined with red.global.add, so the
+    """The tiled kernels (used when the rays are a full detector grid; 4 poses: every ray cut into 12 major-axis pieces)
+    against the one-thread-per-ray kernels on the metric's configuration; gradients too.  Partial sums are combined with red.global.add, so the
     comparison is to fp32 round-off, not bitwise."""
     from diffdrr_b200 import Siddon
     drr, vol, (src, tgt, raylen) = big
@@ -118,7 +118,7 @@ def test_full_size_grid_kernels_match_plain_kernels(big):
     x = torch.linspace(-1, 1, 512, device=DEV)
     smooth = torch.exp(-(x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2) / 0.3)
     # images on the white-noise volume; end-point gradients on a smooth one (on white noise they are fp32-ill-conditioned)
-    for volume, tols in ((vol, (2e-5, None, None, 2e-5)), (smooth, (2e-5, 1e-3, 1e-3, 2e-5))):
+    for volume, tols in ((vol, (3e-5, None, None, 3e-5)), (smooth, (3e-5, 1e-3, 1e-3, 3e-5))):
         outs = []
         for mod in (plain, tiled):
             s, t_, l = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True), raylen.clone().requires_grad_(True)

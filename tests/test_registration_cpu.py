@@ -91,3 +91,19 @@ def test_ncc_kernel_math_matches_the_reference_class_and_autograd():
     score, g1, g2 = emu.ncc(np.full((1, 1, 8, 8), 2.0, np.float32), np.random.default_rng(0).random((1, 1, 8, 8), np.float32),
                             np.ones(1, np.float32))
     assert np.isfinite(score).all() and np.isfinite(g1).all() and np.isfinite(g2).all() and abs(float(score[0])) < 1e-3
+
+
+def test_cached_detector_axes_follow_the_detector():
+    """DRR._grid_axes: the pixel-row / pixel-column coordinates handed to the pose-in kernels are cached contiguous copies of
+    detector.target[:, 0, 1] / [0, :, 0]; a row block (ray sharding) and a detector rebuilt by set_intrinsics_ get their own."""
+    vol = synthetic.make_volume((20, 24, 28), "phantom", seed=3)
+    drr = DRR(synthetic.make_subject(vol), **synthetic.detector_kwargs(32))
+    grid = drr.detector.target.view(32, 32, 3)
+    rows, cols = drr._grid_axes(None)
+    assert torch.equal(rows, grid[:, 0, 1]) and torch.equal(cols, grid[0, :, 0]) and rows.is_contiguous() and cols.is_contiguous()
+    assert drr._grid_axes(None)[0] is rows                     # cached
+    block, _ = drr._grid_axes((2, 5))
+    assert torch.equal(block, grid[2:5, 0, 1])
+    drr.set_intrinsics_(height=16, width=20)
+    rows2, cols2 = drr._grid_axes(None)
+    assert rows2.numel() == 16 and cols2.numel() == 20
