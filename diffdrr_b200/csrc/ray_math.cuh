@@ -313,6 +313,14 @@ B200_HD Walk start_walk_box(const Ray& ray, const int lo_v[3], const int hi_v[3]
 // entry alpha and (near-)ties between a slab face and another axis' plane are ordered the same way on both sides.
 // The backward pass needs this: an inconsistent order drops or doubles one crossing coefficient (the forward sum
 // does not care, the affected segment has ~zero length).
+// CUT = true (boxes cut along an axis other than 0: the major-axis pieces): the exit tail of the lean backward / sensitivities
+// walks takes the crossings that TIE with the exit alpha on axes BELOW the exit axis before it leaves (stable order, lowest axis
+// first), and leaves the ties on higher axes to the next box.  The entry rule below must mirror that at an INTERIOR face, or a
+// tied crossing of a lower axis is counted by both boxes (its coefficient doubled on that axis and taken off the face axis: the
+// sum of the coefficients still telescopes, their attribution does not -- found as 3-13 rays per 10^6 that run through a voxel
+// edge exactly on a cut, 4e-3 of the largest gradient).  Slabs along axis 0 have no lower axis, so CUT = false is exact for them
+// (and keeps the production slab kernels' code unchanged).
+template <bool CUT = false>
 B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_v[3], const int hi_v[3], float shift)
 {
     Walk w;
@@ -365,6 +373,19 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
     }
     // a_in == a_out is a (zero-length) hit here: the voxel touched still takes part in the crossing bookkeeping
     w.hit = (av_in < av_out) && (w.a_in <= w.a_out);
+    // CUT: does the ray enter this box through an interior face (a cut), i.e. did another box's tail run just before?  A cut
+    // face that TIES with a face of the whole volume is the entry face (the box before it counts as touched: a_in <= a_out above).
+    bool interior = false;
+    if constexpr (CUT) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int p = w.sti[a] > 0 ? lo_v[a] : hi_v[a];
+            const bool cut_face = p > 0 && p < dims.d[a];
+            const bool take = cut_face && lo[a] == w.a_in;
+            w.entry_axis = take ? a : w.entry_axis;
+            interior = interior || take;
+        }
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const bool fwd = w.sti[a] > 0;
@@ -374,8 +395,18 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
         i = i < lo_i ? lo_i : (i > hi_i ? hi_i : i);
         const float a_behind = fmaf(((float)(fwd ? i : i + 1) - pref[a]) * sg, w.da[a], w.a0[a]);
         const float a_ahead = fmaf(((float)(fwd ? i + 1 : i) - pref[a]) * sg, w.da[a], w.a0[a]);
-        const bool back = (a_behind >= w.a_in) && (fwd ? i > lo_i : i < hi_i);
-        const bool ahead = !(a_behind >= w.a_in) && (a_ahead < w.a_in) && (fwd ? i < hi_i : i > lo_i);
+        bool back, ahead;
+        if constexpr (CUT) {
+            // ties with a_in on this axis were already crossed by the previous box's tail (see CUT above)
+            const bool prev_took_ties = interior && a < w.entry_axis;
+            const bool behind_is_ours = prev_took_ties ? (a_behind > w.a_in) : (a_behind >= w.a_in);
+            const bool ahead_is_theirs = prev_took_ties ? (a_ahead <= w.a_in) : (a_ahead < w.a_in);
+            back = behind_is_ours && (fwd ? i > lo_i : i < hi_i);
+            ahead = !behind_is_ours && ahead_is_theirs && (fwd ? i < hi_i : i > lo_i);
+        } else {
+            back = (a_behind >= w.a_in) && (fwd ? i > lo_i : i < hi_i);
+            ahead = !(a_behind >= w.a_in) && (a_ahead < w.a_in) && (fwd ? i < hi_i : i > lo_i);
+        }
         i += back ? -w.sti[a] : (ahead ? w.sti[a] : 0);
         i = (lo[a] >= w.a_in) ? (fwd ? lo_i : hi_i) : i;
         w.idx[a] = i;
@@ -952,13 +983,13 @@ struct LoadChunk {
 
 // The sensitivities walk of one ray restricted to a box, for a ray whose major axis is M: same walk, tie order and
 // tail as siddon_ray_bwd_lean_box, two accumulated axes + the telescoping identities.  A, C accumulated INTO.
-template <int U, int M, class Load = LoadPlain>
+template <int U, int M, class Load = LoadPlain, bool CUT = false>
 B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
                                     int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
 {
     using Ax = MinorAxes<M>;
     Load loader;
-    const Walk w = start_walk_frame(ray, dims, lo_v, hi_v, shift);
+    const Walk w = start_walk_frame<CUT>(ray, dims, lo_v, hi_v, shift);
     if (!w.hit) return 0.0f;
     LeanConst k;
     LeanState s;
@@ -999,19 +1030,42 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
     {
         const bool t0 = s.an0 <= k.a_out, t1 = s.an1 <= k.a_out, t2 = s.an2 <= k.a_out;
         const bool b0 = s.nf0 == w.nx[0], b1 = s.nf1 == w.nx[1], b2 = s.nf2 == w.nx[2];
-        if (t0 && b0) ax_exit = 0;
-        if (ax_exit == 3 && t0) {
-            s.off += k.so0;
-            const float vm = loader.at(vol, s.off);
-            minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-            vprev = vm;
-        }
-        if (ax_exit == 3 && t1 && b1) ax_exit = 1;
-        if (ax_exit == 3 && t1) {
-            s.off += k.so1;
-            const float vm = loader.at(vol, s.off);
-            minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-            vprev = vm;
+        if constexpr (CUT) {
+            // a cut face (interior exit plane of the major axis) reached at a_out is THE exit face even when a face of the whole
+            // volume on a lower axis ties with it -- the next box counts itself as touched and leaves through that face
+            // (start_walk_frame<true>); tied crossings of lower axes that are not box faces are still taken first
+            const int pm = w.sti[M] > 0 ? hi_v[M] : lo_v[M];
+            const bool tm = M == 0 ? t0 : (M == 1 ? t1 : t2), bm = M == 0 ? b0 : (M == 1 ? b1 : b2);
+            const bool cut_exit = tm && bm && pm > 0 && pm < dims.d[M];
+            if (t0 && b0 && !(cut_exit && 0 < M)) ax_exit = 0;
+            if (ax_exit == 3 && t0 && !b0) {
+                s.off += k.so0;
+                const float vm = loader.at(vol, s.off);
+                minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+                vprev = vm;
+            }
+            if (ax_exit == 3 && t1 && b1 && !(cut_exit && 1 < M)) ax_exit = 1;
+            if (ax_exit == 3 && t1 && !b1) {
+                s.off += k.so1;
+                const float vm = loader.at(vol, s.off);
+                minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+                vprev = vm;
+            }
+        } else {
+            if (t0 && b0) ax_exit = 0;
+            if (ax_exit == 3 && t0) {
+                s.off += k.so0;
+                const float vm = loader.at(vol, s.off);
+                minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+                vprev = vm;
+            }
+            if (ax_exit == 3 && t1 && b1) ax_exit = 1;
+            if (ax_exit == 3 && t1) {
+                s.off += k.so1;
+                const float vm = loader.at(vol, s.off);
+                minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+                vprev = vm;
+            }
         }
         if (ax_exit == 3 && t2 && b2) ax_exit = 2;
         if (ax_exit == 3) ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
@@ -1027,15 +1081,15 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
 }
 
 // Dispatch on the ray's major axis (uniform per warp except for rays near a 45-degree direction).
-template <int U, class Load = LoadPlain>
+template <int U, class Load = LoadPlain, bool CUT = false>
 B200_HD float siddon_ray_sens_box(const float* vol, const VolDims& dims, const int lo_v[3], const int hi_v[3], int st0,
                                   int st1, int st2, const Ray& ray, float shift, float A[3], float C[3])
 {
     const float a0 = fabsf(ray.d[0]), a1 = fabsf(ray.d[1]), a2 = fabsf(ray.d[2]);
     if (a0 >= a1 && a0 >= a2)
-        return siddon_ray_sens_box_m<U, 0, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
-    if (a1 >= a2) return siddon_ray_sens_box_m<U, 1, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
-    return siddon_ray_sens_box_m<U, 2, Load>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+        return siddon_ray_sens_box_m<U, 0, Load, CUT>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    if (a1 >= a2) return siddon_ray_sens_box_m<U, 1, Load, CUT>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
+    return siddon_ray_sens_box_m<U, 2, Load, CUT>(vol, dims, lo_v, hi_v, st0, st1, st2, ray, shift, A, C);
 }
 
 // Backward of one ray restricted to the sub-box [lo, hi) (closed form, see siddon_ray_bwd below for the algebra).

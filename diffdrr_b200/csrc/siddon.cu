@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(TW* TH, MINB) siddon_sens_slab_kernel(const fl
     if (MAJ && !major_axis_piece(ray, dims, sl, slab, lo_v, hi_v)) return;
     if (box_surely_missed(ray, lo_v, hi_v, shift)) return;  // most (ray, slab) pairs: skip the walk set-up
     float A[3] = {0.0f, 0.0f, 0.0f}, C[3] = {0.0f, 0.0f, 0.0f};
-    const float S = siddon_ray_sens_box<U>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
+    const float S = siddon_ray_sens_box<U, LoadPlain, MAJ>(vol, dims, lo_v, hi_v, dims.d[1] * dims.d[2], dims.d[2], 1, ray, shift, A, C);
     float jt[3], js[3];
     bool any = S != 0.0f;
 #pragma unroll

@@ -167,7 +167,8 @@ void emu_siddon_sens(const float* vol, int D0, int D1, int D2, const float* src,
                 if (slab < 0 && !major_axis_piece(ray, dims, sl, -slab, lo_v, hi_v)) continue;
                 if (slab != 0 && box_surely_missed(ray, lo_v, hi_v, shift)) continue;  // as the slab kernels do
                 float A[3] = {0, 0, 0}, C[3] = {0, 0, 0};
-                const float S = siddon_ray_sens_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C);
+                const float S = slab < 0 ? siddon_ray_sens_box<4, LoadPlain, true>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C)
+                                         : siddon_ray_sens_box<4>(vol, dims, lo_v, hi_v, D1 * D2, D2, 1, ray, shift, A, C);
                 for (int a = 0; a < 3; ++a) {
                     const float k = L * ray.inv[a];
                     sens[a] += -k * A[a];

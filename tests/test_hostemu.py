@@ -578,3 +578,34 @@ def test_major_axis_pieces_forward(name, kw):
         out = emu.siddon_fwd_lean_pieces(g["volume"], g["source"], g["target"], g["raylen"], pieces, **kw)
         assert relerr(out, g["img_f64"]) < IMG_TOL, pieces
         assert relerr(out, whole) < 1e-5, pieces  # fp32 summation order only
+
+
+def test_major_axis_pieces_keep_every_crossing_coefficient_on_its_axis():
+    """Regression (found on B200 as 3-13 rays per 10^6 with per-ray gradients 4e-3 .. 9e-3 of the maximum off): a ray that runs
+    through a voxel EDGE exactly on a cut between two major-axis pieces had the tied crossing of the LOWER axis counted by both
+    pieces (the exit tail takes ties below the exit axis, the entry rule re-took them), and a cut that ties with a face of the
+    whole volume was entered / left through the wrong face -- the coefficients still telescoped (images and source gradients
+    unaffected), their attribution to the axes did not.  512^3 -> 256^2, pose 1 of the bench's pose set, detector rows 45-70
+    (they hold one ray of each kind): 12 pieces against the un-cut walk."""
+    import torch
+    from diffdrr_b200 import DRR, synthetic
+    from diffdrr_b200.pose import convert
+    D, H = 512, 256
+    x = torch.linspace(-1, 1, D)
+    vol = torch.exp(-((x[:, None, None] - 0.1) ** 2 + (x[None, :, None] + 0.2) ** 2 + x[None, None, :] ** 2) / 0.3).numpy()
+    subj = synthetic.make_subject(torch.zeros(1, 1, 1, 1))
+    subj.volume.affine = synthetic.make_affine(D)
+    drr = DRR(subj, **synthetic.detector_kwargs(H))
+    rot, xyz = synthetic.make_poses(2, seed=0)
+    with torch.no_grad():
+        src, tgt = drr.detector(convert(rot[1:], xyz[1:], parameterization="euler_angles", convention="ZXY"), None)
+        raylen = (tgt - src).norm(dim=-1).unsqueeze(1)
+        src, tgt = drr.affine_inverse(src), drr.affine_inverse(tgt)
+    rows = slice(45 * H, 71 * H)
+    s, t, l = src.numpy(), tgt[:, rows].numpy(), raylen[:, :, rows].numpy()
+    w = np.ones_like(l)
+    cut = emu.siddon_sens(vol, s, t, l, w, slab=-12)
+    whole = emu.siddon_sens(vol, s, t, l, w, slab=0)
+    assert relerr(cut["img"], whole["img"]) < 1e-5
+    assert relerr(cut["g_source"], whole["g_source"]) < 1e-5
+    assert relerr(cut["g_target"], whole["g_target"]) < 1e-5   # 1.6e-2 before the fix
