@@ -7,6 +7,7 @@ Only normalized cross correlation is provided -- the loss of the reference's reg
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -30,6 +31,7 @@ class _NCCFunction(torch.autograd.Function):
         return score
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gscore):
         x1, x2, stats = ctx.saved_tensors
         B, C = x1.shape[0], x1.shape[1]
