@@ -54,8 +54,11 @@ int b200drr_siddon_fwd(const float *vol, int D0, int D1, int D2, const float *sr
  * Siddon forward for a FULL detector grid: the N = H*W rays of every pose are the row-major detector
  * pixels (n = h*W + w; reference detector.py:126), which lets the kernel map compact pixel tiles onto
  * warps/CTAs for cache locality.  Same result as b200drr_siddon_fwd(reduce=0, align_corners=0).
- * variant: 0 = tuned default; other values select tile-shape / unroll variants for benchmarking
- * (cudaErrorInvalidValue if unknown).
+ * variant: 0 = tuned default -- up to 16 poses of 256^2 rays (volumes >= 384 voxels; smaller ones up to 4) every ray is cut into
+ * pieces along its own major axis with a thread per (ray, piece), beyond that the volume is cut into 32-plane slabs that the poses
+ * of the batch share through L2; other values select kernels for benchmarking: 15 = the slab-major kernel,
+ * 100+K / 200+K / 300+K / 400+K (K = 1..64) = K major-axis pieces with 16x16/U4, 8x16/U8, 16x8/U4, 8x16/U4 tiles, further ids =
+ * tile-shape / unroll variants (cudaErrorInvalidValue if unknown).
  */
 int b200drr_siddon_fwd_grid(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
                             const float *raylen, float *out, int B, int H, int W, float voxel_shift, float eps,
@@ -119,7 +122,9 @@ int b200drr_siddon_bwd_pose(const float *vol, int D0, int D1, int D2, const floa
  *   sens [B][H*W][8]  { dI/dtgt0, dI/dtgt1, dI/dtgt2, S = out/raylen, dI/dsrc0, dI/dsrc1, dI/dsrc2, 0 }
  * and autograd's backward (what torch derives for renderers.py:40-86 given g = dLoss/dout) is the elementwise
  * b200drr_siddon_bwd_sens below.  Replaces a forward walk + a backward walk by one.  No volume gradient on this path
- * (use b200drr_siddon_bwd_grid when the volume requires grad).  variant 0 = tuned default.
+ * (use b200drr_siddon_bwd_grid when the volume requires grad).  variant 0 = tuned default (major-axis pieces up to 6 poses of
+ * 256^2 rays, 48-plane slabs beyond); 38 = the 48-plane-slab kernel; 100+K / 300+K / 400+K = K major-axis pieces (8x16/U8, 16x8/U8,
+ * 8x16/U4 tiles); further ids = tile / unroll / slab-height variants for benchmarking.
  */
 int b200drr_siddon_fwd_sens(const float *vol, int D0, int D1, int D2, const float *src, const float *tgt,
                             const float *raylen, float *out, float *sens, int B, int64_t N, float voxel_shift, float eps,
