@@ -373,8 +373,14 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
     }
     // a_in == a_out is a (zero-length) hit here: the voxel touched still takes part in the crossing bookkeeping
     w.hit = (av_in < av_out) && (w.a_in <= w.a_out);
-    // CUT: does the ray enter this box through an interior face (a cut), i.e. did another box's tail run just before?  A cut
-    // face that TIES with a face of the whole volume is the entry face (the box before it counts as touched: a_in <= a_out above).
+    // CUT: the un-cut walk processes the events of one alpha in this order -- entry into the volume, then the crossings lowest
+    // axis first, the exit at its axis' turn (tied crossings on higher axes are dropped) -- and a cut on axis M is the M-crossing
+    // of that list: everything before it belongs to the box that is left, everything after it to the box that is entered.  So
+    //  * a cut face that TIES with an entry face of the whole volume is the entry face of this box (the box before it was
+    //    entered through the volume face and counts as touched: a_in <= a_out above);
+    //  * a box that is entered through a cut and left at the same alpha was reached only if the cut comes before that exit in
+    //    axis order (otherwise the previous box's tail already left the volume through the lower axis' face);
+    //  * ties with a_in on axes below the cut were crossed by the previous box's tail (prev_took_ties below).
     bool interior = false;
     if constexpr (CUT) {
 #pragma unroll
@@ -385,6 +391,15 @@ B200_HD Walk start_walk_frame(const Ray& ray, const VolDims& dims, const int lo_
             w.entry_axis = take ? a : w.entry_axis;
             interior = interior || take;
         }
+        int exit_axis = 3;
+#pragma unroll
+        for (int a = 2; a >= 0; --a) {  // lowest axis whose exit plane is at a_out (same expressions as above: bit-identical alphas)
+            const float sg = (float)w.sti[a];
+            const float a0 = fmaf(((float)lo_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
+            const float a1 = fmaf(((float)hi_v[a] - pref[a]) * sg, w.da[a], w.a0[a]);
+            exit_axis = (fmaxf(a0, a1) == w.a_out) ? a : exit_axis;
+        }
+        w.hit = w.hit && !(interior && w.a_in == w.a_out && exit_axis < w.entry_axis);
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -1030,42 +1045,19 @@ B200_HD float siddon_ray_sens_box_m(const float* vol, const VolDims& dims, const
     {
         const bool t0 = s.an0 <= k.a_out, t1 = s.an1 <= k.a_out, t2 = s.an2 <= k.a_out;
         const bool b0 = s.nf0 == w.nx[0], b1 = s.nf1 == w.nx[1], b2 = s.nf2 == w.nx[2];
-        if constexpr (CUT) {
-            // a cut face (interior exit plane of the major axis) reached at a_out is THE exit face even when a face of the whole
-            // volume on a lower axis ties with it -- the next box counts itself as touched and leaves through that face
-            // (start_walk_frame<true>); tied crossings of lower axes that are not box faces are still taken first
-            const int pm = w.sti[M] > 0 ? hi_v[M] : lo_v[M];
-            const bool tm = M == 0 ? t0 : (M == 1 ? t1 : t2), bm = M == 0 ? b0 : (M == 1 ? b1 : b2);
-            const bool cut_exit = tm && bm && pm > 0 && pm < dims.d[M];
-            if (t0 && b0 && !(cut_exit && 0 < M)) ax_exit = 0;
-            if (ax_exit == 3 && t0 && !b0) {
-                s.off += k.so0;
-                const float vm = loader.at(vol, s.off);
-                minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-                vprev = vm;
-            }
-            if (ax_exit == 3 && t1 && b1 && !(cut_exit && 1 < M)) ax_exit = 1;
-            if (ax_exit == 3 && t1 && !b1) {
-                s.off += k.so1;
-                const float vm = loader.at(vol, s.off);
-                minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-                vprev = vm;
-            }
-        } else {
-            if (t0 && b0) ax_exit = 0;
-            if (ax_exit == 3 && t0) {
-                s.off += k.so0;
-                const float vm = loader.at(vol, s.off);
-                minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-                vprev = vm;
-            }
-            if (ax_exit == 3 && t1 && b1) ax_exit = 1;
-            if (ax_exit == 3 && t1) {
-                s.off += k.so1;
-                const float vm = loader.at(vol, s.off);
-                minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
-                vprev = vm;
-            }
+        if (t0 && b0) ax_exit = 0;
+        if (ax_exit == 3 && t0) {
+            s.off += k.so0;
+            const float vm = loader.at(vol, s.off);
+            minor_accumulate(Ax::local(0), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+            vprev = vm;
+        }
+        if (ax_exit == 3 && t1 && b1) ax_exit = 1;
+        if (ax_exit == 3 && t1) {
+            s.off += k.so1;
+            const float vm = loader.at(vol, s.off);
+            minor_accumulate(Ax::local(1), vprev - vm, k.a_out, Au, Av, Cu, Cv);
+            vprev = vm;
         }
         if (ax_exit == 3 && t2 && b2) ax_exit = 2;
         if (ax_exit == 3) ax_exit = (s.an0 <= s.an1 && s.an0 <= s.an2) ? 0 : (s.an1 <= s.an2 ? 1 : 2);
