@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200DRR_VERSION 100 /* major*10000 + minor*100 + patch */
+#define B200DRR_VERSION 200 /* major*10000 + minor*100 + patch */
 
 #define B200DRR_EINVAL (-1)      /* null pointer / non-positive size / bad enum */
 #define B200DRR_EUNSUPPORTED (-2) /* combination the kernels do not implement (documented per call) */

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in the header but not exported by libb200drr.so"
     assert sorted(_lib.exported_symbols()) == declared, "ctypes binding and header disagree"
-    assert lib.b200drr_version() == 100
+    assert lib.b200drr_version() == 200  # 0.2.0: + b200drr_ncc_* (round 2)
 
 
 def test_argument_validation_without_gpu(lib):
